@@ -1,0 +1,111 @@
+/* C ABI of libunitspeech_b200.so -- the B200 (sm_100a) reverse-diffusion mel decoder of UnitSpeech.
+ *
+ * The reference has no FFI: its boundary is the Python class unitspeech.unitspeech.UnitSpeech
+ * (unitspeech/unitspeech.py:220).  This header is the boundary we introduce underneath an identically named
+ * Python class (unitspeech_b200/decoder.py); each entry cites the reference interface it stands in for.
+ *
+ * Conventions
+ *  - plain C types only; every tensor is a raw pointer to contiguous fp32 in the reference's own layout
+ *    ((B, n_feats, T) mels, (B, T) masks, (B, spk_emb_dim) speaker embeddings);
+ *  - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are CPU memory;
+ *  - the caller owns all tensors; the handle owns weights and workspace;
+ *  - every function returns 0 on success, non-zero on failure; usb_last_error() gives the message of the last
+ *    failure on the calling thread.  Nothing throws across the ABI and there is no CPU fallback;
+ *  - a handle is bound to one device and is not thread-safe; all work is enqueued on the given stream
+ *    (pass the integer value of a cudaStream_t, 0 = legacy default stream); no hidden synchronisation except
+ *    where stated (the *_host entry, workspace growth).
+ *  - batch semantics: every utterance is sampled exactly like a batch-1 call of the reference (the reference's
+ *    own B>1 path is broken, unitspeech/unitspeech.py:338-347,301-305).
+ */
+#ifndef UNITSPEECH_B200_H
+#define UNITSPEECH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct usb_handle usb_handle;
+
+/* Constructor arguments of UnitSpeech / GradLogPEstimator2d (unitspeech/unitspeech.py:221-233,125-162). */
+typedef struct usb_config {
+    int32_t n_feats;        /* mel bins (80) */
+    int32_t dim;            /* base channels (128); must be 64, 128 or 256 */
+    int32_t n_mults;        /* len(dim_mults), 2..4 */
+    int32_t dim_mults[8];   /* (1, 2, 4, 8) */
+    int32_t groups;         /* GroupNorm groups (8) */
+    int32_t spk_emb_dim;    /* 256 */
+    float pe_scale;         /* 1000 */
+    float beta_min;         /* 0.05 (kept for completeness; the schedule is computed by the host) */
+    float beta_max;         /* 20 */
+    int32_t device;         /* CUDA device ordinal */
+} usb_config;
+
+const char* usb_last_error(void);
+int usb_version(void);
+
+/* UnitSpeech(...).to(device)                                                  unitspeech/unitspeech.py:221 */
+int usb_create(const usb_config* cfg, usb_handle** out);
+void usb_destroy(usb_handle* h);
+
+/* load_state_dict: one call per state_dict entry, reference key names and shapes (SURVEY Appendix B.3;
+ * inference.py:66-73).  `data` is host fp32.  The extra key "__posemb_freqs" ((dim/2,)) carries the sinusoidal
+ * frequency table computed by the host with the reference's torch ops (unitspeech/unitspeech.py:116-118). */
+int usb_load_param(usb_handle* h, const char* key, const float* host_data, const int64_t* shape, int32_t ndim);
+/* repack to kernel layouts (fp16 K-major GEMM operands) and upload; call after the last usb_load_param */
+int usb_finalize_params(usb_handle* h);
+
+/* GradLogPEstimator2d.forward(x, mask, mu, t, spk_emb)                         unitspeech/unitspeech.py:164-201
+ * x, mu: (Be, n_feats, T) dev; mask: (Be, T) dev; t: (Be,) dev; spk: (Be, spk_emb_dim) dev; out: (Be, n_feats, T) dev */
+int usb_estimator_forward(usb_handle* h, const float* x, const float* mu, const float* mask, const float* t,
+                          const float* spk, float* out, int32_t Be, int32_t T, uint64_t stream);
+
+/* UnitSpeech.reverse_diffusion(z, mask, cond, spk_emb, n_timesteps, tg, sg)     unitspeech/unitspeech.py:334-374
+ * z, cond: (B, n_feats, T) dev; mask: (B, T) dev; spk: (B, spk_emb_dim) dev;
+ * noise: (n, B, n_feats, T) dev, the per-step randn draws (:367), or NULL for all-zero noise;
+ * coef: host (n, 3) = [c_x, c_s, sigma] per step i (closed form of :273-296 at table index n-1-i);
+ * t_steps: host (n,) = t_i (:361);  text_uncon (n_feats,) and spk_uncon_normed (spk_emb_dim,) come from the
+ * loaded parameters (spk_uncon is normalised by its own L2 norm, :358).
+ * out: (B, n_feats, T) dev; trace: optional dev (n, B, n_feats, T) receiving x_t after every step (drift reports). */
+int usb_reverse_diffusion(usb_handle* h, const float* z, const float* cond, const float* mask, const float* spk,
+                          const float* noise, const float* coef_host, const float* t_steps_host, int32_t n_steps,
+                          float text_scale, float spk_scale, float* out, float* trace, int32_t B, int32_t T,
+                          uint64_t stream);
+
+/* Same call with HOST buffers (pinned or pageable): uploads inputs, runs, downloads `out`, synchronises the stream.
+ * This is the end-to-end entry a caller holding CPU tensors uses (inference.py:128-140 with .cpu() tensors). */
+int usb_reverse_diffusion_host(usb_handle* h, const float* z, const float* cond, const float* mask,
+                               const float* spk, const float* noise, const float* coef_host,
+                               const float* t_steps_host, int32_t n_steps, float text_scale, float spk_scale,
+                               float* out, int32_t B, int32_t T, uint64_t stream);
+
+/* bytes of device workspace the handle holds for (Be, T); 0 if that shape has not been planned yet */
+int64_t usb_workspace_bytes(usb_handle* h);
+/* number of kernels launched by the handle since creation (bench.py's gpu_launches) */
+int64_t usb_launch_count(usb_handle* h);
+
+/* ---- operator-level entries (parity tests of single kernels against torch fp32) ---------------------------- */
+/* NHWC fp16 convolution on the tcgen05 implicit-GEMM kernel.
+ * kind: 0 = 3x3 stride 1 pad 1, 1 = 3x3 stride 2 pad 1, 2 = 1x1, 3 = ConvTranspose 4x4 stride 2 pad 1.
+ * in0: (N, H, W, C0) fp16 dev; in1: optional second K source (N, H, W, C1) (kind 0/2 only);
+ * weight: host fp32 in the reference's layout ((Cout, C0+C1, k, k); ConvTranspose (Cin, Cout, 4, 4));
+ * bias: host fp32 (Cout) or NULL; mask: dev fp32 (N, Wout) or NULL; residual: dev fp16 shaped like out or NULL;
+ * res_scale: residual blend out = conv*res_scale + residual; stats: dev double (N, groups, 2) accumulated
+ * (sum, sumsq of conv+bias) or NULL; out: (N, Hout, Wout, Cout) fp16 dev. */
+int usb_op_conv(usb_handle* h, int32_t kind, const void* in0, const void* in1, int32_t N, int32_t H, int32_t W,
+                int32_t C0, int32_t C1, int32_t Cout, const float* weight_host, const float* bias_host,
+                const float* mask, const void* residual, float res_scale, double* stats, int32_t groups, void* out,
+                uint64_t stream);
+/* out = (Mish(GroupNorm(raw)) + addvec[n][c] + res) * mask on NHWC fp16; gamma/beta/addvec dev fp32 */
+int usb_op_gn_apply(usb_handle* h, const void* raw, const double* stats, const float* gamma, const float* beta,
+                    const float* addvec, const void* res, const float* mask, void* out, int32_t N, int32_t H,
+                    int32_t W, int32_t C, int32_t groups, uint64_t stream);
+/* LinearAttention context folded with to_out: qkv (N, P, 384) fp16 dev, wo dev fp32 (C, 128) -> weff (N, C, 128) fp16 */
+int usb_op_attn_context(usb_handle* h, const void* qkv, const float* wo, void* weff, int32_t N, int32_t P, int32_t C,
+                        int32_t heads, uint64_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

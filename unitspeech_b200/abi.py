@@ -1,0 +1,81 @@
+"""ctypes binding of libunitspeech_b200.so (declared in include/unitspeech_b200.h).
+
+There is no fallback: if the shared library is missing or fails to load, importing the decoder raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libunitspeech_b200.so")
+
+
+class UsbConfig(ctypes.Structure):
+    _fields_ = [
+        ("n_feats", c_int32),
+        ("dim", c_int32),
+        ("n_mults", c_int32),
+        ("dim_mults", c_int32 * 8),
+        ("groups", c_int32),
+        ("spk_emb_dim", c_int32),
+        ("pe_scale", c_float),
+        ("beta_min", c_float),
+        ("beta_max", c_float),
+        ("device", c_int32),
+    ]
+
+
+class UsbError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); the single source of truth checked against include/unitspeech_b200.h by the tests
+SIGNATURES = {
+    "usb_last_error": (c_char_p, []),
+    "usb_version": (c_int32, []),
+    "usb_create": (c_int32, [POINTER(UsbConfig), POINTER(c_void_p)]),
+    "usb_destroy": (None, [c_void_p]),
+    "usb_load_param": (c_int32, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int32]),
+    "usb_finalize_params": (c_int32, [c_void_p]),
+    "usb_estimator_forward": (c_int32, [c_void_p] + [c_void_p] * 6 + [c_int32, c_int32, c_uint64]),
+    "usb_reverse_diffusion": (c_int32, [c_void_p] + [c_void_p] * 7 + [c_int32, c_float, c_float, c_void_p, c_void_p,
+                                                                    c_int32, c_int32, c_uint64]),
+    "usb_reverse_diffusion_host": (c_int32, [c_void_p] + [c_void_p] * 7 + [c_int32, c_float, c_float, c_void_p,
+                                                                         c_int32, c_int32, c_uint64]),
+    "usb_workspace_bytes": (c_int64, [c_void_p]),
+    "usb_launch_count": (c_int64, [c_void_p]),
+    "usb_op_conv": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                              c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p,
+                              c_uint64]),
+    "usb_op_gn_apply": (c_int32, [c_void_p] + [c_void_p] * 8 + [c_int32] * 5 + [c_uint64]),
+    "usb_op_attn_context": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                      c_uint64]),
+}
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads the CUDA library; raises if it has not been built (python -m unitspeech_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UsbError(f"{LIB_PATH} not found: build it with `python -m unitspeech_b200.build` "
+                       "(there is no CPU or PyTorch fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load_library().usb_last_error()
+        raise UsbError(msg.decode() if msg else f"libunitspeech_b200 call failed ({rc})")

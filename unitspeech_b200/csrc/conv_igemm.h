@@ -1,0 +1,61 @@
+// Parameters of the generalised implicit-GEMM convolution kernel (conv_igemm.cu).
+//
+// One kernel covers every dense contraction of the U-Net except the 2-channel input conv:
+//   3x3 stride-1 convs of Block (unitspeech/unitspeech.py:46-55), with an optional second K source for the
+//   skip concat (:192), 3x3 stride-2 Downsample (:27-33), the 1x1 res_conv/to_qkv/to_out convs (:66,83-84)
+//   (to_out with a per-sample folded weight), and ConvTranspose2d 4x4/s2 (:18-24) as four 2x2 phase convs.
+//
+// GEMM view: M = 128 pixels of one sample (a BH x BW patch of the "tile space"), N = BN output channels,
+// K = taps x input channels, walked in 64-channel steps.  Activations are NHWC fp16; the A operand of a K step
+// is one TMA box {64 ch, BW, 1, BH, 1} of a 5-D view (c', x, p, y, n) of the input tensor, shifted by the tap
+// offset (out-of-bounds rows/columns are zero-filled by TMA = conv padding).  For stride-2 convs the view
+// splits H and W by parity (p = row parity, column parity folded into c') so the box stays dense.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace usb {
+
+constexpr int kConvThreads = 256;      // warp0 TMA producer, warp1 MMA issuer, warp2 TMEM alloc, warps4-7 epilogue
+constexpr int kConvBM = 128;           // pixels per tile (UMMA M)
+constexpr int kConvBK = 64;            // channels per K step (128 B of fp16 = one swizzle row)
+constexpr int kConvMaxTaps = 16;       // phases x taps
+constexpr int kConvSmemBytes = 225 * 1024;
+
+struct ConvTap {
+    int16_t c;    // offset added to the channel coordinate (column-parity * C for stride-2 views)
+    int8_t dx;    // offset added to the x coordinate
+    int8_t dy;    // offset added to the y coordinate
+    int8_t p;     // coordinate in the parity dimension
+    int8_t pad[3];
+};
+
+struct ConvParams {
+    // tile space (per sample): Hm x Wm pixels in BH x BW patches, BH*BW == 128, BH divides Hm
+    int N, Hm, Wm, BH, BW, tiles_y, tiles_x;
+    int Cout, BN, n_tiles_n;
+    int phases, taps;          // taps per phase; tap table indexed [phase*taps + t]
+    int chunks0, chunks1;      // 64-channel K chunks per tap from source 0 / source 1 (0 = no second source)
+    int b_batch_mode;          // B z-coordinate: 0 -> 0, 1 -> phase, 2 -> sample
+    int stages;                // smem pipeline depth
+    ConvTap tap[kConvMaxTaps];
+    // epilogue: v = acc + bias[c]; stats (sum, sumsq per (n, group)) on v; v = v*res_scale + res; v *= mask
+    const float* bias;         // [Cout] or null
+    double* stats;             // [N][groups][2] or null
+    int groups;                // GroupNorm groups (stats only)
+    const __half* res;         // residual, same geometry as out, or null
+    const float* res_scale;    // device scalar (Rezero g) or null (=1)
+    const float* mask;         // [N][mask_stride] indexed by the OUTPUT x coordinate, or null
+    int mask_stride;
+    __half* out;               // element (n, yo, xo, c) at out[n*o_sn + yo*o_sy + xo*o_sx + c]
+    long long o_sn, o_sy, o_sx;
+    int oy_mul, ox_mul;        // yo = y*oy_mul + oy_off[phase], xo = x*ox_mul + ox_off[phase]
+    int8_t oy_off[4], ox_off[4];
+};
+
+// launches on `stream`; returns cudaError_t as int
+int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                      int num_sms, cudaStream_t stream);
+
+}  // namespace usb

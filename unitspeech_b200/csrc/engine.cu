@@ -1,0 +1,1103 @@
+// Host runtime + C ABI of libunitspeech_b200.so: parameter repacking, workspace/plan construction (buffers, TMA
+// tensor maps, kernel parameter blocks) and the launch sequences of the score estimator and the sampler loop.
+// Reference semantics followed here: GradLogPEstimator2d.forward (unitspeech/unitspeech.py:164-201),
+// classifier_free_guidance (:298-331), reverse_diffusion (:334-374).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/unitspeech_b200.h"
+#include "conv_igemm.h"
+#include "kernels.h"
+
+namespace usb {
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+    g_err = m;
+    return 1;
+}
+#define USB_CUDA(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +            \
+                        std::to_string(__LINE__) + ")");                                                     \
+    } while (0)
+#define USB_LAUNCH(h, expr)                                                                                  \
+    do {                                                                                                     \
+        int _e = (expr);                                                                                     \
+        (h)->launches++;                                                                                     \
+        if (_e != 0)                                                                                         \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(static_cast<cudaError_t>(_e)) +       \
+                        " (" __FILE__ ":" + std::to_string(__LINE__) + ")");                                 \
+    } while (0)
+#define USB_TRY(expr)              \
+    do {                           \
+        int _r = (expr);           \
+        if (_r != 0) return _r;    \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA tensor-map encoding through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode_fn() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    USB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || fn == nullptr) return fail("cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u", (int)r,
+                 rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0],
+                 box[1], box[2]);
+        return fail(buf);
+    }
+    return 0;
+}
+
+// 5-D activation view (c', x, p, y, n) of an NHWC fp16 tensor [N][H][W][Ctot], channels [0, Cview) visible.
+// stride2: parity split for stride-2 convs: c' = (x&1)*Ctot + c, x' = x/2, p = y&1, y' = y/2.
+static int make_act_map(CUtensorMap* m, const __half* base, int N, int H, int W, int Ctot, int Cview, bool stride2,
+                        int BH, int BW) {
+    cuuint64_t dims[5], strides[4];
+    const cuuint64_t e = 2;
+    if (!stride2) {
+        dims[0] = Cview; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
+        strides[0] = Ctot * e; strides[1] = (cuuint64_t)W * Ctot * e; strides[2] = (cuuint64_t)W * Ctot * e;
+        strides[3] = (cuuint64_t)H * W * Ctot * e;
+    } else {
+        dims[0] = 2 * Ctot; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+        strides[0] = 2 * Ctot * e; strides[1] = (cuuint64_t)W * Ctot * e; strides[2] = (cuuint64_t)2 * W * Ctot * e;
+        strides[3] = (cuuint64_t)H * W * Ctot * e;
+    }
+    cuuint32_t box[5] = {64, (cuuint32_t)BW, 1, (cuuint32_t)BH, 1};
+    return encode_map(m, base, 5, dims, strides, box);
+}
+
+// weights [Z][Cout][K] fp16, K contiguous
+static int make_w_map(CUtensorMap* m, const __half* base, int Z, int Cout, int K, int BN) {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, (cuuint64_t)Z};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Cout * K * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+    return encode_map(m, base, 3, dims, strides, box);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------------------------
+enum ConvKind { K3S1 = 0, K3S2 = 1, K1 = 2, KT4 = 3 };
+
+struct ConvW {
+    __half* w = nullptr;   // [Z][Cout][K]
+    float* bias = nullptr; // [Cout]
+    int Cout = 0, Cin = 0, K = 0, Z = 1, kind = K3S1;
+};
+
+static inline int taps_of(int kind) { return kind == K3S1 || kind == K3S2 ? 9 : (kind == K1 ? 1 : 4); }
+
+// reference layout -> [Z][Cout][tap*Cin + ci] fp16
+static void pack_conv_host(int kind, const float* w, int Cout, int Cin, std::vector<__half>& out) {
+    if (kind == K3S1 || kind == K3S2) {
+        out.resize((size_t)Cout * 9 * Cin);
+        for (int co = 0; co < Cout; ++co)
+            for (int ci = 0; ci < Cin; ++ci)
+                for (int t = 0; t < 9; ++t)
+                    out[((size_t)co * 9 + t) * Cin + ci] = __float2half_rn(w[((size_t)co * Cin + ci) * 9 + t]);
+    } else if (kind == K1) {
+        out.resize((size_t)Cout * Cin);
+        for (size_t i = 0; i < out.size(); ++i) out[i] = __float2half_rn(w[i]);
+    } else {  // ConvTranspose2d weight (Cin, Cout, 4, 4): out[2a+ph, 2b+pw] phases, 2x2 taps each
+        out.resize((size_t)4 * Cout * 4 * Cin);
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw)
+                for (int co = 0; co < Cout; ++co)
+                    for (int a = 0; a < 2; ++a)
+                        for (int b = 0; b < 2; ++b) {
+                            // ho = 2*hi - 1 + kh: phase 0 uses kh = 1 (hi = a'), 3 (hi = a'-1); phase 1 uses kh = 0 (hi = a'+1), 2
+                            const int kh = ph == 0 ? (a == 0 ? 1 : 3) : (a == 0 ? 0 : 2);
+                            const int kw = pw == 0 ? (b == 0 ? 1 : 3) : (b == 0 ? 0 : 2);
+                            for (int ci = 0; ci < Cin; ++ci)
+                                out[(((size_t)(ph * 2 + pw) * Cout + co) * 4 + (a * 2 + b)) * Cin + ci] =
+                                    __float2half_rn(w[(((size_t)ci * Cout + co) * 4 + kh) * 4 + kw]);
+                        }
+    }
+}
+
+static void fill_taps(int kind, int Ctot0, ConvParams& p) {
+    p.taps = taps_of(kind);
+    p.phases = kind == KT4 ? 4 : 1;
+    memset(p.tap, 0, sizeof p.tap);
+    if (kind == K3S1) {
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                ConvTap& t = p.tap[kh * 3 + kw];
+                t.dy = (int8_t)(kh - 1);
+                t.dx = (int8_t)(kw - 1);
+            }
+    } else if (kind == K3S2) {
+        // input row 2*yo + kh - 1: kh=0 -> odd row yo-1; kh=1 -> even row yo; kh=2 -> odd row yo (same for columns)
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                ConvTap& t = p.tap[kh * 3 + kw];
+                t.dy = (int8_t)(kh == 0 ? -1 : 0);
+                t.p = (int8_t)(kh == 1 ? 0 : 1);
+                t.dx = (int8_t)(kw == 0 ? -1 : 0);
+                t.c = (int16_t)(kw == 1 ? 0 : Ctot0);
+            }
+    } else if (kind == KT4) {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw)
+                for (int a = 0; a < 2; ++a)
+                    for (int b = 0; b < 2; ++b) {
+                        ConvTap& t = p.tap[(ph * 2 + pw) * 4 + a * 2 + b];
+                        t.dy = (int8_t)(ph == 0 ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0));
+                        t.dx = (int8_t)(pw == 0 ? (b == 0 ? 0 : -1) : (b == 0 ? 1 : 0));
+                    }
+    }
+}
+
+struct ConvOp {
+    ConvParams p;
+    CUtensorMap a0, a1, b;
+};
+
+struct ConvEpilogue {
+    const float* bias = nullptr;
+    double* stats = nullptr;
+    int groups = 8;
+    const __half* res = nullptr;
+    const float* res_scale = nullptr;
+    const float* mask = nullptr;  // [N][Wout]
+};
+
+// Builds the parameter block + tensor maps of one convolution launch.
+// in0/in1: NHWC fp16 [N][H][W][Ctot*] of which the first C* channels are contracted; out: [N][Hout][Wout][Cout].
+static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0, const __half* in1, int C1tot, int C1,
+                      int N, int H, int W, const __half* wptr, int wZ, int b_batch_mode, int Cout,
+                      const ConvEpilogue& ep, __half* out) {
+    USB_TRY(load_encode_fn());
+    if (C0 % 64 || C1 % 64 || Cout % 64) return fail("conv channels must be multiples of 64");
+    if (kind == K3S2 && (H % 2 || W % 2 || in1 != nullptr || C0 != C0tot)) return fail("bad stride-2 conv geometry");
+    if (kind == K3S2 && 2 * C0tot > 32767) return fail("stride-2 conv too wide");
+    ConvParams& p = op.p;
+    memset(&p, 0, sizeof p);
+    fill_taps(kind, C0tot, p);
+    p.N = N;
+    p.Hm = kind == K3S2 ? H / 2 : H;
+    p.Wm = kind == K3S2 ? W / 2 : W;
+    int BH = 1;
+    while (BH < 16 && p.Hm % (BH * 2) == 0) BH *= 2;
+    p.BH = BH;
+    p.BW = 128 / BH;
+    p.tiles_y = p.Hm / BH;
+    p.tiles_x = (p.Wm + p.BW - 1) / p.BW;
+    p.Cout = Cout;
+    p.BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    p.n_tiles_n = Cout / p.BN;
+    p.chunks0 = C0 / 64;
+    p.chunks1 = in1 ? C1 / 64 : 0;
+    p.b_batch_mode = b_batch_mode;
+    p.stages = p.BN == 256 ? 4 : (p.BN == 128 ? 6 : 8);
+    p.bias = ep.bias;
+    p.stats = ep.stats;
+    p.groups = ep.groups;
+    if (ep.stats) {
+        const int cpg = Cout / ep.groups;
+        if (Cout % ep.groups || !(cpg == 8 || cpg == 16 || cpg % 32 == 0)) return fail("unsupported GroupNorm width");
+    }
+    p.res = ep.res;
+    p.res_scale = ep.res_scale;
+    p.mask = ep.mask;
+    const int Hout = kind == K3S2 ? H / 2 : (kind == KT4 ? 2 * H : H);
+    const int Wout = kind == K3S2 ? W / 2 : (kind == KT4 ? 2 * W : W);
+    p.mask_stride = Wout;
+    p.out = out;
+    p.o_sx = Cout;
+    p.o_sy = (long long)Wout * Cout;
+    p.o_sn = (long long)Hout * Wout * Cout;
+    p.oy_mul = p.ox_mul = kind == KT4 ? 2 : 1;
+    if (kind == KT4)
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                p.oy_off[ph * 2 + pw] = (int8_t)ph;
+                p.ox_off[ph * 2 + pw] = (int8_t)pw;
+            }
+    USB_TRY(make_act_map(&op.a0, in0, N, H, W, C0tot, C0, kind == K3S2, p.BH, p.BW));
+    if (in1) USB_TRY(make_act_map(&op.a1, in1, N, H, W, C1tot, C1, false, p.BH, p.BW));
+    else op.a1 = op.a0;
+    const int K = p.taps * (C0 + (in1 ? C1 : 0));
+    USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, p.BN));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------------------
+struct HostParam {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+struct GnW {
+    float* gamma = nullptr;
+    float* beta = nullptr;
+};
+struct ResnetW {
+    std::string prefix;
+    int Cin = 0, Cout = 0, emb_off = 0;
+    bool has_res = false;
+    ConvW c1, c2, res;
+    GnW g1, g2;
+};
+struct AttnW {
+    std::string prefix;
+    int C = 0;
+    ConvW qkv;
+    float* wo = nullptr;  // [C][128]
+    float* bo = nullptr;  // [C]
+    float* g = nullptr;   // [1]
+};
+
+struct Op {
+    enum Kind { FIRST, CONV, GN, ATTN } kind;
+    int idx;
+};
+
+struct Plan {
+    int Be = 0, T = 0;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<Op> ops;
+    std::vector<ConvOp> convs;
+    std::vector<GnApplyParams> gns;
+    std::vector<AttnParams> attns;
+    FirstConvParams first;
+    // dynamic inputs
+    float* mask[8] = {nullptr};   // per level [Be][W_l]
+    int* x_row = nullptr;
+    int* mu_row = nullptr;
+    float* spk_rows = nullptr;    // [Be][S]
+    float* t_rows = nullptr;      // [Be]
+    float* u = nullptr;           // [Be][dim+S]
+    float* E = nullptr;           // [Be][J]
+    double* stats = nullptr;      // [slots][Be][groups][2]
+    size_t stats_bytes = 0;
+    __half* final_raw = nullptr;
+    double* final_stats = nullptr;
+    float* xt = nullptr;          // [Be][P0] sampler state (only first B rows used)
+};
+
+}  // namespace usb
+
+using namespace usb;
+
+struct usb_handle {
+    usb_config cfg;
+    int num_sms = 148;
+    int L = 0;
+    int C[8] = {0};
+    int hidden = 128, heads = 4;
+    bool finalized = false;
+    std::map<std::string, HostParam> host;
+    std::vector<void*> dev_allocs;
+    // device weights
+    float *first_w3 = nullptr, *first_b3 = nullptr, *first_w1 = nullptr, *first_b1 = nullptr;
+    std::vector<ResnetW> resnets;   // order: downs.k.0, downs.k.1 ..., mid_block1, mid_block2, ups.k.0, ups.k.1 ...
+    std::vector<AttnW> attns;       // order: downs.k.2 ..., mid_attn, ups.k.2 ...
+    std::vector<ConvW> down_convs, up_convs;
+    ConvW final_block;
+    GnW final_gn;
+    float *final_w = nullptr, *final_b = nullptr;
+    float *text_uncon = nullptr, *spk_uncon_normed = nullptr;
+    float *freqs = nullptr, *mlp_w0 = nullptr, *mlp_b0 = nullptr, *mlp_w2 = nullptr, *mlp_b2 = nullptr;
+    float *wcat = nullptr, *bcat = nullptr;
+    int J = 0;
+    Plan plan;
+    long long launches = 0;
+};
+
+namespace usb {
+
+template <typename T>
+static int upload(usb_handle* h, const T* host, size_t count, T** dev) {
+    void* p = nullptr;
+    USB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    h->dev_allocs.push_back(p);
+    USB_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<T*>(p);
+    return 0;
+}
+
+static int get_param(usb_handle* h, const std::string& key, const HostParam** out, size_t expect_count) {
+    auto it = h->host.find(key);
+    if (it == h->host.end()) return fail("missing parameter: " + key);
+    if (expect_count && it->second.data.size() != expect_count)
+        return fail("parameter " + key + " has " + std::to_string(it->second.data.size()) + " elements, expected " +
+                    std::to_string(expect_count));
+    *out = &it->second;
+    return 0;
+}
+
+static int upload_param(usb_handle* h, const std::string& key, size_t expect_count, float** dev) {
+    const HostParam* p;
+    USB_TRY(get_param(h, key, &p, expect_count));
+    return upload(h, p->data.data(), p->data.size(), dev);
+}
+
+static int load_conv(usb_handle* h, const std::string& prefix, int kind, int Cout, int Cin, bool has_bias, ConvW& w) {
+    const HostParam* p;
+    const int taps = kind == KT4 ? 16 : taps_of(kind);
+    USB_TRY(get_param(h, prefix + ".weight", &p, (size_t)Cout * Cin * taps));
+    std::vector<__half> packed;
+    pack_conv_host(kind, p->data.data(), Cout, Cin, packed);
+    USB_TRY(upload(h, packed.data(), packed.size(), &w.w));
+    if (has_bias) USB_TRY(upload_param(h, prefix + ".bias", Cout, &w.bias));
+    w.Cout = Cout;
+    w.Cin = Cin;
+    w.kind = kind;
+    w.Z = kind == KT4 ? 4 : 1;
+    w.K = taps_of(kind) * Cin;
+    return 0;
+}
+
+static int load_gn(usb_handle* h, const std::string& prefix, int C, GnW& g) {
+    USB_TRY(upload_param(h, prefix + ".weight", C, &g.gamma));
+    USB_TRY(upload_param(h, prefix + ".bias", C, &g.beta));
+    return 0;
+}
+
+static int load_resnet(usb_handle* h, const std::string& prefix, int Cin, int Cout, bool first, ResnetW& r) {
+    r.prefix = prefix;
+    r.Cin = Cin;
+    r.Cout = Cout;
+    r.has_res = Cin != Cout;
+    if (!first) {
+        USB_TRY(load_conv(h, prefix + ".block1.block.0", K3S1, Cout, Cin, true, r.c1));
+        if (r.has_res) USB_TRY(load_conv(h, prefix + ".res_conv", K1, Cout, Cin, true, r.res));
+    }
+    USB_TRY(load_conv(h, prefix + ".block2.block.0", K3S1, Cout, Cout, true, r.c2));
+    USB_TRY(load_gn(h, prefix + ".block1.block.1", Cout, r.g1));
+    USB_TRY(load_gn(h, prefix + ".block2.block.1", Cout, r.g2));
+    return 0;
+}
+
+static int load_attn(usb_handle* h, const std::string& prefix, int C, AttnW& a) {
+    a.prefix = prefix;
+    a.C = C;
+    USB_TRY(load_conv(h, prefix + ".fn.fn.to_qkv", K1, 3 * h->hidden, C, false, a.qkv));
+    USB_TRY(upload_param(h, prefix + ".fn.fn.to_out.weight", (size_t)C * h->hidden, &a.wo));
+    USB_TRY(upload_param(h, prefix + ".fn.fn.to_out.bias", C, &a.bo));
+    USB_TRY(upload_param(h, prefix + ".fn.g", 1, &a.g));
+    return 0;
+}
+
+static int finalize_params(usb_handle* h) {
+    const usb_config& c = h->cfg;
+    const int L = h->L, dim = c.dim, S = c.spk_emb_dim;
+    const std::string e = "estimator.";
+    // ---- first conv (2 -> C0) and its res_conv, fp32 tap-major
+    {
+        const int C0 = h->C[0];
+        const HostParam *w3, *w1;
+        USB_TRY(get_param(h, e + "downs.0.0.block1.block.0.weight", &w3, (size_t)C0 * 2 * 9));
+        USB_TRY(get_param(h, e + "downs.0.0.res_conv.weight", &w1, (size_t)C0 * 2));
+        std::vector<float> a((size_t)18 * C0), b((size_t)2 * C0);
+        for (int co = 0; co < C0; ++co)
+            for (int ci = 0; ci < 2; ++ci) {
+                for (int t = 0; t < 9; ++t) a[((size_t)t * 2 + ci) * C0 + co] = w3->data[((size_t)co * 2 + ci) * 9 + t];
+                b[(size_t)ci * C0 + co] = w1->data[(size_t)co * 2 + ci];
+            }
+        USB_TRY(upload(h, a.data(), a.size(), &h->first_w3));
+        USB_TRY(upload(h, b.data(), b.size(), &h->first_w1));
+        USB_TRY(upload_param(h, e + "downs.0.0.block1.block.0.bias", C0, &h->first_b3));
+        USB_TRY(upload_param(h, e + "downs.0.0.res_conv.bias", C0, &h->first_b1));
+    }
+    // ---- resnets / attention / resampling convs, in forward order
+    h->resnets.clear();
+    h->attns.clear();
+    auto add_resnet = [&](const std::string& pre, int Cin, int Cout, bool first) -> int {
+        h->resnets.emplace_back();
+        return load_resnet(h, pre, Cin, Cout, first, h->resnets.back());
+    };
+    auto add_attn = [&](const std::string& pre, int C) -> int {
+        h->attns.emplace_back();
+        return load_attn(h, pre, C, h->attns.back());
+    };
+    for (int k = 0; k < L; ++k) {
+        const int Cin = k == 0 ? 2 : h->C[k - 1], Cout = h->C[k];
+        const std::string pre = e + "downs." + std::to_string(k);
+        USB_TRY(add_resnet(pre + ".0", Cin, Cout, k == 0));
+        USB_TRY(add_resnet(pre + ".1", Cout, Cout, false));
+        USB_TRY(add_attn(pre + ".2", Cout));
+        if (k < L - 1) {
+            h->down_convs.emplace_back();
+            USB_TRY(load_conv(h, pre + ".3.conv", K3S2, Cout, Cout, true, h->down_convs.back()));
+        }
+    }
+    const int mid = h->C[L - 1];
+    USB_TRY(add_resnet(e + "mid_block1", mid, mid, false));
+    USB_TRY(add_attn(e + "mid_attn", mid));
+    USB_TRY(add_resnet(e + "mid_block2", mid, mid, false));
+    for (int k = 0; k < L - 1; ++k) {
+        const int j = L - 1 - k;  // level of this up stage
+        const int Cj = h->C[j], Cn = h->C[j - 1];
+        const std::string pre = e + "ups." + std::to_string(k);
+        USB_TRY(add_resnet(pre + ".0", 2 * Cj, Cn, false));
+        USB_TRY(add_resnet(pre + ".1", Cn, Cn, false));
+        USB_TRY(add_attn(pre + ".2", Cn));
+        h->up_convs.emplace_back();
+        USB_TRY(load_conv(h, pre + ".3.conv", KT4, Cn, Cn, true, h->up_convs.back()));
+    }
+    USB_TRY(load_conv(h, e + "final_block.block.0", K3S1, dim, dim, true, h->final_block));
+    USB_TRY(load_gn(h, e + "final_block.block.1", dim, h->final_gn));
+    USB_TRY(upload_param(h, e + "final_conv.weight", dim, &h->final_w));
+    USB_TRY(upload_param(h, e + "final_conv.bias", 1, &h->final_b));
+    // ---- embeddings
+    USB_TRY(upload_param(h, "__posemb_freqs", dim / 2, &h->freqs));
+    USB_TRY(upload_param(h, e + "mlp.0.weight", (size_t)4 * dim * dim, &h->mlp_w0));
+    USB_TRY(upload_param(h, e + "mlp.0.bias", 4 * dim, &h->mlp_b0));
+    USB_TRY(upload_param(h, e + "mlp.2.weight", (size_t)4 * dim * dim, &h->mlp_w2));
+    USB_TRY(upload_param(h, e + "mlp.2.bias", dim, &h->mlp_b2));
+    {
+        int J = 0;
+        for (auto& r : h->resnets) {
+            r.emb_off = J;
+            J += r.Cout;
+        }
+        h->J = J;
+        const int K = dim + S;
+        std::vector<float> wc((size_t)J * K), bc(J);
+        for (auto& r : h->resnets) {
+            const HostParam *w, *b;
+            USB_TRY(get_param(h, r.prefix + ".mlp.1.weight", &w, (size_t)r.Cout * K));
+            USB_TRY(get_param(h, r.prefix + ".mlp.1.bias", &b, r.Cout));
+            memcpy(&wc[(size_t)r.emb_off * K], w->data.data(), w->data.size() * sizeof(float));
+            memcpy(&bc[r.emb_off], b->data.data(), b->data.size() * sizeof(float));
+        }
+        USB_TRY(upload(h, wc.data(), wc.size(), &h->wcat));
+        USB_TRY(upload(h, bc.data(), bc.size(), &h->bcat));
+    }
+    // ---- CFG unconditionals: text_uncon (1, n_feats, 1); spk_uncon / ||spk_uncon|| (unitspeech.py:355,358)
+    USB_TRY(upload_param(h, "text_uncon", c.n_feats, &h->text_uncon));
+    {
+        const HostParam* su;
+        USB_TRY(get_param(h, "spk_uncon", &su, S));
+        // torch .norm(): fp32 sqrt of the fp32 sum of squares
+        float ssq = 0.f;
+        for (float v : su->data) ssq += v * v;
+        const float nrm = std::sqrt(ssq);
+        std::vector<float> sn(S);
+        for (int i = 0; i < S; ++i) sn[i] = su->data[i] / nrm;
+        USB_TRY(upload(h, sn.data(), sn.size(), &h->spk_uncon_normed));
+    }
+    h->finalized = true;
+    h->host.clear();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// plan: buffers + launch parameter blocks for one (Be, T)
+// ---------------------------------------------------------------------------------------------------------------
+struct Bump {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 1023) & ~size_t(1023);
+        return o;
+    }
+};
+
+static void free_plan(Plan& pl) {
+    if (pl.arena) cudaFree(pl.arena);
+    pl = Plan();
+}
+
+static int build_plan(usb_handle* h, int Be, int T) {
+    Plan& pl = h->plan;
+    if (pl.Be == Be && pl.T == T && pl.arena) return 0;
+    cudaDeviceSynchronize();
+    free_plan(pl);
+    const usb_config& c = h->cfg;
+    const int L = h->L, S = c.spk_emb_dim, dim = c.dim, G = c.groups, hid = h->hidden;
+    if (T <= 0 || T % (1 << (L - 1))) return fail("T must be a positive multiple of 2^(len(dim_mults)-1)");
+    if (Be <= 0) return fail("empty batch");
+    int H[8], W[8];
+    size_t PC[8];
+    for (int l = 0; l < L; ++l) {
+        H[l] = c.n_feats >> l;
+        W[l] = T >> l;
+        PC[l] = (size_t)Be * H[l] * W[l];
+    }
+    const int n_slots = 2 * (int)h->resnets.size() + 1;
+    // ---- carve the arena (two passes: size, then pointers)
+    size_t o_raw[8], o_h1[8], o_r[8], o_y0[8], o_y1[8], o_qkv[8], o_skip[8], o_xin[8], o_upx[8], o_weff[8], o_mask[8];
+    Bump b;
+    size_t max_part = 0;
+    for (int l = 0; l < L; ++l) {
+        const size_t act = PC[l] * h->C[l] * sizeof(__half);
+        o_raw[l] = b.take(act); o_h1[l] = b.take(act); o_r[l] = b.take(act);
+        o_y0[l] = b.take(act); o_y1[l] = b.take(act); o_skip[l] = b.take(act);
+        o_qkv[l] = b.take(PC[l] * 3 * hid * sizeof(__half));
+        o_xin[l] = l > 0 ? b.take(PC[l] * h->C[l - 1] * sizeof(__half)) : 0;
+        o_upx[l] = l < L - 1 ? b.take(PC[l] * h->C[l] * sizeof(__half)) : 0;
+        o_weff[l] = b.take((size_t)Be * h->C[l] * hid * sizeof(__half));
+        o_mask[l] = b.take((size_t)Be * W[l] * sizeof(float));
+        const size_t part = (size_t)Be * h->heads * attn_chunks(H[l] * W[l], 1024) * (32 * 32 + 64) * sizeof(float);
+        if (part > max_part) max_part = part;
+    }
+    const size_t o_part = b.take(max_part);
+    const size_t o_xrow = b.take(Be * sizeof(int)), o_murow = b.take(Be * sizeof(int));
+    const size_t o_spk = b.take((size_t)Be * S * sizeof(float)), o_t = b.take(Be * sizeof(float));
+    const size_t o_u = b.take((size_t)Be * (dim + S) * sizeof(float)), o_E = b.take((size_t)Be * h->J * sizeof(float));
+    pl.stats_bytes = (size_t)n_slots * Be * G * 2 * sizeof(double);
+    const size_t o_stats = b.take(pl.stats_bytes);
+    const size_t o_xt = b.take((size_t)Be * c.n_feats * T * sizeof(float));
+    pl.arena_bytes = b.off;
+    {
+        cudaError_t e = cudaMalloc(&pl.arena, pl.arena_bytes);
+        if (e != cudaSuccess) {
+            pl.arena = nullptr;
+            return fail("workspace allocation of " + std::to_string(pl.arena_bytes >> 20) + " MiB failed: " +
+                        cudaGetErrorString(e));
+        }
+    }
+    char* A = static_cast<char*>(pl.arena);
+    auto HP = [&](size_t o) { return reinterpret_cast<__half*>(A + o); };
+    for (int l = 0; l < L; ++l) pl.mask[l] = reinterpret_cast<float*>(A + o_mask[l]);
+    pl.x_row = reinterpret_cast<int*>(A + o_xrow);
+    pl.mu_row = reinterpret_cast<int*>(A + o_murow);
+    pl.spk_rows = reinterpret_cast<float*>(A + o_spk);
+    pl.t_rows = reinterpret_cast<float*>(A + o_t);
+    pl.u = reinterpret_cast<float*>(A + o_u);
+    pl.E = reinterpret_cast<float*>(A + o_E);
+    pl.stats = reinterpret_cast<double*>(A + o_stats);
+    pl.xt = reinterpret_cast<float*>(A + o_xt);
+    float* part = reinterpret_cast<float*>(A + o_part);
+    pl.Be = Be;
+    pl.T = T;
+
+    int slot = 0;
+    auto next_stats = [&]() { return pl.stats + (size_t)(slot++) * Be * G * 2; };
+    auto push_conv = [&](int kind, const __half* in0, int C0tot, int C0, const __half* in1, int C1tot, int C1, int l,
+                         const ConvW* w, const __half* wptr, int wZ, int bmode, int Cout, const ConvEpilogue& ep,
+                         __half* out) -> int {
+        pl.convs.emplace_back();
+        USB_TRY(build_conv(pl.convs.back(), kind, in0, C0tot, C0, in1, C1tot, C1, Be, H[l], W[l], w ? w->w : wptr,
+                           w ? w->Z : wZ, bmode, Cout, ep, out));
+        pl.ops.push_back({Op::CONV, (int)pl.convs.size() - 1});
+        return 0;
+    };
+    auto push_gn = [&](const __half* raw, const double* stats, const GnW& g, const float* addvec, const __half* res,
+                       int l, int Cc, __half* out) {
+        GnApplyParams p;
+        p.raw = raw; p.stats = stats; p.gamma = g.gamma; p.beta = g.beta; p.addvec = addvec; p.addvec_stride = h->J;
+        p.res = res; p.mask = pl.mask[l]; p.out = out; p.N = Be; p.P = H[l] * W[l]; p.W = W[l]; p.C = Cc; p.groups = G;
+        p.eps = 1e-5f;
+        pl.gns.push_back(p);
+        pl.ops.push_back({Op::GN, (int)pl.gns.size() - 1});
+    };
+    // ResnetBlock (unitspeech.py:70-75); in1 = second K source of the skip concat (:192)
+    auto push_resnet = [&](const ResnetW& r, int l, const __half* in0, int C0, const __half* in1, int C1,
+                           __half* out) -> int {
+        __half *raw = HP(o_raw[l]), *h1 = HP(o_h1[l]), *rb = HP(o_r[l]);
+        ConvEpilogue ep;
+        ep.groups = G;
+        double* s1 = next_stats();
+        ep.bias = r.c1.bias; ep.stats = s1;
+        USB_TRY(push_conv(K3S1, in0, C0, C0, in1, C1, C1, l, &r.c1, nullptr, 0, 0, r.Cout, ep, raw));
+        push_gn(raw, s1, r.g1, pl.E + r.emb_off, nullptr, l, r.Cout, h1);
+        double* s2 = next_stats();
+        ep.bias = r.c2.bias; ep.stats = s2;
+        USB_TRY(push_conv(K3S1, h1, r.Cout, r.Cout, nullptr, 0, 0, l, &r.c2, nullptr, 0, 0, r.Cout, ep, raw));
+        const __half* resid = in0;
+        if (r.has_res) {
+            ConvEpilogue er;
+            er.bias = r.res.bias;
+            USB_TRY(push_conv(K1, in0, C0, C0, in1, C1, C1, l, &r.res, nullptr, 0, 0, r.Cout, er, rb));
+            resid = rb;
+        } else if (in1) {
+            return fail("identity residual with a concatenated input");
+        }
+        push_gn(raw, s2, r.g2, nullptr, resid, l, r.Cout, out);
+        return 0;
+    };
+    // Residual(Rezero(LinearAttention)) (unitspeech.py:36-43,78-106), output stored masked
+    auto push_attn = [&](const AttnW& a, int l, const __half* x, __half* out) -> int {
+        __half *qkv = HP(o_qkv[l]), *weff = HP(o_weff[l]);
+        ConvEpilogue e1;
+        USB_TRY(push_conv(K1, x, a.C, a.C, nullptr, 0, 0, l, &a.qkv, nullptr, 0, 0, 3 * hid, e1, qkv));
+        AttnParams ap;
+        ap.qkv = qkv; ap.wo = a.wo; ap.part = part; ap.weff = weff; ap.N = Be; ap.P = H[l] * W[l]; ap.C = a.C;
+        ap.heads = h->heads; ap.chunk = 1024;
+        pl.attns.push_back(ap);
+        pl.ops.push_back({Op::ATTN, (int)pl.attns.size() - 1});
+        ConvEpilogue e2;
+        e2.bias = a.bo; e2.res = x; e2.res_scale = a.g; e2.mask = pl.mask[l];
+        USB_TRY(push_conv(K1, qkv, 3 * hid, hid, nullptr, 0, 0, l, nullptr, weff, Be, 2, a.C, e2, out));
+        return 0;
+    };
+
+    size_t ri = 0, ai = 0;
+    // ---- down path
+    const __half* x = nullptr;
+    for (int k = 0; k < L; ++k) {
+        __half *y0 = HP(o_y0[k]), *y1 = HP(o_y1[k]), *skip = HP(o_skip[k]);
+        const ResnetW& r0 = h->resnets[ri++];
+        if (k == 0) {
+            __half *raw = HP(o_raw[0]), *h1 = HP(o_h1[0]), *rb = HP(o_r[0]);
+            double* s1 = next_stats();
+            FirstConvParams& f = pl.first;
+            memset(&f, 0, sizeof f);
+            f.x_row = pl.x_row; f.mu_row = pl.mu_row; f.mask = pl.mask[0];
+            f.w3 = h->first_w3; f.b3 = h->first_b3; f.w1 = h->first_w1; f.b1 = h->first_b1;
+            f.raw = raw; f.res = rb; f.stats = s1; f.N = Be; f.H = H[0]; f.W = W[0]; f.C = h->C[0]; f.groups = G;
+            pl.ops.push_back({Op::FIRST, 0});
+            push_gn(raw, s1, r0.g1, pl.E + r0.emb_off, nullptr, 0, r0.Cout, h1);
+            double* s2 = next_stats();
+            ConvEpilogue ep;
+            ep.groups = G; ep.bias = r0.c2.bias; ep.stats = s2;
+            USB_TRY(push_conv(K3S1, h1, r0.Cout, r0.Cout, nullptr, 0, 0, 0, &r0.c2, nullptr, 0, 0, r0.Cout, ep, raw));
+            push_gn(raw, s2, r0.g2, nullptr, rb, 0, r0.Cout, y0);
+        } else {
+            USB_TRY(push_resnet(r0, k, x, h->C[k - 1], nullptr, 0, y0));
+        }
+        USB_TRY(push_resnet(h->resnets[ri++], k, y0, h->C[k], nullptr, 0, y1));
+        USB_TRY(push_attn(h->attns[ai++], k, y1, skip));
+        if (k < L - 1) {
+            ConvEpilogue ed;
+            ed.bias = h->down_convs[k].bias; ed.mask = pl.mask[k + 1];
+            __half* xin = HP(o_xin[k + 1]);
+            USB_TRY(push_conv(K3S2, skip, h->C[k], h->C[k], nullptr, 0, 0, k, &h->down_convs[k], nullptr, 0, 0, h->C[k],
+                              ed, xin));
+            x = xin;
+        }
+    }
+    // ---- middle
+    const int D = L - 1;
+    USB_TRY(push_resnet(h->resnets[ri++], D, HP(o_skip[D]), h->C[D], nullptr, 0, HP(o_y0[D])));
+    USB_TRY(push_attn(h->attns[ai++], D, HP(o_y0[D]), HP(o_y1[D])));
+    USB_TRY(push_resnet(h->resnets[ri++], D, HP(o_y1[D]), h->C[D], nullptr, 0, HP(o_y0[D])));
+    // ---- up path
+    const __half* cur = HP(o_y0[D]);
+    for (int k = 0; k < L - 1; ++k) {
+        const int j = D - k;
+        const int Cj = h->C[j], Cn = h->C[j - 1];
+        USB_TRY(push_resnet(h->resnets[ri++], j, cur, Cj, HP(o_skip[j]), Cj, HP(o_y1[j])));
+        USB_TRY(push_resnet(h->resnets[ri++], j, HP(o_y1[j]), Cn, nullptr, 0, HP(o_y0[j])));
+        USB_TRY(push_attn(h->attns[ai++], j, HP(o_y0[j]), HP(o_h1[j])));
+        ConvEpilogue eu;
+        eu.bias = h->up_convs[k].bias; eu.mask = pl.mask[j - 1];
+        USB_TRY(push_conv(KT4, HP(o_h1[j]), Cn, Cn, nullptr, 0, 0, j, &h->up_convs[k], nullptr, 0, 1, Cn, eu,
+                          HP(o_upx[j - 1])));
+        cur = HP(o_upx[j - 1]);
+    }
+    // ---- final block conv (GroupNorm/Mish/1x1 are fused into the final kernel)
+    {
+        ConvEpilogue ef;
+        ef.groups = G; ef.bias = h->final_block.bias;
+        pl.final_stats = next_stats();
+        ef.stats = pl.final_stats;
+        pl.final_raw = HP(o_raw[0]);
+        USB_TRY(push_conv(K3S1, cur, h->C[0], h->C[0], nullptr, 0, 0, 0, &h->final_block, nullptr, 0, 0, dim, ef,
+                          pl.final_raw));
+    }
+    if (slot != n_slots) return fail("internal: stats slot count mismatch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// execution
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void fill_kernel(float* p, float v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void mul_mask_kernel(const float* z, const float* mask, float* out, int B, int P, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * P) return;
+    const int b = (int)(i / P), w = (int)((i % P) % W);
+    out[i] = z[i] * mask[(long long)b * W + w];
+}
+
+struct EstInputs {
+    const float* x;           // [*][H][W]
+    const float* cond;        // [*][H][W]
+    const float* text_uncon;  // [H] or null
+    const float* t_rows;      // [Be]
+    const float* spk_rows;    // [Be][S]
+};
+
+// masks for all levels from pl.mask[0]
+static int prepare_masks(usb_handle* h, cudaStream_t s) {
+    Plan& pl = h->plan;
+    for (int l = 1; l < h->L; ++l)
+        USB_LAUNCH(h, launch_downsample_mask(pl.mask[l - 1], pl.mask[l], pl.Be, pl.T >> (l - 1), pl.T >> l, s));
+    return 0;
+}
+
+// everything up to and including the final_block conv
+static int run_estimator(usb_handle* h, const EstInputs& in, cudaStream_t s) {
+    Plan& pl = h->plan;
+    const usb_config& c = h->cfg;
+    EmbedParams ep;
+    ep.t = in.t_rows; ep.spk = in.spk_rows; ep.freqs = h->freqs; ep.w0 = h->mlp_w0; ep.b0 = h->mlp_b0;
+    ep.w2 = h->mlp_w2; ep.b2 = h->mlp_b2; ep.wcat = h->wcat; ep.bcat = h->bcat; ep.u = pl.u; ep.e = pl.E;
+    ep.N = pl.Be; ep.dim = c.dim; ep.S = c.spk_emb_dim; ep.J = h->J; ep.pe_scale = c.pe_scale;
+    USB_LAUNCH(h, launch_embed(ep, s));
+    h->launches++;  // launch_embed issues two kernels
+    USB_CUDA(cudaMemsetAsync(pl.stats, 0, pl.stats_bytes, s));
+    for (const Op& op : pl.ops) {
+        switch (op.kind) {
+            case Op::FIRST: {
+                FirstConvParams f = pl.first;
+                f.x = in.x; f.cond = in.cond; f.text_uncon = in.text_uncon;
+                USB_LAUNCH(h, launch_first_conv(f, s));
+                break;
+            }
+            case Op::CONV: {
+                const ConvOp& co = pl.convs[op.idx];
+                USB_LAUNCH(h, launch_conv_igemm(co.p, co.a0, co.a1, co.b, h->num_sms, s));
+                break;
+            }
+            case Op::GN:
+                USB_LAUNCH(h, launch_gn_apply(pl.gns[op.idx], h->num_sms, s));
+                break;
+            case Op::ATTN:
+                USB_LAUNCH(h, launch_attn_context(pl.attns[op.idx], s));
+                h->launches++;  // two kernels
+                break;
+        }
+    }
+    return 0;
+}
+
+static FinalParams final_params(usb_handle* h, int B, int nb) {
+    Plan& pl = h->plan;
+    const usb_config& c = h->cfg;
+    FinalParams f;
+    memset(&f, 0, sizeof f);
+    f.raw = pl.final_raw; f.stats = pl.final_stats; f.gamma = h->final_gn.gamma; f.beta = h->final_gn.beta;
+    f.wf = h->final_w; f.bf = h->final_b; f.mask = pl.mask[0]; f.B = B; f.nb = nb; f.P = c.n_feats * pl.T;
+    f.W = pl.T; f.C = c.dim; f.groups = c.groups; f.eps = 1e-5f;
+    return f;
+}
+
+static int check_ready(usb_handle* h) {
+    if (!h) return fail("null handle");
+    if (!h->finalized) return fail("parameters not finalized (call usb_finalize_params)");
+    USB_CUDA(cudaSetDevice(h->cfg.device));
+    return 0;
+}
+
+static int estimator_forward(usb_handle* h, const float* x, const float* mu, const float* mask, const float* t,
+                             const float* spk, float* out, int Be, int T, cudaStream_t s) {
+    USB_TRY(check_ready(h));
+    USB_TRY(build_plan(h, Be, T));
+    Plan& pl = h->plan;
+    std::vector<int> ident(Be);
+    for (int i = 0; i < Be; ++i) ident[i] = i;
+    USB_CUDA(cudaMemcpyAsync(pl.x_row, ident.data(), Be * sizeof(int), cudaMemcpyHostToDevice, s));
+    USB_CUDA(cudaMemcpyAsync(pl.mu_row, ident.data(), Be * sizeof(int), cudaMemcpyHostToDevice, s));
+    USB_CUDA(cudaMemcpyAsync(pl.mask[0], mask, (size_t)Be * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    USB_CUDA(cudaStreamSynchronize(s));  // `ident` is pageable host memory
+    USB_TRY(prepare_masks(h, s));
+    EstInputs in{x, mu, nullptr, t, spk};
+    USB_TRY(run_estimator(h, in, s));
+    FinalParams f = final_params(h, Be, 1);
+    f.score = out;
+    USB_LAUNCH(h, launch_final(f, h->num_sms, s));
+    return 0;
+}
+
+static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, const float* mask, const float* spk,
+                             const float* noise, const float* coef, const float* t_steps, int n_steps, float tg,
+                             float sg, float* out, float* trace, int B, int T, cudaStream_t s) {
+    USB_TRY(check_ready(h));
+    if (n_steps < 2) return fail("n_timesteps must be >= 2 (the reference crashes for 1)");
+    if (B <= 0) return fail("empty batch");
+    const usb_config& c = h->cfg;
+    const bool use_t = tg > 0.f, use_s = sg > 0.f;
+    const int nb = 1 + (use_t ? 1 : 0) + (use_s ? 1 : 0);
+    const int Be = nb * B;
+    USB_TRY(build_plan(h, Be, T));
+    Plan& pl = h->plan;
+    const int S = c.spk_emb_dim, P = c.n_feats * T;
+    // branch order of classifier_free_guidance (unitspeech.py:301-317): [text-uncond] [spk-uncond] full
+    std::vector<int> xrow(Be), murow(Be);
+    int kb = 0, k_tu = -1, k_su = -1;
+    if (use_t) k_tu = kb++;
+    if (use_s) k_su = kb++;
+    for (int k = 0; k < nb; ++k)
+        for (int b = 0; b < B; ++b) {
+            xrow[k * B + b] = b;
+            murow[k * B + b] = k == k_tu ? -1 : b;
+        }
+    USB_CUDA(cudaMemcpyAsync(pl.x_row, xrow.data(), Be * sizeof(int), cudaMemcpyHostToDevice, s));
+    USB_CUDA(cudaMemcpyAsync(pl.mu_row, murow.data(), Be * sizeof(int), cudaMemcpyHostToDevice, s));
+    USB_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < nb; ++k) {
+        USB_CUDA(cudaMemcpyAsync(pl.mask[0] + (size_t)k * B * T, mask, (size_t)B * T * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+        if (k == k_su) {
+            for (int b = 0; b < B; ++b)
+                USB_CUDA(cudaMemcpyAsync(pl.spk_rows + ((size_t)k * B + b) * S, h->spk_uncon_normed, S * sizeof(float),
+                                         cudaMemcpyDeviceToDevice, s));
+        } else {
+            USB_CUDA(cudaMemcpyAsync(pl.spk_rows + (size_t)k * B * S, spk, (size_t)B * S * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    USB_TRY(prepare_masks(h, s));
+    {
+        const long long tot = (long long)B * P;
+        mul_mask_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(z, mask, pl.xt, B, P, T);
+        USB_LAUNCH(h, (int)cudaGetLastError());
+    }
+    EstInputs in{pl.xt, cond, h->text_uncon, pl.t_rows, pl.spk_rows};
+    for (int i = 0; i < n_steps; ++i) {
+        fill_kernel<<<(Be + 255) / 256, 256, 0, s>>>(pl.t_rows, t_steps[i], Be);
+        USB_LAUNCH(h, (int)cudaGetLastError());
+        USB_TRY(run_estimator(h, in, s));
+        FinalParams f = final_params(h, B, nb);
+        f.a0 = nb == 3 ? tg : (use_t ? tg : sg);
+        f.a1 = sg;
+        f.xt = pl.xt;
+        f.noise = noise ? noise + (size_t)i * B * P : nullptr;
+        f.c_x = coef[i * 3 + 0]; f.c_s = coef[i * 3 + 1]; f.sigma = coef[i * 3 + 2];
+        USB_LAUNCH(h, launch_final(f, h->num_sms, s));
+        if (trace)
+            USB_CUDA(cudaMemcpyAsync(trace + (size_t)i * B * P, pl.xt, (size_t)B * P * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, s));
+    }
+    // the reference returns xt * mask (:373); xt is already masked by the update
+    USB_CUDA(cudaMemcpyAsync(out, pl.xt, (size_t)B * P * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+}  // namespace usb
+
+// ===================================================================================================================
+// C ABI
+// ===================================================================================================================
+extern "C" {
+
+const char* usb_last_error(void) { return g_err.c_str(); }
+int usb_version(void) { return 1; }
+
+int usb_create(const usb_config* cfg, usb_handle** out) {
+    if (!cfg || !out) return fail("null argument");
+    if (!(cfg->dim == 64 || cfg->dim == 128 || cfg->dim == 256)) return fail("dim must be 64, 128 or 256");
+    if (cfg->n_mults < 2 || cfg->n_mults > 4) return fail("len(dim_mults) must be 2..4");
+    if (cfg->groups != 8) return fail("groups must be 8");
+    if (cfg->n_feats % (1 << (cfg->n_mults - 1))) return fail("n_feats must be divisible by 2^(len(dim_mults)-1)");
+    if (cfg->spk_emb_dim <= 0) return fail("spk_emb_dim must be positive");
+    int ndev = 0;
+    USB_CUDA(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("no such CUDA device");
+    USB_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    USB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(std::string("this library only runs on sm_100 (B200); found ") + prop.name);
+    usb_handle* h = new usb_handle();
+    h->cfg = *cfg;
+    h->num_sms = prop.multiProcessorCount;
+    h->L = cfg->n_mults;
+    for (int i = 0; i < h->L; ++i) {
+        h->C[i] = cfg->dim * cfg->dim_mults[i];
+        if (h->C[i] > 2048) {
+            delete h;
+            return fail("channel count above 2048 is not supported");
+        }
+    }
+    if (load_encode_fn()) {
+        delete h;
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+void usb_destroy(usb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    free_plan(h->plan);
+    for (void* p : h->dev_allocs) cudaFree(p);
+    delete h;
+}
+
+int usb_load_param(usb_handle* h, const char* key, const float* data, const int64_t* shape, int32_t ndim) {
+    if (!h || !key || !data) return fail("null argument");
+    if (h->finalized) return fail("parameters already finalized");
+    HostParam p;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        p.shape.push_back(shape[i]);
+        n *= (size_t)shape[i];
+    }
+    p.data.assign(data, data + n);
+    h->host[key] = std::move(p);
+    return 0;
+}
+
+int usb_finalize_params(usb_handle* h) {
+    if (!h) return fail("null handle");
+    if (h->finalized) return fail("parameters already finalized");
+    USB_CUDA(cudaSetDevice(h->cfg.device));
+    return finalize_params(h);
+}
+
+int usb_estimator_forward(usb_handle* h, const float* x, const float* mu, const float* mask, const float* t,
+                          const float* spk, float* out, int32_t Be, int32_t T, uint64_t stream) {
+    return estimator_forward(h, x, mu, mask, t, spk, out, Be, T, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int usb_reverse_diffusion(usb_handle* h, const float* z, const float* cond, const float* mask, const float* spk,
+                          const float* noise, const float* coef_host, const float* t_steps_host, int32_t n_steps,
+                          float text_scale, float spk_scale, float* out, float* trace, int32_t B, int32_t T,
+                          uint64_t stream) {
+    return reverse_diffusion(h, z, cond, mask, spk, noise, coef_host, t_steps_host, n_steps, text_scale, spk_scale, out,
+                             trace, B, T, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int usb_reverse_diffusion_host(usb_handle* h, const float* z, const float* cond, const float* mask, const float* spk,
+                               const float* noise, const float* coef_host, const float* t_steps_host, int32_t n_steps,
+                               float text_scale, float spk_scale, float* out, int32_t B, int32_t T, uint64_t stream) {
+    USB_TRY(check_ready(h));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t P = (size_t)h->cfg.n_feats * T, S = h->cfg.spk_emb_dim;
+    const size_t n_z = (size_t)B * P, n_mask = (size_t)B * T, n_spk = (size_t)B * S;
+    const size_t n_noise = noise ? (size_t)n_steps * B * P : 0;
+    float* d = nullptr;
+    USB_CUDA(cudaMalloc(&d, (3 * n_z + n_mask + n_spk + n_noise) * sizeof(float)));
+    float *dz = d, *dc = dz + n_z, *dout = dc + n_z, *dm = dout + n_z, *ds = dm + n_mask, *dn = ds + n_spk;
+    int rc = 0;
+    auto H2D = [&](float* dst, const float* src, size_t n) {
+        return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, s);
+    };
+    cudaError_t e = H2D(dz, z, n_z);
+    if (e == cudaSuccess) e = H2D(dc, cond, n_z);
+    if (e == cudaSuccess) e = H2D(dm, mask, n_mask);
+    if (e == cudaSuccess) e = H2D(ds, spk, n_spk);
+    if (e == cudaSuccess && noise) e = H2D(dn, noise, n_noise);
+    if (e != cudaSuccess) rc = fail(std::string("host->device copy: ") + cudaGetErrorString(e));
+    if (!rc)
+        rc = reverse_diffusion(h, dz, dc, dm, ds, noise ? dn : nullptr, coef_host, t_steps_host, n_steps, text_scale,
+                               spk_scale, dout, nullptr, B, T, s);
+    if (!rc) {
+        e = cudaMemcpyAsync(out, dout, n_z * sizeof(float), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(std::string("device->host copy: ") + cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(s);
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int64_t usb_workspace_bytes(usb_handle* h) { return h ? (int64_t)h->plan.arena_bytes : 0; }
+int64_t usb_launch_count(usb_handle* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- operator-level
+int usb_op_conv(usb_handle* h, int32_t kind, const void* in0, const void* in1, int32_t N, int32_t H, int32_t W,
+                int32_t C0, int32_t C1, int32_t Cout, const float* weight_host, const float* bias_host,
+                const float* mask, const void* residual, float res_scale, double* stats, int32_t groups, void* out,
+                uint64_t stream) {
+    if (!h) return fail("null handle");
+    USB_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (kind < 0 || kind > 3) return fail("bad conv kind");
+    const int Cin = C0 + (in1 ? C1 : 0);
+    std::vector<__half> packed;
+    pack_conv_host(kind, weight_host, Cout, Cin, packed);
+    __half* dw = nullptr;
+    float* db = nullptr;
+    float* dscale = nullptr;
+    USB_CUDA(cudaMalloc(&dw, packed.size() * sizeof(__half)));
+    USB_CUDA(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    if (bias_host) {
+        USB_CUDA(cudaMalloc(&db, Cout * sizeof(float)));
+        USB_CUDA(cudaMemcpy(db, bias_host, Cout * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (residual) {
+        USB_CUDA(cudaMalloc(&dscale, sizeof(float)));
+        USB_CUDA(cudaMemcpy(dscale, &res_scale, sizeof(float), cudaMemcpyHostToDevice));
+    }
+    ConvEpilogue ep;
+    ep.bias = db; ep.stats = stats; ep.groups = groups > 0 ? groups : 8; ep.res = static_cast<const __half*>(residual);
+    ep.res_scale = dscale; ep.mask = mask;
+    ConvOp op;
+    int rc = build_conv(op, kind, static_cast<const __half*>(in0), C0, C0, static_cast<const __half*>(in1), C1, C1, N, H,
+                        W, dw, kind == KT4 ? 4 : 1, kind == KT4 ? 1 : 0, Cout, ep, static_cast<__half*>(out));
+    if (!rc) {
+        int e = launch_conv_igemm(op.p, op.a0, op.a1, op.b, h->num_sms, s);
+        h->launches++;
+        if (e) rc = fail(std::string("conv launch: ") + cudaGetErrorString((cudaError_t)e));
+    }
+    cudaError_t se = cudaStreamSynchronize(s);
+    if (!rc && se != cudaSuccess) rc = fail(std::string("conv kernel: ") + cudaGetErrorString(se));
+    cudaFree(dw);
+    if (db) cudaFree(db);
+    if (dscale) cudaFree(dscale);
+    return rc;
+}
+
+int usb_op_gn_apply(usb_handle* h, const void* raw, const double* stats, const float* gamma, const float* beta,
+                    const float* addvec, const void* res, const float* mask, void* out, int32_t N, int32_t H, int32_t W,
+                    int32_t C, int32_t groups, uint64_t stream) {
+    if (!h) return fail("null handle");
+    USB_CUDA(cudaSetDevice(h->cfg.device));
+    GnApplyParams p;
+    p.raw = static_cast<const __half*>(raw); p.stats = stats; p.gamma = gamma; p.beta = beta; p.addvec = addvec;
+    p.addvec_stride = C; p.res = static_cast<const __half*>(res); p.mask = mask; p.out = static_cast<__half*>(out);
+    p.N = N; p.P = H * W; p.W = W; p.C = C; p.groups = groups; p.eps = 1e-5f;
+    USB_LAUNCH(h, launch_gn_apply(p, h->num_sms, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int usb_op_attn_context(usb_handle* h, const void* qkv, const float* wo, void* weff, int32_t N, int32_t P, int32_t C,
+                        int32_t heads, uint64_t stream) {
+    if (!h) return fail("null handle");
+    USB_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    AttnParams ap;
+    ap.qkv = static_cast<const __half*>(qkv); ap.wo = wo; ap.weff = static_cast<__half*>(weff); ap.N = N; ap.P = P;
+    ap.C = C; ap.heads = heads; ap.chunk = 1024;
+    const size_t part_bytes = (size_t)N * heads * attn_chunks(P, 1024) * (32 * 32 + 64) * sizeof(float);
+    float* part = nullptr;
+    USB_CUDA(cudaMalloc(&part, part_bytes));
+    ap.part = part;
+    int e = launch_attn_context(ap, s);
+    h->launches += 2;
+    cudaError_t se = cudaStreamSynchronize(s);
+    cudaFree(part);
+    if (e) return fail(std::string("attention launch: ") + cudaGetErrorString((cudaError_t)e));
+    if (se != cudaSuccess) return fail(std::string("attention kernel: ") + cudaGetErrorString(se));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// Launchers of the streaming (HBM-bound) kernels of the reverse-diffusion path.  All tensors are device pointers;
+// activations are NHWC fp16 ([row n][pixel p = y*W + x][channel]), statistics are [n][group][sum, sumsq] doubles.
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace usb {
+
+// ---- input conv (K = 18) + 1x1 res_conv of downs.0.0 on the 2-channel stack [mu, x]  (unitspeech.py:170,49,66)
+struct FirstConvParams {
+    const float* x;           // [B][H][W] current x_t
+    const float* cond;        // [B][H][W] conditioning mel
+    const float* text_uncon;  // [H] (used by rows with mu_row < 0) or null
+    const int* x_row;         // [N] utterance index of x for row n
+    const int* mu_row;        // [N] utterance index of cond for row n, or -1 -> text_uncon
+    const float* mask;        // [N][W]
+    const float* w3;          // [9][2][C] fp32 (tap-major repack of block1 conv weight)
+    const float* b3;          // [C]
+    const float* w1;          // [2][C] res_conv weight repack
+    const float* b1;          // [C]
+    __half* raw;              // [N][P][C] conv + bias (GroupNorm input)
+    __half* res;              // [N][P][C] res_conv + bias
+    double* stats;            // [N][groups][2]
+    int N, H, W, C, groups;
+};
+int launch_first_conv(const FirstConvParams& p, cudaStream_t s);
+
+// ---- out = (Mish(GroupNorm(raw)) + addvec[n][c] + res) * mask   (unitspeech.py:50-55,72-75)
+struct GnApplyParams {
+    const __half* raw;     // [N][P][C]
+    const double* stats;   // [N][groups][2]
+    const float* gamma;    // [C]
+    const float* beta;     // [C]
+    const float* addvec;   // [N][addvec_stride] (+ offset already applied) or null
+    long long addvec_stride;
+    const __half* res;     // [N][P][C] or null
+    const float* mask;     // [N][W]
+    __half* out;           // [N][P][C]
+    int N, P, W, C, groups;
+    float eps;
+};
+int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s);
+
+// ---- final_block GN+Mish -> final_conv 1x1 -> CFG combine -> posterior update  (unitspeech.py:198-201,322-324,366-370)
+struct FinalParams {
+    const __half* raw;     // [nb*B][P][C] final_block conv output
+    const double* stats;   // [nb*B][groups][2]
+    const float* gamma;    // [C]
+    const float* beta;     // [C]
+    const float* wf;       // [C] final_conv weight
+    const float* bf;       // [1] final_conv bias (device)
+    const float* mask;     // [B][W] (rows 0..B-1 of the level-0 mask)
+    int B, nb, P, W, C, groups;
+    float eps;
+    float a0, a1;          // score = s_full + a0*(s_full - s_0) + a1*(s_full - s_1)   (full = last branch)
+    // sampler (null xt -> estimator mode: only `score` rows are written)
+    float* xt;             // [B][P] in/out, updated in place
+    const float* noise;    // [B][P] or null (treated as 0)
+    float c_x, c_s, sigma;
+    float* score;          // estimator mode: [nb*B][P] per-row outputs; sampler mode: optional [B][P] combined score
+};
+int launch_final(const FinalParams& p, int num_sms, cudaStream_t s);
+
+// ---- time / speaker embedding  (unitspeech.py:109-121,133-134,165-168,61)
+struct EmbedParams {
+    const float* t;        // [N]
+    const float* spk;      // [N][S]
+    const float* freqs;    // [dim/2] sinusoidal frequencies (host-computed with the reference's torch ops)
+    const float* w0;       // [4*dim][dim]
+    const float* b0;       // [4*dim]
+    const float* w2;       // [dim][4*dim]
+    const float* b2;       // [dim]
+    const float* wcat;     // [J][dim+S] all ResnetBlock.mlp Linear weights stacked
+    const float* bcat;     // [J]
+    float* u;              // [N][dim+S] scratch: Mish(cat(time_mlp(t), spk))
+    float* e;              // [N][J] output
+    int N, dim, S, J;
+    float pe_scale;
+};
+int launch_embed(const EmbedParams& p, cudaStream_t s);
+
+// ---- LinearAttention context: softmax over positions of k, ctx = k_sm^T v, folded with to_out  (unitspeech.py:86-96)
+struct AttnParams {
+    const __half* qkv;     // [N][P][3*hidden], channel = qkv*hidden + head*dh + c
+    const float* wo;       // [C][hidden] to_out weight
+    float* part;           // scratch [N][heads][chunks][dh*dh + 2*dh]
+    __half* weff;          // [N][C][hidden] folded per-sample weight (K-major B operand of the to_out GEMM)
+    int N, P, C, heads, chunk;   // dh = 32, hidden = heads*32
+};
+int attn_chunks(int P, int chunk);
+int launch_attn_context(const AttnParams& p, cudaStream_t s);
+
+// ---- small utilities
+int launch_downsample_mask(const float* src, float* dst, int N, int Wsrc, int Wdst, cudaStream_t s);
+int launch_gather_rows(const float* src, const int* idx, float* dst, int N, int len, cudaStream_t s);
+
+}  // namespace usb

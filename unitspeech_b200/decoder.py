@@ -1,0 +1,354 @@
+"""Drop-in `UnitSpeech` decoder for the reverse-diffusion path, backed by libunitspeech_b200.so (sm_100a CUDA).
+
+Mirrors the call surface of the reference class unitspeech.unitspeech.UnitSpeech (unitspeech/unitspeech.py:220):
+same constructor, same `state_dict` key names and shapes (so reference checkpoints load with
+``load_state_dict(ckpt["model"])``, inference.py:66-73), and the entry points the reference's callers use on this
+path: ``forward`` / ``reverse_diffusion`` (scripts/text_to_speech.py:42), ``execute_text_to_speech``
+(inference.py:128, evaluation/evaluation_generate_samples.py:325) and ``estimator(x, mask, mu, t, spk_emb)``.
+
+PyTorch is used for tensor plumbing only: parameters are handed to the C library, every FLOP of the estimator and
+the sampler update runs in the hand-written kernels.  There is no fallback path.
+
+Differences from the reference, all deliberate:
+  * a batch is sampled as "the reference's batch-1 call per utterance" (the reference's own B>1 schedule is wrong and
+    its CFG path crashes for B>1);
+  * ``noise=`` injects the per-step randn draws for reproducibility; with ``noise=None`` they are drawn with
+    ``torch.randn`` in the reference's order (one (B, n_feats, T) draw per step);
+  * tensors may live on the CPU: the call then goes through the host-buffer entry of the library (copies included)
+    and returns a CPU tensor;
+  * ``n_timesteps=1`` raises ValueError (the reference crashes with an indexing error).
+The training-side methods (``compute_loss``, ``fine_tune``) are not part of this path and raise NotImplementedError.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import abi, schedule
+from .util import fix_len_compatibility, generate_path, sequence_mask
+
+
+class _Holder(torch.nn.Module):
+    """Parameter container; exists only so state_dict() has the reference's key names."""
+
+
+def _uniform(shape, bound):
+    return torch.nn.Parameter((torch.rand(shape) * 2 - 1) * bound)
+
+
+def _conv_params(mod: torch.nn.Module, cout: int, cin: int, k: int, bias: bool = True, transposed: bool = False):
+    # torch default init of Conv2d/ConvTranspose2d: U(+-1/sqrt(fan_in)) for weight and bias
+    shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    fan_in = shape[1] * k * k
+    bound = 1.0 / math.sqrt(fan_in)
+    mod.weight = _uniform(shape, bound)
+    if bias:
+        mod.bias = _uniform((cout,), bound)
+    return mod
+
+
+def _linear_params(mod: torch.nn.Module, cout: int, cin: int):
+    bound = 1.0 / math.sqrt(cin)
+    mod.weight = _uniform((cout, cin), bound)
+    mod.bias = _uniform((cout,), bound)
+    return mod
+
+
+def _gn_params(mod: torch.nn.Module, c: int):
+    mod.weight = torch.nn.Parameter(torch.ones(c))
+    mod.bias = torch.nn.Parameter(torch.zeros(c))
+    return mod
+
+
+def _seq(**children) -> _Holder:
+    h = _Holder()
+    for name, child in children.items():
+        h.add_module(name.lstrip("_"), child)
+    return h
+
+
+def _block(cin: int, cout: int) -> _Holder:
+    # Block.block = Sequential(Conv2d, GroupNorm, Mish) -> keys block.0.*, block.1.*   (unitspeech.py:46-51)
+    return _seq(block=_seq(_0=_conv_params(_Holder(), cout, cin, 3), _1=_gn_params(_Holder(), cout)))
+
+
+def _resnet(cin: int, cout: int, temb: int) -> _Holder:
+    r = _seq(mlp=_seq(_1=_linear_params(_Holder(), cout, temb)), block1=_block(cin, cout), block2=_block(cout, cout))
+    if cin != cout:
+        r.add_module("res_conv", _conv_params(_Holder(), cout, cin, 1))
+    return r
+
+
+def _attn(c: int, hidden: int = 128) -> _Holder:
+    # Residual(Rezero(LinearAttention)) -> keys fn.g, fn.fn.to_qkv.weight, fn.fn.to_out.{weight,bias}
+    la = _seq(to_qkv=_conv_params(_Holder(), hidden * 3, c, 1, bias=False), to_out=_conv_params(_Holder(), c, hidden, 1))
+    rz = _seq(fn=la)
+    rz.g = torch.nn.Parameter(torch.zeros(1))
+    return _seq(fn=rz)
+
+
+class GradLogPEstimator2d(torch.nn.Module):
+    """Parameter tree of the reference U-Net (unitspeech/unitspeech.py:124-162); forward runs on the CUDA library."""
+
+    def __init__(self, dim, dim_mults=(1, 2, 4), groups=8, pe_scale=1000, spk_emb_dim=0):
+        super().__init__()
+        self.dim, self.dim_mults, self.groups, self.pe_scale = dim, tuple(dim_mults), groups, pe_scale
+        temb = dim + spk_emb_dim
+        self.mlp = _seq(_0=_linear_params(_Holder(), dim * 4, dim), _2=_linear_params(_Holder(), dim, dim * 4))
+        dims = [2] + [dim * m for m in dim_mults]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        self.downs = torch.nn.ModuleList()
+        self.ups = torch.nn.ModuleList()
+        for ind, (ci, co) in enumerate(in_out):
+            last = ind >= len(in_out) - 1
+            down = _Holder() if last else _seq(conv=_conv_params(_Holder(), co, co, 3))
+            self.downs.append(torch.nn.ModuleList([_resnet(ci, co, temb), _resnet(co, co, temb), _attn(co), down]))
+        mid = dims[-1]
+        self.mid_block1 = _resnet(mid, mid, temb)
+        self.mid_attn = _attn(mid)
+        self.mid_block2 = _resnet(mid, mid, temb)
+        for ci, co in reversed(in_out[1:]):
+            up = _seq(conv=_conv_params(_Holder(), ci, ci, 4, transposed=True))
+            self.ups.append(torch.nn.ModuleList([_resnet(co * 2, ci, temb), _resnet(ci, ci, temb), _attn(ci), up]))
+        self.final_block = _block(dim, dim)
+        self.final_conv = _conv_params(_Holder(), 1, dim, 1)
+        object.__setattr__(self, "_owner", None)
+
+    @torch.no_grad()
+    def forward(self, x, mask, mu, t, spk_emb=None):
+        """GradLogPEstimator2d.forward (unitspeech/unitspeech.py:164-201): (B,F,T),(B,1,T),(B,F,T),(B,),(B,1,S)."""
+        owner = self._owner
+        if owner is None:
+            raise RuntimeError("estimator is not attached to a UnitSpeech decoder")
+        return owner._estimator_forward(x, mask, mu, t, spk_emb)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class UnitSpeech(torch.nn.Module):
+    def __init__(self, n_feats, dim, dim_mults, beta_min=0.05, beta_max=20, pe_scale=1000, spk_emb_dim=0):
+        super().__init__()
+        self.n_feats = n_feats
+        self.dim = dim
+        self.dim_mults = tuple(dim_mults)
+        self.beta_min = beta_min
+        self.beta_max = beta_max
+        self.pe_scale = pe_scale
+        self.spk_emb_dim = spk_emb_dim
+        self.text_uncon = torch.nn.Parameter(torch.zeros(1, n_feats, 1))
+        self.spk_uncon = torch.nn.Parameter(torch.zeros(1, 1, spk_emb_dim))
+        self.estimator = GradLogPEstimator2d(dim, dim_mults=dim_mults, pe_scale=pe_scale, spk_emb_dim=spk_emb_dim)
+        object.__setattr__(self.estimator, "_owner", self)
+        self._handle = None
+        self._handle_device = None
+        self._weights_version = 0
+        self._synced_version = -1
+
+    # ------------------------------------------------------------------ reference conveniences (unitspeech/base.py)
+    @property
+    def nparams(self):
+        return sum(int(np.prod(p.detach().cpu().numpy().shape)) for _, p in self.named_parameters() if p.requires_grad)
+
+    def relocate_input(self, x: list):
+        device = next(self.parameters()).device
+        return [t.to(device) if isinstance(t, torch.Tensor) and t.device != device else t for t in x]
+
+    # ------------------------------------------------------------------ native handle management
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._weights_version += 1
+        return out
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self._weights_version += 1
+        return out
+
+    def mark_weights_changed(self):
+        """Call after modifying parameters in place; the next call re-uploads them."""
+        self._weights_version += 1
+
+    def _release(self):
+        if self._handle is not None:
+            abi.load_library().usb_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _device_index(self, like: Optional[torch.Tensor] = None) -> int:
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            if like is not None and like.device.type == "cuda":
+                dev = like.device
+            elif torch.cuda.is_available():
+                dev = torch.device("cuda", torch.cuda.current_device())
+            else:
+                raise abi.UsbError("unitspeech_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        return dev.index if dev.index is not None else torch.cuda.current_device()
+
+    def _ensure_handle(self, like: Optional[torch.Tensor] = None):
+        lib = abi.load_library()
+        dev = self._device_index(like)
+        if self._handle is not None and self._synced_version == self._weights_version and self._handle_device == dev:
+            return self._handle
+        self._release()
+        cfg = abi.UsbConfig()
+        cfg.n_feats, cfg.dim, cfg.n_mults = self.n_feats, self.dim, len(self.dim_mults)
+        for i, m in enumerate(self.dim_mults):
+            cfg.dim_mults[i] = int(m)
+        cfg.groups, cfg.spk_emb_dim = 8, self.spk_emb_dim
+        cfg.pe_scale, cfg.beta_min, cfg.beta_max, cfg.device = float(self.pe_scale), self.beta_min, self.beta_max, dev
+        hp = ctypes.c_void_p()
+        abi.check(lib.usb_create(ctypes.byref(cfg), ctypes.byref(hp)))
+        try:
+            params = {k: _f32c(v).cpu() for k, v in self.state_dict().items()}
+            params["__posemb_freqs"] = schedule.posemb_freqs(self.dim)
+            for key, t in params.items():
+                shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+                abi.check(lib.usb_load_param(hp, key.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()))
+            abi.check(lib.usb_finalize_params(hp))
+        except Exception:
+            lib.usb_destroy(hp)
+            raise
+        self._handle, self._handle_device, self._synced_version = hp, dev, self._weights_version
+        return hp
+
+    @staticmethod
+    def _stream(device_index: int) -> int:
+        return int(torch.cuda.current_stream(device_index).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(abi.load_library().usb_launch_count(self._handle)) if self._handle is not None else 0
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(abi.load_library().usb_workspace_bytes(self._handle)) if self._handle is not None else 0
+
+    # ------------------------------------------------------------------ estimator
+    @torch.no_grad()
+    def _estimator_forward(self, x, mask, mu, t, spk_emb):
+        lib = abi.load_library()
+        h = self._ensure_handle(x)
+        dev = torch.device("cuda", self._handle_device)
+        B, F, T = x.shape
+        xd, mud = _f32c(x).to(dev), _f32c(mu).to(dev)
+        md = _f32c(mask).to(dev).reshape(B, T)
+        td = _f32c(t).to(dev).reshape(B)
+        sd = _f32c(spk_emb).to(dev).reshape(B, self.spk_emb_dim)
+        out = torch.empty_like(xd)
+        with torch.cuda.device(dev):
+            abi.check(lib.usb_estimator_forward(h, xd.data_ptr(), mud.data_ptr(), md.data_ptr(), td.data_ptr(),
+                                                sd.data_ptr(), out.data_ptr(), B, T, self._stream(dev.index)))
+        return out.to(x.device)
+
+    # ------------------------------------------------------------------ sampler
+    @torch.no_grad()
+    def reverse_diffusion(self, z, mask, cond, spk_emb, n_timesteps, text_gradient_scale=0.0, spk_gradient_scale=0.0,
+                          noise: Optional[torch.Tensor] = None, trace: bool = False):
+        """UnitSpeech.reverse_diffusion (unitspeech/unitspeech.py:334-374), per-utterance batch-1 semantics.
+
+        z, cond: (B, n_feats, T); mask: (B, 1, T); spk_emb: (B, 1, spk_emb_dim); noise: optional (n, B, n_feats, T).
+        Returns (B, n_feats, T) on z's device; with trace=True also the (n, B, n_feats, T) x_t after every step.
+        """
+        if n_timesteps < 2:
+            raise ValueError("n_timesteps must be >= 2 (the reference fails for 1)")
+        lib = abi.load_library()
+        B, F, T = z.shape
+        if F != self.n_feats:
+            raise ValueError(f"expected {self.n_feats} mel bins, got {F}")
+        if T % (2 ** (len(self.dim_mults) - 1)):
+            raise ValueError("T must be a multiple of 2**(len(dim_mults)-1) (use fix_len_compatibility)")
+        if noise is None:
+            # the reference draws one randn per step from the global generator of z's device (:367)
+            noise = torch.stack([torch.randn(z.shape, dtype=z.dtype, device=z.device) for _ in range(n_timesteps)])
+        if tuple(noise.shape) != (n_timesteps, B, F, T):
+            raise ValueError("noise must have shape (n_timesteps, B, n_feats, T)")
+        coef = schedule.step_coefficients(n_timesteps, self.beta_min, self.beta_max).contiguous()
+        times = schedule.step_times(n_timesteps).contiguous()
+        tg, sg = float(text_gradient_scale), float(spk_gradient_scale)
+        h = self._ensure_handle(z)
+        dev = torch.device("cuda", self._handle_device)
+        on_host = z.device.type != "cuda"
+        with torch.cuda.device(dev):
+            stream = self._stream(dev.index)
+            if on_host and not trace:
+                zc, cc, nc = _f32c(z), _f32c(cond), _f32c(noise)
+                mc = _f32c(mask).reshape(B, T)
+                sc = _f32c(spk_emb).reshape(B, self.spk_emb_dim)
+                out = torch.empty_like(zc)
+                abi.check(lib.usb_reverse_diffusion_host(h, zc.data_ptr(), cc.data_ptr(), mc.data_ptr(), sc.data_ptr(),
+                                                         nc.data_ptr(), coef.data_ptr(), times.data_ptr(), n_timesteps,
+                                                         tg, sg, out.data_ptr(), B, T, stream))
+                return out
+            zd, cd, nd = _f32c(z).to(dev), _f32c(cond).to(dev), _f32c(noise).to(dev)
+            md = _f32c(mask).to(dev).reshape(B, T)
+            sd = _f32c(spk_emb).to(dev).reshape(B, self.spk_emb_dim)
+            out = torch.empty_like(zd)
+            tr = torch.empty_like(nd) if trace else None
+            abi.check(lib.usb_reverse_diffusion(h, zd.data_ptr(), cd.data_ptr(), md.data_ptr(), sd.data_ptr(),
+                                                nd.data_ptr(), coef.data_ptr(), times.data_ptr(), n_timesteps, tg, sg,
+                                                out.data_ptr(), tr.data_ptr() if trace else None, B, T, stream))
+        if on_host:
+            out = out.cpu()
+            tr = tr.cpu() if trace else None
+        return (out, tr) if trace else out
+
+    @torch.no_grad()
+    def forward(self, z, mask, cond, spk_emb, n_timesteps, text_gradient_scale=0.0, spk_gradient_scale=0.0, **kw):
+        """unitspeech/unitspeech.py:387-391."""
+        return self.reverse_diffusion(z, mask, cond, spk_emb, n_timesteps, text_gradient_scale=text_gradient_scale,
+                                      spk_gradient_scale=spk_gradient_scale, **kw)
+
+    @torch.no_grad()
+    def execute_text_to_speech(self, phoneme, phoneme_lengths, spk_emb, text_encoder, duration_predictor,
+                               num_downsamplings_in_unet, diffusion_steps=50, length_scale=1.0,
+                               text_gradient_scale=1.0, spk_gradient_scale=1.0, noise: Optional[torch.Tensor] = None):
+        """unitspeech/unitspeech.py:414-450: encoder -> durations -> alignment -> z -> reverse diffusion -> crop."""
+        cond_x, x, x_mask = text_encoder(phoneme, phoneme_lengths)
+        logw = duration_predictor(x, x_mask, w=None, g=spk_emb, reverse=True)
+        w = torch.exp(logw) * x_mask
+        w_ceil = torch.ceil(w) * length_scale
+        y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+        y_max_length = int(y_lengths.max())
+        y_max_length_ = fix_len_compatibility(y_max_length, num_downsamplings_in_unet)
+        y_mask = sequence_mask(y_lengths, y_max_length_).unsqueeze(1).to(x_mask.dtype)
+        attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
+        attn = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1)).unsqueeze(1)
+        cond_y = torch.matmul(attn.squeeze(1).transpose(1, 2).contiguous(), cond_x.transpose(1, 2).contiguous())
+        cond_y = cond_y.transpose(1, 2).contiguous()
+        encoder_outputs = cond_y[:, :, :y_max_length]
+        z = torch.randn_like(cond_y, device=cond_y.device)
+        decoder_outputs = self.forward(z, y_mask, cond_y, spk_emb, n_timesteps=diffusion_steps,
+                                       text_gradient_scale=text_gradient_scale, spk_gradient_scale=spk_gradient_scale,
+                                       noise=noise)
+        decoder_outputs = decoder_outputs[:, :, :y_max_length]
+        return encoder_outputs, decoder_outputs, attn[:, :, :y_max_length]
+
+    # ------------------------------------------------------------------ out of this path
+    def compute_loss(self, *a, **k):
+        raise NotImplementedError("compute_loss (training) is outside the reverse-diffusion path of unitspeech_b200")
+
+    def fine_tune(self, *a, **k):
+        raise NotImplementedError("fine_tune (training) is outside the reverse-diffusion path of unitspeech_b200")
+
+
+def denormalize_mel(y: torch.Tensor, mel_min: torch.Tensor, mel_max: torch.Tensor) -> torch.Tensor:
+    """The mel normalisation contract of the callers (inference.py:140): [-1, 1] -> log-mel."""
+    return (y + 1) / 2 * (mel_max - mel_min) + mel_min
+
+
+def normalize_mel(mel: torch.Tensor, mel_min: torch.Tensor, mel_max: torch.Tensor) -> torch.Tensor:
+    """Inverse of denormalize_mel (data.py:91, finetune.py:104)."""
+    return (mel - mel_min) / (mel_max - mel_min) * 2 - 1
