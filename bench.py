@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the reverse-diffusion hot path: mel frames/s of 50-step CFG reverse diffusion.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one full pass of the hot path over one batch: a 50-step text+speaker classifier-free-guided reverse
+diffusion (150 U-Net evaluations per utterance) of 16 utterances x 512 frames per GPU (BASELINE.json configs[1]).
+With N > 1 every rank samples its own 16 utterances (weak scaling, sharded by utterance, no collective in the step
+loop); the final mels are all-gathered with NCCL inside the timed region.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same metric through the
+public API with pinned HOST tensors (H2D of z/cond/mask/spk/noise and D2H of the mels inside the timed region);
+`roofline` = the tcgen05 implicit-GEMM conv kernel (algorithmic conv FLOPs / its summed CUDA-event time, measured in a
+separate profiled pass of the same workload, against the measured bf16 GEMM peak); `cpu_baseline` = the CPU port of the
+reference algorithm (oracle/) on a bounded sample of the same workload.
+
+`--impl reference` times the CPU port of the reference (oracle/unitspeech_oracle.py, pinned to the reference's outputs
+by tests/golden) on the host cores: the upstream package is a research script tree whose decoder imports need stubs
+ and its path is pure PyTorch, so the oracle port is the reference arm that can travel to the GPU box.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "mel frames/s of 50-step CFG reverse diffusion"
+UNIT = "frames/s"
+N_STEPS = 50                      # diffusion steps per pass
+TG, SG = 1.0, 1.0                 # text / speaker guidance scales
+BATCH, FRAMES = 16, 512           # per-GPU batch (BASELINE.json configs[1])
+N_FEATS, SPK = 80, 256
+CONV_FLOP_PER_FRAME_EVAL = 647.27e6   # conv FLOPs per mel frame per estimator evaluation
+SCALE = 1.0 / 512                 # harness scale keeping the untrained sampler O(1)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tensor": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "tensor_burst": float(p["bf16_tflops"]),
+                "hbm": float(p["hbm_gbs"]), "src": "measured"}
+    return {"tensor": 1400.0, "tensor_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        busy = [s for s in self.samples if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(busy)}
+
+
+def make_inputs(seed: int, B: int, T: int, n: int):
+    from unitspeech_b200.synthetic import synthetic_inputs
+    return synthetic_inputs(B, T, n, seed=seed, scale=SCALE)
+
+
+def harness_weights(dec=None):
+    """Seeded random-init weights of the reference architecture (same tensors for both arms)."""
+    from unitspeech_b200 import UnitSpeech
+    from unitspeech_b200.synthetic import random_init_state_dict
+    if dec is None:
+        dec = UnitSpeech(N_FEATS, 128, (1, 2, 4, 8), beta_min=0.05, beta_max=20, pe_scale=1000, spk_emb_dim=SPK)
+    return random_init_state_dict(dec, seed=1234, out_scale=SCALE)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference algorithm)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_sample(params, threads: int, T: int = FRAMES, diffusion_steps: int = 1):
+    """One utterance x T frames x `diffusion_steps` CFG steps on the host; returns (seconds, frames/s of the 50-step job)."""
+    from oracle import unitspeech_oracle as O
+    torch.set_num_threads(threads)
+    n = max(2, diffusion_steps)
+    z, mask, cond, spk, noise = make_inputs(7, 1, T, N_STEPS)
+    # run the first `n` steps of the real 50-step schedule: same per-step cost as any other step
+    tb = O.schedule_tables(N_STEPS, 0.05, 20.0)
+    times = O.step_times(N_STEPS)
+    xt = z * mask
+    tu = params["text_uncon"].repeat(1, 1, T)
+    su = (params["spk_uncon"] / params["spk_uncon"].norm()).repeat(1, 1, 1)
+    est = lambda x_, m_, mu_, t_, s_: O.estimator_forward(params, x_, m_, mu_, t_, s_, 128, (1, 2, 4, 8))  # noqa: E731
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(n):
+            t = times[i] * torch.ones(1)
+            score = O.cfg_score(params, xt, mask, cond, t, spk, tu, su, TG, SG, est)
+            xt = O.sampler_step(tb, N_STEPS - 1 - i, xt, score, noise[i], mask)
+    dt = time.perf_counter() - t0
+    per_step = dt / n
+    return dt, T / (N_STEPS * per_step), n
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    params = harness_weights()
+    vals = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_sample(params, threads, diffusion_steps=2)
+    t_total = 0.0
+    for _ in range(args.steps):
+        dt, fps, n = cpu_sample(params, threads, diffusion_steps=2)
+        vals.append(fps)
+        t_total += dt
+    v = statistics.median(vals)
+    sample = f"1 utterance x {FRAMES} frames x 2 of the 50 CFG diffusion steps (6 U-Net evaluations) per bench step, scaled to the 50-step job"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"UnitSpeech decoder, 50-step text+speaker CFG (1.0/1.0) reverse diffusion, {BATCH} utt x {FRAMES} frames per GPU",
+                   "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from unitspeech_b200 import UnitSpeech
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    dec = UnitSpeech(N_FEATS, 128, (1, 2, 4, 8), beta_min=0.05, beta_max=20, pe_scale=1000, spk_emb_dim=SPK)
+    params = harness_weights(dec)
+    dec.load_state_dict(params)
+    dec = dec.to(dev).eval()
+
+    B, T, n = args.batch, args.frames, N_STEPS
+    z, mask, cond, spk, noise = make_inputs(100 + rank, B, T, n)
+    host = [t.pin_memory() for t in (z, mask, cond, spk, noise)]
+    zd, md, cd, sd, nd = (t.to(dev) for t in (z, mask, cond, spk, noise))
+    gathered = [torch.empty(B, N_FEATS, T, device=dev) for _ in range(world)] if world > 1 else None
+
+    def one_pass():
+        out = dec(zd, md, cd, sd, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=nd)
+        if world > 1:
+            dist.all_gather(gathered, out)
+        return out
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 0)):
+        out = one_pass()
+    sync()
+    assert torch.isfinite(out).all(), "non-finite mel from the CUDA decoder"
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = dec.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        one_pass()
+    e1.record()
+    sync()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = dec.launch_count - launches0
+    clocks = sampler.finish()
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    frames_total = world * B * T * args.steps
+    value = frames_total / (elapsed_ms / 1000.0)
+
+    # ---- end-to-end through the public API with pinned host tensors (copies inside the timed region)
+    hz, hm, hc, hs, hn = host
+    for _ in range(1):
+        dec(hz, hm, hc, hs, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=hn)
+    sync()
+    e2e_steps = max(1, min(args.steps, 3))
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        out_h = dec(hz, hm, hc, hs, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=hn)
+    f1.record()
+    sync()
+    e2e_ms = f0.elapsed_time(f1)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T * e2e_steps / (float(t.item()) / 1000.0)
+    h2d = sum(x.numel() * 4 for x in host)
+    d2h = out_h.numel() * 4
+
+    line = None
+    if rank == 0:
+        # ---- roofline: one profiled pass of the same workload (per-launch CUDA events on the launching stream)
+        peaks = _peaks()
+        dec.set_profiling(True)
+        one_pass()
+        torch.cuda.synchronize(dev)
+        prof = dec.get_profile()
+        dec.set_profiling(False)
+        conv_ms, conv_flop, conv_n = prof["conv_igemm"]
+        gn_ms, gn_bytes, gn_n = prof["gn_apply"]
+        at_ms, at_bytes, at_n = prof["attention"]
+        ot_ms, ot_bytes, ot_n = prof["other"]
+        achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
+        total_prof_ms = conv_ms + gn_ms + at_ms + ot_ms
+        roofline = {
+            "kernel": "conv_igemm_kernel (tcgen05.mma kind::f16, fp16 operands, fp32 TMEM accumulators)",
+            "bound": "tensor", "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tensor"] if achieved else None, "traffic": None,
+            "peak_source": f"{peaks['src']} bf16 GEMM, sustained (burst {peaks['tensor_burst']})",
+            "launches_per_pass": conv_n, "ms_per_pass": conv_ms, "share_of_pass": conv_ms / total_prof_ms,
+            "flop_per_launch_avg": conv_flop / max(conv_n, 1),
+            "frames_per_s_at_peak": peaks["tensor"] * 1e12 / (CONV_FLOP_PER_FRAME_EVAL * 3 * N_STEPS),
+        }
+        gn_gbs = gn_bytes / (gn_ms / 1e3) / 1e9 if gn_ms > 0 else None
+        roofline_hbm = {
+            "kernel": "gn_apply_kernel (GroupNorm apply + Mish + embedding/residual + mask, fp16 in/out)",
+            "bound": "hbm", "achieved": gn_gbs, "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": gn_gbs / peaks["hbm"] if gn_gbs else None, "traffic": None, "launches_per_pass": gn_n,
+            "ms_per_pass": gn_ms, "share_of_pass": gn_ms / total_prof_ms,
+        }
+        breakdown = {"conv_igemm_ms": conv_ms, "gn_apply_ms": gn_ms, "attention_ms": at_ms, "other_ms": ot_ms,
+                     "attention_GBps": at_bytes / (at_ms / 1e3) / 1e9 if at_ms > 0 else None,
+                     "other_GBps": ot_bytes / (ot_ms / 1e3) / 1e9 if ot_ms > 0 else None}
+        # ---- CPU baseline on this box's host cores (bounded sample)
+        cpu = None
+        if not args.no_cpu:
+            threads = os.cpu_count() or 1
+            dt, fps, nst = cpu_sample(params, threads, diffusion_steps=2)
+            cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"1 utterance x {T} frames x {nst} of the 50 CFG diffusion steps ({3 * nst} U-Net evaluations, {dt:.1f} s), scaled to the 50-step job"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"UnitSpeech decoder (random-init pretrained_decoder architecture, 119.1M params), "
+                                   f"50-step text+speaker CFG (1.0/1.0) reverse diffusion, {B} utterances x {T} frames "
+                                   f"per GPU (BASELINE.json configs[1]); sharded by utterance across GPUs",
+                       "batch_per_gpu": B, "frames": T, "diffusion_steps": n, "cfg_scales": [TG, SG],
+                       "estimator_evals_per_step": 3, "parallelism": f"utterance-sharded x{world}",
+                       "l2": "per-step working set (multi-GB activations, 131 MB noise) far exceeds the 126 MB L2; no explicit flush",
+                       "rtf": (elapsed_ms / 1000.0 / args.steps) / (B * T * 256 / 22050.0)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "breakdown_ms_per_pass": breakdown,
+            "cpu_baseline": cpu,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -85,20 +85,29 @@ int64_t usb_workspace_bytes(usb_handle* h);
 /* number of kernels launched by the handle since creation (bench.py's gpu_launches) */
 int64_t usb_launch_count(usb_handle* h);
 
+/* Per-kernel-class device timing for roofline reports.  While on, every launch of usb_reverse_diffusion is bracketed
+ * by CUDA events on the caller's stream and the call ends with a stream synchronisation (so never leave it on in a
+ * timed run).  usb_get_profile returns accumulated milliseconds, algorithmic work and launch counts for 4 classes:
+ * 0 = tcgen05 implicit-GEMM convs (work = FLOPs), 1 = GroupNorm-apply/Mish (bytes), 2 = attention context (bytes),
+ * 3 = embedding / input conv / final fused step (bytes).  usb_set_profiling also clears the accumulators. */
+int usb_set_profiling(usb_handle* h, int32_t on);
+int usb_get_profile(usb_handle* h, double* ms4, double* work4, int64_t* launches4);
+
 /* ---- operator-level entries (parity tests of single kernels against torch fp32) ---------------------------- */
 /* NHWC fp16 convolution on the tcgen05 implicit-GEMM kernel.
  * kind: 0 = 3x3 stride 1 pad 1, 1 = 3x3 stride 2 pad 1, 2 = 1x1, 3 = ConvTranspose 4x4 stride 2 pad 1.
  * in0: (N, H, W, C0) fp16 dev; in1: optional second K source (N, H, W, C1) (kind 0/2 only);
  * weight: host fp32 in the reference's layout ((Cout, C0+C1, k, k); ConvTranspose (Cin, Cout, 4, 4));
  * bias: host fp32 (Cout) or NULL; mask: dev fp32 (N, Wout) or NULL; residual: dev fp16 shaped like out or NULL;
- * res_scale: residual blend out = conv*res_scale + residual; stats: dev double (N, groups, 2) accumulated
- * (sum, sumsq of conv+bias) or NULL; out: (N, Hout, Wout, Cout) fp16 dev. */
+ * res_scale: residual blend out = conv*res_scale + residual; stats: dev int64 (N, groups, 2) accumulated fixed-point
+ * GroupNorm partials (sum * 2^24, sumsq * 2^18 of conv+bias; integer atomics make them order-independent) or NULL;
+ * out: (N, Hout, Wout, Cout) fp16 dev. */
 int usb_op_conv(usb_handle* h, int32_t kind, const void* in0, const void* in1, int32_t N, int32_t H, int32_t W,
                 int32_t C0, int32_t C1, int32_t Cout, const float* weight_host, const float* bias_host,
-                const float* mask, const void* residual, float res_scale, double* stats, int32_t groups, void* out,
+                const float* mask, const void* residual, float res_scale, int64_t* stats, int32_t groups, void* out,
                 uint64_t stream);
 /* out = (Mish(GroupNorm(raw)) + addvec[n][c] + res) * mask on NHWC fp16; gamma/beta/addvec dev fp32 */
-int usb_op_gn_apply(usb_handle* h, const void* raw, const double* stats, const float* gamma, const float* beta,
+int usb_op_gn_apply(usb_handle* h, const void* raw, const int64_t* stats, const float* gamma, const float* beta,
                     const float* addvec, const void* res, const float* mask, void* out, int32_t N, int32_t H,
                     int32_t W, int32_t C, int32_t groups, uint64_t stream);
 /* LinearAttention context folded with to_out: qkv (N, P, 384) fp16 dev, wo dev fp32 (C, 128) -> weff (N, C, 128) fp16 */

@@ -32,6 +32,12 @@ CASES = {
     "tiny_textonly": (16, (1, 2), 1, 16, (13,), 3, 1.5, 0.0, 1.0 / 8),
     "tiny_spkonly": (16, (1, 2), 1, 16, (16,), 3, 0.0, 0.7, 1.0 / 8),
     "full_cfg": (128, (1, 2, 4, 8), 2, 32, (32, 27), 3, 1.0, 1.0, 1.0 / 512),
+    # dim=64 cases: the smallest width the CUDA library supports (channels are walked in 64-wide K steps)
+    "d64_cfg": (64, (1, 2), 2, 16, (16, 11), 4, 1.0, 1.0, 1.0 / 32),
+    "d64_nocfg": (64, (1, 2, 4), 1, 24, (24,), 3, 0.0, 0.0, 1.0 / 32),
+    "d64_textonly": (64, (1, 2), 1, 16, (13,), 3, 1.5, 0.0, 1.0 / 32),
+    "d64_spkonly": (64, (1, 2), 2, 16, (16, 9), 3, 0.0, 0.7, 1.0 / 32),
+    "full_nocfg10": (128, (1, 2, 4, 8), 1, 40, (37,), 10, 0.0, 0.0, 1.0 / 512),
 }
 
 

@@ -41,11 +41,13 @@ class OpHandle:
         b = bias.detach().float().contiguous().cpu() if bias is not None else None
         m = mask.detach().float().contiguous().to(self.dev) if mask is not None else None
         r = to_nhwc(residual) if residual is not None else None
-        st = torch.zeros(N, stats_groups, 2, dtype=torch.float64, device=self.dev) if stats_groups else None
+        st = torch.zeros(N, stats_groups, 2, dtype=torch.int64, device=self.dev) if stats_groups else None
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
         abi.check(self.lib.usb_op_conv(self.h, kind, ptr(a0), ptr(a1), N, H, W, C0, C1, Cout, ptr(w), ptr(b), ptr(m),
                                        ptr(r), float(res_scale), ptr(st), stats_groups, ptr(out), self._stream()))
         torch.cuda.synchronize(self.dev)
+        if st is not None:  # fixed point -> (sum, sumsq)
+            st = st.double() / torch.tensor([2.0 ** 24, 2.0 ** 18], dtype=torch.float64, device=self.dev)
         return out.float().permute(0, 3, 1, 2).contiguous(), st
 
     def gn_apply(self, raw, stats, gamma, beta, addvec, res, mask, groups=8):
@@ -55,7 +57,8 @@ class OpHandle:
         a = to_nhwc(raw)
         r = to_nhwc(res) if res is not None else None
         out = torch.empty_like(a)
-        st = stats.to(self.dev, torch.float64).contiguous()
+        st = (stats.double() * torch.tensor([2.0 ** 24, 2.0 ** 18], dtype=torch.float64)).round().to(torch.int64)
+        st = st.to(self.dev).contiguous()
         g, b, av, m = f(gamma), f(beta), f(addvec), f(mask)
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
         abi.check(self.lib.usb_op_gn_apply(self.h, ptr(a), ptr(st), ptr(g), ptr(b), ptr(av), ptr(r), ptr(m), ptr(out),

@@ -1,0 +1,164 @@
+"""End-to-end parity of the CUDA decoder (through the UnitSpeech-compatible class -> C ABI) against the CPU oracle
+and the committed reference-generated golden vectors.
+
+Tolerance (BASELINE.json north_star): final mel max-abs <= 1e-2 and mean-abs <= 1e-3 in normalised mel space
+(|x| = O(1)).  For vectors whose scale is not O(1) the same bounds are applied relative to max(1, |ref|_inf).
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unitspeech_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MAX_TOL, MEAN_TOL = 1e-2, 1e-3
+
+
+def _decoder(dim, mults, params):
+    from unitspeech_b200 import UnitSpeech
+    dec = UnitSpeech(n_feats=80, dim=dim, dim_mults=mults, beta_min=0.05, beta_max=20, pe_scale=1000, spk_emb_dim=256)
+    dec.load_state_dict(params, strict=True)
+    return dec.cuda().eval()
+
+
+def _errs(out, ref):
+    d = (out.detach().cpu().float() - ref).abs()
+    scale = max(1.0, float(ref.abs().max()))
+    return float(d.max()) / scale, float(d.mean()) / scale
+
+
+def _load(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    dim, B, T, n = (int(v) for v in g["meta"])
+    mults = tuple(int(v) for v in g["mults"])
+    lengths = tuple(int(v) for v in g["lengths"])
+    tg, sg, s = (float(v) for v in g["scales"])
+    return g, dim, mults, B, T, n, lengths, tg, sg, s
+
+
+GOLDEN = ["d64_cfg", "d64_nocfg", "d64_textonly", "d64_spkonly", "full_cfg", "full_nocfg10"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_reverse_diffusion_matches_reference_golden(golden_dir, name):
+    g, dim, mults, B, T, n, lengths, tg, sg, s = _load(golden_dir, name)
+    p = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=s)
+    z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=11, scale=s, lengths=lengths)
+    dec = _decoder(dim, mults, p)
+    out = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, text_gradient_scale=tg, spk_gradient_scale=sg,
+              noise=noise.cuda())
+    assert out.shape == (B, 80, T) and out.is_cuda
+    mx, mn = _errs(out, torch.from_numpy(g["out"]))
+    print(f"{name}: rel max-abs {mx:.3e} mean-abs {mn:.3e}")
+    assert mx <= MAX_TOL and mn <= MEAN_TOL
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_estimator_matches_reference_golden(golden_dir, name):
+    g, dim, mults, B, T, n, lengths, tg, sg, s = _load(golden_dir, name)
+    p = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=s)
+    z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=11, scale=s, lengths=lengths)
+    dec = _decoder(dim, mults, p)
+    est = dec.estimator(z.cuda(), mask.cuda(), cond.cuda(), torch.full((B,), 0.37).cuda(), spk.cuda())
+    ref = torch.from_numpy(g["est"])
+    d = (est.cpu() - ref).abs()
+    scale = float(ref.abs().max())
+    print(f"{name}: estimator rel max {float(d.max()) / scale:.3e} mean {float(d.mean()) / scale:.3e}")
+    # one evaluation, fp16 operands/activations: tf32-class accuracy relative to the output scale
+    assert float(d.max()) <= 1e-2 * scale and float(d.mean()) <= 2e-3 * scale
+
+
+def test_fifty_step_cfg_parity_and_drift():
+    """The headline setting: 50 steps, text+speaker CFG 1.0/1.0, full-size network, ragged batch; oracle on CPU."""
+    B, T, n, s = 2, 64, 50, 1.0 / 512
+    p = O.harness_params(seed=1234, out_scale=s)
+    z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=3, scale=s, lengths=(64, 50))
+    ref_trace = []
+    ref = O.reverse_diffusion(p, z, mask, cond, spk, n, 1.0, 1.0, noise=noise, trace=ref_trace)
+    dec = _decoder(128, (1, 2, 4, 8), p)
+    out, tr = dec.reverse_diffusion(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, 1.0, 1.0, noise=noise.cuda(),
+                                    trace=True)
+    d = (out.cpu() - ref).abs()
+    drift = [float((tr[i].cpu() - ref_trace[i]).abs().max()) for i in range(n)]
+    print(f"final |ref|max {float(ref.abs().max()):.3f} max-abs {float(d.max()):.3e} mean-abs {float(d.mean()):.3e}")
+    print("per-step drift (max-abs) every 5 steps:", ["%.2e" % v for v in drift[::5]])
+    assert 0.5 < float(ref.abs().max()) < 8.0          # normalised-mel regime
+    assert float(d.max()) <= MAX_TOL and float(d.mean()) <= MEAN_TOL
+    # padded frames stay exactly zero
+    assert float(out[1, :, 50:].abs().max()) == 0.0
+
+
+def test_batch_equals_per_utterance_calls():
+    """Batched call == the same utterances sampled one by one (the reference's only correct mode)."""
+    B, T, n, s = 3, 32, 4, 1.0 / 512
+    p = O.harness_params(seed=1234, out_scale=s)
+    z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=5, scale=s, lengths=(32, 17, 24))
+    dec = _decoder(128, (1, 2, 4, 8), p)
+    args = lambda sl: (z[sl].cuda(), mask[sl].cuda(), cond[sl].cuda(), spk[sl].cuda())  # noqa: E731
+    full = dec(*args(slice(0, B)), n, 1.0, 1.0, noise=noise.cuda())
+    for b in range(B):
+        one = dec(*args(slice(b, b + 1)), n, 1.0, 1.0, noise=noise[:, b:b + 1].cuda())
+        # identical arithmetic per utterance: tiles never mix samples and the GroupNorm partial sums are
+        # accumulated with integer (associative) atomics -> bitwise batch invariance
+        assert torch.equal(one, full[b:b + 1])
+
+
+def test_noise_none_follows_reference_rng_order():
+    B, T, n, s = 1, 16, 3, 1.0 / 32
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=1234, out_scale=s)
+    z, mask, cond, spk, _ = O.harness_inputs(B, T, n, seed=2, scale=s)
+    dec = _decoder(64, (1, 2), p)
+    zc, mc, cc, sc = z.cuda(), mask.cuda(), cond.cuda(), spk.cuda()
+    torch.manual_seed(77)
+    a = dec(zc, mc, cc, sc, n)
+    torch.manual_seed(77)
+    noise = torch.stack([torch.randn(zc.shape, device="cuda") for _ in range(n)])
+    b = dec(zc, mc, cc, sc, n, noise=noise)
+    assert torch.equal(a, b)
+
+
+def test_host_buffer_entry_matches_device_entry():
+    B, T, n, s = 2, 16, 3, 1.0 / 32
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=1234, out_scale=s)
+    z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=2, scale=s, lengths=(16, 12))
+    dec = _decoder(64, (1, 2), p)
+    dev = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, 1.0, 1.0, noise=noise.cuda())
+    host = dec(z, mask, cond, spk, n, 1.0, 1.0, noise=noise)
+    assert not host.is_cuda
+    assert torch.equal(host, dev.cpu())
+
+
+def test_argument_errors():
+    from unitspeech_b200 import UnitSpeech
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=1)
+    dec = _decoder(64, (1, 2), p)
+    z, mask, cond, spk, noise = O.harness_inputs(1, 16, 2, seed=2)
+    with pytest.raises(ValueError):
+        dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), 1)
+    with pytest.raises(ValueError):
+        dec(z[..., :15].cuda(), mask[..., :15].cuda(), cond[..., :15].cuda(), spk.cuda(), 2)
+    with pytest.raises(NotImplementedError):
+        dec.compute_loss(None, None, None)
+    from unitspeech_b200 import abi
+    with pytest.raises(abi.UsbError):
+        UnitSpeech(80, 48, (1, 2), spk_emb_dim=256).cuda()(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), 2)
+
+
+def test_state_dict_roundtrip_and_reload():
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=1234, out_scale=1 / 32)
+    dec = _decoder(64, (1, 2), p)
+    sd = dec.state_dict()
+    assert set(sd) == set(p) and all(torch.equal(sd[k].cpu(), p[k]) for k in p)
+    z, mask, cond, spk, noise = O.harness_inputs(1, 16, 2, seed=2, scale=1 / 32)
+    a = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), 2, noise=noise.cuda())
+    p2 = O.harness_params(dim=64, dim_mults=(1, 2), seed=99, out_scale=1 / 32)
+    dec.load_state_dict(p2)
+    b = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), 2, noise=noise.cuda())
+    ref = O.reverse_diffusion(p2, z, mask, cond, spk, 2, noise=noise, dim=64, dim_mults=(1, 2))
+    assert float((a - b).abs().max()) > 1e-4          # weights really changed
+    mx, mn = _errs(b, ref)
+    assert mx <= MAX_TOL and mn <= MEAN_TOL

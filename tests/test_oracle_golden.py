@@ -9,7 +9,8 @@ import torch
 
 from oracle import unitspeech_oracle as O
 
-CASES = ["tiny_cfg", "tiny_nocfg", "tiny_textonly", "tiny_spkonly", "full_cfg"]
+CASES = ["tiny_cfg", "tiny_nocfg", "tiny_textonly", "tiny_spkonly", "full_cfg",
+         "d64_cfg", "d64_nocfg", "d64_textonly", "d64_spkonly", "full_nocfg10"]
 
 
 def _load(golden_dir, name):

@@ -47,6 +47,8 @@ SIGNATURES = {
                                                                          c_int32, c_int32, c_uint64]),
     "usb_workspace_bytes": (c_int64, [c_void_p]),
     "usb_launch_count": (c_int64, [c_void_p]),
+    "usb_set_profiling": (c_int32, [c_void_p, c_int32]),
+    "usb_get_profile": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)]),
     "usb_op_conv": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                               c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p,
                               c_uint64]),

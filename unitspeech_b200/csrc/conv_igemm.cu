@@ -33,12 +33,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__device__ __forceinline__ void flush_stats(double* dst, float s, float ss, int lane) {
+__device__ __forceinline__ void flush_stats(long long* dst, float s, float ss, int lane) {
     s = warp_sum(s);
     ss = warp_sum(ss);
     if (lane == 0) {
-        atomicAdd(dst, static_cast<double>(s));
-        atomicAdd(dst + 1, static_cast<double>(ss));
+        atomicAdd(reinterpret_cast<unsigned long long*>(dst),
+                  static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
+        atomicAdd(reinterpret_cast<unsigned long long*>(dst + 1),
+                  static_cast<unsigned long long>(__float2ll_rn(ss * kStatSqScale)));
     }
 }
 
@@ -174,7 +176,7 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
             const int xo = x * p.ox_mul + p.ox_off[tc.ph];
             const long long off = tc.n * p.o_sn + yo * p.o_sy + xo * p.o_sx + tc.nt * p.BN;
             const float m = (p.mask && valid) ? __ldg(p.mask + static_cast<long long>(tc.n) * p.mask_stride + xo) : 1.f;
-            double* stats_n = p.stats ? p.stats + static_cast<long long>(tc.n) * p.groups * 2 : nullptr;
+            long long* stats_n = p.stats ? p.stats + static_cast<long long>(tc.n) * p.groups * 2 : nullptr;
 
             mbar_wait(&tmem_full_bar[as], aphase, 400 + as);
             tc_fence_after();
@@ -215,7 +217,7 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
                             gs += a;
                             gss += a * a;
                         }
-                        if (((c0 + 32) % cpg) == 0) {
+                        if (((c0 + 32) % cpg) == 0 || j == nchunks - 1) {
                             flush_stats(stats_n + (c0 / cpg) * 2, gs, gss, lane);
                             gs = gss = 0.f;
                         }

@@ -22,6 +22,11 @@ constexpr int kConvBM = 128;           // pixels per tile (UMMA M)
 constexpr int kConvBK = 64;            // channels per K step (128 B of fp16 = one swizzle row)
 constexpr int kConvMaxTaps = 16;       // phases x taps
 constexpr int kConvSmemBytes = 225 * 1024;
+// GroupNorm partial sums are accumulated with integer atomics in fixed point: integer addition is
+// associative, so the statistics (and with them every fp16 rounding downstream) are bit-reproducible from
+// run to run and independent of the batch an utterance is in.
+constexpr float kStatSumScale = 16777216.f;   // 2^24
+constexpr float kStatSqScale = 262144.f;      // 2^18
 
 struct ConvTap {
     int16_t c;    // offset added to the channel coordinate (column-parity * C for stride-2 views)
@@ -42,7 +47,7 @@ struct ConvParams {
     ConvTap tap[kConvMaxTaps];
     // epilogue: v = acc + bias[c]; stats (sum, sumsq per (n, group)) on v; v = v*res_scale + res; v *= mask
     const float* bias;         // [Cout] or null
-    double* stats;             // [N][groups][2] or null
+    long long* stats;          // [N][groups][2] fixed-point (sum * 2^24, sumsq * 2^18) or null
     int groups;                // GroupNorm groups (stats only)
     const __half* res;         // residual, same geometry as out, or null
     const float* res_scale;    // device scalar (Rezero g) or null (=1)

@@ -51,11 +51,13 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     return r;
 }
 
-// mean / rstd of GroupNorm group g of row n from the (sum, sumsq) doubles; biased variance, as torch GroupNorm
-__device__ __forceinline__ void group_moments(const double* stats, int n, int groups, int g, double count, float eps,
-                                              float& mean, float& rstd) {
-    const double s = stats[(static_cast<long long>(n) * groups + g) * 2];
-    const double ss = stats[(static_cast<long long>(n) * groups + g) * 2 + 1];
+// mean / rstd of GroupNorm group g of row n from the fixed-point (sum, sumsq); biased variance, as torch GroupNorm
+__device__ __forceinline__ void group_moments(const long long* stats, int n, int groups, int g, double count,
+                                              float eps, float& mean, float& rstd) {
+    const double s = static_cast<double>(stats[(static_cast<long long>(n) * groups + g) * 2]) /
+                     static_cast<double>(kStatSumScale);
+    const double ss = static_cast<double>(stats[(static_cast<long long>(n) * groups + g) * 2 + 1]) /
+                      static_cast<double>(kStatSqScale);
     const double mu = s / count;
     double var = ss / count - mu * mu;
     var = var < 0.0 ? 0.0 : var;
@@ -70,7 +72,7 @@ __device__ __forceinline__ void group_moments(const double* stats, int n, int gr
 // =====================================================================================================================
 __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p, int pix_per_block) {
     extern __shared__ float sw[];  // [18][C] 3x3 weights, then [2][C] 1x1 weights
-    __shared__ float gsum[16];
+    __shared__ unsigned long long gsum[16];
     const int C = p.C;
     const int n = blockIdx.y;
     const int TP = C >> 3;
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
     const int lanes = blockDim.x / TP;
     for (int i = threadIdx.x; i < 18 * C; i += blockDim.x) sw[i] = p.w3[i];
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sw[18 * C + i] = p.w1[i];
-    if (threadIdx.x < 16) gsum[threadIdx.x] = 0.f;
+    if (threadIdx.x < 16) gsum[threadIdx.x] = 0ull;
     __syncthreads();
 
     float b3[8], b1[8];
@@ -148,12 +150,12 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
     }
     const int cpg = C / p.groups;
     const int g = (tq * 8) / cpg;
-    atomicAdd(&gsum[g * 2], s);
-    atomicAdd(&gsum[g * 2 + 1], ss);
+    atomicAdd(&gsum[g * 2], static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
+    atomicAdd(&gsum[g * 2 + 1], static_cast<unsigned long long>(__float2ll_rn(ss * kStatSqScale)));
     __syncthreads();
     if (threadIdx.x < p.groups * 2)
-        atomicAdd(p.stats + static_cast<long long>(n) * p.groups * 2 + threadIdx.x,
-                  static_cast<double>(gsum[threadIdx.x]));
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + static_cast<long long>(n) * p.groups * 2 + threadIdx.x,
+                  gsum[threadIdx.x]);
 }
 
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {

@@ -187,7 +187,7 @@ struct ConvOp {
 
 struct ConvEpilogue {
     const float* bias = nullptr;
-    double* stats = nullptr;
+    long long* stats = nullptr;
     int groups = 8;
     const __half* res = nullptr;
     const float* res_scale = nullptr;
@@ -304,10 +304,10 @@ struct Plan {
     float* t_rows = nullptr;      // [Be]
     float* u = nullptr;           // [Be][dim+S]
     float* E = nullptr;           // [Be][J]
-    double* stats = nullptr;      // [slots][Be][groups][2]
+    long long* stats = nullptr;   // [slots][Be][groups][2] fixed point
     size_t stats_bytes = 0;
     __half* final_raw = nullptr;
-    double* final_stats = nullptr;
+    long long* final_stats = nullptr;
     float* xt = nullptr;          // [Be][P0] sampler state (only first B rows used)
 };
 
@@ -338,6 +338,15 @@ struct usb_handle {
     int J = 0;
     Plan plan;
     long long launches = 0;
+    // optional per-kernel-class timing (bench.py roofline): events around every launch of a profiled call
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Rec { int cls; size_t e0, e1; double work; };
+    std::vector<Rec> recs;
+    double prof_ms[4] = {0, 0, 0, 0};     // class 0 conv (tensor), 1 gn_apply, 2 attention, 3 other
+    double prof_work[4] = {0, 0, 0, 0};   // conv: FLOPs; gn/attn/other: algorithmic bytes
+    long long prof_launches[4] = {0, 0, 0, 0};
 };
 
 namespace usb {
@@ -573,7 +582,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
     const size_t o_xrow = b.take(Be * sizeof(int)), o_murow = b.take(Be * sizeof(int));
     const size_t o_spk = b.take((size_t)Be * S * sizeof(float)), o_t = b.take(Be * sizeof(float));
     const size_t o_u = b.take((size_t)Be * (dim + S) * sizeof(float)), o_E = b.take((size_t)Be * h->J * sizeof(float));
-    pl.stats_bytes = (size_t)n_slots * Be * G * 2 * sizeof(double);
+    pl.stats_bytes = (size_t)n_slots * Be * G * 2 * sizeof(long long);
     const size_t o_stats = b.take(pl.stats_bytes);
     const size_t o_xt = b.take((size_t)Be * c.n_feats * T * sizeof(float));
     pl.arena_bytes = b.off;
@@ -594,7 +603,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
     pl.t_rows = reinterpret_cast<float*>(A + o_t);
     pl.u = reinterpret_cast<float*>(A + o_u);
     pl.E = reinterpret_cast<float*>(A + o_E);
-    pl.stats = reinterpret_cast<double*>(A + o_stats);
+    pl.stats = reinterpret_cast<long long*>(A + o_stats);
     pl.xt = reinterpret_cast<float*>(A + o_xt);
     float* part = reinterpret_cast<float*>(A + o_part);
     pl.Be = Be;
@@ -611,7 +620,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         pl.ops.push_back({Op::CONV, (int)pl.convs.size() - 1});
         return 0;
     };
-    auto push_gn = [&](const __half* raw, const double* stats, const GnW& g, const float* addvec, const __half* res,
+    auto push_gn = [&](const __half* raw, const long long* stats, const GnW& g, const float* addvec, const __half* res,
                        int l, int Cc, __half* out) {
         GnApplyParams p;
         p.raw = raw; p.stats = stats; p.gamma = g.gamma; p.beta = g.beta; p.addvec = addvec; p.addvec_stride = h->J;
@@ -626,11 +635,11 @@ static int build_plan(usb_handle* h, int Be, int T) {
         __half *raw = HP(o_raw[l]), *h1 = HP(o_h1[l]), *rb = HP(o_r[l]);
         ConvEpilogue ep;
         ep.groups = G;
-        double* s1 = next_stats();
+        long long* s1 = next_stats();
         ep.bias = r.c1.bias; ep.stats = s1;
         USB_TRY(push_conv(K3S1, in0, C0, C0, in1, C1, C1, l, &r.c1, nullptr, 0, 0, r.Cout, ep, raw));
         push_gn(raw, s1, r.g1, pl.E + r.emb_off, nullptr, l, r.Cout, h1);
-        double* s2 = next_stats();
+        long long* s2 = next_stats();
         ep.bias = r.c2.bias; ep.stats = s2;
         USB_TRY(push_conv(K3S1, h1, r.Cout, r.Cout, nullptr, 0, 0, l, &r.c2, nullptr, 0, 0, r.Cout, ep, raw));
         const __half* resid = in0;
@@ -669,7 +678,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         const ResnetW& r0 = h->resnets[ri++];
         if (k == 0) {
             __half *raw = HP(o_raw[0]), *h1 = HP(o_h1[0]), *rb = HP(o_r[0]);
-            double* s1 = next_stats();
+            long long* s1 = next_stats();
             FirstConvParams& f = pl.first;
             memset(&f, 0, sizeof f);
             f.x_row = pl.x_row; f.mu_row = pl.mu_row; f.mask = pl.mask[0];
@@ -677,7 +686,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
             f.raw = raw; f.res = rb; f.stats = s1; f.N = Be; f.H = H[0]; f.W = W[0]; f.C = h->C[0]; f.groups = G;
             pl.ops.push_back({Op::FIRST, 0});
             push_gn(raw, s1, r0.g1, pl.E + r0.emb_off, nullptr, 0, r0.Cout, h1);
-            double* s2 = next_stats();
+            long long* s2 = next_stats();
             ConvEpilogue ep;
             ep.groups = G; ep.bias = r0.c2.bias; ep.stats = s2;
             USB_TRY(push_conv(K3S1, h1, r0.Cout, r0.Cout, nullptr, 0, 0, 0, &r0.c2, nullptr, 0, 0, r0.Cout, ep, raw));
@@ -743,6 +752,47 @@ __global__ void mul_mask_kernel(const float* z, const float* mask, float* out, i
     out[i] = z[i] * mask[(long long)b * W + w];
 }
 
+static size_t prof_event(usb_handle* h, cudaStream_t s) {
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev_pool.push_back(e);
+    }
+    cudaEventRecord(h->ev_pool[h->ev_used], s);
+    return h->ev_used++;
+}
+struct ProfScope {
+    usb_handle* h;
+    cudaStream_t s;
+    int cls;
+    double work;
+    size_t e0 = 0;
+    ProfScope(usb_handle* h_, cudaStream_t s_, int cls_, double work_) : h(h_), s(s_), cls(cls_), work(work_) {
+        if (h->profiling) e0 = prof_event(h, s);
+    }
+    ~ProfScope() {
+        if (h->profiling) h->recs.push_back({cls, e0, prof_event(h, s), work});
+    }
+};
+static double conv_flops(const ConvParams& p) {
+    const double px = (double)p.phases * p.N * p.Hm * p.Wm;
+    return 2.0 * px * p.Cout * (double)p.taps * (p.chunks0 + p.chunks1) * 64.0;
+}
+static int prof_collect(usb_handle* h, cudaStream_t s) {
+    if (!h->profiling) return 0;
+    USB_CUDA(cudaStreamSynchronize(s));
+    for (const auto& r : h->recs) {
+        float ms = 0.f;
+        USB_CUDA(cudaEventElapsedTime(&ms, h->ev_pool[r.e0], h->ev_pool[r.e1]));
+        h->prof_ms[r.cls] += ms;
+        h->prof_work[r.cls] += r.work;
+        h->prof_launches[r.cls]++;
+    }
+    h->recs.clear();
+    h->ev_used = 0;
+    return 0;
+}
+
 struct EstInputs {
     const float* x;           // [*][H][W]
     const float* cond;        // [*][H][W]
@@ -767,29 +817,43 @@ static int run_estimator(usb_handle* h, const EstInputs& in, cudaStream_t s) {
     ep.t = in.t_rows; ep.spk = in.spk_rows; ep.freqs = h->freqs; ep.w0 = h->mlp_w0; ep.b0 = h->mlp_b0;
     ep.w2 = h->mlp_w2; ep.b2 = h->mlp_b2; ep.wcat = h->wcat; ep.bcat = h->bcat; ep.u = pl.u; ep.e = pl.E;
     ep.N = pl.Be; ep.dim = c.dim; ep.S = c.spk_emb_dim; ep.J = h->J; ep.pe_scale = c.pe_scale;
-    USB_LAUNCH(h, launch_embed(ep, s));
-    h->launches++;  // launch_embed issues two kernels
+    {
+        ProfScope ps(h, s, 3, 0.0);
+        USB_LAUNCH(h, launch_embed(ep, s));
+        h->launches++;  // launch_embed issues two kernels
+    }
     USB_CUDA(cudaMemsetAsync(pl.stats, 0, pl.stats_bytes, s));
     for (const Op& op : pl.ops) {
         switch (op.kind) {
             case Op::FIRST: {
                 FirstConvParams f = pl.first;
                 f.x = in.x; f.cond = in.cond; f.text_uncon = in.text_uncon;
+                // reads 2 fp32 planes, writes raw + res fp16
+                ProfScope ps(h, s, 3, (double)f.N * f.H * f.W * (8.0 + 4.0 * f.C));
                 USB_LAUNCH(h, launch_first_conv(f, s));
                 break;
             }
             case Op::CONV: {
                 const ConvOp& co = pl.convs[op.idx];
+                ProfScope ps(h, s, 0, conv_flops(co.p));
                 USB_LAUNCH(h, launch_conv_igemm(co.p, co.a0, co.a1, co.b, h->num_sms, s));
                 break;
             }
-            case Op::GN:
-                USB_LAUNCH(h, launch_gn_apply(pl.gns[op.idx], h->num_sms, s));
+            case Op::GN: {
+                const GnApplyParams& g = pl.gns[op.idx];
+                // algorithmic bytes: read raw, (read res), write out, fp16
+                ProfScope ps(h, s, 1, (double)g.N * g.P * g.C * 2.0 * (g.res ? 3.0 : 2.0));
+                USB_LAUNCH(h, launch_gn_apply(g, h->num_sms, s));
                 break;
-            case Op::ATTN:
-                USB_LAUNCH(h, launch_attn_context(pl.attns[op.idx], s));
+            }
+            case Op::ATTN: {
+                const AttnParams& a = pl.attns[op.idx];
+                // algorithmic bytes: k and v read once (fp16, 2*hidden channels)
+                ProfScope ps(h, s, 2, (double)a.N * a.P * 2.0 * a.heads * 32 * 2.0);
+                USB_LAUNCH(h, launch_attn_context(a, s));
                 h->launches++;  // two kernels
                 break;
+            }
         }
     }
     return 0;
@@ -888,13 +952,18 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
         f.xt = pl.xt;
         f.noise = noise ? noise + (size_t)i * B * P : nullptr;
         f.c_x = coef[i * 3 + 0]; f.c_s = coef[i * 3 + 1]; f.sigma = coef[i * 3 + 2];
-        USB_LAUNCH(h, launch_final(f, h->num_sms, s));
+        {
+            // reads the final_block conv output of every CFG branch (fp16) + x_t and noise, writes x_t
+            ProfScope ps(h, s, 3, (double)Be * P * c.dim * 2.0 + (double)B * P * 12.0);
+            USB_LAUNCH(h, launch_final(f, h->num_sms, s));
+        }
         if (trace)
             USB_CUDA(cudaMemcpyAsync(trace + (size_t)i * B * P, pl.xt, (size_t)B * P * sizeof(float),
                                      cudaMemcpyDeviceToDevice, s));
     }
     // the reference returns xt * mask (:373); xt is already masked by the update
     USB_CUDA(cudaMemcpyAsync(out, pl.xt, (size_t)B * P * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    USB_TRY(prof_collect(h, s));
     return 0;
 }
 
@@ -947,6 +1016,7 @@ void usb_destroy(usb_handle* h) {
     cudaDeviceSynchronize();
     free_plan(h->plan);
     for (void* p : h->dev_allocs) cudaFree(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
 
@@ -1019,13 +1089,34 @@ int usb_reverse_diffusion_host(usb_handle* h, const float* z, const float* cond,
     return rc;
 }
 
+int usb_set_profiling(usb_handle* h, int32_t on) {
+    if (!h) return fail("null handle");
+    h->profiling = on != 0;
+    for (int i = 0; i < 4; ++i) {
+        h->prof_ms[i] = 0;
+        h->prof_work[i] = 0;
+        h->prof_launches[i] = 0;
+    }
+    return 0;
+}
+
+int usb_get_profile(usb_handle* h, double* ms4, double* work4, int64_t* launches4) {
+    if (!h || !ms4 || !work4 || !launches4) return fail("null argument");
+    for (int i = 0; i < 4; ++i) {
+        ms4[i] = h->prof_ms[i];
+        work4[i] = h->prof_work[i];
+        launches4[i] = h->prof_launches[i];
+    }
+    return 0;
+}
+
 int64_t usb_workspace_bytes(usb_handle* h) { return h ? (int64_t)h->plan.arena_bytes : 0; }
 int64_t usb_launch_count(usb_handle* h) { return h ? h->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------- operator-level
 int usb_op_conv(usb_handle* h, int32_t kind, const void* in0, const void* in1, int32_t N, int32_t H, int32_t W,
                 int32_t C0, int32_t C1, int32_t Cout, const float* weight_host, const float* bias_host,
-                const float* mask, const void* residual, float res_scale, double* stats, int32_t groups, void* out,
+                const float* mask, const void* residual, float res_scale, int64_t* stats, int32_t groups, void* out,
                 uint64_t stream) {
     if (!h) return fail("null handle");
     USB_CUDA(cudaSetDevice(h->cfg.device));
@@ -1048,7 +1139,7 @@ int usb_op_conv(usb_handle* h, int32_t kind, const void* in0, const void* in1, i
         USB_CUDA(cudaMemcpy(dscale, &res_scale, sizeof(float), cudaMemcpyHostToDevice));
     }
     ConvEpilogue ep;
-    ep.bias = db; ep.stats = stats; ep.groups = groups > 0 ? groups : 8; ep.res = static_cast<const __half*>(residual);
+    ep.bias = db; ep.stats = reinterpret_cast<long long*>(stats); ep.groups = groups > 0 ? groups : 8; ep.res = static_cast<const __half*>(residual);
     ep.res_scale = dscale; ep.mask = mask;
     ConvOp op;
     int rc = build_conv(op, kind, static_cast<const __half*>(in0), C0, C0, static_cast<const __half*>(in1), C1, C1, N, H,
@@ -1066,13 +1157,13 @@ int usb_op_conv(usb_handle* h, int32_t kind, const void* in0, const void* in1, i
     return rc;
 }
 
-int usb_op_gn_apply(usb_handle* h, const void* raw, const double* stats, const float* gamma, const float* beta,
+int usb_op_gn_apply(usb_handle* h, const void* raw, const int64_t* stats, const float* gamma, const float* beta,
                     const float* addvec, const void* res, const float* mask, void* out, int32_t N, int32_t H, int32_t W,
                     int32_t C, int32_t groups, uint64_t stream) {
     if (!h) return fail("null handle");
     USB_CUDA(cudaSetDevice(h->cfg.device));
     GnApplyParams p;
-    p.raw = static_cast<const __half*>(raw); p.stats = stats; p.gamma = gamma; p.beta = beta; p.addvec = addvec;
+    p.raw = static_cast<const __half*>(raw); p.stats = reinterpret_cast<const long long*>(stats); p.gamma = gamma; p.beta = beta; p.addvec = addvec;
     p.addvec_stride = C; p.res = static_cast<const __half*>(res); p.mask = mask; p.out = static_cast<__half*>(out);
     p.N = N; p.P = H * W; p.W = W; p.C = C; p.groups = groups; p.eps = 1e-5f;
     USB_LAUNCH(h, launch_gn_apply(p, h->num_sms, reinterpret_cast<cudaStream_t>(stream)));

@@ -1,9 +1,11 @@
 // Launchers of the streaming (HBM-bound) kernels of the reverse-diffusion path.  All tensors are device pointers;
-// activations are NHWC fp16 ([row n][pixel p = y*W + x][channel]), statistics are [n][group][sum, sumsq] doubles.
+// activations are NHWC fp16 ([row n][pixel p = y*W + x][channel]), statistics are [n][group][sum, sumsq] in int64 fixed point.
 #pragma once
 #include <cstdint>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include "conv_igemm.h"
 
 namespace usb {
 
@@ -21,7 +23,7 @@ struct FirstConvParams {
     const float* b1;          // [C]
     __half* raw;              // [N][P][C] conv + bias (GroupNorm input)
     __half* res;              // [N][P][C] res_conv + bias
-    double* stats;            // [N][groups][2]
+    long long* stats;         // [N][groups][2] fixed point (see conv_igemm.h)
     int N, H, W, C, groups;
 };
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s);
@@ -29,7 +31,7 @@ int launch_first_conv(const FirstConvParams& p, cudaStream_t s);
 // ---- out = (Mish(GroupNorm(raw)) + addvec[n][c] + res) * mask   (unitspeech.py:50-55,72-75)
 struct GnApplyParams {
     const __half* raw;     // [N][P][C]
-    const double* stats;   // [N][groups][2]
+    const long long* stats;  // [N][groups][2] fixed point
     const float* gamma;    // [C]
     const float* beta;     // [C]
     const float* addvec;   // [N][addvec_stride] (+ offset already applied) or null
@@ -45,7 +47,7 @@ int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s);
 // ---- final_block GN+Mish -> final_conv 1x1 -> CFG combine -> posterior update  (unitspeech.py:198-201,322-324,366-370)
 struct FinalParams {
     const __half* raw;     // [nb*B][P][C] final_block conv output
-    const double* stats;   // [nb*B][groups][2]
+    const long long* stats;  // [nb*B][groups][2] fixed point
     const float* gamma;    // [C]
     const float* beta;     // [C]
     const float* wf;       // [C] final_conv weight

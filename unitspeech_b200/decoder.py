@@ -236,6 +236,17 @@ class UnitSpeech(torch.nn.Module):
     def workspace_bytes(self) -> int:
         return int(abi.load_library().usb_workspace_bytes(self._handle)) if self._handle is not None else 0
 
+    def set_profiling(self, on: bool) -> None:
+        """Per-kernel-class CUDA-event timing of the next reverse_diffusion calls (adds a sync; not for timed runs)."""
+        abi.check(abi.load_library().usb_set_profiling(self._ensure_handle(), int(bool(on))))
+
+    def get_profile(self):
+        """{class: (ms, algorithmic work, launches)} accumulated since set_profiling()."""
+        ms, work, n = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_int64 * 4)()
+        abi.check(abi.load_library().usb_get_profile(self._ensure_handle(), ms, work, n))
+        names = ("conv_igemm", "gn_apply", "attention", "other")
+        return {k: (ms[i], work[i], int(n[i])) for i, k in enumerate(names)}
+
     # ------------------------------------------------------------------ estimator
     @torch.no_grad()
     def _estimator_forward(self, x, mask, mu, t, spk_emb):
