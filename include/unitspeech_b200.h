@@ -106,6 +106,9 @@ int usb_op_conv(usb_handle* h, int32_t kind, const void* in0, const void* in1, i
                 int32_t C0, int32_t C1, int32_t Cout, const float* weight_host, const float* bias_host,
                 const float* mask, const void* residual, float res_scale, int64_t* stats, int32_t groups, void* out,
                 uint64_t stream);
+/* kernel-tuning aid: average device milliseconds of one conv launch on internally allocated buffers */
+int usb_dbg_conv_time(usb_handle* h, int32_t kind, int32_t N, int32_t H, int32_t W, int32_t C0, int32_t C1,
+                      int32_t Cout, int32_t with_stats, int32_t iters, float* ms_out);
 /* out = (Mish(GroupNorm(raw)) + addvec[n][c] + res) * mask on NHWC fp16; gamma/beta/addvec dev fp32 */
 int usb_op_gn_apply(usb_handle* h, const void* raw, const int64_t* stats, const float* gamma, const float* beta,
                     const float* addvec, const void* res, const float* mask, void* out, int32_t N, int32_t H,

@@ -1,0 +1,44 @@
+"""Tuning aid: times conv shapes of the bench workload (Be=48, T=512) under USB_DBG_* overrides."""
+import ctypes, os, sys, subprocess, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SHAPES = {  # name: kind, N, H, W, C0, C1, Cout, stats
+    "l0_128": (0, 48, 80, 512, 128, 0, 128, 1),
+    "l1_256": (0, 48, 40, 256, 256, 0, 256, 1),
+    "l1_128to256": (0, 48, 40, 256, 128, 0, 256, 1),
+    "l2_512": (0, 48, 20, 128, 512, 0, 512, 1),
+    "l3_1024": (0, 48, 10, 64, 1024, 0, 1024, 1),
+    "u2_512to128": (0, 48, 40, 256, 256, 256, 128, 1),
+    "qkv_l0": (2, 48, 80, 512, 128, 0, 384, 0),
+    "up_l1": (3, 48, 40, 256, 128, 0, 128, 0),
+}
+
+def run_one(names):
+    from gpu_ops import OpHandle
+    h = OpHandle(0)
+    out = {}
+    for n in names:
+        k, N, H, W, C0, C1, Co, st = SHAPES[n]
+        ms = ctypes.c_float()
+        from unitspeech_b200 import abi
+        abi.check(h.lib.usb_dbg_conv_time(h.h, k, N, H, W, C0, C1, Co, st, 5, ctypes.byref(ms)))
+        taps = {0: 9, 1: 9, 2: 1, 3: 16}[k]
+        px = N * H * W * (0.25 if k == 1 else 1)
+        fl = 2 * px * Co * (C0 + C1) * taps
+        out[n] = (round(ms.value * 1e3, 1), round(fl / ms.value / 1e9, 1))
+    print(json.dumps(out))
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "child":
+        run_one(sys.argv[2:])
+    else:
+        configs = [{"USB_DBG_FLAGS": "7"}, {"USB_DBG_FLAGS": "15"}, {"USB_DBG_FLAGS": "23"}, {"USB_DBG_FLAGS": "55"}, {"USB_DBG_FLAGS": "0"}, {"USB_DBG_FLAGS": "16"}] if os.environ.get("SWEEP") == "mma" else [{}, {"USB_DBG_FLAGS": "1"}, {"USB_DBG_FLAGS": "2"}, {"USB_DBG_FLAGS": "3"}, {"USB_DBG_FLAGS": "4"},
+                   {"USB_DBG_FLAGS": "6"}, {"USB_DBG_FLAGS": "7"},
+                   {"USB_DBG_STAGES": "3"}, {"USB_DBG_STAGES": "4"}, {"USB_DBG_BH": "2"}, {"USB_DBG_BH": "4"},
+                   {"USB_DBG_BH": "8"}, {"USB_DBG_BH": "1"}]
+        names = sys.argv[1:] or list(SHAPES)
+        for c in configs:
+            env = dict(os.environ); env.update(c)
+            r = subprocess.run([sys.executable, __file__, "child"] + names, env=env, capture_output=True, text=True)
+            print(c, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:])

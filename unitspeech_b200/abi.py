@@ -52,6 +52,7 @@ SIGNATURES = {
     "usb_op_conv": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                               c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p,
                               c_uint64]),
+    "usb_dbg_conv_time": (c_int32, [c_void_p] + [c_int32] * 9 + [POINTER(c_float)]),
     "usb_op_gn_apply": (c_int32, [c_void_p] + [c_void_p] * 8 + [c_int32] * 5 + [c_uint64]),
     "usb_op_attn_context": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                       c_uint64]),

@@ -1,9 +1,14 @@
 // Generalised implicit-GEMM convolution for sm_100a: TMA -> swizzled smem -> tcgen05.mma (fp16 operands, fp32
-// accumulators in TMEM) -> fused epilogue (bias, GroupNorm partial statistics, Rezero residual, mask, fp16 store).
-// See conv_igemm.h for the GEMM view.  Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...
-// Warp roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31, one output pixel per thread).
-// Two 256-column accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// accumulators in TMEM) -> fused epilogue (bias, GroupNorm partial statistics, Rezero residual, mask) -> fp16 tile
+// staged in swizzled smem -> TMA store.  See conv_igemm.h for the GEMM view.
+//
+// Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...   384 threads:
+//   warp 0      TMA producer   (whole warp runs the loop, one elected lane issues: keeps ptxas on the uniform path)
+//   warp 1      MMA issuer     (same pattern; 4 x tcgen05.mma per 64-channel K step, tcgen05.commit frees the slot)
+//   warp 2      TMEM allocator (512 columns = two 256-column accumulator stages)
+//   warps 4-11  epilogue, two groups of four warps; group g owns output columns [g*BN/2, (g+1)*BN/2) in 64-column
+//               slabs; warp w reads TMEM lanes 32*(w%4)..+31 (one output pixel per thread).
+// The epilogue of tile i overlaps the MMAs of tile i+1 (double-buffered accumulators).
 #include "conv_igemm.h"
 #include "ptx.cuh"
 
@@ -27,28 +32,90 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int idx) {
     return t;
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
+// Sums NV per-lane values across the warp with NV-1 + (5 - log2 NV) shuffles (recursive halving): afterwards lane L
+// with (L & (32/NV - 1)) == 0 holds in v[0] the warp total of item L / (32/NV).  Fixed order -> deterministic.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_items(float (&v)[NV], int lane) {
+    int n = NV;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-__device__ __forceinline__ void flush_stats(long long* dst, float s, float ss, int lane) {
-    s = warp_sum(s);
-    ss = warp_sum(ss);
-    if (lane == 0) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(dst),
-                  static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
-        atomicAdd(reinterpret_cast<unsigned long long*>(dst + 1),
-                  static_cast<unsigned long long>(__float2ll_rn(ss * kStatSqScale)));
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+            n >>= 1;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) {
+                if (i < n) {
+                    const float send = upper ? v[i] : v[i + n];
+                    const float keep = upper ? v[i + n] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
     }
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+// One 64-column slab of one output pixel row: bias, statistics, residual, mask, fp16 pack, swizzled smem store.
+// G = GroupNorm groups intersecting the slab (64/cpg, or 1 when a group spans >= 64 channels).
+template <int G>
+__device__ __forceinline__ void epilogue_slab(const ConvParams& p, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                              int c_glob, bool valid, float m, float rs, const __half* res_row,
+                                              uint32_t stage_row, int row, long long* stats_n, int cpg, int lane) {
+    constexpr int CPG8 = 8 / G;  // 8-column chunks per group inside the slab (G=8 -> 1, 4 -> 2, 2 -> 4, 1 -> 8)
+    float acc[2 * G];
+#pragma unroll
+    for (int i = 0; i < 2 * G; ++i) acc[i] = 0.f;
+    const float vm = valid ? 1.f : 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(q < 4 ? v0[q * 8 + e] : v1[(q - 4) * 8 + e]);
+        if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c_glob + q * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c_glob + q * 8 + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        }
+        if (stats_n) {
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s += f[e];
+                ss = fmaf(f[e], f[e], ss);
+            }
+            acc[q / CPG8] += s * vm;
+            acc[G + q / CPG8] += ss * vm;
+        }
+        if (res_row && valid) {
+            const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(res_row + q * 8));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 r2 = __half22float2(h2[e]);
+                f[2 * e] = fmaf(f[2 * e], rs, r2.x);
+                f[2 * e + 1] = fmaf(f[2 * e + 1], rs, r2.y);
+            }
+        }
+        // 16-byte chunk q of row `row`, 128-byte swizzle (chunk index XOR row%8) = the layout the TMA store expects
+        sts128(stage_row + (static_cast<uint32_t>(q ^ (row & 7)) << 4), pack_f16x2_sat(f[0] * m, f[1] * m),
+               pack_f16x2_sat(f[2] * m, f[3] * m), pack_f16x2_sat(f[4] * m, f[5] * m),
+               pack_f16x2_sat(f[6] * m, f[7] * m));
+    }
+    if (stats_n) {
+        warp_reduce_items<2 * G>(acc, lane);
+        constexpr int LPI = 32 / (2 * G);  // lanes per item
+        if ((lane & (LPI - 1)) == 0) {
+            const int item = lane / LPI;          // 0..G-1 sums, G..2G-1 sums of squares
+            const int gi = item % G;
+            const bool sq = item >= G;
+            const int group = c_glob / cpg + gi;  // G > 1: cpg = 64/G divides 64; G == 1: slab inside one group
+            const float scale = sq ? kStatSqScale : kStatSumScale;
+            atomicAdd(reinterpret_cast<unsigned long long*>(stats_n + group * 2 + (sq ? 1 : 0)),
+                      static_cast<unsigned long long>(__float2ll_rn(acc[0] * scale)));
+        }
+    }
 }
 
 }  // namespace
@@ -56,13 +123,14 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0,
                   const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b,
-                  int total_tiles) {
+                  const __grid_constant__ CUtensorMap map_out, int total_tiles) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[8];
     __shared__ __align__(8) uint64_t empty_bar[8];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(8) uint64_t scratch_bar;   // experiments only
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -72,11 +140,14 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
     const uint32_t stage_bytes = 16384u + b_bytes;
     const int stages = p.stages;
     const int ksteps = p.taps * (p.chunks0 + p.chunks1);
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < stages; ++i) {
@@ -85,8 +156,9 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], 128);
+            mbar_init(&tmem_empty_bar[i], kConvEpilogueThreads);
         }
+        mbar_init(&scratch_bar, 1u << 20);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -99,72 +171,90 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord tc = decode_tile(p, tile);
-                const int bz = p.b_batch_mode == 0 ? 0 : (p.b_batch_mode == 1 ? tc.ph : tc.n);
-                int kstep = 0;
-                for (int t = 0; t < p.taps; ++t) {
-                    const ConvTap tap = p.tap[tc.ph * p.taps + t];
-                    for (int src = 0; src < 2; ++src) {
-                        const int chunks = src ? p.chunks1 : p.chunks0;
-                        const CUtensorMap* ma = src ? &map_a1 : &map_a0;
-                        for (int cc = 0; cc < chunks; ++cc, ++kstep) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+        // ---------------------------------------------------- TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        const bool ld_a = !(p.dbg_flags & 4), ld_b = !(p.dbg_flags & 1);
+        const uint32_t tx_bytes = (ld_a ? 16384u : 0u) + (ld_b ? b_bytes : 0u);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(p, tile);
+            const int bz = p.b_batch_mode == 0 ? 0 : (p.b_batch_mode == 1 ? tc.ph : tc.n);
+            const int bn0 = tc.nt * p.BN;
+            int kcoord = 0;
+            for (int t = 0; t < p.taps; ++t) {
+                const ConvTap tap = p.tap[tc.ph * p.taps + t];
+                const int cx = tc.x0 + tap.dx, cy = tc.y0 + tap.dy;
+                for (int src = 0; src < 2; ++src) {
+                    const int chunks = src ? p.chunks1 : p.chunks0;
+                    const CUtensorMap* ma = src ? &map_a1 : &map_a0;
+                    for (int cc = 0; cc < chunks; ++cc, kcoord += kConvBK) {
+                        mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 100 + stage);
+                        if (elect_one()) {
                             const uint32_t sa = tiles_base + stage * stage_bytes;
-                            mbar_arrive_expect_tx(&full_bar[stage], 16384u + b_bytes);
-                            tma_load_5d(reinterpret_cast<void*>(__cvta_shared_to_generic(sa)), ma, &full_bar[stage],
-                                        tap.c + cc * kConvBK, tc.x0 + tap.dx, tap.p, tc.y0 + tap.dy, tc.n);
-                            tma_load_3d(reinterpret_cast<void*>(__cvta_shared_to_generic(sa + 16384u)), &map_b,
-                                        &full_bar[stage], kstep * kConvBK, tc.nt * p.BN, bz);
-                            if (++stage == stages) { stage = 0; phase ^= 1u; }
+                            const uint32_t fb = full0 + stage * 8;
+                            mbar_arrive_expect_tx_a(fb, tx_bytes);
+                            if (ld_a) tma_load_5d_a(sa, ma, fb, tap.c + cc * kConvBK, cx, tap.p, cy, tc.n);
+                            if (ld_b) tma_load_3d_a(sa + 16384u, &map_b, fb, kcoord, bn0, bz);
                         }
+                        __syncwarp();
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
-            const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(p.BN));
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[as], aphase ^ 1u, 200 + as);
+        // ---------------------------------------------------- MMA issuer
+        const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(p.BN));
+        // descriptor = constant high word | (smem byte address >> 4) in the low word
+        const uint32_t desc_hi = static_cast<uint32_t>(umma_desc_sw128(0) >> 32);
+        const uint32_t a_lo0 = (tiles_base & 0x3FFFFu) >> 4;
+        const uint32_t stage_lo = stage_bytes >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait_a(tempty0 + as * 8, aphase ^ 1u, 200 + as);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as) * 256u;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                mbar_wait_a(full0 + stage * 8, phase, 300 + stage);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as) * 256u;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    mbar_wait(&full_bar[stage], phase, 300 + stage);
-                    tc_fence_after();
-                    const uint32_t sa = tiles_base + stage * stage_bytes;
-                    const uint32_t sb = sa + 16384u;
+                if (elect_one()) {
+                    const uint32_t a_lo = a_lo0 + stage * stage_lo;
+                    const uint32_t b_lo = a_lo + (16384u >> 4);
 #pragma unroll
                     for (int k = 0; k < kConvBK / 16; ++k) {
-                        const uint64_t da = umma_desc_sw128(sa + k * 32);
-                        const uint64_t db = umma_desc_sw128(sb + k * 32);
+                        const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k);
+                        const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
                         tc_mma_f16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+                        if (p.dbg_flags & 8) tc_mma_f16(tmem_d, da, db, idesc, 1u);  // experiment: double tensor work
                     }
-                    tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                    if (ks == ksteps - 1) tc_commit(&tmem_full_bar[as]);
-                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    if (p.dbg_flags & 16) tc_commit_a(smem_u32(&scratch_bar));   // experiment: cost of a commit
+                    if (p.dbg_flags & 32) { tc_commit_a(smem_u32(&scratch_bar)); tc_commit_a(smem_u32(&scratch_bar)); }
+                    tc_commit_a(empty0 + stage * 8);  // frees the smem slot when these MMAs retire
+                    if (ks == ksteps - 1) tc_commit_a(tfull0 + as * 8);
                 }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------- epilogue
-        const int ew = warp & 3;
+        const int ew = warp & 3;                 // TMEM lane quarter
+        const int grp = (warp - 4) >> 2;         // column half
         const int row = ew * 32 + lane;
         const int bw_shift = 31 - __clz(p.BW);
         const int ty = row >> bw_shift;
         const int tx = row & (p.BW - 1);
-        const int cpg = p.stats ? p.Cout / p.groups : 0;
+        const int cpg = p.stats ? p.Cout / p.groups : 64;
         const float rs = p.res_scale ? __ldg(p.res_scale) : 1.f;
+        const int half_cols = p.BN >= 128 ? p.BN >> 1 : p.BN;
+        const int slabs = (p.BN >= 128 || grp == 0) ? half_cols >> 6 : 0;  // BN == 64: group 1 has no columns
+        const uint32_t stage_buf = tiles_base + stages * stage_bytes + static_cast<uint32_t>(grp) * 16384u;
+        const uint32_t stage_row = stage_buf + static_cast<uint32_t>(row) * 128u;
+        const int bar_id = 1 + grp;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(p, tile);
@@ -174,107 +264,50 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
             const bool valid = x < p.Wm;
             const int yo = y * p.oy_mul + p.oy_off[tc.ph];
             const int xo = x * p.ox_mul + p.ox_off[tc.ph];
-            const long long off = tc.n * p.o_sn + yo * p.o_sy + xo * p.o_sx + tc.nt * p.BN;
             const float m = (p.mask && valid) ? __ldg(p.mask + static_cast<long long>(tc.n) * p.mask_stride + xo) : 1.f;
             long long* stats_n = p.stats ? p.stats + static_cast<long long>(tc.n) * p.groups * 2 : nullptr;
+            const __half* res_px = p.res ? p.res + (tc.n * p.o_sn + yo * p.o_sy + xo * p.o_sx) : nullptr;
 
-            mbar_wait(&tmem_full_bar[as], aphase, 400 + as);
+            mbar_wait_a(tfull0 + as * 8, aphase, 400 + as);
             tc_fence_after();
+            if (slabs == 0 || (p.dbg_flags & 2)) {
+                tc_fence_before();
+                mbar_arrive_a(tempty0 + as * 8);
+                continue;
+            }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
-            const int nchunks = p.BN >> 5;
-            float gs = 0.f, gss = 0.f;  // running sums of the current GroupNorm group (cpg >= 32)
-            for (int j = 0; j < nchunks; ++j) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + j * 32, v);
+            for (int sl = 0; sl < slabs; ++sl) {
+                const int col0 = (p.BN >= 128 ? grp * half_cols : 0) + sl * 64;
+                const int c_glob = tc.nt * p.BN + col0;
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(taddr + col0, v0);
+                tmem_ld_32x32(taddr + col0 + 32, v1);
                 tmem_ld_wait();
-                if (j == nchunks - 1) {
-                    // all of this thread's accumulator reads are done: hand the stage back to the MMA warp
+                if (sl == slabs - 1) {
+                    // this thread's accumulator reads are complete: hand the TMEM stage back to the MMA warp
                     tc_fence_before();
-                    mbar_arrive(&tmem_empty_bar[as]);
+                    mbar_arrive_a(tempty0 + as * 8);
                 }
-                float f[32];
-                const int c0 = tc.nt * p.BN + j * 32;
-                if (p.bias) {
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b4 = __ldg(bp + q);
-                        f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b4.x;
-                        f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b4.y;
-                        f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b4.z;
-                        f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]);
+                // the staging buffer is free once the previous slab's TMA store has read it (the issuing lane waited
+                // on its bulk group before arriving here)
+                named_bar_sync(bar_id, 128);
+                const __half* res_row = res_px ? res_px + c_glob : nullptr;
+                if (cpg >= 64) epilogue_slab<1>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, row, stats_n, cpg, lane);
+                else if (cpg == 32) epilogue_slab<2>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, row, stats_n, cpg, lane);
+                else if (cpg == 16) epilogue_slab<4>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, row, stats_n, cpg, lane);
+                else epilogue_slab<8>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, row, stats_n, cpg, lane);
+                fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+                named_bar_sync(bar_id, 128);
+                if (ew == 0 && elect_one()) {
+                    tma_store_5d_a(&map_out, stage_buf, c_glob + p.ox_off[tc.ph] * p.out_c_phase_mul, tc.x0,
+                                   p.oy_off[tc.ph], tc.y0, tc.n);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
                 }
-                if (stats_n) {
-                    const float vm = valid ? 1.f : 0.f;
-                    if (cpg >= 32) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const float a = f[q] * vm;
-                            gs += a;
-                            gss += a * a;
-                        }
-                        if (((c0 + 32) % cpg) == 0 || j == nchunks - 1) {
-                            flush_stats(stats_n + (c0 / cpg) * 2, gs, gss, lane);
-                            gs = gss = 0.f;
-                        }
-                    } else if (cpg == 16) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            float s = 0.f, ss = 0.f;
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) {
-                                const float a = f[16 * h + q] * vm;
-                                s += a;
-                                ss += a * a;
-                            }
-                            flush_stats(stats_n + ((c0 + 16 * h) / 16) * 2, s, ss, lane);
-                        }
-                    } else {  // cpg == 8
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            float s = 0.f, ss = 0.f;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float a = f[8 * h + q] * vm;
-                                s += a;
-                                ss += a * a;
-                            }
-                            flush_stats(stats_n + ((c0 + 8 * h) / 8) * 2, s, ss, lane);
-                        }
-                    }
-                }
-                if (valid) {
-                    if (p.res) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.res + off + j * 32);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 r4 = __ldg(rp + q);
-                            const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 r2 = __half22float2(h2[e]);
-                                f[8 * q + 2 * e] = f[8 * q + 2 * e] * rs + r2.x;
-                                f[8 * q + 2 * e + 1] = f[8 * q + 2 * e + 1] * rs + r2.y;
-                            }
-                        }
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(p.out + off + j * 32);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 o;
-                        o.x = pack_half2(f[8 * q + 0] * m, f[8 * q + 1] * m);
-                        o.y = pack_half2(f[8 * q + 2] * m, f[8 * q + 3] * m);
-                        o.z = pack_half2(f[8 * q + 4] * m, f[8 * q + 5] * m);
-                        o.w = pack_half2(f[8 * q + 6] * m, f[8 * q + 7] * m);
-                        op[q] = o;
-                    }
-                }
+                __syncwarp();
             }
         }
+        if (ew == 0 && elect_one()) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -283,7 +316,7 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
 }
 
 int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                      int num_sms, cudaStream_t stream) {
+                      const CUtensorMap& out, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -294,9 +327,9 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
     const long long total = static_cast<long long>(p.phases) * p.N * p.tiles_y * p.tiles_x * p.n_tiles_n;
     if (total <= 0 || total > 0x7fffffffLL) return static_cast<int>(cudaErrorInvalidValue);
     const int grid = static_cast<int>(total < num_sms ? total : num_sms);
-    const size_t smem = 1024 + static_cast<size_t>(p.stages) * (16384 + static_cast<size_t>(p.BN) * 128);
+    const size_t smem = 1024 + static_cast<size_t>(p.stages) * (16384 + static_cast<size_t>(p.BN) * 128) + 2 * 16384;
     if (smem > static_cast<size_t>(kConvSmemBytes)) return static_cast<int>(cudaErrorInvalidValue);
-    conv_igemm_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, static_cast<int>(total));
+    conv_igemm_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -17,7 +17,8 @@
 
 namespace usb {
 
-constexpr int kConvThreads = 256;      // warp0 TMA producer, warp1 MMA issuer, warp2 TMEM alloc, warps4-7 epilogue
+constexpr int kConvThreads = 384;      // warp0 TMA producer, warp1 MMA issuer, warp2 TMEM alloc, warps4-11 epilogue
+constexpr int kConvEpilogueThreads = 256;
 constexpr int kConvBM = 128;           // pixels per tile (UMMA M)
 constexpr int kConvBK = 64;            // channels per K step (128 B of fp16 = one swizzle row)
 constexpr int kConvMaxTaps = 16;       // phases x taps
@@ -44,6 +45,7 @@ struct ConvParams {
     int chunks0, chunks1;      // 64-channel K chunks per tap from source 0 / source 1 (0 = no second source)
     int b_batch_mode;          // B z-coordinate: 0 -> 0, 1 -> phase, 2 -> sample
     int stages;                // smem pipeline depth
+    int dbg_flags;             // experiments only: 1 = skip B loads, 2 = skip epilogue math/stores, 4 = skip A loads
     ConvTap tap[kConvMaxTaps];
     // epilogue: v = acc + bias[c]; stats (sum, sumsq per (n, group)) on v; v = v*res_scale + res; v *= mask
     const float* bias;         // [Cout] or null
@@ -53,14 +55,17 @@ struct ConvParams {
     const float* res_scale;    // device scalar (Rezero g) or null (=1)
     const float* mask;         // [N][mask_stride] indexed by the OUTPUT x coordinate, or null
     int mask_stride;
-    __half* out;               // element (n, yo, xo, c) at out[n*o_sn + yo*o_sy + xo*o_sx + c]
+    // the output tile itself is written by TMA (map_out: same 5-D view family as the inputs; for the transposed
+    // conv the parity view of the 2H x 2W output, channel coordinate += ox_off*out_c_phase_mul, p = oy_off);
+    // the strides below address the residual, which shares the output geometry
     long long o_sn, o_sy, o_sx;
+    int out_c_phase_mul;
     int oy_mul, ox_mul;        // yo = y*oy_mul + oy_off[phase], xo = x*ox_mul + ox_off[phase]
     int8_t oy_off[4], ox_off[4];
 };
 
 // launches on `stream`; returns cudaError_t as int
 int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                      int num_sms, cudaStream_t stream);
+                      const CUtensorMap& out, int num_sms, cudaStream_t stream);
 
 }  // namespace usb

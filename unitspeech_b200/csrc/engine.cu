@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -182,7 +183,7 @@ static void fill_taps(int kind, int Ctot0, ConvParams& p) {
 
 struct ConvOp {
     ConvParams p;
-    CUtensorMap a0, a1, b;
+    CUtensorMap a0, a1, b, o;
 };
 
 struct ConvEpilogue {
@@ -221,7 +222,15 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     p.chunks0 = C0 / 64;
     p.chunks1 = in1 ? C1 / 64 : 0;
     p.b_batch_mode = b_batch_mode;
-    p.stages = p.BN == 256 ? 4 : (p.BN == 128 ? 6 : 8);
+    p.stages = p.BN == 256 ? 4 : (p.BN == 128 ? 5 : 7);   // + 2 x 16 KB epilogue staging must fit 227 KB
+    if (const char* e = getenv("USB_DBG_STAGES")) p.stages = atoi(e);
+    if (const char* e = getenv("USB_DBG_FLAGS")) p.dbg_flags = atoi(e);
+    if (const char* e = getenv("USB_DBG_BH")) {
+        const int bh = atoi(e);
+        if (bh > 0 && p.Hm % bh == 0 && 128 % bh == 0) {
+            p.BH = bh; p.BW = 128 / bh; p.tiles_y = p.Hm / bh; p.tiles_x = (p.Wm + p.BW - 1) / p.BW;
+        }
+    }
     p.bias = ep.bias;
     p.stats = ep.stats;
     p.groups = ep.groups;
@@ -235,7 +244,7 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     const int Hout = kind == K3S2 ? H / 2 : (kind == KT4 ? 2 * H : H);
     const int Wout = kind == K3S2 ? W / 2 : (kind == KT4 ? 2 * W : W);
     p.mask_stride = Wout;
-    p.out = out;
+    p.out_c_phase_mul = kind == KT4 ? Cout : 0;
     p.o_sx = Cout;
     p.o_sy = (long long)Wout * Cout;
     p.o_sn = (long long)Hout * Wout * Cout;
@@ -251,6 +260,8 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     else op.a1 = op.a0;
     const int K = p.taps * (C0 + (in1 ? C1 : 0));
     USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, p.BN));
+    // output tile store: plain view, or the parity view of the upsampled tensor for the transposed conv
+    USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BH, p.BW));
     return 0;
 }
 
@@ -836,7 +847,7 @@ static int run_estimator(usb_handle* h, const EstInputs& in, cudaStream_t s) {
             case Op::CONV: {
                 const ConvOp& co = pl.convs[op.idx];
                 ProfScope ps(h, s, 0, conv_flops(co.p));
-                USB_LAUNCH(h, launch_conv_igemm(co.p, co.a0, co.a1, co.b, h->num_sms, s));
+                USB_LAUNCH(h, launch_conv_igemm(co.p, co.a0, co.a1, co.b, co.o, h->num_sms, s));
                 break;
             }
             case Op::GN: {
@@ -1145,7 +1156,7 @@ int usb_op_conv(usb_handle* h, int32_t kind, const void* in0, const void* in1, i
     int rc = build_conv(op, kind, static_cast<const __half*>(in0), C0, C0, static_cast<const __half*>(in1), C1, C1, N, H,
                         W, dw, kind == KT4 ? 4 : 1, kind == KT4 ? 1 : 0, Cout, ep, static_cast<__half*>(out));
     if (!rc) {
-        int e = launch_conv_igemm(op.p, op.a0, op.a1, op.b, h->num_sms, s);
+        int e = launch_conv_igemm(op.p, op.a0, op.a1, op.b, op.o, h->num_sms, s);
         h->launches++;
         if (e) rc = fail(std::string("conv launch: ") + cudaGetErrorString((cudaError_t)e));
     }
@@ -1154,6 +1165,48 @@ int usb_op_conv(usb_handle* h, int32_t kind, const void* in0, const void* in1, i
     cudaFree(dw);
     if (db) cudaFree(db);
     if (dscale) cudaFree(dscale);
+    return rc;
+}
+
+// timing experiment: conv on internally allocated buffers, returns average milliseconds over `iters` launches
+int usb_dbg_conv_time(usb_handle* h, int32_t kind, int32_t N, int32_t H, int32_t W, int32_t C0, int32_t C1,
+                      int32_t Cout, int32_t with_stats, int32_t iters, float* ms_out) {
+    if (!h) return fail("null handle");
+    USB_CUDA(cudaSetDevice(h->cfg.device));
+    const int Cin = C0 + C1;
+    const int taps = taps_of(kind), Z = kind == KT4 ? 4 : 1;
+    const int Hout = kind == K3S2 ? H / 2 : (kind == KT4 ? 2 * H : H), Wout = kind == K3S2 ? W / 2 : (kind == KT4 ? 2 * W : W);
+    __half *a0 = nullptr, *a1 = nullptr, *w = nullptr, *out = nullptr;
+    float* bias = nullptr;
+    long long* st = nullptr;
+    const size_t n0 = (size_t)N * H * W * C0, n1 = (size_t)N * H * W * (C1 ? C1 : 1), nw = (size_t)Z * Cout * taps * Cin;
+    const size_t no = (size_t)N * Hout * Wout * Cout;
+    USB_CUDA(cudaMalloc(&a0, n0 * 2)); USB_CUDA(cudaMalloc(&a1, n1 * 2)); USB_CUDA(cudaMalloc(&w, nw * 2));
+    USB_CUDA(cudaMalloc(&out, no * 2)); USB_CUDA(cudaMalloc(&bias, Cout * 4)); USB_CUDA(cudaMalloc(&st, (size_t)N * 16 * 8));
+    USB_CUDA(cudaMemset(a0, 0x3c, n0 * 2)); USB_CUDA(cudaMemset(a1, 0x3c, n1 * 2)); USB_CUDA(cudaMemset(w, 0x1c, nw * 2));
+    USB_CUDA(cudaMemset(bias, 0, Cout * 4)); USB_CUDA(cudaMemset(st, 0, (size_t)N * 16 * 8));
+    ConvEpilogue ep;
+    ep.bias = bias; ep.stats = with_stats ? st : nullptr; ep.groups = 8;
+    ConvOp op;
+    int rc = build_conv(op, kind, a0, C0, C0, C1 ? a1 : nullptr, C1, C1, N, H, W, w, Z, kind == KT4 ? 1 : 0, Cout, ep, out);
+    if (!rc) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int i = 0; i < 2 && !rc; ++i) rc = launch_conv_igemm(op.p, op.a0, op.a1, op.b, op.o, h->num_sms, 0);
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < iters && !rc; ++i) rc = launch_conv_igemm(op.p, op.a0, op.a1, op.b, op.o, h->num_sms, 0);
+        cudaEventRecord(e1, 0);
+        cudaError_t se = cudaDeviceSynchronize();
+        if (rc) rc = fail(std::string("conv launch: ") + cudaGetErrorString((cudaError_t)rc));
+        else if (se != cudaSuccess) rc = fail(std::string("conv kernel: ") + cudaGetErrorString(se));
+        else {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            *ms_out = ms / iters;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    cudaFree(a0); cudaFree(a1); cudaFree(w); cudaFree(out); cudaFree(bias); cudaFree(st);
     return rc;
 }
 
