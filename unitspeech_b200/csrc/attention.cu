@@ -10,6 +10,11 @@
 namespace usb {
 
 namespace {
+__device__ __forceinline__ float exp2f_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 constexpr int kDh = 32;            // dim_head
 constexpr int kTileP = 128;        // positions staged in shared memory per step
 constexpr int kPartStride = kDh * kDh + 2 * kDh;  // ctx + m + s
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(256) attn_partial_kernel(const AttnParams p, i
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    Ks[pp][hf * 16 + i] = __expf(kf[i] - mmax[hf * 16 + i]);
+                    Ks[pp][hf * 16 + i] = exp2f_ftz((kf[i] - mmax[hf * 16 + i]) * 1.4426950408889634f);
                     Vs[pp][hf * 16 + i] = vf[i];
                 }
             } else {

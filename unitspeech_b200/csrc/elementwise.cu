@@ -2,18 +2,34 @@
 // the fused "final block -> 1x1 -> guidance combine -> posterior update" step, and the time/speaker embedding.
 // All are HBM-bound: 16-byte vector accesses, one channel octet per thread, consecutive threads on consecutive
 // addresses, grids sized in multiples of the SM count.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace usb {
 
 namespace {
 
+// single-instruction special functions (MUFU.EX2 / MUFU.RCP, flush-to-zero): the non-ftz intrinsics expand into
+// denormal-scaling sequences that made the streaming kernels issue-bound
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 // x * tanh(softplus(x)) = x * w / (w + 2) with w = e^x (e^x + 2); exact for x > 20 (ratio rounds to 1), which is
 // the reference's softplus threshold (unitspeech.py:13-15).
 __device__ __forceinline__ float mish_fast(float x) {
-    const float e = __expf(fminf(x, 20.f));
+    const float e = ex2_ftz(fminf(x, 20.f) * kLog2e);
     const float w = e * (e + 2.f);
-    return x * __fdividef(w, w + 2.f);
+    return x * w * rcp_ftz(w + 2.f);
 }
 __device__ __forceinline__ float mish_precise(float x) {
     const float sp = x > 20.f ? x : log1pf(expf(x));
@@ -29,11 +45,10 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
         f[2 * i + 1] = v.y;
     }
 }
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+__device__ __forceinline__ uint32_t pack2(float a, float b) {   // (lo = a, hi = b), +-inf clamped to +-65504
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     uint4 o;
@@ -70,88 +85,113 @@ __device__ __forceinline__ void group_moments(const long long* stats, int n, int
 // =====================================================================================================================
 // input conv
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p, int pix_per_block) {
-    extern __shared__ float sw[];  // [18][C] 3x3 weights, then [2][C] 1x1 weights
+// One block = one image row segment of up to 64 pixels: the masked 3 x 66 x 2 input halo is staged in shared memory
+// once; each warp then walks 8 pixels, every lane producing CL consecutive output channels (weights in registers),
+// so a warp writes one pixel's contiguous channel vector per store instruction.
+template <int CL>
+__global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p) {
+    constexpr int TW = 64;
+    __shared__ float tile[3][TW + 2][2];
     __shared__ unsigned long long gsum[16];
-    const int C = p.C;
     const int n = blockIdx.y;
-    const int TP = C >> 3;
-    const int tq = threadIdx.x % TP;
-    const int pl = threadIdx.x / TP;
-    const int lanes = blockDim.x / TP;
-    for (int i = threadIdx.x; i < 18 * C; i += blockDim.x) sw[i] = p.w3[i];
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sw[18 * C + i] = p.w1[i];
-    if (threadIdx.x < 16) gsum[threadIdx.x] = 0ull;
-    __syncthreads();
-
-    float b3[8], b1[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        b3[i] = p.b3[tq * 8 + i];
-        b1[i] = p.b1[tq * 8 + i];
-    }
-    const int xr = p.x_row[n];
-    const int mr = p.mu_row[n];
-    const int H = p.H, W = p.W, P = H * W;
+    const int W = p.W, H = p.H, P = H * W, C = p.C;
+    const int tiles_x = (W + TW - 1) / TW;
+    const int y = blockIdx.x / tiles_x;
+    const int x0 = (blockIdx.x - y * tiles_x) * TW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xr = p.x_row[n], mr = p.mu_row[n];
     const float* xs = p.x + static_cast<long long>(xr) * P;
     const float* ms = mr >= 0 ? p.cond + static_cast<long long>(mr) * P : nullptr;
     const float* mk = p.mask + static_cast<long long>(n) * W;
-
+    if (threadIdx.x < 16) gsum[threadIdx.x] = 0ull;
+    for (int i = threadIdx.x; i < 3 * (TW + 2); i += blockDim.x) {
+        const int r = i / (TW + 2), c = i - r * (TW + 2);
+        const int yy = y + r - 1, xx = x0 + c - 1;
+        float vm = 0.f, vx = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float m = __ldg(mk + xx);
+            vm = (ms ? __ldg(ms + yy * W + xx) : __ldg(p.text_uncon + yy)) * m;   // channel 0 = mu
+            vx = __ldg(xs + yy * W + xx) * m;                                     // channel 1 = x_t
+        }
+        tile[r][c][0] = vm;
+        tile[r][c][1] = vx;
+    }
+    const int passes = C / (32 * CL);
     float s = 0.f, ss = 0.f;
-    const int p_begin = blockIdx.x * pix_per_block;
-    const int p_end = min(P, p_begin + pix_per_block);
-    for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
-        const int y = pix / W, x = pix - y * W;
-        float in[18];
+    __syncthreads();
+    for (int ps = 0; ps < passes; ++ps) {
+        const int c0 = ps * 32 * CL + lane * CL;
+        float w3[18][CL], w1[2][CL], b3[CL], b1[CL];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
+        for (int k = 0; k < 18; ++k)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const int yy = y + dy - 1, xx = x + dx - 1;
-                float vm = 0.f, vx = 0.f;
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-                    const float m = __ldg(mk + xx);
-                    vm = (ms ? __ldg(ms + yy * W + xx) : __ldg(p.text_uncon + yy)) * m;
-                    vx = __ldg(xs + yy * W + xx) * m;
+            for (int i = 0; i < CL; ++i) w3[k][i] = __ldg(p.w3 + k * C + c0 + i);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int i = 0; i < CL; ++i) w1[k][i] = __ldg(p.w1 + k * C + c0 + i);
+#pragma unroll
+        for (int i = 0; i < CL; ++i) {
+            b3[i] = __ldg(p.b3 + c0 + i);
+            b1[i] = __ldg(p.b1 + c0 + i);
+        }
+        for (int j = 0; j < TW / 8; ++j) {
+            const int px = warp * (TW / 8) + j;
+            const int x = x0 + px;
+            if (x >= W) break;
+            float acc[CL], rr[CL];
+#pragma unroll
+            for (int i = 0; i < CL; ++i) {
+                acc[i] = b3[i];
+                rr[i] = b1[i];
+            }
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float2 v = *reinterpret_cast<const float2*>(&tile[dy][px + dx][0]);
+#pragma unroll
+                    for (int i = 0; i < CL; ++i) {
+                        acc[i] = fmaf(v.x, w3[(dy * 3 + dx) * 2][i], acc[i]);
+                        acc[i] = fmaf(v.y, w3[(dy * 3 + dx) * 2 + 1][i], acc[i]);
+                    }
                 }
-                in[(dy * 3 + dx) * 2 + 0] = vm;  // channel 0 = mu, channel 1 = x (torch.stack([mu, x], 1))
-                in[(dy * 3 + dx) * 2 + 1] = vx;
+            {
+                const float2 v = *reinterpret_cast<const float2*>(&tile[1][px + 1][0]);
+#pragma unroll
+                for (int i = 0; i < CL; ++i) rr[i] = fmaf(v.y, w1[1][i], fmaf(v.x, w1[0][i], rr[i]));
+            }
+#pragma unroll
+            for (int i = 0; i < CL; ++i) {
+                s += acc[i];
+                ss = fmaf(acc[i], acc[i], ss);
+            }
+            const long long o = (static_cast<long long>(n) * P + static_cast<long long>(y) * W + x) * C + c0;
+            if (CL == 4) {
+                uint2 a, r;
+                a.x = pack2(acc[0], acc[1]); a.y = pack2(acc[2], acc[3]);
+                r.x = pack2(rr[0], rr[1]);   r.y = pack2(rr[2], rr[3]);
+                *reinterpret_cast<uint2*>(p.raw + o) = a;
+                *reinterpret_cast<uint2*>(p.res + o) = r;
+            } else {
+                *reinterpret_cast<uint32_t*>(p.raw + o) = pack2(acc[0], acc[1]);
+                *reinterpret_cast<uint32_t*>(p.res + o) = pack2(rr[0], rr[1]);
             }
         }
-        float acc[8], rr[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            acc[i] = b3[i];
-            rr[i] = b1[i];
+        // GroupNorm partials of this pass: lanes of one group are adjacent (cpg / CL lanes)
+        const int cpg = C / p.groups;
+        const int lpg = cpg / CL;  // lanes per group (power of two, <= 32)
+        for (int o = lpg >> 1; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
         }
-#pragma unroll
-        for (int k = 0; k < 18; ++k) {
-            const float4 w0 = *reinterpret_cast<const float4*>(sw + k * C + tq * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(sw + k * C + tq * 8 + 4);
-            acc[0] += in[k] * w0.x; acc[1] += in[k] * w0.y; acc[2] += in[k] * w0.z; acc[3] += in[k] * w0.w;
-            acc[4] += in[k] * w1.x; acc[5] += in[k] * w1.y; acc[6] += in[k] * w1.z; acc[7] += in[k] * w1.w;
+        if ((lane & (lpg - 1)) == 0) {
+            const int g = c0 / cpg;
+            atomicAdd(&gsum[g * 2], static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
+            atomicAdd(&gsum[g * 2 + 1], static_cast<unsigned long long>(__float2ll_rn(ss * kStatSqScale)));
         }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float v = in[8 + k];  // centre tap
-            const float4 w0 = *reinterpret_cast<const float4*>(sw + (18 + k) * C + tq * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(sw + (18 + k) * C + tq * 8 + 4);
-            rr[0] += v * w0.x; rr[1] += v * w0.y; rr[2] += v * w0.z; rr[3] += v * w0.w;
-            rr[4] += v * w1.x; rr[5] += v * w1.y; rr[6] += v * w1.z; rr[7] += v * w1.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            s += acc[i];
-            ss += acc[i] * acc[i];
-        }
-        const long long o = (static_cast<long long>(n) * P + pix) * C + tq * 8;
-        *reinterpret_cast<uint4*>(p.raw + o) = pack8(acc);
-        *reinterpret_cast<uint4*>(p.res + o) = pack8(rr);
+        s = ss = 0.f;
     }
-    const int cpg = C / p.groups;
-    const int g = (tq * 8) / cpg;
-    atomicAdd(&gsum[g * 2], static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
-    atomicAdd(&gsum[g * 2 + 1], static_cast<unsigned long long>(__float2ll_rn(ss * kStatSqScale)));
     __syncthreads();
     if (threadIdx.x < p.groups * 2)
         atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + static_cast<long long>(n) * p.groups * 2 + threadIdx.x,
@@ -159,56 +199,99 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
 }
 
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
-    const int TP = p.C / 8;
-    if (p.C % 8 || TP > 256 || 256 % TP || p.groups > 8 || (p.C / p.groups) % 8) return (int)cudaErrorInvalidValue;
-    const int P = p.H * p.W;
-    int ppb = 1024;
-    while (ppb > 64 && (long long)((P + ppb - 1) / ppb) * p.N < 148 * 4) ppb >>= 1;
-    dim3 grid((P + ppb - 1) / ppb, p.N);
-    first_conv_kernel<<<grid, 256, 20 * p.C * sizeof(float), s>>>(p, ppb);
+    if (p.groups != 8 || !(p.C == 64 || p.C == 128 || p.C == 256)) return (int)cudaErrorInvalidValue;
+    const int tiles_x = (p.W + 63) / 64;
+    dim3 grid(tiles_x * p.H, p.N);
+    if (p.C == 64) first_conv_kernel<2><<<grid, 256, 0, s>>>(p);
+    else first_conv_kernel<4><<<grid, 256, 0, s>>>(p);
     return (int)cudaGetLastError();
 }
 
 // =====================================================================================================================
 // GroupNorm apply + Mish (+ embedding vector) (+ residual) * mask
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, int pix_per_block, int TP) {
+// out = (Mish(a*v + b) + add + res) * m for 8 channels, with Mish(x) = x - 2x/d, d = e^x(e^x + 2) + 2, and one
+// reciprocal shared by two channels.  12-13 issue slots per element (the kernel is close to issue-bound otherwise).
+template <bool HAS_RES>
+__device__ __forceinline__ uint4 gn_mish8(const uint4& rv, const uint4& rr, const float (&a)[8], const float (&b)[8],
+                                          const float (&al)[8], const float (&bl)[8], const float (&ba)[8], float m) {
+    float v[8], r[8], x[8], d[8], y[8];
+    unpack8(rv, v);
+    if (HAS_RES) unpack8(rr, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = fmaf(v[i], a[i], b[i]);
+        const float e = ex2_ftz(fminf(fmaf(v[i], al[i], bl[i]), 20.f * kLog2e));
+        d[i] = fmaf(e, e + 2.f, 2.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        const float rn = rcp_ftz(d[i] * d[i + 1]) * -2.f;   // d <= ~2.4e17 each: the product stays finite
+        float y0 = fmaf(x[i], d[i + 1] * rn, fmaf(v[i], a[i], ba[i]));           // x - 2x/d + (b + add - b) ...
+        float y1 = fmaf(x[i + 1], d[i] * rn, fmaf(v[i + 1], a[i + 1], ba[i + 1]));
+        if (HAS_RES) {
+            y0 += r[i];
+            y1 += r[i + 1];
+        }
+        y[i] = y0 * m;
+        y[i + 1] = y1 * m;
+    }
+    return pack8(y);
+}
+
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, HAS_RES ? 2 : 3) gn_apply_kernel(const GnApplyParams p, int pix_per_block, int TP) {
+    constexpr int U = 4;  // pixels in flight per thread
     const int n = blockIdx.y;
     const int tq = threadIdx.x % TP;
     const int pl = threadIdx.x / TP;
     const int lanes = blockDim.x / TP;
     const int C = p.C, cpg = C / p.groups;
-    float a[8], b[8], add[8];
-    {
+    __shared__ float s_mean[8], s_rstd[8];
+    if (threadIdx.x < p.groups) {   // the double-precision moments once per (sample, group), not per thread
         const double count = static_cast<double>(p.P) * cpg;
+        group_moments(p.stats, n, p.groups, threadIdx.x, count, p.eps, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
+    }
+    __syncthreads();
+    float a[8], b[8], al[8], bl[8], ba[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = tq * 8 + i;
-            float mean, rstd;
-            group_moments(p.stats, n, p.groups, c / cpg, count, p.eps, mean, rstd);
-            a[i] = rstd * __ldg(p.gamma + c);
-            b[i] = __ldg(p.beta + c) - mean * a[i];
-            add[i] = p.addvec ? __ldg(p.addvec + static_cast<long long>(n) * p.addvec_stride + c) : 0.f;
-        }
+    for (int i = 0; i < 8; ++i) {
+        const int c = tq * 8 + i;
+        const int g = c / cpg;
+        a[i] = s_rstd[g] * __ldg(p.gamma + c);
+        b[i] = __ldg(p.beta + c) - s_mean[g] * a[i];
+        al[i] = a[i] * kLog2e;
+        bl[i] = b[i] * kLog2e;
+        ba[i] = b[i] + (p.addvec ? __ldg(p.addvec + static_cast<long long>(n) * p.addvec_stride + c) : 0.f);
     }
     const float* mk = p.mask + static_cast<long long>(n) * p.W;
     const int p_begin = blockIdx.x * pix_per_block;
     const int p_end = min(p.P, p_begin + pix_per_block);
     const long long base = static_cast<long long>(n) * p.P * C + tq * 8;
-    for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
-        const long long o = base + static_cast<long long>(pix) * C;
-        const float m = __ldg(mk + pix % p.W);
-        float v[8];
-        unpack8(ldg_stream(reinterpret_cast<const uint4*>(p.raw + o)), v);
-        float r[8];
-        if (p.res) unpack8(ldg_stream(reinterpret_cast<const uint4*>(p.res + o)), r);
+    int xcol = (p_begin + pl) % p.W;   // column of the thread's next pixel, advanced incrementally
+    for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += lanes * U) {
+        uint4 rv[U], rr[U];
+        float m[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float y = mish_fast(v[i] * a[i] + b[i]) + add[i];
-            if (p.res) y += r[i];
-            v[i] = y * m;
+        for (int u = 0; u < U; ++u) {
+            const int pix = pix0 + u * lanes;
+            if (pix < p_end) {
+                const long long o = base + static_cast<long long>(pix) * C;
+                rv[u] = ldg_stream(reinterpret_cast<const uint4*>(p.raw + o));
+                if (HAS_RES) rr[u] = ldg_stream(reinterpret_cast<const uint4*>(p.res + o));
+                m[u] = __ldg(mk + xcol);
+            }
+            xcol += lanes;
+            while (xcol >= p.W) xcol -= p.W;
         }
-        *reinterpret_cast<uint4*>(p.out + o) = pack8(v);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pix = pix0 + u * lanes;
+            if (pix < p_end) {
+                const uint4 o4 = gn_mish8<HAS_RES>(rv[u], rr[u], a, b, al, bl, ba, m[u]);
+                if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(p.out + base + static_cast<long long>(pix) * C) = o4;
+            }
+        }
     }
 }
 
@@ -217,11 +300,15 @@ int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s) {
     if (p.C % 8 || TP > 256 || (p.C / p.groups) < 1 || p.C % p.groups) return (int)cudaErrorInvalidValue;
     const int lanes = TP >= 256 ? 1 : 256 / TP;
     const int threads = TP * lanes;
-    // aim for ~8 blocks per SM over the whole tensor
+    // aim for >= ~16 blocks per SM over the whole tensor, at least 4 pixels per thread
     int ppb = lanes * 64;
-    while (ppb > lanes * 4 && (long long)((p.P + ppb - 1) / ppb) * p.N < (long long)num_sms * 8) ppb >>= 1;
+    while (ppb > lanes * 4 && (long long)((p.P + ppb - 1) / ppb) * p.N < (long long)num_sms * 16) ppb >>= 1;
     dim3 grid((p.P + ppb - 1) / ppb, p.N);
-    gn_apply_kernel<<<grid, threads, 0, s>>>(p, ppb, TP);
+    GnApplyParams q = p;
+    static const char* dbg_env = getenv("USB_DBG_GN");
+    q.dbg = dbg_env ? atoi(dbg_env) : 0;
+    if (p.res) gn_apply_kernel<true><<<grid, threads, 0, s>>>(q, ppb, TP);
+    else gn_apply_kernel<false><<<grid, threads, 0, s>>>(q, ppb, TP);
     return (int)cudaGetLastError();
 }
 
@@ -235,18 +322,21 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalParams p, int pix
     const int lanes = blockDim.x / TP;
     const int C = p.C, cpg = C / p.groups;
     float a[3][8], sh[3][8], wf[8];
-    const double count = static_cast<double>(p.P) * cpg;
+    __shared__ float s_mean[3][8], s_rstd[3][8];
+    if (threadIdx.x < p.nb * p.groups) {
+        const int k = threadIdx.x / p.groups, g = threadIdx.x % p.groups;
+        const double count = static_cast<double>(p.P) * cpg;
+        group_moments(p.stats, k * p.B + b, p.groups, g, count, p.eps, s_mean[k][g], s_rstd[k][g]);
+    }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (k < p.nb) {
-            const int n = k * p.B + b;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = tq * 8 + i;
-                float mean, rstd;
-                group_moments(p.stats, n, p.groups, c / cpg, count, p.eps, mean, rstd);
-                a[k][i] = rstd * __ldg(p.gamma + c);
-                sh[k][i] = __ldg(p.beta + c) - mean * a[k][i];
+                a[k][i] = s_rstd[k][c / cpg] * __ldg(p.gamma + c);
+                sh[k][i] = __ldg(p.beta + c) - s_mean[k][c / cpg] * a[k][i];
             }
         }
     }

@@ -637,6 +637,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         p.raw = raw; p.stats = stats; p.gamma = g.gamma; p.beta = g.beta; p.addvec = addvec; p.addvec_stride = h->J;
         p.res = res; p.mask = pl.mask[l]; p.out = out; p.N = Be; p.P = H[l] * W[l]; p.W = W[l]; p.C = Cc; p.groups = G;
         p.eps = 1e-5f;
+        p.dbg = 0;
         pl.gns.push_back(p);
         pl.ops.push_back({Op::GN, (int)pl.gns.size() - 1});
     };
@@ -1218,7 +1219,7 @@ int usb_op_gn_apply(usb_handle* h, const void* raw, const int64_t* stats, const 
     GnApplyParams p;
     p.raw = static_cast<const __half*>(raw); p.stats = reinterpret_cast<const long long*>(stats); p.gamma = gamma; p.beta = beta; p.addvec = addvec;
     p.addvec_stride = C; p.res = static_cast<const __half*>(res); p.mask = mask; p.out = static_cast<__half*>(out);
-    p.N = N; p.P = H * W; p.W = W; p.C = C; p.groups = groups; p.eps = 1e-5f;
+    p.N = N; p.P = H * W; p.W = W; p.C = C; p.groups = groups; p.eps = 1e-5f; p.dbg = 0;
     USB_LAUNCH(h, launch_gn_apply(p, h->num_sms, reinterpret_cast<cudaStream_t>(stream)));
     return 0;
 }

@@ -41,6 +41,7 @@ struct GnApplyParams {
     __half* out;           // [N][P][C]
     int N, P, W, C, groups;
     float eps;
+    int dbg;               // experiments: 1 = skip Mish, 2 = skip the store
 };
 int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s);
 
