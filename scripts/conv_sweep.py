@@ -33,7 +33,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         run_one(sys.argv[2:])
     else:
-        configs = [{"USB_DBG_FLAGS": "7"}, {"USB_DBG_FLAGS": "15"}, {"USB_DBG_FLAGS": "23"}, {"USB_DBG_FLAGS": "55"}, {"USB_DBG_FLAGS": "0"}, {"USB_DBG_FLAGS": "16"}] if os.environ.get("SWEEP") == "mma" else [{}, {"USB_DBG_FLAGS": "1"}, {"USB_DBG_FLAGS": "2"}, {"USB_DBG_FLAGS": "3"}, {"USB_DBG_FLAGS": "4"},
+        configs = [{}, {"USB_NO_SWAP_AB": "1"}] if os.environ.get("SWEEP") == "swap" else [{}, {"USB_DBG_FLAGS": "1"}, {"USB_DBG_FLAGS": "2"}, {"USB_DBG_FLAGS": "3"}, {"USB_DBG_FLAGS": "4"},
                    {"USB_DBG_FLAGS": "6"}, {"USB_DBG_FLAGS": "7"},
                    {"USB_DBG_STAGES": "3"}, {"USB_DBG_STAGES": "4"}, {"USB_DBG_BH": "2"}, {"USB_DBG_BH": "4"},
                    {"USB_DBG_BH": "8"}, {"USB_DBG_BH": "1"}]

@@ -42,6 +42,12 @@ CONV_CASES = [
     (2, 2, 20, 24, 256, 256, 128),   # 1x1 res_conv over the concat
     (3, 2, 10, 12, 64, 0, 64),       # transposed 4x4 s2
     (3, 1, 20, 64, 256, 0, 256),
+    # Cout == 128 with H % 4 == 0 runs the swapped-operand kernel (channels on the MMA M axis, 256-pixel tiles)
+    (0, 1, 20, 40, 128, 0, 128),     # BH=4, BW=64, ragged W
+    (0, 2, 80, 72, 256, 0, 128),     # BH=16, BW=16, ragged W, long K
+    (3, 2, 20, 24, 128, 0, 128),     # transposed conv, W < BW
+    (3, 1, 40, 64, 128, 0, 128),
+    (1, 2, 40, 96, 128, 0, 128),     # stride 2 -> tile space 20 x 48
 ]
 
 
@@ -88,6 +94,29 @@ def test_conv_epilogue_stats_mask_residual(ops):
     out2, _ = ops.conv(0, x, w, b, mask=mask, residual=res, res_scale=0.37)
     ref2 = (conv * 0.37 + res) * mask.view(N, 1, 1, W)
     _check(out2, ref2)
+
+
+def test_swapped_conv_stats_and_mask(ops):
+    """Cout == 128: statistics and output mask through the swapped-operand kernel."""
+    g = torch.Generator().manual_seed(9)
+    N, C, H, W, Cout = 2, 128, 40, 56, 128
+    x = r16(torch.randn(N, C, H, W, generator=g))
+    w = r16(torch.randn(Cout, C, 3, 3, generator=g) / (C * 9) ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    conv = F.conv2d(x, w, b, padding=1)
+    out, st = ops.conv(0, x, w, b, stats_groups=8)
+    cg = conv.reshape(N, 8, -1).double()
+    ref_st = torch.stack([cg.sum(-1), (cg * cg).sum(-1)], -1)
+    assert torch.allclose(st.cpu(), ref_st, rtol=2e-5, atol=1e-2), (st.cpu() - ref_st).abs().max()
+    _check(out, conv)
+    mask = (torch.arange(W).unsqueeze(0) < torch.tensor([W, 31]).unsqueeze(1)).float()
+    out2, _ = ops.conv(0, x, w, b, mask=mask)
+    _check(out2, conv * mask.view(N, 1, 1, W))
+    # transposed conv with the (finer) output mask
+    wt = r16(torch.randn(C, Cout, 4, 4, generator=g) / (C * 4) ** 0.5)
+    mask2 = (torch.arange(2 * W).unsqueeze(0) < torch.tensor([2 * W, 61]).unsqueeze(1)).float()
+    out3, _ = ops.conv(3, x, wt, b, mask=mask2)
+    _check(out3, F.conv_transpose2d(x, wt, b, stride=2, padding=1) * mask2.view(N, 1, 1, 2 * W))
 
 
 @pytest.mark.parametrize("C,cpg_note", [(64, "cpg8"), (128, "cpg16"), (512, "cpg64"), (1024, "cpg128")])

@@ -315,6 +315,249 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// =====================================================================================================================
+// Swapped-operand variant (Cout % 128 == 0, no residual): 128 output channels are the MMA M dimension (A = weight
+// tile) and 256 pixels the N dimension (B = two independent 128-pixel activation patches).  On B200 this issues the
+// same M128 x N256 x K16 instructions as the kernel above but measures 20-45 % faster, and it gives Cout = 128 layers
+// the N = 256 instruction shape they cannot reach otherwise (a N = 128 instruction runs at half rate).
+// The accumulator is transposed in TMEM (lane = channel, column = pixel): bias and GroupNorm partials are per-thread
+// scalars, and the tile is transposed through the swizzled staging buffer on its way to the TMA store.
+// Epilogue group g owns patch g of the pair: its own coordinates, staging buffer and named barrier.
+// =====================================================================================================================
+namespace {
+struct PatchCoord {
+    int ph, n, y0, x0;
+    bool valid;
+};
+// patch `lp` (0 .. patches_per_phase) of phase ph: x fastest, then y, then sample
+__device__ __forceinline__ PatchCoord decode_patch(const ConvParams& p, int ph, int lp) {
+    PatchCoord c;
+    c.ph = ph;
+    c.valid = lp < p.patches_per_phase;
+    const int tx = lp % p.tiles_x; lp /= p.tiles_x;
+    const int ty = lp % p.tiles_y;
+    c.n = lp / p.tiles_y;
+    c.y0 = ty * p.BH;
+    c.x0 = tx * p.BW;
+    return c;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0,
+                          const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b,
+                          const __grid_constant__ CUtensorMap map_out, int total_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t kWBytes = 16384u, kPBytes = 16384u, kStageBytes = kWBytes + 2 * kPBytes;
+    const int stages = p.stages;
+    const int ksteps = p.taps * (p.chunks0 + p.chunks1);
+    const int pairs_per_phase = (p.patches_per_phase + 1) >> 1;
+    const int tiles_per_phase = pairs_per_phase * p.n_tiles_n;
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a0);
+        tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], kConvEpilogueThreads);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&tmem_base_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ---------------------------------------------------- TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int ph = tile / tiles_per_phase;
+            const int rem = tile - ph * tiles_per_phase;
+            const int nt = rem % p.n_tiles_n;
+            const int pair = rem / p.n_tiles_n;
+            const PatchCoord c0 = decode_patch(p, ph, 2 * pair), c1 = decode_patch(p, ph, 2 * pair + 1);
+            const int bz = p.b_batch_mode == 1 ? ph : 0;
+            const uint32_t tx_bytes = kWBytes + kPBytes + (c1.valid ? kPBytes : 0u);
+            int kcoord = 0;
+            for (int t = 0; t < p.taps; ++t) {
+                const ConvTap tap = p.tap[ph * p.taps + t];
+                for (int src = 0; src < 2; ++src) {
+                    const int chunks = src ? p.chunks1 : p.chunks0;
+                    const CUtensorMap* ma = src ? &map_a1 : &map_a0;
+                    for (int cc = 0; cc < chunks; ++cc, kcoord += kConvBK) {
+                        mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 100 + stage);
+                        if (elect_one()) {
+                            const uint32_t sw = tiles_base + stage * kStageBytes;
+                            const uint32_t fb = full0 + stage * 8;
+                            const int cch = tap.c + cc * kConvBK;
+                            mbar_arrive_expect_tx_a(fb, tx_bytes);
+                            tma_load_3d_a(sw, &map_b, fb, kcoord, nt * 128, bz);
+                            tma_load_5d_a(sw + kWBytes, ma, fb, cch, c0.x0 + tap.dx, tap.p, c0.y0 + tap.dy, c0.n);
+                            if (c1.valid)
+                                tma_load_5d_a(sw + kWBytes + kPBytes, ma, fb, cch, c1.x0 + tap.dx, tap.p, c1.y0 + tap.dy,
+                                              c1.n);
+                        }
+                        __syncwarp();
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------- MMA issuer: D[ch][px] += W[ch][k] * X[px][k]^T
+        const uint32_t idesc = umma_idesc_f16(256u);
+        const uint32_t desc_hi = static_cast<uint32_t>(umma_desc_sw128(0) >> 32);
+        const uint32_t w_lo0 = (tiles_base & 0x3FFFFu) >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait_a(tempty0 + as * 8, aphase ^ 1u, 200 + as);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as) * 256u;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                mbar_wait_a(full0 + stage * 8, phase, 300 + stage);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t w_lo = w_lo0 + stage * (kStageBytes >> 4);
+                    const uint32_t x_lo = w_lo + (kWBytes >> 4);
+#pragma unroll
+                    for (int k = 0; k < kConvBK / 16; ++k) {
+                        const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (w_lo + 2u * k);
+                        const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (x_lo + 2u * k);
+                        tc_mma_f16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit_a(empty0 + stage * 8);
+                    if (ks == ksteps - 1) tc_commit_a(tfull0 + as * 8);
+                }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------- epilogue: thread = output channel, columns = pixels
+        const int ew = warp & 3;
+        const int grp = (warp - 4) >> 2;          // which patch of the pair
+        const int c = ew * 32 + lane;             // output channel within the 128-channel tile
+        const int bw_shift = 31 - __clz(p.BW);
+        const int cpg = p.stats ? p.Cout / p.groups : 16;
+        const uint32_t stage_buf = tiles_base + stages * kStageBytes + static_cast<uint32_t>(grp) * 16384u;
+        // staging layout per group: [slab = c/64][64 pixel rows][128 B], 128-byte swizzle on the 16-byte chunk index
+        const uint32_t slab_base = stage_buf + static_cast<uint32_t>(c >> 6) * 8192u + static_cast<uint32_t>(c & 7) * 2u;
+        const uint32_t chunk = static_cast<uint32_t>((c & 63) >> 3);
+        const int bar_id = 1 + grp;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int ph = tile / tiles_per_phase;
+            const int rem = tile - ph * tiles_per_phase;
+            const int nt = rem % p.n_tiles_n;
+            const PatchCoord pc = decode_patch(p, ph, 2 * (rem / p.n_tiles_n) + grp);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait_a(tfull0 + as * 8, aphase, 400 + as);
+            tc_fence_after();
+            if (!pc.valid) {   // odd patch count: the second half of the last pair holds no image
+                tc_fence_before();
+                mbar_arrive_a(tempty0 + as * 8);
+                continue;
+            }
+            const int wlim = p.Wm - pc.x0;        // pixels with tx >= wlim lie outside the image
+            const int cg = nt * 128 + c;          // global output channel
+            const float bias = p.bias ? __ldg(p.bias + cg) : 0.f;
+            long long* stats_n = p.stats ? p.stats + static_cast<long long>(pc.n) * p.groups * 2 : nullptr;
+            const float* mrow = p.mask ? p.mask + static_cast<long long>(pc.n) * p.mask_stride + p.ox_off[ph] : nullptr;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
+            float s = 0.f, ss = 0.f;
+            for (int hc = 0; hc < 2; ++hc) {
+                const int pb = hc * 64;           // first pixel of this 64-pixel sub-block inside the patch
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(taddr + grp * 128 + pb, v0);
+                tmem_ld_32x32(taddr + grp * 128 + pb + 32, v1);
+                tmem_ld_wait();
+                if (hc == 1) {
+                    tc_fence_before();
+                    mbar_arrive_a(tempty0 + as * 8);
+                }
+                named_bar_sync(bar_id, 128);   // staging buffer free (previous stores have been read)
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    float f = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]) + bias;
+                    const int tx = (pb + j) & (p.BW - 1);
+                    const bool valid = tx < wlim;
+                    if (stats_n && valid) {
+                        s += f;
+                        ss = fmaf(f, f, ss);
+                    }
+                    if (mrow) f *= valid ? __ldg(mrow + (pc.x0 + tx) * p.ox_mul) : 0.f;
+                    const __half h = __float2half_rn(fminf(fmaxf(f, -65504.f), 65504.f));
+                    const uint32_t addr = slab_base + static_cast<uint32_t>(j) * 128u + ((chunk ^ (j & 7)) << 4);
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__half_as_ushort(h)) : "memory");
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(bar_id, 128);
+                if (ew == 0 && elect_one()) {
+                    const int yb = pc.y0 + (pb >> bw_shift);
+                    const int xb = pc.x0 + (pb & (p.BW - 1));
+                    const int cph = p.ox_off[ph] * p.out_c_phase_mul + nt * 128;
+                    tma_store_5d_a(&map_out, stage_buf, cph, xb, p.oy_off[ph], yb, pc.n);
+                    tma_store_5d_a(&map_out, stage_buf + 8192u, cph + 64, xb, p.oy_off[ph], yb, pc.n);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
+                }
+                __syncwarp();
+            }
+            if (stats_n) {
+                // channels of one GroupNorm group are adjacent lanes; a warp holds 32 channels = 32/cpg groups
+                // (or part of one group when cpg >= 32)
+                const int span = cpg < 32 ? cpg : 32;
+                for (int o = span >> 1; o > 0; o >>= 1) {
+                    s += __shfl_xor_sync(0xffffffffu, s, o);
+                    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                }
+                if ((lane & (span - 1)) == 0) {
+                    long long* dst = stats_n + (cg / cpg) * 2;
+                    atomicAdd(reinterpret_cast<unsigned long long*>(dst),
+                              static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(dst + 1),
+                              static_cast<unsigned long long>(__float2ll_rn(ss * kStatSqScale)));
+                }
+            }
+        }
+        if (ew == 0 && elect_one()) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                       const CUtensorMap& out, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
@@ -322,11 +565,20 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kConvSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
+        e = cudaFuncSetAttribute(conv_igemm_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
-    const long long total = static_cast<long long>(p.phases) * p.N * p.tiles_y * p.tiles_x * p.n_tiles_n;
+    long long total = static_cast<long long>(p.phases) * p.N * p.tiles_y * p.tiles_x * p.n_tiles_n;
+    if (p.swap_ab) total = static_cast<long long>(p.phases) * ((p.patches_per_phase + 1) / 2) * p.n_tiles_n;
     if (total <= 0 || total > 0x7fffffffLL) return static_cast<int>(cudaErrorInvalidValue);
     const int grid = static_cast<int>(total < num_sms ? total : num_sms);
+    if (p.swap_ab) {
+        const size_t smem = 1024 + static_cast<size_t>(p.stages) * 49152 + 2 * 16384;
+        if (smem > static_cast<size_t>(kConvSmemBytes)) return static_cast<int>(cudaErrorInvalidValue);
+        conv_igemm_swapped_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));
+        return static_cast<int>(cudaGetLastError());
+    }
     const size_t smem = 1024 + static_cast<size_t>(p.stages) * (16384 + static_cast<size_t>(p.BN) * 128) + 2 * 16384;
     if (smem > static_cast<size_t>(kConvSmemBytes)) return static_cast<int>(cudaErrorInvalidValue);
     conv_igemm_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));

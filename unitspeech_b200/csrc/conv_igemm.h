@@ -45,6 +45,8 @@ struct ConvParams {
     int chunks0, chunks1;      // 64-channel K chunks per tap from source 0 / source 1 (0 = no second source)
     int b_batch_mode;          // B z-coordinate: 0 -> 0, 1 -> phase, 2 -> sample
     int stages;                // smem pipeline depth
+    int swap_ab;               // 1: swapped-operand kernel: channels on the MMA M axis, two 128-pixel patches on N
+    int patches_per_phase;     // N * tiles_y * tiles_x
     int dbg_flags;             // experiments only: 1 = skip B loads, 2 = skip epilogue math/stores, 4 = skip A loads
     ConvTap tap[kConvMaxTaps];
     // epilogue: v = acc + bias[c]; stats (sum, sumsq per (n, group)) on v; v = v*res_scale + res; v *= mask

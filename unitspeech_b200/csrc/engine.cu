@@ -212,17 +212,21 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     p.Wm = kind == K3S2 ? W / 2 : W;
     int BH = 1;
     while (BH < 16 && p.Hm % (BH * 2) == 0) BH *= 2;
+    // swapped-operand kernel (see conv_igemm.cu) for every 3x3 / strided / transposed conv whose Cout is a multiple of 128
+    static const bool allow_swap = getenv("USB_NO_SWAP_AB") == nullptr;
+    p.swap_ab = (allow_swap && Cout % 128 == 0 && kind != K1 && ep.res == nullptr && b_batch_mode != 2) ? 1 : 0;
     p.BH = BH;
     p.BW = 128 / BH;
     p.tiles_y = p.Hm / BH;
     p.tiles_x = (p.Wm + p.BW - 1) / p.BW;
+    p.patches_per_phase = N * p.tiles_y * p.tiles_x;
     p.Cout = Cout;
-    p.BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    p.BN = p.swap_ab ? 128 : (Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64));
     p.n_tiles_n = Cout / p.BN;
     p.chunks0 = C0 / 64;
     p.chunks1 = in1 ? C1 / 64 : 0;
     p.b_batch_mode = b_batch_mode;
-    p.stages = p.BN == 256 ? 4 : (p.BN == 128 ? 5 : 7);   // + 2 x 16 KB epilogue staging must fit 227 KB
+    p.stages = p.swap_ab ? 4 : (p.BN == 256 ? 4 : (p.BN == 128 ? 5 : 7));   // + 2 x 16 KB epilogue staging must fit 227 KB
     if (const char* e = getenv("USB_DBG_STAGES")) p.stages = atoi(e);
     if (const char* e = getenv("USB_DBG_FLAGS")) p.dbg_flags = atoi(e);
     if (const char* e = getenv("USB_DBG_BH")) {
@@ -260,8 +264,13 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     else op.a1 = op.a0;
     const int K = p.taps * (C0 + (in1 ? C1 : 0));
     USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, p.BN));
-    // output tile store: plain view, or the parity view of the upsampled tensor for the transposed conv
-    USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BH, p.BW));
+    // output tile store: plain view, or the parity view of the upsampled tensor for the transposed conv;
+    // the swapped kernel stores 64-pixel sub-blocks (64 / BW image rows) per TMA
+    if (p.swap_ab)
+        USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BW >= 64 ? 1 : 64 / p.BW,
+                             p.BW >= 64 ? 64 : p.BW));
+    else
+        USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BH, p.BW));
     return 0;
 }
 
