@@ -2,9 +2,12 @@
 //   ctx[h][d][e] = sum_p softmax_p(k[h][d][:])[p] * v[h][e][p]          (softmax over ALL positions, no mask)
 //   attn(x)[co][p] = sum_{h,d} Weff[co][h*32+d] * q[h][d][p] + b_o[co],  Weff[co][h*32+d] = sum_e Wo[co][h*32+e] ctx[h][d][e]
 // Pass 1 (attn_partial_kernel): each block reduces one (sample, head, chunk of positions) with a chunk-local max
-// (online-softmax partial: m[d], s[d] = sum exp(k-m), c[d][e] = sum exp(k-m) v).
-// Pass 2 (attn_fold_kernel): merges the chunk partials exactly (rescale by exp(m_chunk - m_global)), normalises, and
-// folds to_out into the per-sample fp16 weight consumed by the tcgen05 GEMM kernel.
+//   (online-softmax partial: m[d], s[d] = sum exp(k-m), c[d][e] = sum exp(k-m) v).  The 32x32 outer-product sums run
+//   on the warp-level tensor cores (mma.sync m16n8k16, fp16 operands = the stored fp16 v and the fp16-rounded exp,
+//   fp32 accumulate); the kernel is bound by reading k and v once from HBM.
+// Pass 2 (attn_merge_kernel): merges the chunk partials exactly (rescale by exp(m_chunk - m_global)) and normalises.
+// Pass 3 (attn_fold_kernel): folds to_out into the per-sample fp16 weight consumed by the tcgen05 GEMM kernel.
+// All reductions run in a fixed order: results are bit-reproducible.
 #include "kernels.h"
 
 namespace usb {
@@ -15,21 +18,38 @@ __device__ __forceinline__ float exp2f_ftz(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-constexpr int kDh = 32;            // dim_head
-constexpr int kTileP = 128;        // positions staged in shared memory per step
-constexpr int kPartStride = kDh * kDh + 2 * kDh;  // ctx + m + s
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kDh = 32;                             // dim_head
+constexpr int kPartStride = kDh * kDh + 2 * kDh;    // ctx + m + s
+constexpr int kWarpTile = 64;                       // positions staged per warp iteration
+constexpr int kRowHalfs = 40;                       // 32 halfs + 8 pad: 80-byte rows make ldmatrix conflict-free
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 }  // namespace
 
 int attn_chunks(int P, int chunk) { return (P + chunk - 1) / chunk; }
 
-__global__ void __launch_bounds__(256) attn_partial_kernel(const AttnParams p, int nchunks) {
-    __shared__ __align__(16) float stage[2 * kTileP * kDh];   // Ks | Vs, reused for the slice reduction
-    __shared__ float red[8][kDh];
+// grid (chunks, heads, N), 128 threads = 4 warps; warp w takes positions p0 + w*64 + 256*i
+__global__ void __launch_bounds__(128) attn_partial_kernel(const AttnParams p, int nchunks) {
+    // per-warp staging tiles Ps (exp(k - m)) and Vs; the same memory holds the cross-warp reduction afterwards
+    __shared__ __align__(16) unsigned char sbuf[2 * 4 * kWarpTile * kRowHalfs * 2];
+    __half (*Ps)[kWarpTile][kRowHalfs] = reinterpret_cast<__half (*)[kWarpTile][kRowHalfs]>(sbuf);
+    __half (*Vs)[kWarpTile][kRowHalfs] =
+        reinterpret_cast<__half (*)[kWarpTile][kRowHalfs]>(sbuf + 4 * kWarpTile * kRowHalfs * 2);
+    float (*csum)[kDh][kDh + 1] = reinterpret_cast<float (*)[kDh][kDh + 1]>(sbuf);   // [4][32][33] after the loop
+    __shared__ float red[4][kDh];
     __shared__ float mmax[kDh];
-    __shared__ float sum_s[4][kDh];
-    float (*Ks)[kDh] = reinterpret_cast<float (*)[kDh]>(stage);                 // exp(k - m)
-    float (*Vs)[kDh] = reinterpret_cast<float (*)[kDh]>(stage + kTileP * kDh);
-    float (*acc_s)[kDh][kDh + 1] = reinterpret_cast<float (*)[kDh][kDh + 1]>(stage);  // [4][32][33] after the loop
 
     const int chunk_id = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
     const int hidden = p.heads * kDh;
@@ -39,146 +59,187 @@ __global__ void __launch_bounds__(256) attn_partial_kernel(const AttnParams p, i
     const __half* base = p.qkv + static_cast<long long>(n) * p.P * ld;
     const int koff = hidden + head * kDh;
     const int voff = 2 * hidden + head * kDh;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- chunk-local max of k per d
+    // ---- chunk-local max of k per d: thread = (position slice, 8 channels)
     {
-        const int d = tid & 31, sl = tid >> 5;
-        float m = -INFINITY;
-        for (int pos = p0 + sl; pos < p1; pos += 8)
-            m = fmaxf(m, __half2float(base[static_cast<long long>(pos) * ld + koff + d]));
-        red[sl][d] = m;
-        __syncthreads();
-        if (tid < kDh) {
-            float mm = red[0][tid];
+        const int oct = tid & 3, sl = tid >> 2;   // 32 position slices
+        float m[8];
 #pragma unroll
-            for (int i = 1; i < 8; ++i) mm = fmaxf(mm, red[i][tid]);
-            mmax[tid] = mm;
-        }
-        __syncthreads();
-    }
-
-    // ---- accumulate: 4 position slices x 64 threads, each thread 2 d x 8 e
-    const int slice = tid >> 6;
-    const int t64 = tid & 63;
-    const int dp = t64 >> 2;   // d pair 0..15
-    const int eo = t64 & 3;    // e octet 0..3
-    float acc[2][8];
+        for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+        for (int pos = p0 + sl; pos < p1; pos += 32) {
+            const uint4 kv = *reinterpret_cast<const uint4*>(base + static_cast<long long>(pos) * ld + koff + oct * 8);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&kv);
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    float s0 = 0.f, s1 = 0.f;
-
-    for (int t0 = p0; t0 < p1; t0 += kTileP) {
-        // stage: 2 threads per position, 16 channels of k and v each
-        {
-            const int pp = tid >> 1, hf = tid & 1;
-            const int pos = t0 + pp;
-            float kf[16], vf[16];
-            if (pos < p1) {
-                const __half* kp = base + static_cast<long long>(pos) * ld + koff + hf * 16;
-                const __half* vp = base + static_cast<long long>(pos) * ld + voff + hf * 16;
-                const uint4 k0 = *reinterpret_cast<const uint4*>(kp);
-                const uint4 k1 = *reinterpret_cast<const uint4*>(kp + 8);
-                const uint4 v0 = *reinterpret_cast<const uint4*>(vp);
-                const uint4 v1 = *reinterpret_cast<const uint4*>(vp + 8);
-                const __half2* hk0 = reinterpret_cast<const __half2*>(&k0);
-                const __half2* hk1 = reinterpret_cast<const __half2*>(&k1);
-                const __half2* hv0 = reinterpret_cast<const __half2*>(&v0);
-                const __half2* hv1 = reinterpret_cast<const __half2*>(&v1);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float2 a = __half22float2(hk0[i]); kf[2 * i] = a.x; kf[2 * i + 1] = a.y;
-                    a = __half22float2(hk1[i]); kf[8 + 2 * i] = a.x; kf[8 + 2 * i + 1] = a.y;
-                    a = __half22float2(hv0[i]); vf[2 * i] = a.x; vf[2 * i + 1] = a.y;
-                    a = __half22float2(hv1[i]); vf[8 + 2 * i] = a.x; vf[8 + 2 * i + 1] = a.y;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    Ks[pp][hf * 16 + i] = exp2f_ftz((kf[i] - mmax[hf * 16 + i]) * 1.4426950408889634f);
-                    Vs[pp][hf * 16 + i] = vf[i];
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    Ks[pp][hf * 16 + i] = 0.f;
-                    Vs[pp][hf * 16 + i] = 0.f;
-                }
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h2[i]);
+                m[2 * i] = fmaxf(m[2 * i], f.x);
+                m[2 * i + 1] = fmaxf(m[2 * i + 1], f.y);
             }
         }
-        __syncthreads();
-#pragma unroll 4
-        for (int i = 0; i < kTileP / 4; ++i) {
-            const int pp = slice * (kTileP / 4) + i;
-            const float2 w = *reinterpret_cast<const float2*>(&Ks[pp][dp * 2]);
-            const float4 va = *reinterpret_cast<const float4*>(&Vs[pp][eo * 8]);
-            const float4 vb = *reinterpret_cast<const float4*>(&Vs[pp][eo * 8 + 4]);
-            acc[0][0] += w.x * va.x; acc[0][1] += w.x * va.y; acc[0][2] += w.x * va.z; acc[0][3] += w.x * va.w;
-            acc[0][4] += w.x * vb.x; acc[0][5] += w.x * vb.y; acc[0][6] += w.x * vb.z; acc[0][7] += w.x * vb.w;
-            acc[1][0] += w.y * va.x; acc[1][1] += w.y * va.y; acc[1][2] += w.y * va.z; acc[1][3] += w.y * va.w;
-            acc[1][4] += w.y * vb.x; acc[1][5] += w.y * vb.y; acc[1][6] += w.y * vb.z; acc[1][7] += w.y * vb.w;
-            s0 += w.x;
-            s1 += w.y;
+        // lanes with equal (lane & 3) hold the same channels: xor 4, 8, 16 within the warp, then across the 4 warps
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 4));
+            m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 8));
+            m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 16));
         }
+        if (lane < 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = m[i];
+        }
+        __syncthreads();
+        if (tid < kDh) mmax[tid] = fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid]));
         __syncthreads();
     }
 
-    // ---- reduce the 4 slices and write the partial
+    // ---- accumulate ctx[d][e] on tensor cores: A = P^T (d x pos), B = V (pos x e)
+    float acc[2][4][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc_s[slice][dp * 2 + i][eo * 8 + j] = acc[i][j];
-    if (eo == 0) {
-        sum_s[slice][dp * 2] = s0;
-        sum_s[slice][dp * 2 + 1] = s1;
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+    const int oct = lane & 3;          // this lane stages channels oct*8 .. oct*8+7 of every position it touches
+    float mloc[8], ssum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        mloc[i] = mmax[oct * 8 + i] * kLog2e;
+        ssum[i] = 0.f;
+    }
+    const uint32_t ps_base = static_cast<uint32_t>(__cvta_generic_to_shared(&Ps[warp][0][0]));
+    const uint32_t vs_base = static_cast<uint32_t>(__cvta_generic_to_shared(&Vs[warp][0][0]));
+    // ldmatrix source rows: lane supplies row (lane & 7) of 8x8 matrix (lane >> 3)
+    const int lm_r = lane & 7, lm_j = lane >> 3;
+
+    for (int t0 = p0 + warp * kWarpTile; t0 < p1; t0 += 4 * kWarpTile) {
+        // stage 64 positions: item = lane + 32*it -> position item/4, channel octet item%4 (= lane & 3)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int pp = (lane >> 2) + it * 8;
+            const int pos = t0 + pp;
+            uint4 pk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (pos < p1) {
+                const __half* row = base + static_cast<long long>(pos) * ld;
+                const uint4 kv = *reinterpret_cast<const uint4*>(row + koff + oct * 8);
+                vv = *reinterpret_cast<const uint4*>(row + voff + oct * 8);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&kv);
+                __half2 o2[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h2[i]);
+                    o2[i] = __floats2half2_rn(exp2f_ftz(fmaf(f.x, kLog2e, -mloc[2 * i])),
+                                              exp2f_ftz(fmaf(f.y, kLog2e, -mloc[2 * i + 1])));
+                    const float2 r = __half22float2(o2[i]);   // the normaliser sums the values the MMA sees
+                    ssum[2 * i] += r.x;
+                    ssum[2 * i + 1] += r.y;
+                }
+                pk = *reinterpret_cast<const uint4*>(o2);
+            }
+            *reinterpret_cast<uint4*>(&Ps[warp][pp][oct * 8]) = pk;
+            *reinterpret_cast<uint4*>(&Vs[warp][pp][oct * 8]) = vv;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < kWarpTile / 16; ++ks) {
+            const int pk0 = ks * 16;
+            uint32_t a[2][4], b[4][2];
+            // A fragments (16 d x 16 pos) for d0 = 0 and 16: matrices (pos half, d half) read transposed
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int prow = pk0 + (lm_j >> 1) * 8 + lm_r, dcol = mt * 16 + (lm_j & 1) * 8;
+                ldmatrix_x4_trans(ps_base + (prow * kRowHalfs + dcol) * 2, a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+            }
+            // B fragments (16 pos x 8 e) for e0 = 0, 8, 16, 24: two n-tiles per ldmatrix.x4
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                const int prow = pk0 + (lm_j & 1) * 8 + lm_r, ecol = np * 16 + (lm_j >> 1) * 8;
+                ldmatrix_x4_trans(vs_base + (prow * kRowHalfs + ecol) * 2, b[2 * np][0], b[2 * np][1], b[2 * np + 1][0],
+                                  b[2 * np + 1][1]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_16816(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b[nt][0], b[nt][1]);
+        }
+        __syncwarp();
+    }
+
+    // ---- fixed-order reduction over the 4 warps (csum aliases the staging tiles: wait until every warp is done)
+    __syncthreads();
+    {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                csum[warp][mt * 16 + g][nt * 8 + 2 * t] = acc[mt][nt][0];
+                csum[warp][mt * 16 + g][nt * 8 + 2 * t + 1] = acc[mt][nt][1];
+                csum[warp][mt * 16 + g + 8][nt * 8 + 2 * t] = acc[mt][nt][2];
+                csum[warp][mt * 16 + g + 8][nt * 8 + 2 * t + 1] = acc[mt][nt][3];
+            }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 4);
+            ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 8);
+            ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 16);
+        }
+        if (lane < 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = ssum[i];
+        }
     }
     __syncthreads();
     float* out = p.part + ((static_cast<long long>(n) * p.heads + head) * nchunks + chunk_id) * kPartStride;
-    for (int i = tid; i < kDh * kDh; i += 256) {
+    for (int i = tid; i < kDh * kDh; i += 128) {
         const int d = i >> 5, e = i & 31;
-        out[i] = acc_s[0][d][e] + acc_s[1][d][e] + acc_s[2][d][e] + acc_s[3][d][e];
+        out[i] = (csum[0][d][e] + csum[1][d][e]) + (csum[2][d][e] + csum[3][d][e]);
     }
     if (tid < kDh) {
         out[kDh * kDh + tid] = mmax[tid];
-        out[kDh * kDh + kDh + tid] = sum_s[0][tid] + sum_s[1][tid] + sum_s[2][tid] + sum_s[3][tid];
+        out[kDh * kDh + kDh + tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
     }
 }
 
-// grid (ceil(C/64), N): merge chunk partials -> ctx (all heads) in smem, then Weff rows for 64 output channels
-__global__ void __launch_bounds__(256) attn_fold_kernel(const AttnParams p, int nchunks) {
-    extern __shared__ float ctx[];  // [heads][32][33]
-    __shared__ float M_s[8][kDh], S_s[8][kDh];
-    const int n = blockIdx.y;
-    const int tid = threadIdx.x;
-    const int heads = p.heads;
-    const int hidden = heads * kDh;
-    const float* part_n = p.part + static_cast<long long>(n) * heads * nchunks * kPartStride;
-
-    // global max and normaliser per (head, d)
-    for (int i = tid; i < heads * kDh; i += 256) {
-        const int h = i / kDh, d = i % kDh;
-        const float* ph = part_n + static_cast<long long>(h) * nchunks * kPartStride;
+// grid (heads, N), 256 threads: ctx[n][h][d][e] = sum_c part_c[d][e] exp(m_c[d] - M[d]) / sum_c s_c[d] exp(m_c[d] - M[d])
+__global__ void __launch_bounds__(256) attn_merge_kernel(const AttnParams p, int nchunks, float* ctx_out) {
+    __shared__ float M_s[kDh], S_s[kDh];
+    const int h = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+    const float* ph = p.part + (static_cast<long long>(n) * p.heads + h) * nchunks * kPartStride;
+    if (tid < kDh) {
         float M = -INFINITY;
-        for (int c = 0; c < nchunks; ++c) M = fmaxf(M, ph[c * kPartStride + kDh * kDh + d]);
+        for (int c = 0; c < nchunks; ++c) M = fmaxf(M, ph[c * kPartStride + kDh * kDh + tid]);
         float S = 0.f;
         for (int c = 0; c < nchunks; ++c)
-            S += ph[c * kPartStride + kDh * kDh + kDh + d] * __expf(ph[c * kPartStride + kDh * kDh + d] - M);
-        M_s[h][d] = M;
-        S_s[h][d] = S;
+            S += ph[c * kPartStride + kDh * kDh + kDh + tid] *
+                 exp2f_ftz((ph[c * kPartStride + kDh * kDh + tid] - M) * kLog2e);
+        M_s[tid] = M;
+        S_s[tid] = S;
     }
     __syncthreads();
-    for (int i = tid; i < heads * kDh * kDh; i += 256) {
-        const int h = i / (kDh * kDh), r = i % (kDh * kDh), d = r >> 5, e = r & 31;
-        const float* ph = part_n + static_cast<long long>(h) * nchunks * kPartStride;
-        const float M = M_s[h][d];
+    float* o = ctx_out + (static_cast<long long>(n) * p.heads + h) * kDh * kDh;
+    for (int i = tid; i < kDh * kDh; i += 256) {
+        const int d = i >> 5;
+        const float M = M_s[d];
         float a = 0.f;
         for (int c = 0; c < nchunks; ++c)
-            a += ph[c * kPartStride + r] * __expf(ph[c * kPartStride + kDh * kDh + d] - M);
-        ctx[(h * kDh + d) * (kDh + 1) + e] = a / S_s[h][d];
+            a += ph[c * kPartStride + i] * exp2f_ftz((ph[c * kPartStride + kDh * kDh + d] - M) * kLog2e);
+        o[i] = a / S_s[d];
+    }
+}
+
+// grid (ceil(C/64), N): Weff[n][co][h*32+d] = sum_e Wo[co][h*32+e] * ctx[n][h][d][e] for 64 output channels
+__global__ void __launch_bounds__(256) attn_fold_kernel(const AttnParams p, const float* ctx_in) {
+    extern __shared__ float ctx[];  // [heads][32][33]
+    const int n = blockIdx.y, tid = threadIdx.x;
+    const int heads = p.heads, hidden = heads * kDh;
+    const float* cn = ctx_in + static_cast<long long>(n) * heads * kDh * kDh;
+    for (int i = tid; i < heads * kDh * kDh; i += 256) {
+        const int hd = i >> 5, e = i & 31;
+        ctx[hd * (kDh + 1) + e] = cn[i];
     }
     __syncthreads();
-    // Weff[n][co][h*32+d] = sum_e Wo[co][h*32+e] * ctx[h][d][e]
     const int co0 = blockIdx.x * 64;
     for (int i = tid; i < 64 * hidden; i += 256) {
         const int co = co0 + i / hidden;
@@ -197,12 +258,23 @@ int launch_attn_context(const AttnParams& p, cudaStream_t s) {
     if (p.heads > 8 || p.heads < 1) return (int)cudaErrorInvalidValue;
     const int nchunks = attn_chunks(p.P, p.chunk);
     dim3 g1(nchunks, p.heads, p.N);
-    attn_partial_kernel<<<g1, 256, 0, s>>>(p, nchunks);
+    attn_partial_kernel<<<g1, 128, 0, s>>>(p, nchunks);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    dim3 g2((p.C + 63) / 64, p.N);
-    attn_fold_kernel<<<g2, 256, p.heads * kDh * (kDh + 1) * sizeof(float), s>>>(p, nchunks);
+    // merged context lives behind the partials in the same scratch buffer
+    float* ctx = p.part + static_cast<long long>(p.N) * p.heads * nchunks * kPartStride;
+    dim3 g2(p.heads, p.N);
+    attn_merge_kernel<<<g2, 256, 0, s>>>(p, nchunks, ctx);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    dim3 g3((p.C + 63) / 64, p.N);
+    attn_fold_kernel<<<g3, 256, p.heads * kDh * (kDh + 1) * sizeof(float), s>>>(p, ctx);
     return (int)cudaGetLastError();
+}
+
+size_t attn_scratch_bytes(int N, int heads, int P, int chunk) {
+    return (static_cast<size_t>(N) * heads * attn_chunks(P, chunk) * kPartStride + static_cast<size_t>(N) * heads * kDh * kDh) *
+           sizeof(float);
 }
 
 }  // namespace usb

@@ -111,6 +111,7 @@ static int make_w_map(CUtensorMap* m, const __half* base, int Z, int Cout, int K
 // weights
 // ---------------------------------------------------------------------------------------------------------------
 enum ConvKind { K3S1 = 0, K3S2 = 1, K1 = 2, KT4 = 3 };
+constexpr int kAttnChunk = 2048;   // positions per attention partial block
 
 struct ConvW {
     __half* w = nullptr;   // [Z][Cout][K]
@@ -595,7 +596,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         o_upx[l] = l < L - 1 ? b.take(PC[l] * h->C[l] * sizeof(__half)) : 0;
         o_weff[l] = b.take((size_t)Be * h->C[l] * hid * sizeof(__half));
         o_mask[l] = b.take((size_t)Be * W[l] * sizeof(float));
-        const size_t part = (size_t)Be * h->heads * attn_chunks(H[l] * W[l], 1024) * (32 * 32 + 64) * sizeof(float);
+        const size_t part = attn_scratch_bytes(Be, h->heads, H[l] * W[l], kAttnChunk);
         if (part > max_part) max_part = part;
     }
     const size_t o_part = b.take(max_part);
@@ -682,7 +683,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         USB_TRY(push_conv(K1, x, a.C, a.C, nullptr, 0, 0, l, &a.qkv, nullptr, 0, 0, 3 * hid, e1, qkv));
         AttnParams ap;
         ap.qkv = qkv; ap.wo = a.wo; ap.part = part; ap.weff = weff; ap.N = Be; ap.P = H[l] * W[l]; ap.C = a.C;
-        ap.heads = h->heads; ap.chunk = 1024;
+        ap.heads = h->heads; ap.chunk = kAttnChunk;
         pl.attns.push_back(ap);
         pl.ops.push_back({Op::ATTN, (int)pl.attns.size() - 1});
         ConvEpilogue e2;
@@ -872,7 +873,7 @@ static int run_estimator(usb_handle* h, const EstInputs& in, cudaStream_t s) {
                 // algorithmic bytes: k and v read once (fp16, 2*hidden channels)
                 ProfScope ps(h, s, 2, (double)a.N * a.P * 2.0 * a.heads * 32 * 2.0);
                 USB_LAUNCH(h, launch_attn_context(a, s));
-                h->launches++;  // two kernels
+                h->launches += 2;  // three kernels
                 break;
             }
         }
@@ -1240,13 +1241,13 @@ int usb_op_attn_context(usb_handle* h, const void* qkv, const float* wo, void* w
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     AttnParams ap;
     ap.qkv = static_cast<const __half*>(qkv); ap.wo = wo; ap.weff = static_cast<__half*>(weff); ap.N = N; ap.P = P;
-    ap.C = C; ap.heads = heads; ap.chunk = 1024;
-    const size_t part_bytes = (size_t)N * heads * attn_chunks(P, 1024) * (32 * 32 + 64) * sizeof(float);
+    ap.C = C; ap.heads = heads; ap.chunk = kAttnChunk;
+    const size_t part_bytes = attn_scratch_bytes(N, heads, P, kAttnChunk);
     float* part = nullptr;
     USB_CUDA(cudaMalloc(&part, part_bytes));
     ap.part = part;
     int e = launch_attn_context(ap, s);
-    h->launches += 2;
+    h->launches += 3;
     cudaError_t se = cudaStreamSynchronize(s);
     cudaFree(part);
     if (e) return fail(std::string("attention launch: ") + cudaGetErrorString((cudaError_t)e));

@@ -87,11 +87,12 @@ int launch_embed(const EmbedParams& p, cudaStream_t s);
 struct AttnParams {
     const __half* qkv;     // [N][P][3*hidden], channel = qkv*hidden + head*dh + c
     const float* wo;       // [C][hidden] to_out weight
-    float* part;           // scratch [N][heads][chunks][dh*dh + 2*dh]
+    float* part;           // scratch of attn_scratch_bytes(): [N][heads][chunks][dh*dh + 2*dh] partials + merged ctx
     __half* weff;          // [N][C][hidden] folded per-sample weight (K-major B operand of the to_out GEMM)
     int N, P, C, heads, chunk;   // dh = 32, hidden = heads*32
 };
 int attn_chunks(int P, int chunk);
+size_t attn_scratch_bytes(int N, int heads, int P, int chunk);   // partials + merged context
 int launch_attn_context(const AttnParams& p, cudaStream_t s);
 
 // ---- small utilities
