@@ -2,7 +2,8 @@
 per-conv TFLOP/s of one diffusion step (conv order reconstructed from the plan for Be=48, T=512)."""
 import collections, csv, sys
 path = sys.argv[1]
-Be, T = int(sys.argv[2]) if len(sys.argv) > 2 else 48, int(sys.argv[3]) if len(sys.argv) > 3 else 512
+args = [a for a in sys.argv[2:] if not a.startswith("-")]
+Be, T = (int(args[0]) if len(args) > 0 else 48), (int(args[1]) if len(args) > 1 else 512)
 with open(path) as f:
     lines = [l for l in f if l.startswith('"')]
 rows = [(r['Kernel Name'].split('(')[0].replace('usb::', ''), float(r['Metric Value']) / 1e3) for r in csv.DictReader(lines)]
@@ -29,7 +30,7 @@ for k in range(3):
     j = 3 - k
     resnet(f'u{k}.0', j, 2 * C[j], C[j - 1]); resnet(f'u{k}.1', j, C[j - 1], C[j - 1]); attn(f'u{k}.2', j, C[j - 1]); conv(f'u{k}.up', j, C[j - 1], C[j - 1], 16)
 conv('final', 0, 128, 128, 9)
-convs = [r for r in rows if r[0] == 'conv_igemm_kernel']
+convs = [r for r in rows if r[0].startswith('conv_igemm')]
 step = convs[-60:]
 cls = collections.defaultdict(lambda: [0.0, 0.0])
 for o, c in zip(ops, step):

@@ -353,6 +353,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float mask_s[2][128];   // per epilogue group: output mask of the patch's columns (0 outside the image)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -493,6 +494,10 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
             const float bias = p.bias ? __ldg(p.bias + cg) : 0.f;
             long long* stats_n = p.stats ? p.stats + static_cast<long long>(pc.n) * p.groups * 2 : nullptr;
             const float* mrow = p.mask ? p.mask + static_cast<long long>(pc.n) * p.mask_stride + p.ox_off[ph] : nullptr;
+            if (mrow) {   // published to the group by the "staging buffer free" barrier below
+                const int et = ew * 32 + lane;
+                if (et < p.BW) mask_s[grp][et] = et < wlim ? __ldg(mrow + (pc.x0 + et) * p.ox_mul) : 0.f;
+            }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
             float s = 0.f, ss = 0.f;
             for (int hc = 0; hc < 2; ++hc) {
@@ -515,7 +520,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                         s += f;
                         ss = fmaf(f, f, ss);
                     }
-                    if (mrow) f *= valid ? __ldg(mrow + (pc.x0 + tx) * p.ox_mul) : 0.f;
+                    if (mrow) f *= mask_s[grp][tx];
                     const __half h = __float2half_rn(fminf(fmaxf(f, -65504.f), 65504.f));
                     const uint32_t addr = slab_base + static_cast<uint32_t>(j) * 128u + ((chunk ^ (j & 7)) << 4);
                     asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__half_as_ushort(h)) : "memory");

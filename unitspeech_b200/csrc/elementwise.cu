@@ -89,36 +89,22 @@ __device__ __forceinline__ void group_moments(const long long* stats, int n, int
 // once; each warp then walks 8 pixels, every lane producing CL consecutive output channels (weights in registers),
 // so a warp writes one pixel's contiguous channel vector per store instruction.
 template <int CL>
-__global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p) {
+__global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p, int tiles_per_block) {
     constexpr int TW = 64;
     __shared__ float tile[3][TW + 2][2];
     __shared__ unsigned long long gsum[16];
     const int n = blockIdx.y;
     const int W = p.W, H = p.H, P = H * W, C = p.C;
     const int tiles_x = (W + TW - 1) / TW;
-    const int y = blockIdx.x / tiles_x;
-    const int x0 = (blockIdx.x - y * tiles_x) * TW;
+    const int n_tiles = tiles_x * H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int xr = p.x_row[n], mr = p.mu_row[n];
     const float* xs = p.x + static_cast<long long>(xr) * P;
     const float* ms = mr >= 0 ? p.cond + static_cast<long long>(mr) * P : nullptr;
     const float* mk = p.mask + static_cast<long long>(n) * W;
     if (threadIdx.x < 16) gsum[threadIdx.x] = 0ull;
-    for (int i = threadIdx.x; i < 3 * (TW + 2); i += blockDim.x) {
-        const int r = i / (TW + 2), c = i - r * (TW + 2);
-        const int yy = y + r - 1, xx = x0 + c - 1;
-        float vm = 0.f, vx = 0.f;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            const float m = __ldg(mk + xx);
-            vm = (ms ? __ldg(ms + yy * W + xx) : __ldg(p.text_uncon + yy)) * m;   // channel 0 = mu
-            vx = __ldg(xs + yy * W + xx) * m;                                     // channel 1 = x_t
-        }
-        tile[r][c][0] = vm;
-        tile[r][c][1] = vx;
-    }
     const int passes = C / (32 * CL);
-    float s = 0.f, ss = 0.f;
-    __syncthreads();
+    const int t_begin = blockIdx.x * tiles_per_block, t_end = min(n_tiles, t_begin + tiles_per_block);
     for (int ps = 0; ps < passes; ++ps) {
         const int c0 = ps * 32 * CL + lane * CL;
         float w3[18][CL], w1[2][CL], b3[CL], b1[CL];
@@ -135,47 +121,66 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
             b3[i] = __ldg(p.b3 + c0 + i);
             b1[i] = __ldg(p.b1 + c0 + i);
         }
-        for (int j = 0; j < TW / 8; ++j) {
-            const int px = warp * (TW / 8) + j;
-            const int x = x0 + px;
-            if (x >= W) break;
-            float acc[CL], rr[CL];
-#pragma unroll
-            for (int i = 0; i < CL; ++i) {
-                acc[i] = b3[i];
-                rr[i] = b1[i];
-            }
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const float2 v = *reinterpret_cast<const float2*>(&tile[dy][px + dx][0]);
-#pragma unroll
-                    for (int i = 0; i < CL; ++i) {
-                        acc[i] = fmaf(v.x, w3[(dy * 3 + dx) * 2][i], acc[i]);
-                        acc[i] = fmaf(v.y, w3[(dy * 3 + dx) * 2 + 1][i], acc[i]);
-                    }
+        float s = 0.f, ss = 0.f;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int y = t / tiles_x;
+            const int x0 = (t - y * tiles_x) * TW;
+            __syncthreads();   // previous tile fully consumed
+            for (int i = threadIdx.x; i < 3 * (TW + 2); i += blockDim.x) {
+                const int r = i / (TW + 2), c = i - r * (TW + 2);
+                const int yy = y + r - 1, xx = x0 + c - 1;
+                float vm = 0.f, vx = 0.f;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                    const float m = __ldg(mk + xx);
+                    vm = (ms ? __ldg(ms + yy * W + xx) : __ldg(p.text_uncon + yy)) * m;   // channel 0 = mu
+                    vx = __ldg(xs + yy * W + xx) * m;                                     // channel 1 = x_t
                 }
-            {
-                const float2 v = *reinterpret_cast<const float2*>(&tile[1][px + 1][0]);
-#pragma unroll
-                for (int i = 0; i < CL; ++i) rr[i] = fmaf(v.y, w1[1][i], fmaf(v.x, w1[0][i], rr[i]));
+                tile[r][c][0] = vm;
+                tile[r][c][1] = vx;
             }
+            __syncthreads();
+            for (int j = 0; j < TW / 8; ++j) {
+                const int px = warp * (TW / 8) + j;
+                const int x = x0 + px;
+                if (x >= W) break;
+                float acc[CL], rr[CL];
 #pragma unroll
-            for (int i = 0; i < CL; ++i) {
-                s += acc[i];
-                ss = fmaf(acc[i], acc[i], ss);
-            }
-            const long long o = (static_cast<long long>(n) * P + static_cast<long long>(y) * W + x) * C + c0;
-            if (CL == 4) {
-                uint2 a, r;
-                a.x = pack2(acc[0], acc[1]); a.y = pack2(acc[2], acc[3]);
-                r.x = pack2(rr[0], rr[1]);   r.y = pack2(rr[2], rr[3]);
-                *reinterpret_cast<uint2*>(p.raw + o) = a;
-                *reinterpret_cast<uint2*>(p.res + o) = r;
-            } else {
-                *reinterpret_cast<uint32_t*>(p.raw + o) = pack2(acc[0], acc[1]);
-                *reinterpret_cast<uint32_t*>(p.res + o) = pack2(rr[0], rr[1]);
+                for (int i = 0; i < CL; ++i) {
+                    acc[i] = b3[i];
+                    rr[i] = b1[i];
+                }
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const float2 v = *reinterpret_cast<const float2*>(&tile[dy][px + dx][0]);
+#pragma unroll
+                        for (int i = 0; i < CL; ++i) {
+                            acc[i] = fmaf(v.x, w3[(dy * 3 + dx) * 2][i], acc[i]);
+                            acc[i] = fmaf(v.y, w3[(dy * 3 + dx) * 2 + 1][i], acc[i]);
+                        }
+                    }
+                {
+                    const float2 v = *reinterpret_cast<const float2*>(&tile[1][px + 1][0]);
+#pragma unroll
+                    for (int i = 0; i < CL; ++i) rr[i] = fmaf(v.y, w1[1][i], fmaf(v.x, w1[0][i], rr[i]));
+                }
+#pragma unroll
+                for (int i = 0; i < CL; ++i) {
+                    s += acc[i];
+                    ss = fmaf(acc[i], acc[i], ss);
+                }
+                const long long o = (static_cast<long long>(n) * P + static_cast<long long>(y) * W + x) * C + c0;
+                if (CL == 4) {
+                    uint2 a, r;
+                    a.x = pack2(acc[0], acc[1]); a.y = pack2(acc[2], acc[3]);
+                    r.x = pack2(rr[0], rr[1]);   r.y = pack2(rr[2], rr[3]);
+                    *reinterpret_cast<uint2*>(p.raw + o) = a;
+                    *reinterpret_cast<uint2*>(p.res + o) = r;
+                } else {
+                    *reinterpret_cast<uint32_t*>(p.raw + o) = pack2(acc[0], acc[1]);
+                    *reinterpret_cast<uint32_t*>(p.res + o) = pack2(rr[0], rr[1]);
+                }
             }
         }
         // GroupNorm partials of this pass: lanes of one group are adjacent (cpg / CL lanes)
@@ -190,7 +195,6 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
             atomicAdd(&gsum[g * 2], static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
             atomicAdd(&gsum[g * 2 + 1], static_cast<unsigned long long>(__float2ll_rn(ss * kStatSqScale)));
         }
-        s = ss = 0.f;
     }
     __syncthreads();
     if (threadIdx.x < p.groups * 2)
@@ -200,10 +204,12 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
 
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
     if (p.groups != 8 || !(p.C == 64 || p.C == 128 || p.C == 256)) return (int)cudaErrorInvalidValue;
-    const int tiles_x = (p.W + 63) / 64;
-    dim3 grid(tiles_x * p.H, p.N);
-    if (p.C == 64) first_conv_kernel<2><<<grid, 256, 0, s>>>(p);
-    else first_conv_kernel<4><<<grid, 256, 0, s>>>(p);
+    const int n_tiles = ((p.W + 63) / 64) * p.H;
+    int tpb = 16;   // row tiles per block: amortises the per-lane weight loads; keep >= ~8 blocks per SM
+    while (tpb > 1 && (long long)((n_tiles + tpb - 1) / tpb) * p.N < 148 * 8) tpb >>= 1;
+    dim3 grid((n_tiles + tpb - 1) / tpb, p.N);
+    if (p.C == 64) first_conv_kernel<2><<<grid, 256, 0, s>>>(p, tpb);
+    else first_conv_kernel<4><<<grid, 256, 0, s>>>(p, tpb);
     return (int)cudaGetLastError();
 }
 
