@@ -1,0 +1,74 @@
+"""Multi-process (gloo, world_size 2) test of the utterance-sharding path used by bench.py --gpus N."""
+
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from unitspeech_b200.sharding import shard_range
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 16, 255, 256):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+class _FakeDecoder:
+    """Stands in for the CUDA decoder: a per-utterance function of its inputs (so order/ownership errors show)."""
+
+    def __call__(self, z, mask, cond, spk, n, tg=0.0, sg=0.0, noise=None):
+        out = z * 2 + cond * mask + spk.sum(-1, keepdim=True)
+        if noise is not None:
+            out = out + noise.sum(0)
+        return out
+
+
+def _worker(rank, world, port, n_utt, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unitspeech_b200.sharding import gather_utterances, sample_sharded
+    g = torch.Generator().manual_seed(1)
+    z, cond = torch.randn(n_utt, 80, 8, generator=g), torch.randn(n_utt, 80, 8, generator=g)
+    mask = torch.ones(n_utt, 1, 8)
+    spk = torch.randn(n_utt, 1, 4, generator=g)
+    noise = torch.randn(3, n_utt, 80, 8, generator=g)
+    dec = _FakeDecoder()
+    got = sample_sharded(dec, z, mask, cond, spk, 3, 1.0, 1.0, noise=noise)
+    ref = dec(z, mask, cond, spk, 3, noise=noise)
+    ok = torch.equal(got, ref)
+    b, e = shard_range(n_utt, rank, world)
+    ok = ok and torch.equal(gather_utterances(ref[b:e], n_utt), ref)
+    # timing-style reduction used by bench.py: max over ranks
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = ok and float(t) == float(world)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, ok))
+
+
+@pytest.mark.parametrize("n_utt", [5, 4, 1])
+def test_sample_sharded_world2(n_utt):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_utt, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

@@ -1,0 +1,57 @@
+"""Utterance sharding across the GPUs of one node (one process per GPU).
+
+The sampler has no cross-utterance dependency (GroupNorm and attention are per sample, the update is elementwise), so
+the only multi-GPU structure is: split the utterance list, run independent sampling loops, gather the mels.  There is
+no collective inside the step loop.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) of `n_items` owned by `rank`; sizes differ by at most one, earlier ranks get the extra."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad rank/world_size")
+    base, extra = divmod(n_items, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def gather_utterances(local: torch.Tensor, n_items: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All ranks contribute their (n_local, ...) shard (shard_range order); every rank gets the (n_items, ...) whole.
+
+    Uses all_gather on equal-size padded shards (NCCL on GPUs, gloo in the CPU tests)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_range(n_items, r, world) for r in range(world)]
+    max_n = max(e - b for b, e in sizes)
+    b, e = sizes[rank]
+    if local.shape[0] != e - b:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} utterances, expected {e - b}")
+    padded = local.new_zeros((max_n,) + tuple(local.shape[1:]))
+    padded[: e - b] = local
+    parts: List[torch.Tensor] = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([parts[r][: sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
+
+
+def sample_sharded(decoder, z, mask, cond, spk_emb, n_timesteps, text_gradient_scale=0.0, spk_gradient_scale=0.0,
+                   noise: Optional[torch.Tensor] = None, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Every rank passes the FULL batch; each samples its own shard with `decoder` and the result is gathered."""
+    n = z.shape[0]
+    if not dist.is_available() or not dist.is_initialized():
+        return decoder(z, mask, cond, spk_emb, n_timesteps, text_gradient_scale, spk_gradient_scale, noise=noise)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    b, e = shard_range(n, rank, world)
+    if e > b:
+        out = decoder(z[b:e], mask[b:e], cond[b:e], spk_emb[b:e], n_timesteps, text_gradient_scale, spk_gradient_scale,
+                      noise=None if noise is None else noise[:, b:e])
+    else:
+        out = z.new_zeros((0,) + tuple(z.shape[1:]))
+    return gather_utterances(out, n, group)
