@@ -252,9 +252,12 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
         const float rs = p.res_scale ? __ldg(p.res_scale) : 1.f;
         const int half_cols = p.BN >= 128 ? p.BN >> 1 : p.BN;
         const int slabs = (p.BN >= 128 || grp == 0) ? half_cols >> 6 : 0;  // BN == 64: group 1 has no columns
-        const uint32_t stage_buf = tiles_base + stages * stage_bytes + static_cast<uint32_t>(grp) * 16384u;
-        const uint32_t stage_row = stage_buf + static_cast<uint32_t>(row) * 128u;
-        const int bar_id = 1 + grp;
+        // per-warp staging (32 pixel rows x 128 B) and per-warp TMA stores: no cross-warp barrier in the epilogue
+        // (two 4 KB buffers per warp, alternating, so a store only waits for the one issued two slabs earlier)
+        const uint32_t warp_buf0 = tiles_base + stages * stage_bytes + static_cast<uint32_t>(grp * 4 + ew) * 8192u;
+        uint32_t buf_sel = 0;
+        const int q0 = ew * 32;                       // first tile pixel of this warp
+        const int wty0 = q0 >> bw_shift, wtx0 = q0 & (p.BW - 1);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(p, tile);
@@ -288,26 +291,27 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
                     tc_fence_before();
                     mbar_arrive_a(tempty0 + as * 8);
                 }
-                // the staging buffer is free once the previous slab's TMA store has read it (the issuing lane waited
-                // on its bulk group before arriving here)
-                named_bar_sync(bar_id, 128);
-                const __half* res_row = res_px ? res_px + c_glob : nullptr;
-                if (cpg >= 64) epilogue_slab<1>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, row, stats_n, cpg, lane);
-                else if (cpg == 32) epilogue_slab<2>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, row, stats_n, cpg, lane);
-                else if (cpg == 16) epilogue_slab<4>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, row, stats_n, cpg, lane);
-                else epilogue_slab<8>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, row, stats_n, cpg, lane);
-                fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-                named_bar_sync(bar_id, 128);
-                if (ew == 0 && elect_one()) {
-                    tma_store_5d_a(&map_out, stage_buf, c_glob + p.ox_off[tc.ph] * p.out_c_phase_mul, tc.x0,
-                                   p.oy_off[tc.ph], tc.y0, tc.n);
-                    tma_store_commit();
-                    tma_store_wait_read<0>();
-                }
+                // this staging buffer is free once the store issued from it two slabs ago has been read
+                const uint32_t warp_buf = warp_buf0 + buf_sel * 4096u;
+                const uint32_t stage_row = warp_buf + static_cast<uint32_t>(lane) * 128u;
+                buf_sel ^= 1u;
+                if (lane == 0) tma_store_wait_read<1>();
                 __syncwarp();
+                const __half* res_row = res_px ? res_px + c_glob : nullptr;
+                if (cpg >= 64) epilogue_slab<1>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane);
+                else if (cpg == 32) epilogue_slab<2>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane);
+                else if (cpg == 16) epilogue_slab<4>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane);
+                else epilogue_slab<8>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane);
+                fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_5d_a(&map_out, warp_buf, c_glob + p.ox_off[tc.ph] * p.out_c_phase_mul, tc.x0 + wtx0,
+                                   p.oy_off[tc.ph], tc.y0 + wty0, tc.n);
+                    tma_store_commit();
+                }
             }
         }
-        if (ew == 0 && elect_one()) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -584,7 +588,7 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         conv_igemm_swapped_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));
         return static_cast<int>(cudaGetLastError());
     }
-    const size_t smem = 1024 + static_cast<size_t>(p.stages) * (16384 + static_cast<size_t>(p.BN) * 128) + 2 * 16384;
+    const size_t smem = 1024 + static_cast<size_t>(p.stages) * (16384 + static_cast<size_t>(p.BN) * 128) + 8 * 8192;
     if (smem > static_cast<size_t>(kConvSmemBytes)) return static_cast<int>(cudaErrorInvalidValue);
     conv_igemm_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));
     return static_cast<int>(cudaGetLastError());

@@ -215,7 +215,8 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     while (BH < 16 && p.Hm % (BH * 2) == 0) BH *= 2;
     // swapped-operand kernel (see conv_igemm.cu) for every 3x3 / strided / transposed conv whose Cout is a multiple of 128
     static const bool allow_swap = getenv("USB_NO_SWAP_AB") == nullptr;
-    p.swap_ab = (allow_swap && Cout % 128 == 0 && kind != K1 && ep.res == nullptr && b_batch_mode != 2) ? 1 : 0;
+    static const bool swap_k1 = getenv("USB_SWAP_K1") != nullptr;
+    p.swap_ab = (allow_swap && Cout % 128 == 0 && (kind != K1 || swap_k1) && ep.res == nullptr && b_batch_mode != 2) ? 1 : 0;
     p.BH = BH;
     p.BW = 128 / BH;
     p.tiles_y = p.Hm / BH;
@@ -227,7 +228,8 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     p.chunks0 = C0 / 64;
     p.chunks1 = in1 ? C1 / 64 : 0;
     p.b_batch_mode = b_batch_mode;
-    p.stages = p.swap_ab ? 4 : (p.BN == 256 ? 4 : (p.BN == 128 ? 5 : 7));   // + 2 x 16 KB epilogue staging must fit 227 KB
+    // pipeline stages + epilogue staging (swapped: 2 x 16 KB, plain: 8 warps x 2 x 4 KB) must fit 225 KB
+    p.stages = p.swap_ab ? 4 : (p.BN == 256 ? 3 : (p.BN == 128 ? 5 : 6));
     if (const char* e = getenv("USB_DBG_STAGES")) p.stages = atoi(e);
     if (const char* e = getenv("USB_DBG_FLAGS")) p.dbg_flags = atoi(e);
     if (const char* e = getenv("USB_DBG_BH")) {
@@ -270,8 +272,9 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     if (p.swap_ab)
         USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BW >= 64 ? 1 : 64 / p.BW,
                              p.BW >= 64 ? 64 : p.BW));
-    else
-        USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BH, p.BW));
+    else   // per-warp stores: 32 pixels (one TMEM lane quarter) x 64 channels
+        USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BW >= 32 ? 1 : 32 / p.BW,
+                             p.BW >= 32 ? 32 : p.BW));
     return 0;
 }
 
