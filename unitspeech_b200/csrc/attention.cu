@@ -22,6 +22,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kDh = 32;                             // dim_head
 constexpr int kPartStride = kDh * kDh + 2 * kDh;    // ctx + m + s
 constexpr int kWarpTile = 64;                       // positions staged per warp iteration
+constexpr int kFoldRows = 32;                       // output channels per fold block
 constexpr int kRowHalfs = 40;                       // 32 halfs + 8 pad: 80-byte rows make ldmatrix conflict-free
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -52,13 +53,12 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const AttnParams p, i
     __shared__ float mmax[kDh];
 
     const int chunk_id = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
-    const int hidden = p.heads * kDh;
-    const int ld = 3 * hidden;
+    const int ld = p.ld;
     const int p0 = chunk_id * p.chunk;
     const int p1 = min(p.P, p0 + p.chunk);
     const __half* base = p.qkv + static_cast<long long>(n) * p.P * ld;
-    const int koff = hidden + head * kDh;
-    const int voff = 2 * hidden + head * kDh;
+    const int koff = p.koff + head * kDh;
+    const int voff = p.voff + head * kDh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- chunk-local max of k per d: thread = (position slice, 8 channels)
@@ -229,29 +229,69 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnParams p, int
     }
 }
 
-// grid (ceil(C/64), N): Weff[n][co][h*32+d] = sum_e Wo[co][h*32+e] * ctx[n][h][d][e] for 64 output channels
+// grid (ceil(C/32), N): Weff[n][co][h*32+d] = sum_e Wo[co][h*32+e] * ctx[n][h][d][e] for 32 output channels.
+// Plain mode writes Weff (fp16).  Fused-q mode goes on to W'[n][co][c] = g * sum_d' Weff[co][d'] Wq[d'][c] + (co == c),
+// the per-sample 1x1 weight of the whole Residual(Rezero(LinearAttention)) block, and b' = g * b_o.
 __global__ void __launch_bounds__(256) attn_fold_kernel(const AttnParams p, const float* ctx_in) {
-    extern __shared__ float ctx[];  // [heads][32][33]
+    extern __shared__ float sm[];   // ctx [heads][32][33], then weff tile [32][hidden + 1]
     const int n = blockIdx.y, tid = threadIdx.x;
     const int heads = p.heads, hidden = heads * kDh;
+    float* ctx = sm;
+    float* wt = sm + heads * kDh * (kDh + 1);
     const float* cn = ctx_in + static_cast<long long>(n) * heads * kDh * kDh;
     for (int i = tid; i < heads * kDh * kDh; i += 256) {
         const int hd = i >> 5, e = i & 31;
         ctx[hd * (kDh + 1) + e] = cn[i];
     }
     __syncthreads();
-    const int co0 = blockIdx.x * 64;
-    for (int i = tid; i < 64 * hidden; i += 256) {
-        const int co = co0 + i / hidden;
-        if (co >= p.C) break;
+    const int co0 = blockIdx.x * kFoldRows;
+    for (int i = tid; i < kFoldRows * hidden; i += 256) {
+        const int r = i / hidden, co = co0 + r;
         const int k = i % hidden, h = k / kDh, d = k % kDh;
-        const float* w = p.wo + static_cast<long long>(co) * hidden + h * kDh;
-        const float* c = ctx + (h * kDh + d) * (kDh + 1);
         float a = 0.f;
+        if (co < p.C) {
+            const float* w = p.wo + static_cast<long long>(co) * hidden + h * kDh;
+            const float* c = ctx + (h * kDh + d) * (kDh + 1);
 #pragma unroll 8
-        for (int e = 0; e < kDh; ++e) a += __ldg(w + e) * c[e];
-        p.weff[(static_cast<long long>(n) * p.C + co) * hidden + k] = __float2half_rn(a);
+            for (int e = 0; e < kDh; ++e) a += __ldg(w + e) * c[e];
+            if (!p.wq) p.weff[(static_cast<long long>(n) * p.C + co) * hidden + k] = __float2half_rn(a);
+        }
+        wt[r * (hidden + 1) + k] = a;
     }
+    if (!p.wq) return;
+    __syncthreads();
+    // W'[co0 + r][c] for the block's 32 rows: thread = column c, RPT rows each, Wq streamed once per thread
+    const int groups = 256 / p.C;                 // C in {64, 128, 256}
+    const int rpt = kFoldRows / groups;           // rows per thread: 8, 16 or 32
+    const int c = tid % p.C, r0 = (tid / p.C) * rpt;
+    const float g = __ldg(p.g);
+    float acc[kFoldRows];
+#pragma unroll
+    for (int r = 0; r < kFoldRows; ++r) acc[r] = 0.f;
+    for (int d0 = 0; d0 < hidden; d0 += 8) {
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __ldg(p.wq + static_cast<long long>(d0 + i) * p.C + c);
+#pragma unroll
+        for (int r = 0; r < kFoldRows; ++r) {
+            if (r < rpt) {
+                const float* wr = wt + (r0 + r) * (hidden + 1) + d0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[r] = fmaf(wr[i], w[i], acc[r]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kFoldRows; ++r) {
+        if (r < rpt) {
+            const int co = co0 + r0 + r;
+            if (co < p.C)
+                p.weff[(static_cast<long long>(n) * p.C + co) * p.C + c] =
+                    __float2half_rn(acc[r] * g + (co == c ? 1.f : 0.f));
+        }
+    }
+    if (n == 0)
+        for (int r = tid; r < kFoldRows && co0 + r < p.C; r += 256) p.bprime[co0 + r] = g * __ldg(p.bo + co0 + r);
 }
 
 int launch_attn_context(const AttnParams& p, cudaStream_t s) {
@@ -267,8 +307,8 @@ int launch_attn_context(const AttnParams& p, cudaStream_t s) {
     attn_merge_kernel<<<g2, 256, 0, s>>>(p, nchunks, ctx);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    dim3 g3((p.C + 63) / 64, p.N);
-    attn_fold_kernel<<<g3, 256, p.heads * kDh * (kDh + 1) * sizeof(float), s>>>(p, ctx);
+    dim3 g3((p.C + kFoldRows - 1) / kFoldRows, p.N);
+    attn_fold_kernel<<<g3, 256, (p.heads * kDh * (kDh + 1) + kFoldRows * (p.heads * kDh + 1)) * sizeof(float), s>>>(p, ctx);
     return (int)cudaGetLastError();
 }
 

@@ -300,6 +300,10 @@ struct ResnetW {
 struct AttnW {
     std::string prefix;
     int C = 0;
+    bool fused_q = false;  // C <= 256: q is never materialised (see AttnParams)
+    ConvW kv;              // fused_q: rows [hidden, 3*hidden) of to_qkv
+    float* wq = nullptr;   // fused_q: rows [0, hidden) of to_qkv, fp32 [hidden][C]
+    float* bprime = nullptr;
     ConvW qkv;
     float* wo = nullptr;  // [C][128]
     float* bo = nullptr;  // [C]
@@ -441,7 +445,22 @@ static int load_resnet(usb_handle* h, const std::string& prefix, int Cin, int Co
 static int load_attn(usb_handle* h, const std::string& prefix, int C, AttnW& a) {
     a.prefix = prefix;
     a.C = C;
-    USB_TRY(load_conv(h, prefix + ".fn.fn.to_qkv", K1, 3 * h->hidden, C, false, a.qkv));
+    static const bool no_fuse = getenv("USB_NO_FUSED_Q") != nullptr;
+    a.fused_q = C <= 256 && !no_fuse;
+    if (a.fused_q) {
+        const HostParam* p;
+        const int hid = h->hidden;
+        USB_TRY(get_param(h, prefix + ".fn.fn.to_qkv.weight", &p, (size_t)3 * hid * C));
+        std::vector<__half> packed;
+        pack_conv_host(K1, p->data.data() + (size_t)hid * C, 2 * hid, C, packed);   // k and v rows
+        USB_TRY(upload(h, packed.data(), packed.size(), &a.kv.w));
+        a.kv.Cout = 2 * hid; a.kv.Cin = C; a.kv.kind = K1; a.kv.Z = 1; a.kv.K = C;
+        USB_TRY(upload(h, p->data.data(), (size_t)hid * C, &a.wq));                  // q rows, fp32
+        std::vector<float> zeros(C, 0.f);
+        USB_TRY(upload(h, zeros.data(), zeros.size(), &a.bprime));
+    } else {
+        USB_TRY(load_conv(h, prefix + ".fn.fn.to_qkv", K1, 3 * h->hidden, C, false, a.qkv));
+    }
     USB_TRY(upload_param(h, prefix + ".fn.fn.to_out.weight", (size_t)C * h->hidden, &a.wo));
     USB_TRY(upload_param(h, prefix + ".fn.fn.to_out.bias", C, &a.bo));
     USB_TRY(upload_param(h, prefix + ".fn.g", 1, &a.g));
@@ -597,7 +616,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         o_qkv[l] = b.take(PC[l] * 3 * hid * sizeof(__half));
         o_xin[l] = l > 0 ? b.take(PC[l] * h->C[l - 1] * sizeof(__half)) : 0;
         o_upx[l] = l < L - 1 ? b.take(PC[l] * h->C[l] * sizeof(__half)) : 0;
-        o_weff[l] = b.take((size_t)Be * h->C[l] * hid * sizeof(__half));
+        o_weff[l] = b.take((size_t)Be * h->C[l] * (h->C[l] <= 256 ? 256 : hid) * sizeof(__half));
         o_mask[l] = b.take((size_t)Be * W[l] * sizeof(float));
         const size_t part = attn_scratch_bytes(Be, h->heads, H[l] * W[l], kAttnChunk);
         if (part > max_part) max_part = part;
@@ -682,11 +701,24 @@ static int build_plan(usb_handle* h, int Be, int T) {
     // Residual(Rezero(LinearAttention)) (unitspeech.py:36-43,78-106), output stored masked
     auto push_attn = [&](const AttnW& a, int l, const __half* x, __half* out) -> int {
         __half *qkv = HP(o_qkv[l]), *weff = HP(o_weff[l]);
-        ConvEpilogue e1;
-        USB_TRY(push_conv(K1, x, a.C, a.C, nullptr, 0, 0, l, &a.qkv, nullptr, 0, 0, 3 * hid, e1, qkv));
         AttnParams ap;
-        ap.qkv = qkv; ap.wo = a.wo; ap.part = part; ap.weff = weff; ap.N = Be; ap.P = H[l] * W[l]; ap.C = a.C;
-        ap.heads = h->heads; ap.chunk = kAttnChunk;
+        memset(&ap, 0, sizeof ap);
+        ap.wo = a.wo; ap.part = part; ap.weff = weff; ap.N = Be; ap.P = H[l] * W[l]; ap.C = a.C;
+        ap.heads = h->heads; ap.chunk = kAttnChunk; ap.g = a.g; ap.bo = a.bo; ap.qkv = qkv;
+        ConvEpilogue e1;
+        if (a.fused_q) {
+            // kv = W_kv x; context from (k, v); the block's output is one per-sample 1x1 conv on x (no q, no residual read)
+            USB_TRY(push_conv(K1, x, a.C, a.C, nullptr, 0, 0, l, &a.kv, nullptr, 0, 0, 2 * hid, e1, qkv));
+            ap.ld = 2 * hid; ap.koff = 0; ap.voff = hid; ap.wq = a.wq; ap.bprime = a.bprime;
+            pl.attns.push_back(ap);
+            pl.ops.push_back({Op::ATTN, (int)pl.attns.size() - 1});
+            ConvEpilogue e2;
+            e2.bias = a.bprime; e2.mask = pl.mask[l];
+            USB_TRY(push_conv(K1, x, a.C, a.C, nullptr, 0, 0, l, nullptr, weff, Be, 2, a.C, e2, out));
+            return 0;
+        }
+        USB_TRY(push_conv(K1, x, a.C, a.C, nullptr, 0, 0, l, &a.qkv, nullptr, 0, 0, 3 * hid, e1, qkv));
+        ap.ld = 3 * hid; ap.koff = hid; ap.voff = 2 * hid;
         pl.attns.push_back(ap);
         pl.ops.push_back({Op::ATTN, (int)pl.attns.size() - 1});
         ConvEpilogue e2;
@@ -1243,8 +1275,9 @@ int usb_op_attn_context(usb_handle* h, const void* qkv, const float* wo, void* w
     USB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     AttnParams ap;
+    memset(&ap, 0, sizeof ap);
     ap.qkv = static_cast<const __half*>(qkv); ap.wo = wo; ap.weff = static_cast<__half*>(weff); ap.N = N; ap.P = P;
-    ap.C = C; ap.heads = heads; ap.chunk = kAttnChunk;
+    ap.C = C; ap.heads = heads; ap.chunk = kAttnChunk; ap.ld = 3 * heads * 32; ap.koff = heads * 32; ap.voff = 2 * heads * 32;
     const size_t part_bytes = attn_scratch_bytes(N, heads, P, kAttnChunk);
     float* part = nullptr;
     USB_CUDA(cudaMalloc(&part, part_bytes));

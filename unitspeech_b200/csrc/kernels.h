@@ -85,10 +85,17 @@ int launch_embed(const EmbedParams& p, cudaStream_t s);
 
 // ---- LinearAttention context: softmax over positions of k, ctx = k_sm^T v, folded with to_out  (unitspeech.py:86-96)
 struct AttnParams {
-    const __half* qkv;     // [N][P][3*hidden], channel = qkv*hidden + head*dh + c
+    const __half* qkv;     // [N][P][ld] fp16; k channels at koff + head*dh, v channels at voff + head*dh
+    int ld, koff, voff;
     const float* wo;       // [C][hidden] to_out weight
     float* part;           // scratch of attn_scratch_bytes(): [N][heads][chunks][dh*dh + 2*dh] partials + merged ctx
-    __half* weff;          // [N][C][hidden] folded per-sample weight (K-major B operand of the to_out GEMM)
+    __half* weff;          // plain mode: [N][C][hidden] folded per-sample weight (K-major B operand of the to_out GEMM)
+    // fused-q mode (wq != null): the whole block collapses to one per-sample 1x1 conv on x,
+    //   attn(x)*g + x = (g * Weff[n] * Wq + I) x + g*b_o;  weff then is [N][C][C] and bprime [C]
+    const float* wq;       // [hidden][C] query rows of to_qkv, or null
+    const float* g;        // Rezero scalar (device)
+    const float* bo;       // [C] to_out bias
+    float* bprime;         // [C] g * b_o
     int N, P, C, heads, chunk;   // dh = 32, hidden = heads*32
 };
 int attn_chunks(int P, int chunk);
