@@ -473,11 +473,16 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
         const int c = ew * 32 + lane;             // output channel within the 128-channel tile
         const int bw_shift = 31 - __clz(p.BW);
         const int cpg = p.stats ? p.Cout / p.groups : 16;
-        const uint32_t stage_buf = tiles_base + stages * kStageBytes + static_cast<uint32_t>(grp) * 16384u;
-        // staging layout per group: [slab = c/64][64 pixel rows][128 B], 128-byte swizzle on the 16-byte chunk index
-        const uint32_t slab_base = stage_buf + static_cast<uint32_t>(c >> 6) * 8192u + static_cast<uint32_t>(c & 7) * 2u;
-        const uint32_t chunk = static_cast<uint32_t>((c & 63) >> 3);
-        const int bar_id = 1 + grp;
+        // per-warp staging: 64 pixel rows x 32 channels (64 B rows, 64-byte swizzle) = 4 KB, stored by the warp's own
+        // TMA (box {32 ch, 64 px}), so the epilogue needs no cross-warp barrier
+        const uint32_t warp_buf = tiles_base + stages * kStageBytes + static_cast<uint32_t>(grp * 4 + ew) * 4096u;
+        // element (row j, channel lane): byte = j*64 + ((lane>>3) ^ ((j>>1)&3))*16 + (lane&7)*2; the XOR term only depends
+        // on (j>>1)&3, so four per-thread bases + a compile-time row offset address every element
+        uint32_t sbase[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            sbase[q] = warp_buf + ((static_cast<uint32_t>(lane >> 3) ^ static_cast<uint32_t>(q)) << 4) +
+                       static_cast<uint32_t>(lane & 7) * 2u;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int ph = tile / tiles_per_phase;
@@ -498,12 +503,14 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
             const float bias = p.bias ? __ldg(p.bias + cg) : 0.f;
             long long* stats_n = p.stats ? p.stats + static_cast<long long>(pc.n) * p.groups * 2 : nullptr;
             const float* mrow = p.mask ? p.mask + static_cast<long long>(pc.n) * p.mask_stride + p.ox_off[ph] : nullptr;
-            if (mrow) {   // published to the group by the "staging buffer free" barrier below
-                const int et = ew * 32 + lane;
-                if (et < p.BW) mask_s[grp][et] = et < wlim ? __ldg(mrow + (pc.x0 + et) * p.ox_mul) : 0.f;
-            }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
             float s = 0.f, ss = 0.f;
+            const bool full = wlim >= p.BW;       // every pixel column of the patch lies inside the image
+            if (mrow) {
+                const int et = lane + ew * 32;    // any 128 threads of the group cover BW <= 128 columns
+                if (et < p.BW) mask_s[grp][et] = et < wlim ? __ldg(mrow + (pc.x0 + et) * p.ox_mul) : 0.f;
+                named_bar_sync(1 + grp, 128);
+            }
             for (int hc = 0; hc < 2; ++hc) {
                 const int pb = hc * 64;           // first pixel of this 64-pixel sub-block inside the patch
                 uint32_t v0[32], v1[32];
@@ -514,34 +521,36 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                     tc_fence_before();
                     mbar_arrive_a(tempty0 + as * 8);
                 }
-                named_bar_sync(bar_id, 128);   // staging buffer free (previous stores have been read)
+                if (lane == 0) tma_store_wait_read<0>();   // the warp's staging buffer has been read by its last store
+                __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 64; ++j) {
                     float f = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]) + bias;
-                    const int tx = (pb + j) & (p.BW - 1);
-                    const bool valid = tx < wlim;
-                    if (stats_n && valid) {
-                        s += f;
-                        ss = fmaf(f, f, ss);
+                    if (stats_n) {
+                        if (full) {
+                            s += f;
+                            ss = fmaf(f, f, ss);
+                        } else if (((pb + j) & (p.BW - 1)) < wlim) {
+                            s += f;
+                            ss = fmaf(f, f, ss);
+                        }
                     }
-                    if (mrow) f *= mask_s[grp][tx];
-                    const __half h = __float2half_rn(fminf(fmaxf(f, -65504.f), 65504.f));
-                    const uint32_t addr = slab_base + static_cast<uint32_t>(j) * 128u + ((chunk ^ (j & 7)) << 4);
-                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__half_as_ushort(h)) : "memory");
+                    if (mrow) f *= mask_s[grp][(pb + j) & (p.BW - 1)];
+                    unsigned short hbits;
+                    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hbits) : "f"(f));
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(sbase[(j >> 1) & 3] + j * 64), "h"(hbits) : "memory");
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(bar_id, 128);
-                if (ew == 0 && elect_one()) {
+                __syncwarp();
+                if (lane == 0) {
                     const int yb = pc.y0 + (pb >> bw_shift);
                     const int xb = pc.x0 + (pb & (p.BW - 1));
-                    const int cph = p.ox_off[ph] * p.out_c_phase_mul + nt * 128;
-                    tma_store_5d_a(&map_out, stage_buf, cph, xb, p.oy_off[ph], yb, pc.n);
-                    tma_store_5d_a(&map_out, stage_buf + 8192u, cph + 64, xb, p.oy_off[ph], yb, pc.n);
+                    const int cph = p.ox_off[ph] * p.out_c_phase_mul + nt * 128 + ew * 32;
+                    tma_store_5d_a(&map_out, warp_buf, cph, xb, p.oy_off[ph], yb, pc.n);
                     tma_store_commit();
-                    tma_store_wait_read<0>();
                 }
-                __syncwarp();
             }
+            if (mrow) named_bar_sync(1 + grp, 128);   // mask_s is rewritten by the next tile
             if (stats_n) {
                 // channels of one GroupNorm group are adjacent lanes; a warp holds 32 channels = 32/cpg groups
                 // (or part of one group when cpg >= 32)
@@ -559,7 +568,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                 }
             }
         }
-        if (ew == 0 && elect_one()) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();

@@ -65,10 +65,10 @@ static int load_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[256];
@@ -83,7 +83,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 // 5-D activation view (c', x, p, y, n) of an NHWC fp16 tensor [N][H][W][Ctot], channels [0, Cview) visible.
 // stride2: parity split for stride-2 convs: c' = (x&1)*Ctot + c, x' = x/2, p = y&1, y' = y/2.
 static int make_act_map(CUtensorMap* m, const __half* base, int N, int H, int W, int Ctot, int Cview, bool stride2,
-                        int BH, int BW) {
+                        int BH, int BW, int box_c = 64) {
     cuuint64_t dims[5], strides[4];
     const cuuint64_t e = 2;
     if (!stride2) {
@@ -95,8 +95,8 @@ static int make_act_map(CUtensorMap* m, const __half* base, int N, int H, int W,
         strides[0] = 2 * Ctot * e; strides[1] = (cuuint64_t)W * Ctot * e; strides[2] = (cuuint64_t)2 * W * Ctot * e;
         strides[3] = (cuuint64_t)H * W * Ctot * e;
     }
-    cuuint32_t box[5] = {64, (cuuint32_t)BW, 1, (cuuint32_t)BH, 1};
-    return encode_map(m, base, 5, dims, strides, box);
+    cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)BW, 1, (cuuint32_t)BH, 1};
+    return encode_map(m, base, 5, dims, strides, box, box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // weights [Z][Cout][K] fp16, K contiguous
@@ -269,9 +269,9 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, p.BN));
     // output tile store: plain view, or the parity view of the upsampled tensor for the transposed conv;
     // the swapped kernel stores 64-pixel sub-blocks (64 / BW image rows) per TMA
-    if (p.swap_ab)
+    if (p.swap_ab)   // per-warp stores: 64 pixels x 32 channels (64-byte rows, SWIZZLE_64B)
         USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BW >= 64 ? 1 : 64 / p.BW,
-                             p.BW >= 64 ? 64 : p.BW));
+                             p.BW >= 64 ? 64 : p.BW, 32));
     else   // per-warp stores: 32 pixels (one TMEM lane quarter) x 64 channels
         USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BW >= 32 ? 1 : 32 / p.BW,
                              p.BW >= 32 ? 32 : p.BW));
