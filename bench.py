@@ -174,7 +174,7 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -204,12 +204,12 @@ def run_gpu_arm(args):
     z, mask, cond, spk, noise = make_inputs(100 + rank, B, T, n)
     host = [t.pin_memory() for t in (z, mask, cond, spk, noise)]
     zd, md, cd, sd, nd = (t.to(dev) for t in (z, mask, cond, spk, noise))
-    gathered = [torch.empty(B, N_FEATS, T, device=dev) for _ in range(world)] if world > 1 else None
+    from unitspeech_b200.sharding import gather_utterances
 
     def one_pass():
         out = dec(zd, md, cd, sd, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=nd)
         if world > 1:
-            dist.all_gather(gathered, out)
+            gather_utterances(out, world * B)      # the job's mels on every rank (NCCL all_gather)
         return out
 
     def sync():
@@ -267,7 +267,7 @@ def run_gpu_arm(args):
         # ---- roofline: one profiled pass of the same workload (per-launch CUDA events on the launching stream)
         peaks = _peaks()
         dec.set_profiling(True)
-        one_pass()
+        dec(zd, md, cd, sd, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=nd)   # rank-local: no collective here
         torch.cuda.synchronize(dev)
         prof = dec.get_profile()
         dec.set_profiling(False)
@@ -325,10 +325,34 @@ def run_gpu_arm(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        _emit(line)
 
 
 def main():
+    # Only the JSON line may reach stdout: libraries (e.g. NCCL's version banner) print there too, so fd 1 is pointed at
+    # stderr for the duration of the run and restored for the final print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _RESULT_LINE is not None:
+        print(_RESULT_LINE, flush=True)
+
+
+_RESULT_LINE = None
+
+
+def _emit(line: dict) -> None:
+    global _RESULT_LINE
+    _RESULT_LINE = json.dumps(line)
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

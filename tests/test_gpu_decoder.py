@@ -162,3 +162,20 @@ def test_state_dict_roundtrip_and_reload():
     assert float((a - b).abs().max()) > 1e-4          # weights really changed
     mx, mn = _errs(b, ref)
     assert mx <= MAX_TOL and mn <= MEAN_TOL
+
+
+def test_long_odd_width_utterances_and_microbatching():
+    """T = 1000 (widths 1000/500/250/125: ragged tiles at every level) and automatic micro-batching of a large batch."""
+    B, T, n, s = 3, 1000, 2, 1.0 / 512
+    p = O.harness_params(seed=1234, out_scale=s)
+    z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=9, scale=s, lengths=(1000, 777, 1000))
+    ref = O.reverse_diffusion(p, z[:2], mask[:2], cond[:2], spk[:2], n, 1.0, 1.0, noise=noise[:, :2])
+    dec = _decoder(128, (1, 2, 4, 8), p)
+    full = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, 1.0, 1.0, noise=noise.cuda())
+    mx, mn = _errs(full[:2], ref)
+    print(f"T=1000: rel max-abs {mx:.3e} mean-abs {mn:.3e}")
+    assert mx <= MAX_TOL and mn <= MEAN_TOL
+    assert float(full[1, :, 777:].abs().max()) == 0.0
+    dec.max_rows_frames = 3 * 1000          # forces one utterance per library call
+    chunked = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, 1.0, 1.0, noise=noise.cuda())
+    assert torch.equal(chunked, full)       # micro-batching is exact (bitwise batch invariance)

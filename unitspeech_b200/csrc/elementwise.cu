@@ -121,8 +121,13 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
             b3[i] = __ldg(p.b3 + c0 + i);
             b1[i] = __ldg(p.b1 + c0 + i);
         }
-        float s = 0.f, ss = 0.f;
+        // GroupNorm partials: one fp32 partial per (warp, row tile, group) -- a partition that does not depend on
+        // the launch geometry -- converted to fixed point and accumulated as integers (bitwise batch invariance)
+        const int cpg = C / p.groups;
+        const int lpg = cpg / CL;  // lanes per group (power of two, <= 32); lanes of one group are adjacent
+        long long is = 0, iss = 0;
         for (int t = t_begin; t < t_end; ++t) {
+            float s = 0.f, ss = 0.f;
             const int y = t / tiles_x;
             const int x0 = (t - y * tiles_x) * TW;
             __syncthreads();   // previous tile fully consumed
@@ -182,18 +187,17 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
                     *reinterpret_cast<uint32_t*>(p.res + o) = pack2(rr[0], rr[1]);
                 }
             }
-        }
-        // GroupNorm partials of this pass: lanes of one group are adjacent (cpg / CL lanes)
-        const int cpg = C / p.groups;
-        const int lpg = cpg / CL;  // lanes per group (power of two, <= 32)
-        for (int o = lpg >> 1; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            for (int o = lpg >> 1; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            }
+            is += __float2ll_rn(s * kStatSumScale);
+            iss += __float2ll_rn(ss * kStatSqScale);
         }
         if ((lane & (lpg - 1)) == 0) {
             const int g = c0 / cpg;
-            atomicAdd(&gsum[g * 2], static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
-            atomicAdd(&gsum[g * 2 + 1], static_cast<unsigned long long>(__float2ll_rn(ss * kStatSqScale)));
+            atomicAdd(&gsum[g * 2], static_cast<unsigned long long>(is));
+            atomicAdd(&gsum[g * 2 + 1], static_cast<unsigned long long>(iss));
         }
     }
     __syncthreads();
@@ -411,39 +415,45 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// one block per row: sinusoidal embedding -> Linear -> Mish -> Linear -> cat speaker -> Mish
+// one block per row: sinusoidal embedding -> Linear -> Mish -> Linear -> cat speaker -> Mish.
+// p.t == null: the time half of u is 0; p.spk == null: the speaker half is 0 (Mish(0) = 0), which lets the caller
+// split the stacked Linear into a per-step part and a per-row part.
 __global__ void __launch_bounds__(256) time_mlp_kernel(const EmbedParams p) {
     extern __shared__ float sm[];  // e[dim], h[4*dim], tm[dim]
     float* e = sm;
     float* h = sm + p.dim;
     float* tm = h + 4 * p.dim;
     const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int half = p.dim / 2;
-    const float ts = p.pe_scale * p.t[n];
-    for (int j = threadIdx.x; j < half; j += blockDim.x) {
-        const float arg = ts * p.freqs[j];
-        e[j] = sinf(arg);
-        e[j + half] = cosf(arg);
-    }
-    __syncthreads();
-    for (int i = warp; i < 4 * p.dim; i += 8) {
-        float acc = 0.f;
-        for (int j = lane; j < p.dim; j += 32) acc += p.w0[static_cast<long long>(i) * p.dim + j] * e[j];
-        acc = warp_sum_f(acc);
-        if (lane == 0) h[i] = mish_precise(acc + p.b0[i]);
-    }
-    __syncthreads();
-    for (int i = warp; i < p.dim; i += 8) {
-        float acc = 0.f;
-        for (int j = lane; j < 4 * p.dim; j += 32) acc += p.w2[static_cast<long long>(i) * 4 * p.dim + j] * h[j];
-        acc = warp_sum_f(acc);
-        if (lane == 0) tm[i] = acc + p.b2[i];
-    }
-    __syncthreads();
     const int K = p.dim + p.S;
+    if (p.t) {
+        const int half = p.dim / 2;
+        const float ts = p.pe_scale * p.t[n];
+        for (int j = threadIdx.x; j < half; j += blockDim.x) {
+            const float arg = ts * p.freqs[j];
+            e[j] = sinf(arg);
+            e[j + half] = cosf(arg);
+        }
+        __syncthreads();
+        for (int i = warp; i < 4 * p.dim; i += 8) {
+            float acc = 0.f;
+            for (int j = lane; j < p.dim; j += 32) acc += p.w0[static_cast<long long>(i) * p.dim + j] * e[j];
+            acc = warp_sum_f(acc);
+            if (lane == 0) h[i] = mish_precise(acc + p.b0[i]);
+        }
+        __syncthreads();
+        for (int i = warp; i < p.dim; i += 8) {
+            float acc = 0.f;
+            for (int j = lane; j < 4 * p.dim; j += 32) acc += p.w2[static_cast<long long>(i) * 4 * p.dim + j] * h[j];
+            acc = warp_sum_f(acc);
+            if (lane == 0) tm[i] = acc + p.b2[i];
+        }
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
-        const float v = i < p.dim ? tm[i] : p.spk[static_cast<long long>(n) * p.S + (i - p.dim)];
-        p.u[static_cast<long long>(n) * K + i] = mish_precise(v);
+        float v;
+        if (i < p.dim) v = p.t ? mish_precise(tm[i]) : 0.f;
+        else v = p.spk ? mish_precise(p.spk[static_cast<long long>(n) * p.S + (i - p.dim)]) : 0.f;
+        p.u[static_cast<long long>(n) * K + i] = v;
     }
 }
 
@@ -454,7 +464,7 @@ __global__ void __launch_bounds__(256) emb_linear_kernel(const EmbedParams p) {
     if (j >= p.J) return;
     const int K = p.dim + p.S;
     const float* w = p.wcat + static_cast<long long>(j) * K;
-    const float bj = p.bcat[j];
+    const float bj = p.bcat ? p.bcat[j] : 0.f;
     for (int n = 0; n < p.N; ++n) {
         const float* u = p.u + static_cast<long long>(n) * K;
         float acc = 0.f;
@@ -484,6 +494,18 @@ __global__ void downsample_mask_kernel(const float* src, float* dst, int N, int 
 int launch_downsample_mask(const float* src, float* dst, int N, int Wsrc, int Wdst, cudaStream_t s) {
     const int total = N * Wdst;
     downsample_mask_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, dst, N, Wsrc, Wdst);
+    return (int)cudaGetLastError();
+}
+
+// E[n][j] = T[j] + S[n][j]: per-step time part + per-row speaker part of the stacked ResnetBlock.mlp Linears
+__global__ void emb_combine_kernel(const float* t_part, const float* s_part, float* e, int N, int J) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(N) * J) return;
+    e[i] = t_part[i % J] + s_part[i];
+}
+int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, cudaStream_t s) {
+    const long long total = static_cast<long long>(N) * J;
+    emb_combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(t_part, s_part, e, N, J);
     return (int)cudaGetLastError();
 }
 

@@ -332,6 +332,7 @@ struct Plan {
     float* t_rows = nullptr;      // [Be]
     float* u = nullptr;           // [Be][dim+S]
     float* E = nullptr;           // [Be][J]
+    float* Spart = nullptr;       // [Be][J] speaker part of the embedding Linears (sampler path)
     long long* stats = nullptr;   // [slots][Be][groups][2] fixed point
     size_t stats_bytes = 0;
     __half* final_raw = nullptr;
@@ -365,6 +366,8 @@ struct usb_handle {
     float *wcat = nullptr, *bcat = nullptr;
     int J = 0;
     Plan plan;
+    float* tpart_buf = nullptr;   // sampler: [n_steps] t, [n_steps][dim+S] u, [n_steps][J] time part
+    size_t tpart_cap = 0;
     long long launches = 0;
     // optional per-kernel-class timing (bench.py roofline): events around every launch of a profiled call
     bool profiling = false;
@@ -625,6 +628,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
     const size_t o_xrow = b.take(Be * sizeof(int)), o_murow = b.take(Be * sizeof(int));
     const size_t o_spk = b.take((size_t)Be * S * sizeof(float)), o_t = b.take(Be * sizeof(float));
     const size_t o_u = b.take((size_t)Be * (dim + S) * sizeof(float)), o_E = b.take((size_t)Be * h->J * sizeof(float));
+    const size_t o_Sp = b.take((size_t)Be * h->J * sizeof(float));
     pl.stats_bytes = (size_t)n_slots * Be * G * 2 * sizeof(long long);
     const size_t o_stats = b.take(pl.stats_bytes);
     const size_t o_xt = b.take((size_t)Be * c.n_feats * T * sizeof(float));
@@ -646,6 +650,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
     pl.t_rows = reinterpret_cast<float*>(A + o_t);
     pl.u = reinterpret_cast<float*>(A + o_u);
     pl.E = reinterpret_cast<float*>(A + o_E);
+    pl.Spart = reinterpret_cast<float*>(A + o_Sp);
     pl.stats = reinterpret_cast<long long*>(A + o_stats);
     pl.xt = reinterpret_cast<float*>(A + o_xt);
     float* part = reinterpret_cast<float*>(A + o_part);
@@ -867,14 +872,28 @@ static int prepare_masks(usb_handle* h, cudaStream_t s) {
 }
 
 // everything up to and including the final_block conv
-static int run_estimator(usb_handle* h, const EstInputs& in, cudaStream_t s) {
+static EmbedParams embed_params(usb_handle* h) {
+    const usb_config& c = h->cfg;
+    EmbedParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.freqs = h->freqs; ep.w0 = h->mlp_w0; ep.b0 = h->mlp_b0; ep.w2 = h->mlp_w2; ep.b2 = h->mlp_b2;
+    ep.wcat = h->wcat; ep.bcat = h->bcat; ep.dim = c.dim; ep.S = c.spk_emb_dim; ep.J = h->J; ep.pe_scale = c.pe_scale;
+    return ep;
+}
+
+static int run_estimator(usb_handle* h, const EstInputs& in, cudaStream_t s, const float* t_part = nullptr) {
     Plan& pl = h->plan;
     const usb_config& c = h->cfg;
+    if (t_part) {
+        // sampler path: E = (time part of this step, computed once per call) + (speaker part, once per call)
+        ProfScope ps(h, s, 3, 0.0);
+        USB_LAUNCH(h, launch_emb_combine(t_part, pl.Spart, pl.E, pl.Be, h->J, s));
+    }
     EmbedParams ep;
     ep.t = in.t_rows; ep.spk = in.spk_rows; ep.freqs = h->freqs; ep.w0 = h->mlp_w0; ep.b0 = h->mlp_b0;
     ep.w2 = h->mlp_w2; ep.b2 = h->mlp_b2; ep.wcat = h->wcat; ep.bcat = h->bcat; ep.u = pl.u; ep.e = pl.E;
     ep.N = pl.Be; ep.dim = c.dim; ep.S = c.spk_emb_dim; ep.J = h->J; ep.pe_scale = c.pe_scale;
-    {
+    if (!t_part) {
         ProfScope ps(h, s, 3, 0.0);
         USB_LAUNCH(h, launch_embed(ep, s));
         h->launches++;  // launch_embed issues two kernels
@@ -998,11 +1017,34 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
         mul_mask_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(z, mask, pl.xt, B, P, T);
         USB_LAUNCH(h, (int)cudaGetLastError());
     }
+    // The embedding Linears are linear in [Mish(time_mlp(t)), Mish(spk)]: the time part depends only on the step and
+    // the speaker part only on the row, so both are computed once per call (unitspeech.py:165-168,61,72).
+    const int Kemb = c.dim + S;
+    {
+        const size_t need = (size_t)n_steps * (1 + Kemb + h->J);
+        if (need > h->tpart_cap) {
+            USB_CUDA(cudaStreamSynchronize(s));
+            if (h->tpart_buf) cudaFree(h->tpart_buf);
+            h->tpart_buf = nullptr; h->tpart_cap = 0;
+            USB_CUDA(cudaMalloc(&h->tpart_buf, need * sizeof(float)));
+            h->tpart_cap = need;
+        }
+        float* d_t = h->tpart_buf;
+        float* d_ut = d_t + n_steps;
+        float* d_tp = d_ut + (size_t)n_steps * Kemb;
+        USB_CUDA(cudaMemcpyAsync(d_t, t_steps, n_steps * sizeof(float), cudaMemcpyHostToDevice, s));
+        EmbedParams et = embed_params(h);
+        et.t = d_t; et.spk = nullptr; et.u = d_ut; et.e = d_tp; et.N = n_steps;             // time part (+ bias)
+        USB_LAUNCH(h, launch_embed(et, s));
+        EmbedParams es = embed_params(h);
+        es.t = nullptr; es.spk = pl.spk_rows; es.u = pl.u; es.e = pl.Spart; es.N = Be; es.bcat = nullptr;   // speaker part
+        USB_LAUNCH(h, launch_embed(es, s));
+        h->launches += 2;
+    }
+    const float* d_tpart = h->tpart_buf + n_steps + (size_t)n_steps * Kemb;
     EstInputs in{pl.xt, cond, h->text_uncon, pl.t_rows, pl.spk_rows};
     for (int i = 0; i < n_steps; ++i) {
-        fill_kernel<<<(Be + 255) / 256, 256, 0, s>>>(pl.t_rows, t_steps[i], Be);
-        USB_LAUNCH(h, (int)cudaGetLastError());
-        USB_TRY(run_estimator(h, in, s));
+        USB_TRY(run_estimator(h, in, s, d_tpart + (size_t)i * h->J));
         FinalParams f = final_params(h, B, nb);
         f.a0 = nb == 3 ? tg : (use_t ? tg : sg);
         f.a1 = sg;
@@ -1074,6 +1116,7 @@ void usb_destroy(usb_handle* h) {
     free_plan(h->plan);
     for (void* p : h->dev_allocs) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->tpart_buf) cudaFree(h->tpart_buf);
     delete h;
 }
 

@@ -81,7 +81,8 @@ struct EmbedParams {
     int N, dim, S, J;
     float pe_scale;
 };
-int launch_embed(const EmbedParams& p, cudaStream_t s);
+int launch_embed(const EmbedParams& p, cudaStream_t s);   // t or spk may be null (that half of u is 0); bcat may be null
+int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, cudaStream_t s);
 
 // ---- LinearAttention context: softmax over positions of k, ctx = k_sm^T v, folded with to_out  (unitspeech.py:86-96)
 struct AttnParams {

@@ -146,6 +146,7 @@ class UnitSpeech(torch.nn.Module):
         self.spk_uncon = torch.nn.Parameter(torch.zeros(1, 1, spk_emb_dim))
         self.estimator = GradLogPEstimator2d(dim, dim_mults=dim_mults, pe_scale=pe_scale, spk_emb_dim=spk_emb_dim)
         object.__setattr__(self.estimator, "_owner", self)
+        self.max_rows_frames = 96 * 1000   # (CFG branches x utterances) x frames per library call; see reverse_diffusion
         self._handle = None
         self._handle_device = None
         self._weights_version = 0
@@ -286,6 +287,21 @@ class UnitSpeech(torch.nn.Module):
             noise = torch.stack([torch.randn(z.shape, dtype=z.dtype, device=z.device) for _ in range(n_timesteps)])
         if tuple(noise.shape) != (n_timesteps, B, F, T):
             raise ValueError("noise must have shape (n_timesteps, B, n_feats, T)")
+        # micro-batching: the workspace grows with (CFG branches x utterances x frames); split large batches so one call
+        # stays within `max_rows_frames` (about 35 GB at the default) -- utterances are independent, so this is exact
+        nb = 1 + (1 if float(text_gradient_scale) > 0 else 0) + (1 if float(spk_gradient_scale) > 0 else 0)
+        max_b = max(1, int(self.max_rows_frames) // (nb * T))
+        if B > max_b:
+            outs, traces = [], []
+            for b0 in range(0, B, max_b):
+                sl = slice(b0, min(B, b0 + max_b))
+                r = self.reverse_diffusion(z[sl], mask[sl], cond[sl], spk_emb[sl], n_timesteps, text_gradient_scale,
+                                           spk_gradient_scale, noise=noise[:, sl], trace=trace)
+                outs.append(r[0] if trace else r)
+                if trace:
+                    traces.append(r[1])
+            out = torch.cat(outs, 0)
+            return (out, torch.cat(traces, 1)) if trace else out
         coef = schedule.step_coefficients(n_timesteps, self.beta_min, self.beta_max).contiguous()
         times = schedule.step_times(n_timesteps).contiguous()
         tg, sg = float(text_gradient_scale), float(spk_gradient_scale)
