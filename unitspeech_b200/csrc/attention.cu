@@ -21,8 +21,8 @@ __device__ __forceinline__ float exp2f_ftz(float x) {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kDh = 32;                             // dim_head
 constexpr int kPartStride = kDh * kDh + 2 * kDh;    // ctx + m + s
-constexpr int kWarpTile = 64;                       // positions staged per warp iteration
 constexpr int kFoldRows = 32;                       // output channels per fold block
+constexpr int kCtxLd = kDh + 4;                     // 36: float4-aligned, conflict-free row stride
 constexpr int kRowHalfs = 40;                       // 32 halfs + 8 pad: 80-byte rows make ldmatrix conflict-free
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -41,59 +41,39 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
 
 int attn_chunks(int P, int chunk) { return (P + chunk - 1) / chunk; }
 
-// grid (chunks, heads, N), 128 threads = 4 warps; warp w takes positions p0 + w*64 + 256*i
-__global__ void __launch_bounds__(128) attn_partial_kernel(const AttnParams p, int nchunks) {
-    // per-warp staging tiles Ps (exp(k - m)) and Vs; the same memory holds the cross-warp reduction afterwards
-    __shared__ __align__(16) unsigned char sbuf[2 * 4 * kWarpTile * kRowHalfs * 2];
-    __half (*Ps)[kWarpTile][kRowHalfs] = reinterpret_cast<__half (*)[kWarpTile][kRowHalfs]>(sbuf);
-    __half (*Vs)[kWarpTile][kRowHalfs] =
-        reinterpret_cast<__half (*)[kWarpTile][kRowHalfs]>(sbuf + 4 * kWarpTile * kRowHalfs * 2);
-    float (*csum)[kDh][kDh + 1] = reinterpret_cast<float (*)[kDh][kDh + 1]>(sbuf);   // [4][32][33] after the loop
-    __shared__ float red[4][kDh];
-    __shared__ float mmax[kDh];
+// grid (chunks, N), one warp per head (<= 8 heads).  Each warp streams its head's 64-byte k and v slices with
+// cp.async into a double-buffered 32-position staging tile (the next tile is in flight while the current one is
+// reduced), keeps a running max per channel (online softmax) and accumulates ctx on mma.sync.
+constexpr int kTileP = 32;   // positions per warp tile
 
-    const int chunk_id = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256) attn_partial_kernel(const AttnParams p, int nchunks) {
+    // per warp: Kraw[2][32][40], V[2][32][40], P[32][40] halfs = 5 x 2560 B
+    extern __shared__ __align__(16) unsigned char sbuf[];
+    __shared__ float wscale_s[8][kDh];
+    const int chunk_id = blockIdx.x, n = blockIdx.y;
     const int ld = p.ld;
     const int p0 = chunk_id * p.chunk;
     const int p1 = min(p.P, p0 + p.chunk);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int head = warp;
     const __half* base = p.qkv + static_cast<long long>(n) * p.P * ld;
     const int koff = p.koff + head * kDh;
     const int voff = p.voff + head * kDh;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int kTileBytes = kTileP * kRowHalfs * 2;   // 2560
+    const uint32_t wbase = static_cast<uint32_t>(__cvta_generic_to_shared(sbuf)) + warp * 5 * kTileBytes;
+    const uint32_t kraw0 = wbase, vt0 = wbase + 2 * kTileBytes, pt = wbase + 4 * kTileBytes;
+    unsigned char* wptr = sbuf + warp * 5 * kTileBytes;
 
-    // ---- chunk-local max of k per d: thread = (position slice, 8 channels)
-    {
-        const int oct = tid & 3, sl = tid >> 2;   // 32 position slices
-        float m[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
-        for (int pos = p0 + sl; pos < p1; pos += 32) {
-            const uint4 kv = *reinterpret_cast<const uint4*>(base + static_cast<long long>(pos) * ld + koff + oct * 8);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&kv);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h2[i]);
-                m[2 * i] = fmaxf(m[2 * i], f.x);
-                m[2 * i + 1] = fmaxf(m[2 * i + 1], f.y);
-            }
-        }
-        // lanes with equal (lane & 3) hold the same channels: xor 4, 8, 16 within the warp, then across the 4 warps
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 4));
-            m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 8));
-            m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 16));
-        }
-        if (lane < 4) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = m[i];
-        }
-        __syncthreads();
-        if (tid < kDh) mmax[tid] = fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid]));
-        __syncthreads();
-    }
-
-    // ---- accumulate ctx[d][e] on tensor cores: A = P^T (d x pos), B = V (pos x e)
+    const int oct = lane & 3;          // this lane handles channels oct*8 .. oct*8+7 of positions (lane>>2) + 8*it
+    const int g = lane >> 2;
     float acc[2][4][4];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -101,57 +81,116 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const AttnParams p, i
         for (int b = 0; b < 4; ++b)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
-    const int oct = lane & 3;          // this lane stages channels oct*8 .. oct*8+7 of every position it touches
-    float mloc[8], ssum[8];
+    float mrun[8], ssum[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        mloc[i] = mmax[oct * 8 + i] * kLog2e;
+        mrun[i] = -INFINITY;
         ssum[i] = 0.f;
     }
-    const uint32_t ps_base = static_cast<uint32_t>(__cvta_generic_to_shared(&Ps[warp][0][0]));
-    const uint32_t vs_base = static_cast<uint32_t>(__cvta_generic_to_shared(&Vs[warp][0][0]));
-    // ldmatrix source rows: lane supplies row (lane & 7) of 8x8 matrix (lane >> 3)
     const int lm_r = lane & 7, lm_j = lane >> 3;
 
-    for (int t0 = p0 + warp * kWarpTile; t0 < p1; t0 += 4 * kWarpTile) {
-        // stage 64 positions: item = lane + 32*it -> position item/4, channel octet item%4 (= lane & 3)
+    auto issue = [&](int t0, int buf) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int pp = (lane >> 2) + it * 8;
+        for (int it = 0; it < kTileP / 8; ++it) {
+            const int pp = g + it * 8;
             const int pos = t0 + pp;
-            uint4 pk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-            if (pos < p1) {
-                const __half* row = base + static_cast<long long>(pos) * ld;
-                const uint4 kv = *reinterpret_cast<const uint4*>(row + koff + oct * 8);
-                vv = *reinterpret_cast<const uint4*>(row + voff + oct * 8);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&kv);
+            const bool ok = pos < p1;
+            const __half* row = base + static_cast<long long>(ok ? pos : p0) * ld;
+            const uint32_t off = buf * kTileBytes + (pp * kRowHalfs + oct * 8) * 2;
+            cp_async16(kraw0 + off, row + koff + oct * 8, ok);
+            cp_async16(vt0 + off, row + voff + oct * 8, ok);
+        }
+        cp_async_commit();
+    };
+
+    int buf = 0;
+    issue(p0, 0);
+    for (int t0 = p0; t0 < p1; t0 += kTileP, buf ^= 1) {
+        if (t0 + kTileP < p1) {
+            issue(t0 + kTileP, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        // tile max per channel: own 4 positions, then the 8 lanes sharing the channel octet
+        const unsigned char* kt = wptr + buf * kTileBytes;
+        uint4 kraw[kTileP / 8];
+        float tmax[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tmax[i] = -INFINITY;
+#pragma unroll
+        for (int it = 0; it < kTileP / 8; ++it) {
+            const int pp = g + it * 8;
+            kraw[it] = *reinterpret_cast<const uint4*>(kt + (pp * kRowHalfs + oct * 8) * 2);
+            if (t0 + pp < p1) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&kraw[it]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h2[i]);
+                    tmax[2 * i] = fmaxf(tmax[2 * i], f.x);
+                    tmax[2 * i + 1] = fmaxf(tmax[2 * i + 1], f.y);
+                }
+            }
+        }
+        float scale[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float m = tmax[i];
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+            const float mnew = fmaxf(mrun[i], m * kLog2e);
+            scale[i] = exp2f_ftz(mrun[i] - mnew);       // 0 on the first tile (mrun = -inf), 1 when unchanged
+            mrun[i] = mnew;
+            ssum[i] *= scale[i];
+        }
+        if (lane < 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wscale_s[warp][lane * 8 + i] = scale[i];
+        }
+        // P = exp2(k*log2e - mrun) in fp16 (rows beyond the chunk are zero)
+#pragma unroll
+        for (int it = 0; it < kTileP / 8; ++it) {
+            const int pp = g + it * 8;
+            uint4 pk = make_uint4(0, 0, 0, 0);
+            if (t0 + pp < p1) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&kraw[it]);
                 __half2 o2[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 f = __half22float2(h2[i]);
-                    o2[i] = __floats2half2_rn(exp2f_ftz(fmaf(f.x, kLog2e, -mloc[2 * i])),
-                                              exp2f_ftz(fmaf(f.y, kLog2e, -mloc[2 * i + 1])));
+                    o2[i] = __floats2half2_rn(exp2f_ftz(fmaf(f.x, kLog2e, -mrun[2 * i])),
+                                              exp2f_ftz(fmaf(f.y, kLog2e, -mrun[2 * i + 1])));
                     const float2 r = __half22float2(o2[i]);   // the normaliser sums the values the MMA sees
                     ssum[2 * i] += r.x;
                     ssum[2 * i + 1] += r.y;
                 }
                 pk = *reinterpret_cast<const uint4*>(o2);
             }
-            *reinterpret_cast<uint4*>(&Ps[warp][pp][oct * 8]) = pk;
-            *reinterpret_cast<uint4*>(&Vs[warp][pp][oct * 8]) = vv;
+            *reinterpret_cast<uint4*>(wptr + 4 * kTileBytes + (pp * kRowHalfs + oct * 8) * 2) = pk;
         }
         __syncwarp();
+        // rescale the accumulator rows this thread owns: d = mt*16 + g and + 8
 #pragma unroll
-        for (int ks = 0; ks < kWarpTile / 16; ++ks) {
+        for (int mt = 0; mt < 2; ++mt) {
+            const float sc0 = wscale_s[warp][mt * 16 + g], sc1 = wscale_s[warp][mt * 16 + g + 8];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                acc[mt][nt][0] *= sc0; acc[mt][nt][1] *= sc0;
+                acc[mt][nt][2] *= sc1; acc[mt][nt][3] *= sc1;
+            }
+        }
+        const uint32_t vs_base = vt0 + buf * kTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < kTileP / 16; ++ks) {
             const int pk0 = ks * 16;
             uint32_t a[2][4], b[4][2];
-            // A fragments (16 d x 16 pos) for d0 = 0 and 16: matrices (pos half, d half) read transposed
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 const int prow = pk0 + (lm_j >> 1) * 8 + lm_r, dcol = mt * 16 + (lm_j & 1) * 8;
-                ldmatrix_x4_trans(ps_base + (prow * kRowHalfs + dcol) * 2, a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+                ldmatrix_x4_trans(pt + (prow * kRowHalfs + dcol) * 2, a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
             }
-            // B fragments (16 pos x 8 e) for e0 = 0, 8, 16, 24: two n-tiles per ldmatrix.x4
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
                 const int prow = pk0 + (lm_j & 1) * 8 + lm_r, ecol = np * 16 + (lm_j >> 1) * 8;
@@ -163,21 +202,19 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const AttnParams p, i
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) mma_16816(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b[nt][0], b[nt][1]);
         }
-        __syncwarp();
+        __syncwarp();   // the tile buffers are rewritten by the next iterations' cp.async / P stores
     }
 
-    // ---- fixed-order reduction over the 4 warps (csum aliases the staging tiles: wait until every warp is done)
-    __syncthreads();
+    // ---- each warp owns one head: write its partial (ctx, max in the natural-log domain, normaliser)
+    float* out = p.part + ((static_cast<long long>(n) * p.heads + head) * nchunks + chunk_id) * kPartStride;
     {
-        const int g = lane >> 2, t = lane & 3;
+        const int t = lane & 3;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-                csum[warp][mt * 16 + g][nt * 8 + 2 * t] = acc[mt][nt][0];
-                csum[warp][mt * 16 + g][nt * 8 + 2 * t + 1] = acc[mt][nt][1];
-                csum[warp][mt * 16 + g + 8][nt * 8 + 2 * t] = acc[mt][nt][2];
-                csum[warp][mt * 16 + g + 8][nt * 8 + 2 * t + 1] = acc[mt][nt][3];
+                *reinterpret_cast<float2*>(out + (mt * 16 + g) * kDh + nt * 8 + 2 * t) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+                *reinterpret_cast<float2*>(out + (mt * 16 + g + 8) * kDh + nt * 8 + 2 * t) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
             }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -187,18 +224,11 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const AttnParams p, i
         }
         if (lane < 4) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = ssum[i];
+            for (int i = 0; i < 8; ++i) {
+                out[kDh * kDh + lane * 8 + i] = mrun[i] * 0.6931471805599453f;
+                out[kDh * kDh + kDh + lane * 8 + i] = ssum[i];
+            }
         }
-    }
-    __syncthreads();
-    float* out = p.part + ((static_cast<long long>(n) * p.heads + head) * nchunks + chunk_id) * kPartStride;
-    for (int i = tid; i < kDh * kDh; i += 128) {
-        const int d = i >> 5, e = i & 31;
-        out[i] = (csum[0][d][e] + csum[1][d][e]) + (csum[2][d][e] + csum[3][d][e]);
-    }
-    if (tid < kDh) {
-        out[kDh * kDh + tid] = mmax[tid];
-        out[kDh * kDh + kDh + tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
     }
 }
 
@@ -233,34 +263,41 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnParams p, int
 // Plain mode writes Weff (fp16).  Fused-q mode goes on to W'[n][co][c] = g * sum_d' Weff[co][d'] Wq[d'][c] + (co == c),
 // the per-sample 1x1 weight of the whole Residual(Rezero(LinearAttention)) block, and b' = g * b_o.
 __global__ void __launch_bounds__(256) attn_fold_kernel(const AttnParams p, const float* ctx_in) {
-    extern __shared__ float sm[];   // ctx [heads][32][33], then weff tile [32][hidden + 1]
+    extern __shared__ __align__(16) float sm[];   // ctx [heads*32][36], weff tile [32][hidden + 4], Wo tile [32][hidden]
     const int n = blockIdx.y, tid = threadIdx.x;
     const int heads = p.heads, hidden = heads * kDh;
+    const int wld = hidden + 4;
     float* ctx = sm;
-    float* wt = sm + heads * kDh * (kDh + 1);
+    float* wt = sm + heads * kDh * kCtxLd;
+    float* wos = wt + kFoldRows * wld;
     const float* cn = ctx_in + static_cast<long long>(n) * heads * kDh * kDh;
     for (int i = tid; i < heads * kDh * kDh; i += 256) {
         const int hd = i >> 5, e = i & 31;
-        ctx[hd * (kDh + 1) + e] = cn[i];
+        ctx[hd * kCtxLd + e] = cn[i];
+    }
+    const int co0 = blockIdx.x * kFoldRows;
+    for (int i = tid; i < kFoldRows * hidden; i += 256) {
+        const int co = co0 + i / hidden;
+        wos[i] = co < p.C ? __ldg(p.wo + static_cast<long long>(co) * hidden + i % hidden) : 0.f;
     }
     __syncthreads();
-    const int co0 = blockIdx.x * kFoldRows;
     for (int i = tid; i < kFoldRows * hidden; i += 256) {
         const int r = i / hidden, co = co0 + r;
         const int k = i % hidden, h = k / kDh, d = k % kDh;
+        const float4* w = reinterpret_cast<const float4*>(wos + r * hidden + h * kDh);
+        const float4* c = reinterpret_cast<const float4*>(ctx + (h * kDh + d) * kCtxLd);
         float a = 0.f;
-        if (co < p.C) {
-            const float* w = p.wo + static_cast<long long>(co) * hidden + h * kDh;
-            const float* c = ctx + (h * kDh + d) * (kDh + 1);
-#pragma unroll 8
-            for (int e = 0; e < kDh; ++e) a += __ldg(w + e) * c[e];
-            if (!p.wq) p.weff[(static_cast<long long>(n) * p.C + co) * hidden + k] = __float2half_rn(a);
+#pragma unroll
+        for (int e = 0; e < kDh / 4; ++e) {
+            const float4 wv = w[e], cv = c[e];
+            a = fmaf(wv.x, cv.x, a); a = fmaf(wv.y, cv.y, a); a = fmaf(wv.z, cv.z, a); a = fmaf(wv.w, cv.w, a);
         }
-        wt[r * (hidden + 1) + k] = a;
+        if (co < p.C && !p.wq) p.weff[(static_cast<long long>(n) * p.C + co) * hidden + k] = __float2half_rn(a);
+        wt[r * wld + k] = a;
     }
     if (!p.wq) return;
     __syncthreads();
-    // W'[co0 + r][c] for the block's 32 rows: thread = column c, RPT rows each, Wq streamed once per thread
+    // W'[co0 + r][c] for the block's 32 rows: thread = column c, rpt rows each, Wq streamed once per thread
     const int groups = 256 / p.C;                 // C in {64, 128, 256}
     const int rpt = kFoldRows / groups;           // rows per thread: 8, 16 or 32
     const int c = tid % p.C, r0 = (tid / p.C) * rpt;
@@ -275,9 +312,12 @@ __global__ void __launch_bounds__(256) attn_fold_kernel(const AttnParams p, cons
 #pragma unroll
         for (int r = 0; r < kFoldRows; ++r) {
             if (r < rpt) {
-                const float* wr = wt + (r0 + r) * (hidden + 1) + d0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[r] = fmaf(wr[i], w[i], acc[r]);
+                const float4* wr = reinterpret_cast<const float4*>(wt + (r0 + r) * wld + d0);
+                const float4 a0 = wr[0], a1 = wr[1];
+                acc[r] = fmaf(a0.x, w[0], acc[r]); acc[r] = fmaf(a0.y, w[1], acc[r]);
+                acc[r] = fmaf(a0.z, w[2], acc[r]); acc[r] = fmaf(a0.w, w[3], acc[r]);
+                acc[r] = fmaf(a1.x, w[4], acc[r]); acc[r] = fmaf(a1.y, w[5], acc[r]);
+                acc[r] = fmaf(a1.z, w[6], acc[r]); acc[r] = fmaf(a1.w, w[7], acc[r]);
             }
         }
     }
@@ -297,8 +337,14 @@ __global__ void __launch_bounds__(256) attn_fold_kernel(const AttnParams p, cons
 int launch_attn_context(const AttnParams& p, cudaStream_t s) {
     if (p.heads > 8 || p.heads < 1) return (int)cudaErrorInvalidValue;
     const int nchunks = attn_chunks(p.P, p.chunk);
-    dim3 g1(nchunks, p.heads, p.N);
-    attn_partial_kernel<<<g1, 128, 0, s>>>(p, nchunks);
+    static bool part_attr = false;
+    if (!part_attr) {   // heads x 12.5 KB of staging
+        cudaError_t ea = cudaFuncSetAttribute(attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        if (ea != cudaSuccess) return (int)ea;
+        part_attr = true;
+    }
+    dim3 g1(nchunks, p.N);
+    attn_partial_kernel<<<g1, 32 * p.heads, p.heads * 5 * kTileP * kRowHalfs * 2, s>>>(p, nchunks);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     // merged context lives behind the partials in the same scratch buffer
@@ -307,8 +353,14 @@ int launch_attn_context(const AttnParams& p, cudaStream_t s) {
     attn_merge_kernel<<<g2, 256, 0, s>>>(p, nchunks, ctx);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
+    static bool fold_attr = false;
+    if (!fold_attr) {   // ctx + Weff tile + Wo tile = 48.6 KB of dynamic shared memory
+        e = cudaFuncSetAttribute(attn_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        fold_attr = true;
+    }
     dim3 g3((p.C + kFoldRows - 1) / kFoldRows, p.N);
-    attn_fold_kernel<<<g3, 256, (p.heads * kDh * (kDh + 1) + kFoldRows * (p.heads * kDh + 1)) * sizeof(float), s>>>(p, ctx);
+    attn_fold_kernel<<<g3, 256, (p.heads * kDh * kCtxLd + kFoldRows * (2 * p.heads * kDh + 4)) * sizeof(float), s>>>(p, ctx);
     return (int)cudaGetLastError();
 }
 

@@ -310,9 +310,12 @@ int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s) {
     if (p.C % 8 || TP > 256 || (p.C / p.groups) < 1 || p.C % p.groups) return (int)cudaErrorInvalidValue;
     const int lanes = TP >= 256 ? 1 : 256 / TP;
     const int threads = TP * lanes;
-    // aim for >= ~16 blocks per SM over the whole tensor, at least 4 pixels per thread
+    // 64 pixels per thread for big tensors; shrink (down to 16 per thread: the per-thread prologue loads 24 affine /
+    // embedding values) only while the grid would leave SMs idle
+    static const int min_ppt = getenv("USB_GN_PPT") ? atoi(getenv("USB_GN_PPT")) : 32;
+    static const int min_bps = getenv("USB_GN_BPS") ? atoi(getenv("USB_GN_BPS")) : 4;
     int ppb = lanes * 64;
-    while (ppb > lanes * 4 && (long long)((p.P + ppb - 1) / ppb) * p.N < (long long)num_sms * 16) ppb >>= 1;
+    while (ppb > lanes * min_ppt && (long long)((p.P + ppb - 1) / ppb) * p.N < (long long)num_sms * min_bps) ppb >>= 1;
     dim3 grid((p.P + ppb - 1) / ppb, p.N);
     GnApplyParams q = p;
     static const char* dbg_env = getenv("USB_DBG_GN");

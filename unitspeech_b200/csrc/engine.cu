@@ -111,7 +111,12 @@ static int make_w_map(CUtensorMap* m, const __half* base, int Z, int Cout, int K
 // weights
 // ---------------------------------------------------------------------------------------------------------------
 enum ConvKind { K3S1 = 0, K3S2 = 1, K1 = 2, KT4 = 3 };
-constexpr int kAttnChunk = 2048;   // positions per attention partial block
+constexpr int kAttnChunk = 2048;   // positions per attention partial block (upper bound)
+// positions per partial block: ~16 chunks per sample so small levels still fill the GPU, multiples of 64
+static inline int attn_chunk_for(int P) {
+    int c = ((P / 16 + 63) / 64) * 64;
+    return c < 256 ? 256 : (c > kAttnChunk ? kAttnChunk : c);
+}
 
 struct ConvW {
     __half* w = nullptr;   // [Z][Cout][K]
@@ -621,7 +626,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         o_upx[l] = l < L - 1 ? b.take(PC[l] * h->C[l] * sizeof(__half)) : 0;
         o_weff[l] = b.take((size_t)Be * h->C[l] * (h->C[l] <= 256 ? 256 : hid) * sizeof(__half));
         o_mask[l] = b.take((size_t)Be * W[l] * sizeof(float));
-        const size_t part = attn_scratch_bytes(Be, h->heads, H[l] * W[l], kAttnChunk);
+        const size_t part = attn_scratch_bytes(Be, h->heads, H[l] * W[l], attn_chunk_for(H[l] * W[l]));
         if (part > max_part) max_part = part;
     }
     const size_t o_part = b.take(max_part);
@@ -709,7 +714,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         AttnParams ap;
         memset(&ap, 0, sizeof ap);
         ap.wo = a.wo; ap.part = part; ap.weff = weff; ap.N = Be; ap.P = H[l] * W[l]; ap.C = a.C;
-        ap.heads = h->heads; ap.chunk = kAttnChunk; ap.g = a.g; ap.bo = a.bo; ap.qkv = qkv;
+        ap.heads = h->heads; ap.chunk = attn_chunk_for(H[l] * W[l]); ap.g = a.g; ap.bo = a.bo; ap.qkv = qkv;
         ConvEpilogue e1;
         if (a.fused_q) {
             // kv = W_kv x; context from (k, v); the block's output is one per-sample 1x1 conv on x (no q, no residual read)
@@ -1320,8 +1325,8 @@ int usb_op_attn_context(usb_handle* h, const void* qkv, const float* wo, void* w
     AttnParams ap;
     memset(&ap, 0, sizeof ap);
     ap.qkv = static_cast<const __half*>(qkv); ap.wo = wo; ap.weff = static_cast<__half*>(weff); ap.N = N; ap.P = P;
-    ap.C = C; ap.heads = heads; ap.chunk = kAttnChunk; ap.ld = 3 * heads * 32; ap.koff = heads * 32; ap.voff = 2 * heads * 32;
-    const size_t part_bytes = attn_scratch_bytes(N, heads, P, kAttnChunk);
+    ap.C = C; ap.heads = heads; ap.chunk = attn_chunk_for(P); ap.ld = 3 * heads * 32; ap.koff = heads * 32; ap.voff = 2 * heads * 32;
+    const size_t part_bytes = attn_scratch_bytes(N, heads, P, attn_chunk_for(P));
     float* part = nullptr;
     USB_CUDA(cudaMalloc(&part, part_bytes));
     ap.part = part;
