@@ -155,15 +155,17 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     params = harness_weights()
     vals = []
+    ref_steps = 4   # CFG diffusion steps per bench step: ~4 s of CPU work each
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_sample(params, threads, diffusion_steps=2)
     t_total = 0.0
     for _ in range(args.steps):
-        dt, fps, n = cpu_sample(params, threads, diffusion_steps=2)
+        dt, fps, n = cpu_sample(params, threads, diffusion_steps=ref_steps)
         vals.append(fps)
         t_total += dt
     v = statistics.median(vals)
-    sample = f"1 utterance x {FRAMES} frames x 2 of the 50 CFG diffusion steps (6 U-Net evaluations) per bench step, scaled to the 50-step job"
+    sample = (f"1 utterance x {FRAMES} frames x {ref_steps} of the 50 CFG diffusion steps ({3 * ref_steps} U-Net evaluations) "
+              f"per bench step, scaled to the 50-step job")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(1, args.steps), "higher_is_better": True,
@@ -300,7 +302,7 @@ def run_gpu_arm(args):
         cpu = None
         if not args.no_cpu:
             threads = os.cpu_count() or 1
-            dt, fps, nst = cpu_sample(params, threads, diffusion_steps=2)
+            dt, fps, nst = cpu_sample(params, threads, diffusion_steps=12)   # ~10-20 s of CPU work
             cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"1 utterance x {T} frames x {nst} of the 50 CFG diffusion steps ({3 * nst} U-Net evaluations, {dt:.1f} s), scaled to the 50-step job"}
         line = {
