@@ -128,3 +128,23 @@ def test_mel_normalisation_contract_roundtrip():
     mel = denormalize_mel(y, mel_min, mel_max)                      # inference.py:140
     assert torch.allclose(mel, (y + 1) / 2 * (mel_max - mel_min) + mel_min)
     assert torch.allclose(normalize_mel(mel, mel_min, mel_max), y, atol=1e-5)
+
+
+def test_checkpoint_roundtrip_in_reference_format(tmp_path):
+    """{"model", "spk_emb", "mel_min", "mel_max", "iteration"} (train_STEP1.py:297-304) written, read back, arch inferred."""
+    from unitspeech_b200 import UnitSpeech, load_decoder_checkpoint, save_decoder_checkpoint
+    p = O.harness_params(dim=64, dim_mults=(1, 2, 4), seed=3)
+    dec = UnitSpeech(80, 64, (1, 2, 4), spk_emb_dim=256)
+    dec.load_state_dict(p)
+    g = torch.Generator().manual_seed(0)
+    spk, mn, mx = torch.randn(1, 256, generator=g), -torch.rand(80, 1, generator=g) * 8, torch.rand(80, 1, generator=g)
+    f = tmp_path / "dec.pt"
+    save_decoder_checkpoint(f, dec, spk_emb=spk, mel_min=mn, mel_max=mx, iteration=123)
+    raw = torch.load(f)
+    assert set(raw) == {"model", "spk_emb", "mel_min", "mel_max", "iteration"} and set(raw["model"]) == set(p)
+    b = load_decoder_checkpoint(f, device="cpu")
+    assert (b.decoder.n_feats, b.decoder.dim, b.decoder.dim_mults, b.decoder.spk_emb_dim) == (80, 64, (1, 2, 4), 256)
+    assert all(torch.equal(b.decoder.state_dict()[k], p[k]) for k in p)
+    assert b.iteration == 123 and torch.equal(b.spk_emb, spk)
+    y = torch.rand(1, 80, 8, generator=g) * 2 - 1
+    assert torch.allclose(b.denormalize(y), (y + 1) / 2 * (mx - mn) + mn)

@@ -179,3 +179,60 @@ def test_long_odd_width_utterances_and_microbatching():
     dec.max_rows_frames = 3 * 1000          # forces one utterance per library call
     chunked = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, 1.0, 1.0, noise=noise.cuda())
     assert torch.equal(chunked, full)       # micro-batching is exact (bitwise batch invariance)
+
+
+class _StubEncoder(torch.nn.Module):
+    """Deterministic stand-in for the text/unit encoder (unitspeech/encoder.py:294): (cond_x, x, x_mask)."""
+
+    def __init__(self, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.table = torch.nn.Parameter(torch.randn(50, 80, generator=g).clamp(-1, 1))
+
+    def forward(self, tokens, lengths):
+        cond_x = self.table[tokens].transpose(1, 2)                                   # (B, 80, L)
+        L = tokens.shape[1]
+        x_mask = (torch.arange(L, device=tokens.device)[None] < lengths[:, None]).unsqueeze(1).to(cond_x.dtype)
+        return cond_x * x_mask, cond_x * x_mask, x_mask
+
+
+class _StubDuration(torch.nn.Module):
+    def forward(self, x, x_mask, w=None, g=None, reverse=True):
+        # log-durations 3..6 frames per token, depends on the token content
+        return torch.log(3.0 + 3.0 * torch.sigmoid(x[:, :1] * 4)) * x_mask
+
+
+def test_execute_text_to_speech_matches_reference_glue():
+    """execute_text_to_speech (unitspeech.py:414-450): durations -> alignment -> cond_y -> z -> sampler -> crop."""
+    from unitspeech_b200 import fix_len_compatibility, generate_path, sequence_mask
+    s = 1.0 / 32
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=1234, out_scale=s)
+    dec = _decoder(64, (1, 2), p)
+    enc, dur = _StubEncoder().cuda(), _StubDuration().cuda()
+    tokens = torch.tensor([[3, 7, 11, 2, 40, 5]]).cuda()
+    lengths = torch.tensor([6]).cuda()
+    spk = torch.nn.functional.normalize(torch.randn(1, 1, 256, generator=torch.Generator().manual_seed(4)), dim=-1).cuda()
+    n = 3
+    torch.manual_seed(5)
+    y_enc, y_dec, attn = dec.execute_text_to_speech(tokens, lengths, spk, enc, dur, num_downsamplings_in_unet=1,
+                                                    diffusion_steps=n, length_scale=1.0, text_gradient_scale=1.0,
+                                                    spk_gradient_scale=1.0)
+    # the same glue restated with the oracle sampler
+    with torch.no_grad():
+        cond_x, x, x_mask = enc(tokens, lengths)
+        w_ceil = torch.ceil(torch.exp(dur(x, x_mask)) * x_mask)
+        y_len = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+        T = fix_len_compatibility(int(y_len.max()), 1)
+        y_mask = sequence_mask(y_len, T).unsqueeze(1).to(x_mask.dtype)
+        path = generate_path(w_ceil.squeeze(1), (x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)).squeeze(1))
+        cond_y = torch.matmul(path.transpose(1, 2), cond_x.transpose(1, 2)).transpose(1, 2).contiguous()
+    torch.manual_seed(5)
+    z = torch.randn_like(cond_y)
+    noise = torch.stack([torch.randn(z.shape, device="cuda") for _ in range(n)])
+    ref = O.reverse_diffusion(p, z.cpu(), y_mask.cpu(), cond_y.cpu(), spk.cpu(), n, 1.0, 1.0, noise=noise.cpu(),
+                              dim=64, dim_mults=(1, 2))[:, :, :int(y_len.max())]
+    # (the reference slices attn[:, :, :y_max] on the TOKEN axis of the (B,1,Tx,Ty) map, unitspeech.py:450 -- kept)
+    assert y_dec.shape == ref.shape and tuple(attn.shape) == (1, 1, 6, T)
+    assert torch.equal(y_enc, cond_y[:, :, :int(y_len.max())])
+    mx, mn = _errs(y_dec, ref)
+    assert mx <= MAX_TOL and mn <= MEAN_TOL
