@@ -20,6 +20,7 @@
 #ifndef UNITSPEECH_B200_H
 #define UNITSPEECH_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -116,6 +117,54 @@ int usb_op_gn_apply(usb_handle* h, const void* raw, const int64_t* stats, const 
 /* LinearAttention context folded with to_out: qkv (N, P, 384) fp16 dev, wo dev fp32 (C, 128) -> weff (N, C, 128) fp16 */
 int usb_op_attn_context(usb_handle* h, const void* qkv, const float* wo, void* weff, int32_t N, int32_t P, int32_t C,
                         int32_t heads, uint64_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Vocoder stage: the BigVGAN generator the reference runs after the decoder.
+ * Stands in for unitspeech.vocoder.models.BigVGAN (unitspeech/vocoder/models.py:121-191) as built by
+ * unitspeech/util.py:174-181 (get_vocoder: load generator weights, remove_weight_norm, eval).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct usb_vocoder usb_vocoder;
+
+/* The fields of the reference's vocoder config.json that the generator reads (models.py:125-167). */
+typedef struct usb_vocoder_config {
+    int32_t num_mels;                    /* 80 */
+    int32_t n_upsamples;                 /* len(upsample_rates) */
+    int32_t upsample_rates[8];           /* each 1..4 */
+    int32_t upsample_kernel_sizes[8];    /* must equal 2 * rate */
+    int32_t upsample_initial_channel;    /* 1536 */
+    int32_t resblock_type;               /* 1 = AMPBlock1, 2 = AMPBlock2 */
+    int32_t n_resblock_kernels;          /* len(resblock_kernel_sizes) */
+    int32_t resblock_kernel_sizes[4];    /* odd, <= 15 */
+    int32_t n_dilations;                 /* dilations per resblock (same count for every kernel size) */
+    int32_t resblock_dilations[4][4];
+    int32_t activation;                  /* 0 = "snake", 1 = "snakebeta" */
+    int32_t snake_logscale;              /* 0 / 1 */
+    int32_t device;
+} usb_vocoder_config;
+
+/* BigVGAN(h)                                                                   unitspeech/vocoder/models.py:123-167 */
+int usb_vocoder_create(const usb_vocoder_config* cfg, usb_vocoder** out);
+void usb_vocoder_destroy(usb_vocoder* h);
+/* generator.load_state_dict(...) after remove_weight_norm(): keys conv_pre.weight, ups.i.0.weight,
+ * resblocks.j.convs1.l.weight, resblocks.j.activations.l.act.alpha, ... (host fp32, reference shapes).  A caller
+ * holding weight-norm tensors folds them first (weight = g * v / ||v||; unitspeech_b200/vocoder.py does). */
+int usb_vocoder_load_param(usb_vocoder* h, const char* key, const float* host_data, const int64_t* shape, int32_t ndim);
+int usb_vocoder_finalize_params(usb_vocoder* h);
+/* BigVGAN.forward(mel)                                                         unitspeech/vocoder/models.py:169-191
+ * mel: (B, num_mels, T) dev fp32; out: (B, T * prod(upsample_rates)) dev fp32 (the reference's (B, 1, samples)). */
+int usb_vocoder_forward(usb_vocoder* h, const float* mel, int32_t B, int32_t T, float* out, uint64_t stream);
+/* same with host buffers: upload, run, download, synchronise */
+int usb_vocoder_forward_host(usb_vocoder* h, const float* mel_host, int32_t B, int32_t T, float* out_host);
+long long usb_vocoder_launch_count(const usb_vocoder* h);
+size_t usb_vocoder_workspace_bytes(const usb_vocoder* h);
+/* tensor-core FLOPs (padded channel counts) of one forward at the current (B, T) plan */
+double usb_vocoder_flops_per_call(const usb_vocoder* h);
+/* Activation1d (alias_free_torch/act.py:23-28) on NLC fp16: x, out (N, L, C) dev, C % 64 == 0; alpha (C) dev =
+ * snake frequency, invbeta (C) dev = 1 / (beta + 1e-9), both already exp'd when the parameters are log-scale. */
+int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, int32_t N, int32_t L, int32_t C, void* out,
+                     uint64_t stream);
+/* kaiser_sinc_filter1d(0.25, 0.3, 12) as the library computes it (alias_free_torch/filter.py:28-57) */
+int usb_vocoder_filter(float* out12);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,138 @@
+"""B200 parity tests of the vocoder stage (usb_vocoder_* through unitspeech_b200.BigVGAN) against the oracle
+(oracle/bigvgan_oracle.py) and the golden vectors produced by the unmodified reference generator.
+
+Tolerance: the waveform lives in [-1, 1]; activations are stored in fp16 between kernels, accumulation is fp32.
+The bar written here is max-abs <= 1e-2 and mean-abs <= 1e-3 against the fp32 reference (the mel bar of the
+decoder, applied to the audio)."""
+
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from oracle import bigvgan_oracle as V  # noqa: E402
+
+from make_golden_vocoder import CONFIGS  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS, MEAN_ABS = 1e-2, 1e-3
+
+
+def _mel(h, B, T, seed=17):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, h["num_mels"], T, generator=g) * 2 - 4
+
+
+def _vocoder(h, seed=4321):
+    from unitspeech_b200 import BigVGAN
+    voc = BigVGAN(h)
+    voc.load_state_dict(V.harness_params(h, seed))
+    return voc.cuda().eval()
+
+
+def _report(name, out, ref):
+    d = (out - ref).abs()
+    print(f"{name}: max-abs {float(d.max()):.3e} mean-abs {float(d.mean()):.3e} ref-absmax {float(ref.abs().max()):.3f}")
+    return float(d.max()), float(d.mean())
+
+
+@pytest.mark.parametrize("N,L,C", [(1, 1, 64), (2, 5, 64), (1, 64, 128), (2, 200, 64), (1, 777, 192)])
+def test_snake_activation_kernel(N, L, C):
+    from unitspeech_b200 import abi
+    lib = abi.load_library()
+    g = torch.Generator().manual_seed(L * 7 + C)
+    x = (torch.randn(N, C, L, generator=g) * 1.5).half().float()
+    alpha, beta = torch.randn(C, generator=g) * 0.4, torch.randn(C, generator=g) * 0.4
+    p = {"a.act.alpha": alpha, "a.act.beta": beta}
+    filt = V.kaiser_sinc_filter1d(0.25, 0.3, 12)
+    ref = V.activation1d(p, "a", x, filt, dict(activation="snakebeta", snake_logscale=True))
+    xd = x.permute(0, 2, 1).contiguous().cuda().half()
+    out = torch.full_like(xd, float("nan"))
+    al, ib = torch.exp(alpha).cuda(), (1.0 / (torch.exp(beta) + 1e-9)).cuda()
+    abi.check(lib.usb_op_snake_act(xd.data_ptr(), al.data_ptr(), ib.data_ptr(), N, L, C, out.data_ptr(),
+                                   int(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    got = out.float().cpu().permute(0, 2, 1)
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs()
+    assert float(err.max()) <= 4e-3 * max(1.0, float(ref.abs().max())), float(err.max())
+
+
+def test_library_filter_equals_reference_filter(golden_dir):
+    from unitspeech_b200 import abi
+    buf = (ctypes.c_float * 12)()
+    abi.check(abi.load_library().usb_vocoder_filter(buf))
+    g = np.load(os.path.join(golden_dir, "vocoder_small.npz"))
+    assert np.abs(np.array(buf[:], dtype=np.float32) - g["filt"]).max() <= 1e-7
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_vocoder_matches_reference_golden(golden_dir, name):
+    h, B, T = CONFIGS[name]
+    ref = torch.from_numpy(np.load(os.path.join(golden_dir, name + ".npz"))["out"])
+    voc = _vocoder(h)
+    out = voc(_mel(h, B, T).cuda()).cpu()
+    assert out.shape == ref.shape
+    mx, mn = _report(name, out, ref)
+    assert mx <= MAX_ABS and mn <= MEAN_ABS
+
+
+def test_vocoder_public_config_batch_vs_oracle():
+    h = dict(V.PUBLIC_22KHZ_80BAND)
+    B, T = 2, 40
+    mel = _mel(h, B, T, seed=5)
+    ref = V.bigvgan_forward(V.harness_params(h), mel, h)
+    voc = _vocoder(h)
+    out = voc(mel.cuda()).cpu()
+    assert out.shape == (B, 1, T * 256)
+    mx, mn = _report("public B2 T40", out, ref)
+    assert mx <= MAX_ABS and mn <= MEAN_ABS
+    # an utterance is synthesised identically alone and inside a batch; a second call repeats bit for bit
+    solo = voc(mel[1:2].cuda()).cpu()
+    assert torch.equal(solo[0], out[1])
+    assert torch.equal(voc(mel.cuda()).cpu(), out)
+    assert voc.launch_count > 0 and voc.workspace_bytes > 0 and voc.flops_per_call > 0
+
+
+def test_vocoder_host_entry_microbatching_and_weight_norm_checkpoint():
+    h = dict(V.PUBLIC_22KHZ_80BAND, upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=128)
+    mel = _mel(h, 3, 37, seed=9)
+    voc = _vocoder(h)
+    dev_out = voc(mel.cuda()).cpu()
+    host_out = voc(mel)                      # CPU tensor in -> usb_vocoder_forward_host -> CPU tensor out
+    assert not host_out.is_cuda and torch.equal(host_out, dev_out)
+    voc.max_frames_per_call = 40             # forces one utterance per call
+    assert torch.equal(voc(mel.cuda()).cpu(), dev_out)
+    # a reference-format checkpoint (weight_g / weight_v + filter buffers) loads to the same generator
+    from unitspeech_b200 import BigVGAN
+    p = V.harness_params(h)
+    ck = {}
+    for k, v in p.items():
+        if k.endswith(".weight"):
+            g = v.flatten(1).norm(dim=1).view(-1, 1, 1)
+            ck[k + "_g"], ck[k + "_v"] = g, v * 3.0          # any positive rescaling of v folds back to v * g/||v||
+        else:
+            ck[k] = v
+    ck["activation_post.upsample.filter"] = torch.zeros(1, 1, 12)
+    voc2 = BigVGAN(h)
+    voc2.load_state_dict(ck)
+    voc2.cuda().eval().remove_weight_norm()
+    d = (voc2(mel.cuda()).cpu() - dev_out).abs().max()
+    assert float(d) <= 2e-3
+
+
+def test_vocoder_errors_are_loud():
+    from unitspeech_b200 import BigVGAN, abi
+    h = dict(V.PUBLIC_22KHZ_80BAND, upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=128)
+    voc = _vocoder(h)
+    with pytest.raises(ValueError):
+        voc(torch.zeros(1, 79, 8).cuda())
+    bad = dict(h, upsample_kernel_sizes=[7, 4])
+    v2 = BigVGAN(bad).cuda()
+    with pytest.raises(abi.UsbError):
+        v2(torch.zeros(1, 80, 8).cuda())

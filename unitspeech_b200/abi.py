@@ -28,6 +28,24 @@ class UsbConfig(ctypes.Structure):
     ]
 
 
+class UsbVocoderConfig(ctypes.Structure):
+    _fields_ = [
+        ("num_mels", c_int32),
+        ("n_upsamples", c_int32),
+        ("upsample_rates", c_int32 * 8),
+        ("upsample_kernel_sizes", c_int32 * 8),
+        ("upsample_initial_channel", c_int32),
+        ("resblock_type", c_int32),
+        ("n_resblock_kernels", c_int32),
+        ("resblock_kernel_sizes", c_int32 * 4),
+        ("n_dilations", c_int32),
+        ("resblock_dilations", (c_int32 * 4) * 4),
+        ("activation", c_int32),
+        ("snake_logscale", c_int32),
+        ("device", c_int32),
+    ]
+
+
 class UsbError(RuntimeError):
     pass
 
@@ -56,6 +74,17 @@ SIGNATURES = {
     "usb_op_gn_apply": (c_int32, [c_void_p] + [c_void_p] * 8 + [c_int32] * 5 + [c_uint64]),
     "usb_op_attn_context": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                       c_uint64]),
+    "usb_vocoder_create": (c_int32, [POINTER(UsbVocoderConfig), POINTER(c_void_p)]),
+    "usb_vocoder_destroy": (None, [c_void_p]),
+    "usb_vocoder_load_param": (c_int32, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int32]),
+    "usb_vocoder_finalize_params": (c_int32, [c_void_p]),
+    "usb_vocoder_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_uint64]),
+    "usb_vocoder_forward_host": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "usb_vocoder_launch_count": (c_int64, [c_void_p]),
+    "usb_vocoder_workspace_bytes": (ctypes.c_size_t, [c_void_p]),
+    "usb_vocoder_flops_per_call": (c_double, [c_void_p]),
+    "usb_op_snake_act": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_uint64]),
+    "usb_vocoder_filter": (c_int32, [POINTER(c_float)]),
 }
 
 _lib = None

@@ -12,6 +12,7 @@
 // splits H and W by parity (p = row parity, column parity folded into c') so the box stays dense.
 #pragma once
 #include <cstdint>
+#include <string>
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -65,6 +66,17 @@ struct ConvParams {
     int oy_mul, ox_mul;        // yo = y*oy_mul + oy_off[phase], xo = x*ox_mul + ox_off[phase]
     int8_t oy_off[4], ox_off[4];
 };
+
+struct ConvOp {
+    ConvParams p;
+    CUtensorMap a0, a1, b, o;
+};
+
+// engine.cu: records the thread's last error message (usb_last_error) and returns 1
+int set_error(const std::string& m);
+// engine.cu: parameter block + tensor maps of a 1-D (transposed) convolution over NLC fp16 tensors
+int build_conv1d(ConvOp& op, const int8_t* dx, int taps, int phases, const __half* in, int Cin, int N, int L,
+                 const __half* w, int Cout, const float* bias, const __half* res, __half* out);
 
 // launches on `stream`; returns cudaError_t as int
 int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,

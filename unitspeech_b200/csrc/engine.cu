@@ -25,6 +25,7 @@ static int fail(const std::string& m) {
     g_err = m;
     return 1;
 }
+int set_error(const std::string& m) { return fail(m); }
 #define USB_CUDA(expr)                                                                                       \
     do {                                                                                                     \
         cudaError_t _e = (expr);                                                                             \
@@ -187,11 +188,6 @@ static void fill_taps(int kind, int Ctot0, ConvParams& p) {
     }
 }
 
-struct ConvOp {
-    ConvParams p;
-    CUtensorMap a0, a1, b, o;
-};
-
 struct ConvEpilogue {
     const float* bias = nullptr;
     long long* stats = nullptr;
@@ -280,6 +276,55 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     else   // per-warp stores: 32 pixels (one TMEM lane quarter) x 64 channels
         USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BW >= 32 ? 1 : 32 / p.BW,
                              p.BW >= 32 ? 32 : p.BW));
+    return 0;
+}
+
+// 1-D convolution / transposed convolution (vocoder.cu) on the same kernel: NLC fp16 tensors are NHWC with H = 1.
+// taps x-offsets are explicit (dilated kernels); phases > 1 = ConvTranspose1d with stride `phases`, whose output
+// [N][phases*L][Cout] is addressed as [N][L][phases*Cout] (phase ph lands in channels [ph*Cout, (ph+1)*Cout)).
+int build_conv1d(ConvOp& op, const int8_t* dx, int taps, int phases, const __half* in, int Cin, int N, int L,
+                 const __half* w, int Cout, const float* bias, const __half* res, __half* out) {
+    USB_TRY(load_encode_fn());
+    if (Cin % 64 || Cout % 64) return fail("conv channels must be multiples of 64");
+    if (phases < 1 || phases > 4 || taps < 1 || phases * taps > kConvMaxTaps) return fail("unsupported 1-D conv tap table");
+    if (res != nullptr && phases != 1) return fail("residual epilogue needs a plain conv");
+    ConvParams& p = op.p;
+    memset(&p, 0, sizeof p);
+    p.taps = taps;
+    p.phases = phases;
+    for (int i = 0; i < phases * taps; ++i) p.tap[i].dx = dx[i];
+    p.N = N;
+    p.Hm = 1;
+    p.Wm = L;
+    static const bool allow_swap = getenv("USB_NO_SWAP_AB") == nullptr;
+    p.swap_ab = (allow_swap && Cout % 128 == 0 && res == nullptr) ? 1 : 0;
+    p.BH = 1;
+    p.BW = 128;
+    p.tiles_y = 1;
+    p.tiles_x = (L + 127) / 128;
+    p.patches_per_phase = N * p.tiles_x;
+    p.Cout = Cout;
+    p.BN = p.swap_ab ? 128 : (Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64));
+    p.n_tiles_n = Cout / p.BN;
+    p.chunks0 = Cin / 64;
+    p.chunks1 = 0;
+    p.b_batch_mode = phases > 1 ? 1 : 0;
+    p.stages = p.swap_ab ? 4 : (p.BN == 256 ? 3 : (p.BN == 128 ? 5 : 6));
+    p.bias = bias;
+    p.groups = 8;
+    p.res = res;
+    p.mask_stride = L;
+    p.out_c_phase_mul = phases > 1 ? Cout : 0;
+    p.o_sx = Cout;
+    p.o_sy = (long long)L * Cout;
+    p.o_sn = (long long)L * Cout;
+    p.oy_mul = p.ox_mul = 1;
+    for (int ph = 0; ph < phases; ++ph) p.ox_off[ph] = (int8_t)(phases > 1 ? ph : 0);
+    USB_TRY(make_act_map(&op.a0, in, N, 1, L, Cin, Cin, false, 1, 128));
+    op.a1 = op.a0;
+    USB_TRY(make_w_map(&op.b, w, phases, Cout, taps * Cin, p.BN));
+    if (p.swap_ab) USB_TRY(make_act_map(&op.o, out, N, 1, L, phases * Cout, phases * Cout, false, 1, 64, 32));
+    else USB_TRY(make_act_map(&op.o, out, N, 1, L, phases * Cout, phases * Cout, false, 1, 32));
     return 0;
 }
 

@@ -1,0 +1,749 @@
+// BigVGAN generator (mel -> waveform), the optional second stage of the reference pipeline
+// (unitspeech/vocoder/models.py:121-191; called from unitspeech/util.py:174-181 get_vocoder and the scripts).
+//
+// Data layout: every activation is NLC fp16 ([utterance][sample][channel], channels padded with zeros to a multiple
+// of 64) so that all Conv1d / ConvTranspose1d layers run on the tcgen05 implicit-GEMM kernel of conv_igemm.cu with
+// H = 1 (dilated taps are x-offsets of the TMA box; the transposed convs are `stride` phase convs with two taps
+// each whose outputs interleave as channel blocks of a [N][L][stride*C] view of the upsampled tensor).
+// The anti-aliased activation (alias_free_torch/act.py:23-28: replicate-pad, x2 kaiser-sinc upsample, Snake /
+// SnakeBeta, low-pass, stride-2 downsample) is ONE kernel: the 2x-rate signal only ever exists in shared memory.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/unitspeech_b200.h"
+#include "conv_igemm.h"
+
+namespace usb {
+
+#define VOC_CUDA(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +       \
+                             std::to_string(__LINE__) + ")");                                                \
+    } while (0)
+#define VOC_TRY(expr)              \
+    do {                           \
+        int _r = (expr);           \
+        if (_r != 0) return _r;    \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kActTL = 64;                    // output samples per block
+constexpr int kActXRows = kActTL + 12;        // input rows t0-6 .. t0+TL+5
+constexpr int kActSRows = 2 * kActTL + 10;    // 2x-rate rows 2*t0-5 .. 2*t0+2*TL+4
+constexpr int kActSmemBytes = (kActXRows + kActSRows) * 64 * 4;
+
+struct ActParams {
+    const __half* x;       // [N][L][C]
+    __half* out;           // [N][L][C]
+    const float* alpha;    // [C] frequency a (already exp'd for log-scale parameters); 0 in padding channels
+    const float* invbeta;  // [C] 1 / (b + 1e-9); 0 in padding channels
+    int L, C;
+    float filt[12];        // kaiser_sinc_filter1d(0.25, 0.3, 12) -- shared by the up- and the down-sampler
+};
+
+// shared-memory element (row, vector cv of 8 channels, j in 0..7): two 128-byte halves per row so that the eight
+// threads of a row read/write contiguous float4s
+__device__ __forceinline__ int act_sidx(int row, int cv, int half) { return row * 64 + half * 32 + cv * 4; }
+
+__device__ __forceinline__ float sin_reduced(float v) {
+    const float k = rintf(v * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, v);       // 2*pi split in two fp32 terms
+    r = fmaf(-k, -1.7484556000744883e-7f, r);
+    return __sinf(r);
+}
+
+// Activation1d.forward (alias_free_torch/act.py:23-28) fused:
+//   u[2m]   = 2 * sum_{q=-3..2} f[5-2q] * x[clamp(m+q)]        (UpSample1d, resample.py:26-33)
+//   u[2m+1] = 2 * sum_{q=-2..3} f[6-2q] * x[clamp(m+q)]
+//   s[i]    = u[i] + invbeta * sin(alpha * u[i])^2             (activations.py:47-59,107-120)
+//   out[t]  = sum_{k=0..11} f[k] * s[clamp(2t+k-5)]            (LowPassFilter1d stride 2, filter.py:84-95)
+__global__ void __launch_bounds__(256) snake_act_kernel(const ActParams p) {
+    extern __shared__ float act_smem[];
+    float* xs = act_smem;
+    float* ss = act_smem + kActXRows * 64;
+    const int tid = threadIdx.x;
+    const int cv = tid & 7, r = tid >> 3;
+    const int t0 = blockIdx.x * kActTL;
+    const int c0 = blockIdx.y * 64 + cv * 8;
+    const long long nbase = static_cast<long long>(blockIdx.z) * p.L;
+
+    for (int row = r; row < kActXRows; row += 32) {
+        int t = t0 - 6 + row;
+        t = t < 0 ? 0 : (t > p.L - 1 ? p.L - 1 : t);
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.x + (nbase + t) * p.C + c0));
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]), d = __half22float2(h2[3]);
+        *reinterpret_cast<float4*>(xs + act_sidx(row, cv, 0)) = make_float4(a.x, a.y, b.x, b.y);
+        *reinterpret_cast<float4*>(xs + act_sidx(row, cv, 1)) = make_float4(c.x, c.y, d.x, d.y);
+    }
+    float al[8], ib[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        al[j] = __ldg(p.alpha + c0 + j);
+        ib[j] = __ldg(p.invbeta + c0 + j);
+    }
+    __syncthreads();
+
+    for (int ii = r; ii < kActSRows; ii += 32) {
+        int i = 2 * t0 - 5 + ii;
+        i = i < 0 ? 0 : (i > 2 * p.L - 1 ? 2 * p.L - 1 : i);
+        const int m = i >> 1, odd = i & 1;
+        // first contributing input row: x[m-3] (even) or x[m-2] (odd); filter taps 11,9,..,1 (even) or 10,8,..,0 (odd)
+        const int row0 = m - 3 + odd - (t0 - 6);
+        float u[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float w = 2.f * (odd ? p.filt[10 - 2 * j] : p.filt[11 - 2 * j]);
+            const float4 lo = *reinterpret_cast<const float4*>(xs + act_sidx(row0 + j, cv, 0));
+            const float4 hi = *reinterpret_cast<const float4*>(xs + act_sidx(row0 + j, cv, 1));
+            u[0] = fmaf(w, lo.x, u[0]); u[1] = fmaf(w, lo.y, u[1]); u[2] = fmaf(w, lo.z, u[2]); u[3] = fmaf(w, lo.w, u[3]);
+            u[4] = fmaf(w, hi.x, u[4]); u[5] = fmaf(w, hi.y, u[5]); u[6] = fmaf(w, hi.z, u[6]); u[7] = fmaf(w, hi.w, u[7]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float sn = sin_reduced(al[j] * u[j]);
+            u[j] = fmaf(ib[j] * sn, sn, u[j]);
+        }
+        *reinterpret_cast<float4*>(ss + act_sidx(ii, cv, 0)) = make_float4(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<float4*>(ss + act_sidx(ii, cv, 1)) = make_float4(u[4], u[5], u[6], u[7]);
+    }
+    __syncthreads();
+
+    for (int tt = r; tt < kActTL; tt += 32) {
+        const int t = t0 + tt;
+        if (t >= p.L) break;
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const float w = p.filt[k];
+            const float4 lo = *reinterpret_cast<const float4*>(ss + act_sidx(2 * tt + k, cv, 0));
+            const float4 hi = *reinterpret_cast<const float4*>(ss + act_sidx(2 * tt + k, cv, 1));
+            o[0] = fmaf(w, lo.x, o[0]); o[1] = fmaf(w, lo.y, o[1]); o[2] = fmaf(w, lo.z, o[2]); o[3] = fmaf(w, lo.w, o[3]);
+            o[4] = fmaf(w, hi.x, o[4]); o[5] = fmaf(w, hi.y, o[5]); o[6] = fmaf(w, hi.z, o[6]); o[7] = fmaf(w, hi.w, o[7]);
+        }
+        uint4 pk;
+        __half2* h2 = reinterpret_cast<__half2*>(&pk);
+        h2[0] = __floats2half2_rn(o[0], o[1]); h2[1] = __floats2half2_rn(o[2], o[3]);
+        h2[2] = __floats2half2_rn(o[4], o[5]); h2[3] = __floats2half2_rn(o[6], o[7]);
+        *reinterpret_cast<uint4*>(p.out + (nbase + t) * p.C + c0) = pk;
+    }
+}
+
+// mel (B, M, T) fp32 -> [B][T][Cp] fp16, zero padded channels
+__global__ void mel_pack_kernel(const float* __restrict__ mel, __half* __restrict__ out, int B, int M, int T, int Cp) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int groups = Cp / 8;
+    if (idx >= static_cast<long long>(B) * groups * T) return;
+    const int t = static_cast<int>(idx % T);
+    const int cg = static_cast<int>((idx / T) % groups);
+    const int b = static_cast<int>(idx / (static_cast<long long>(T) * groups));
+    uint4 pk;
+    __half* h = reinterpret_cast<__half*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        h[j] = __float2half_rn(c < M ? __ldg(mel + (static_cast<long long>(b) * M + c) * T + t) : 0.f);
+    }
+    *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * T + t) * Cp + cg * 8) = pk;
+}
+
+// sum of the resblock outputs of one stage (models.py:177-184): mode 0: acc = r; 1: acc += r; 2: out = (acc + r)*scale;
+// 3: out = r * scale (single resblock)
+__global__ void stage_accum_kernel(const __half* __restrict__ r, float* __restrict__ acc, __half* __restrict__ out,
+                                   long long n8, int mode, float scale) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(r) + i);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+    }
+    float4* a4 = reinterpret_cast<float4*>(acc) + 2 * i;
+    if (mode == 1 || mode == 2) {
+        const float4 a = a4[0], b = a4[1];
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (mode <= 1) {
+        a4[0] = make_float4(v[0], v[1], v[2], v[3]);
+        a4[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        uint4 pk;
+        __half2* o2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(v[2 * j] * scale, v[2 * j + 1] * scale);
+        reinterpret_cast<uint4*>(out)[i] = pk;
+    }
+}
+
+// conv_post (Conv1d(ch, 1, 7, padding 3)) + tanh (models.py:188-189): one thread per output sample
+// w: [7][Cin8] fp32 (Cin8 = real channels rounded up to 8, zero padded)
+__global__ void __launch_bounds__(256) conv_post_kernel(const __half* __restrict__ a, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out, int N,
+                                                        int L, int C, int Cin8) {
+    extern __shared__ float post_w[];
+    for (int i = threadIdx.x; i < 7 * Cin8; i += blockDim.x) post_w[i] = __ldg(w + i);
+    __syncthreads();
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * L) return;
+    const int t = static_cast<int>(idx % L);
+    const long long nbase = idx - t;
+    float acc = __ldg(bias);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int tt = t + k - 3;
+        if (tt < 0 || tt >= L) continue;
+        const __half* row = a + (nbase + tt) * C;
+        for (int c = 0; c < Cin8; c += 8) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row + c));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+            const float* wk = post_w + k * Cin8 + c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                acc = fmaf(f.x, wk[2 * j], acc);
+                acc = fmaf(f.y, wk[2 * j + 1], acc);
+            }
+        }
+    }
+    out[idx] = tanhf(acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }
+
+// kaiser_sinc_filter1d(cutoff 0.25, half_width 0.3, kernel 12) -- alias_free_torch/filter.py:28-57, in double precision
+static double bessel_i0(double x) {
+    double sum = 1.0, term = 1.0;
+    for (int k = 1; k < 64; ++k) {
+        term *= (x / (2.0 * k)) * (x / (2.0 * k));
+        sum += term;
+        if (term < 1e-18 * sum) break;
+    }
+    return sum;
+}
+static void kaiser_sinc_12(float* out) {
+    const int K = 12, half_size = 6;
+    const double cutoff = 0.25, half_width = 0.3, pi = 3.14159265358979323846;
+    const double delta_f = 4 * half_width;
+    const double A = 2.285 * (half_size - 1) * pi * delta_f + 7.95;
+    const double beta = A > 50.0 ? 0.1102 * (A - 8.7) : (A >= 21.0 ? 0.5842 * pow(A - 21, 0.4) + 0.07886 * (A - 21.0) : 0.0);
+    double f[12], sum = 0;
+    for (int n = 0; n < K; ++n) {
+        const double r = 2.0 * n / (K - 1) - 1.0;                       // torch.kaiser_window(periodic=False)
+        const double win = bessel_i0(beta * sqrt(fmax(0.0, 1.0 - r * r))) / bessel_i0(beta);
+        const double time = (n - half_size) + 0.5;
+        const double xx = 2 * cutoff * time;
+        const double sinc = xx == 0.0 ? 1.0 : sin(pi * xx) / (pi * xx);
+        f[n] = 2 * cutoff * win * sinc;
+        sum += f[n];
+    }
+    for (int n = 0; n < K; ++n) out[n] = static_cast<float>(f[n] / sum);
+}
+
+struct VocParam {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+struct VocConvW {
+    __half* w = nullptr;
+    float* bias = nullptr;
+    int Cin = 0, Cout = 0;     // padded
+    int taps = 0, phases = 1;
+    int8_t dx[kConvMaxTaps] = {0};
+};
+
+struct VocActW {
+    float* alpha = nullptr;
+    float* invbeta = nullptr;
+    int C = 0;
+};
+
+struct VocOp {
+    enum Type { PACK, CONV, ACT, ACCUM, POST } type;
+    ConvOp conv;
+    ActParams act;
+    int N = 0;
+    // ACCUM
+    const __half* r = nullptr;
+    float* acc = nullptr;
+    __half* out16 = nullptr;
+    long long n8 = 0;
+    int mode = 0;
+    float scale = 1.f;
+    double flops = 0;
+};
+
+}  // namespace usb
+
+using namespace usb;
+
+struct usb_vocoder {
+    usb_vocoder_config cfg;
+    int num_sms = 148;
+    bool finalized = false;
+    std::map<std::string, VocParam> host;
+    std::vector<void*> dev_allocs;
+    int n_stage = 0, nk = 0, nd = 0;
+    int ch[9] = {0};            // real channels: ch[0] = initial, ch[i+1] after stage i
+    VocConvW conv_pre;
+    std::vector<VocConvW> ups;
+    std::vector<VocConvW> rb_convs;   // [stage][kernel][layer][0|1]  (AMPBlock2: one conv per layer)
+    std::vector<VocActW> rb_acts;     // same order as the reference's activations ModuleList per resblock
+    VocActW act_post;
+    float *post_w = nullptr, *post_b = nullptr;
+    int post_cin8 = 0;
+    float filt[12];
+    // plan
+    int plan_B = 0, plan_T = 0;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    __half* melp = nullptr;
+    __half* final_act = nullptr;
+    int final_L = 0, final_C = 0;
+    std::vector<VocOp> ops;
+    long long launches = 0;
+    double flops_per_call = 0;
+};
+
+namespace usb {
+
+template <typename T>
+static int voc_upload(usb_vocoder* h, const std::vector<T>& host, T** dev) {
+    void* p = nullptr;
+    VOC_CUDA(cudaMalloc(&p, host.size() * sizeof(T)));
+    h->dev_allocs.push_back(p);
+    VOC_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<T*>(p);
+    return 0;
+}
+
+static int voc_get(usb_vocoder* h, const std::string& key, const std::vector<int64_t>& shape, const VocParam** out) {
+    auto it = h->host.find(key);
+    if (it == h->host.end()) return set_error("missing vocoder parameter: " + key);
+    if (it->second.shape != shape) {
+        std::string s = "vocoder parameter " + key + " has shape (";
+        for (int64_t d : it->second.shape) s += std::to_string(d) + ",";
+        s += ") expected (";
+        for (int64_t d : shape) s += std::to_string(d) + ",";
+        return set_error(s + ")");
+    }
+    *out = &it->second;
+    return 0;
+}
+
+static int voc_load_bias(usb_vocoder* h, const std::string& key, int C, int Cp, float** dev) {
+    const VocParam* b;
+    VOC_TRY(voc_get(h, key, {C}, &b));
+    std::vector<float> v(Cp, 0.f);
+    for (int i = 0; i < C; ++i) v[i] = b->data[i];
+    return voc_upload(h, v, dev);
+}
+
+// Conv1d weight (Cout, Cin, k), dilation d, "same" padding (xutils.get_padding) -> [Cout_p][k*Cin_p] fp16
+static int voc_load_conv(usb_vocoder* h, const std::string& prefix, int Cout, int Cin, int k, int dil, VocConvW& w) {
+    const VocParam* p;
+    VOC_TRY(voc_get(h, prefix + ".weight", {Cout, Cin, k}, &p));
+    if (k > kConvMaxTaps || (k & 1) == 0) return set_error("unsupported Conv1d kernel size in " + prefix);
+    const int pad = (k * dil - dil) / 2;
+    if (pad > 127) return set_error("dilation too large in " + prefix);
+    w.Cin = pad64(Cin);
+    w.Cout = pad64(Cout);
+    w.taps = k;
+    w.phases = 1;
+    for (int t = 0; t < k; ++t) w.dx[t] = static_cast<int8_t>(t * dil - pad);
+    std::vector<__half> packed(static_cast<size_t>(w.Cout) * k * w.Cin, __float2half_rn(0.f));
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int t = 0; t < k; ++t)
+                packed[(static_cast<size_t>(co) * k + t) * w.Cin + ci] =
+                    __float2half_rn(p->data[(static_cast<size_t>(co) * Cin + ci) * k + t]);
+    VOC_TRY(voc_upload(h, packed, &w.w));
+    return voc_load_bias(h, prefix + ".bias", Cout, w.Cout, &w.bias);
+}
+
+// ConvTranspose1d weight (Cin, Cout, ku), stride u, padding (ku-u)/2, ku == 2u (models.py:141-146):
+//   out[u*x + ph] = sum_a sum_ci in[x + q - a][ci] * w[ci][co][k0 + a*u],  k0 = (ph+pad) % u, q = (ph+pad) / u
+// -> [u][Cout_p][2*Cin_p] fp16
+static int voc_load_convT(usb_vocoder* h, const std::string& prefix, int Cin, int Cout, int ku, int u, VocConvW& w) {
+    const VocParam* p;
+    VOC_TRY(voc_get(h, prefix + ".weight", {Cin, Cout, ku}, &p));
+    if (ku != 2 * u || u < 1 || u > 4) return set_error("ConvTranspose1d needs kernel == 2*stride and stride <= 4: " + prefix);
+    const int pad = (ku - u) / 2;
+    w.Cin = pad64(Cin);
+    w.Cout = pad64(Cout);
+    w.taps = 2;
+    w.phases = u;
+    std::vector<__half> packed(static_cast<size_t>(u) * w.Cout * 2 * w.Cin, __float2half_rn(0.f));
+    for (int ph = 0; ph < u; ++ph) {
+        const int k0 = (ph + pad) % u, q = (ph + pad) / u;
+        for (int a = 0; a < 2; ++a) {
+            w.dx[ph * 2 + a] = static_cast<int8_t>(q - a);
+            for (int co = 0; co < Cout; ++co)
+                for (int ci = 0; ci < Cin; ++ci)
+                    packed[((static_cast<size_t>(ph) * w.Cout + co) * 2 + a) * w.Cin + ci] =
+                        __float2half_rn(p->data[(static_cast<size_t>(ci) * Cout + co) * ku + k0 + a * u]);
+        }
+    }
+    VOC_TRY(voc_upload(h, packed, &w.w));
+    return voc_load_bias(h, prefix + ".bias", Cout, w.Cout, &w.bias);
+}
+
+static int voc_load_act(usb_vocoder* h, const std::string& prefix, int C, VocActW& a) {
+    const VocParam *pa, *pb;
+    VOC_TRY(voc_get(h, prefix + ".act.alpha", {C}, &pa));
+    const bool is_beta = h->cfg.activation == 1;
+    if (is_beta) VOC_TRY(voc_get(h, prefix + ".act.beta", {C}, &pb));
+    else pb = pa;
+    a.C = pad64(C);
+    std::vector<float> al(a.C, 0.f), ib(a.C, 0.f);
+    for (int c = 0; c < C; ++c) {
+        // activations.py:54-59,113-120: exp() in log-scale mode, then 1 / (beta + 1e-9); same fp32 operations
+        const float av = h->cfg.snake_logscale ? expf(pa->data[c]) : pa->data[c];
+        const float bv = h->cfg.snake_logscale ? expf(pb->data[c]) : pb->data[c];
+        al[c] = av;
+        ib[c] = 1.0f / (bv + 1e-9f);
+    }
+    VOC_TRY(voc_upload(h, al, &a.alpha));
+    return voc_upload(h, ib, &a.invbeta);
+}
+
+static int voc_finalize(usb_vocoder* h) {
+    if (h->finalized) return set_error("vocoder parameters already finalized");
+    const usb_vocoder_config& c = h->cfg;
+    VOC_CUDA(cudaSetDevice(c.device));
+    h->n_stage = c.n_upsamples;
+    h->nk = c.n_resblock_kernels;
+    h->nd = c.n_dilations;
+    h->ch[0] = c.upsample_initial_channel;
+    for (int i = 0; i < h->n_stage; ++i) h->ch[i + 1] = c.upsample_initial_channel >> (i + 1);
+    VOC_TRY(voc_load_conv(h, "conv_pre", h->ch[0], c.num_mels, 7, 1, h->conv_pre));
+    h->ups.resize(h->n_stage);
+    const int convs_per_layer = c.resblock_type == 1 ? 2 : 1;
+    for (int i = 0; i < h->n_stage; ++i) {
+        VOC_TRY(voc_load_convT(h, "ups." + std::to_string(i) + ".0", h->ch[i], h->ch[i + 1], c.upsample_kernel_sizes[i],
+                               c.upsample_rates[i], h->ups[i]));
+        for (int j = 0; j < h->nk; ++j) {
+            const std::string pre = "resblocks." + std::to_string(i * h->nk + j);
+            const int k = c.resblock_kernel_sizes[j];
+            for (int l = 0; l < h->nd; ++l) {
+                const int d = c.resblock_dilations[j][l];
+                if (convs_per_layer == 2) {
+                    VocConvW w1, w2;
+                    VOC_TRY(voc_load_conv(h, pre + ".convs1." + std::to_string(l), h->ch[i + 1], h->ch[i + 1], k, d, w1));
+                    VOC_TRY(voc_load_conv(h, pre + ".convs2." + std::to_string(l), h->ch[i + 1], h->ch[i + 1], k, 1, w2));
+                    h->rb_convs.push_back(w1);
+                    h->rb_convs.push_back(w2);
+                } else {
+                    VocConvW w1;
+                    VOC_TRY(voc_load_conv(h, pre + ".convs." + std::to_string(l), h->ch[i + 1], h->ch[i + 1], k, d, w1));
+                    h->rb_convs.push_back(w1);
+                }
+            }
+            for (int l = 0; l < h->nd * convs_per_layer; ++l) {
+                VocActW a;
+                VOC_TRY(voc_load_act(h, pre + ".activations." + std::to_string(l), h->ch[i + 1], a));
+                h->rb_acts.push_back(a);
+            }
+        }
+    }
+    const int cl = h->ch[h->n_stage];
+    VOC_TRY(voc_load_act(h, "activation_post", cl, h->act_post));
+    const VocParam *pw, *pb;
+    VOC_TRY(voc_get(h, "conv_post.weight", {1, cl, 7}, &pw));
+    VOC_TRY(voc_get(h, "conv_post.bias", {1}, &pb));
+    h->post_cin8 = (cl + 7) / 8 * 8;
+    std::vector<float> w(7 * h->post_cin8, 0.f);
+    for (int ci = 0; ci < cl; ++ci)
+        for (int k = 0; k < 7; ++k) w[k * h->post_cin8 + ci] = pw->data[ci * 7 + k];
+    VOC_TRY(voc_upload(h, w, &h->post_w));
+    VOC_TRY(voc_upload(h, pb->data, &h->post_b));
+    kaiser_sinc_12(h->filt);
+    VOC_CUDA(cudaFuncSetAttribute(snake_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kActSmemBytes));
+    h->host.clear();
+    h->finalized = true;
+    return 0;
+}
+
+static double conv1d_flops(const VocConvW& w, int N, int L) {
+    return 2.0 * N * L * w.phases * w.taps * static_cast<double>(w.Cin) * w.Cout;
+}
+
+static int voc_push_conv(usb_vocoder* h, const VocConvW& w, const __half* in, int N, int L, const __half* res, __half* out) {
+    VocOp op;
+    op.type = VocOp::CONV;
+    VOC_TRY(build_conv1d(op.conv, w.dx, w.taps, w.phases, in, w.Cin, N, L, w.w, w.Cout, w.bias, res, out));
+    op.flops = conv1d_flops(w, N, L);
+    h->flops_per_call += op.flops;
+    h->ops.push_back(op);
+    return 0;
+}
+
+static void voc_push_act(usb_vocoder* h, const VocActW& a, const __half* x, __half* out, int N, int L) {
+    VocOp op;
+    op.type = VocOp::ACT;
+    op.N = N;
+    op.act.x = x;
+    op.act.out = out;
+    op.act.alpha = a.alpha;
+    op.act.invbeta = a.invbeta;
+    op.act.L = L;
+    op.act.C = a.C;
+    memcpy(op.act.filt, h->filt, sizeof h->filt);
+    h->ops.push_back(op);
+}
+
+static int voc_build_plan(usb_vocoder* h, int B, int T) {
+    if (h->plan_B == B && h->plan_T == T) return 0;
+    const usb_vocoder_config& c = h->cfg;
+    VOC_CUDA(cudaDeviceSynchronize());
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr;
+    h->ops.clear();
+    h->flops_per_call = 0;
+    h->plan_B = h->plan_T = 0;
+    // buffer sizes: the largest [B][L][Cp] activation of any stage
+    size_t max_elems = static_cast<size_t>(B) * T * pad64(h->ch[0]);
+    {
+        long long L = T;
+        for (int i = 0; i < h->n_stage; ++i) {
+            L *= c.upsample_rates[i];
+            const size_t e = static_cast<size_t>(B) * L * pad64(h->ch[i + 1]);
+            if (e > max_elems) max_elems = e;
+        }
+        if (L * static_cast<long long>(B) > 2000000000LL) return set_error("vocoder batch too long (B*T*hop must stay below 2^31)");
+    }
+    const int melC = h->conv_pre.Cin;
+    const size_t mel_bytes = (static_cast<size_t>(B) * T * melC * 2 + 255) / 256 * 256;
+    const size_t buf_bytes = (max_elems * 2 + 255) / 256 * 256;
+    h->arena_bytes = mel_bytes + 5 * buf_bytes + 2 * buf_bytes;
+    VOC_CUDA(cudaMalloc(&h->arena, h->arena_bytes));
+    char* base = static_cast<char*>(h->arena);
+    h->melp = reinterpret_cast<__half*>(base);
+    __half* P = reinterpret_cast<__half*>(base + mel_bytes);
+    __half* X = reinterpret_cast<__half*>(base + mel_bytes + buf_bytes);
+    __half* R = reinterpret_cast<__half*>(base + mel_bytes + 2 * buf_bytes);
+    __half* A = reinterpret_cast<__half*>(base + mel_bytes + 3 * buf_bytes);
+    __half* Cc = reinterpret_cast<__half*>(base + mel_bytes + 4 * buf_bytes);
+    float* acc = reinterpret_cast<float*>(base + mel_bytes + 5 * buf_bytes);
+
+    int L = T;
+    VOC_TRY(voc_push_conv(h, h->conv_pre, h->melp, B, L, nullptr, P));           // models.py:171
+    const int cpl = c.resblock_type == 1 ? 2 : 1;
+    size_t conv_i = 0, act_i = 0;
+    for (int i = 0; i < h->n_stage; ++i) {
+        VOC_TRY(voc_push_conv(h, h->ups[i], P, B, L, nullptr, X));                 // models.py:175-176
+        L *= c.upsample_rates[i];
+        const int Cp = pad64(h->ch[i + 1]);
+        for (int j = 0; j < h->nk; ++j) {
+            for (int l = 0; l < h->nd; ++l) {
+                const __half* src = l == 0 ? X : R;
+                if (cpl == 2) {   // AMPBlock1.forward, models.py:60-69
+                    voc_push_act(h, h->rb_acts[act_i + 2 * l], src, A, B, L);
+                    VOC_TRY(voc_push_conv(h, h->rb_convs[conv_i + 2 * l], A, B, L, nullptr, Cc));
+                    voc_push_act(h, h->rb_acts[act_i + 2 * l + 1], Cc, A, B, L);
+                    VOC_TRY(voc_push_conv(h, h->rb_convs[conv_i + 2 * l + 1], A, B, L, src, R));
+                } else {          // AMPBlock2.forward, models.py:105-112
+                    voc_push_act(h, h->rb_acts[act_i + l], src, A, B, L);
+                    VOC_TRY(voc_push_conv(h, h->rb_convs[conv_i + l], A, B, L, src, R));
+                }
+            }
+            conv_i += static_cast<size_t>(h->nd) * cpl;
+            act_i += static_cast<size_t>(h->nd) * cpl;
+            VocOp op;
+            op.type = VocOp::ACCUM;
+            op.r = R;
+            op.acc = acc;
+            op.out16 = P;
+            op.n8 = static_cast<long long>(B) * L * Cp / 8;
+            op.mode = h->nk == 1 ? 3 : (j == 0 ? 0 : (j == h->nk - 1 ? 2 : 1));
+            op.scale = 1.0f / h->nk;
+            h->ops.push_back(op);
+        }
+    }
+    voc_push_act(h, h->act_post, P, A, B, L);                                     // models.py:187
+    h->final_act = A;
+    h->final_L = L;
+    h->final_C = pad64(h->ch[h->n_stage]);
+    h->plan_B = B;
+    h->plan_T = T;
+    return 0;
+}
+
+static int voc_forward(usb_vocoder* h, const float* mel, int B, int T, float* out, cudaStream_t s) {
+    if (!h->finalized) return set_error("usb_vocoder_finalize_params has not been called");
+    if (B < 1 || T < 1) return set_error("vocoder needs B >= 1 and T >= 1");
+    VOC_CUDA(cudaSetDevice(h->cfg.device));
+    VOC_TRY(voc_build_plan(h, B, T));
+    {
+        const int Cp = h->conv_pre.Cin;
+        const long long n = static_cast<long long>(B) * (Cp / 8) * T;
+        mel_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(mel, h->melp, B, h->cfg.num_mels, T, Cp);
+        h->launches++;
+    }
+    for (const VocOp& op : h->ops) {
+        switch (op.type) {
+            case VocOp::CONV: {
+                const int e = launch_conv_igemm(op.conv.p, op.conv.a0, op.conv.a1, op.conv.b, op.conv.o, h->num_sms, s);
+                if (e != 0) return set_error(std::string("vocoder conv launch: ") + cudaGetErrorString(static_cast<cudaError_t>(e)));
+                break;
+            }
+            case VocOp::ACT: {
+                const dim3 grid((op.act.L + kActTL - 1) / kActTL, op.act.C / 64, op.N);
+                snake_act_kernel<<<grid, 256, kActSmemBytes, s>>>(op.act);
+                break;
+            }
+            case VocOp::ACCUM:
+                stage_accum_kernel<<<static_cast<unsigned>((op.n8 + 255) / 256), 256, 0, s>>>(op.r, op.acc, op.out16, op.n8,
+                                                                                            op.mode, op.scale);
+                break;
+            default: break;
+        }
+        h->launches++;
+    }
+    {
+        const long long n = static_cast<long long>(B) * h->final_L;
+        conv_post_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 7 * h->post_cin8 * sizeof(float), s>>>(
+            h->final_act, h->post_w, h->post_b, out, B, h->final_L, h->final_C, h->post_cin8);
+        h->launches++;
+    }
+    VOC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace usb
+
+// ===================================================================================================================
+// C ABI
+// ===================================================================================================================
+extern "C" {
+
+int usb_vocoder_create(const usb_vocoder_config* cfg, usb_vocoder** out) {
+    if (!cfg || !out) return set_error("null argument");
+    if (cfg->n_upsamples < 1 || cfg->n_upsamples > 8) return set_error("vocoder needs 1..8 upsample stages");
+    if (cfg->n_resblock_kernels < 1 || cfg->n_resblock_kernels > 4) return set_error("vocoder needs 1..4 resblock kernel sizes");
+    if (cfg->n_dilations < 1 || cfg->n_dilations > 4) return set_error("vocoder needs 1..4 dilations per resblock");
+    if (cfg->resblock_type != 1 && cfg->resblock_type != 2) return set_error("resblock must be 1 or 2");
+    if (cfg->activation != 0 && cfg->activation != 1) return set_error("activation must be 0 (snake) or 1 (snakebeta)");
+    if (cfg->num_mels < 1 || cfg->upsample_initial_channel < (1 << cfg->n_upsamples) ||
+        cfg->upsample_initial_channel % (1 << cfg->n_upsamples))
+        return set_error("upsample_initial_channel must be divisible by 2^len(upsample_rates)");
+    if ((cfg->upsample_initial_channel >> cfg->n_upsamples) > 64) return set_error("last stage wider than 64 channels is not supported");
+    int ndev = 0;
+    VOC_CUDA(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return set_error("no such CUDA device");
+    VOC_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    VOC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return set_error(std::string("this library only runs on sm_100 (B200); found ") + prop.name);
+    usb_vocoder* h = new usb_vocoder();
+    h->cfg = *cfg;
+    h->num_sms = prop.multiProcessorCount;
+    *out = h;
+    return 0;
+}
+
+void usb_vocoder_destroy(usb_vocoder* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    if (h->arena) cudaFree(h->arena);
+    for (void* p : h->dev_allocs) cudaFree(p);
+    delete h;
+}
+
+int usb_vocoder_load_param(usb_vocoder* h, const char* key, const float* data, const int64_t* shape, int32_t ndim) {
+    if (!h || !key || !data || (ndim > 0 && !shape)) return set_error("null argument");
+    if (h->finalized) return set_error("vocoder parameters already finalized");
+    VocParam p;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        p.shape.push_back(shape[i]);
+        n *= static_cast<size_t>(shape[i]);
+    }
+    p.data.assign(data, data + n);
+    h->host[key] = std::move(p);
+    return 0;
+}
+
+int usb_vocoder_finalize_params(usb_vocoder* h) {
+    if (!h) return set_error("null argument");
+    return voc_finalize(h);
+}
+
+int usb_vocoder_forward(usb_vocoder* h, const float* mel, int32_t B, int32_t T, float* out, uint64_t stream) {
+    if (!h || !mel || !out) return set_error("null argument");
+    return voc_forward(h, mel, B, T, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int usb_vocoder_forward_host(usb_vocoder* h, const float* mel_host, int32_t B, int32_t T, float* out_host) {
+    if (!h || !mel_host || !out_host) return set_error("null argument");
+    VOC_CUDA(cudaSetDevice(h->cfg.device));
+    long long hop = 1;
+    for (int i = 0; i < h->cfg.n_upsamples; ++i) hop *= h->cfg.upsample_rates[i];
+    const size_t in_b = static_cast<size_t>(B) * h->cfg.num_mels * T * sizeof(float);
+    const size_t out_b = static_cast<size_t>(B) * T * hop * sizeof(float);
+    float *d_in = nullptr, *d_out = nullptr;
+    VOC_CUDA(cudaMalloc(&d_in, in_b));
+    if (cudaMalloc(&d_out, out_b) != cudaSuccess) {
+        cudaFree(d_in);
+        return set_error("cudaMalloc failed for the vocoder output");
+    }
+    int rc = 0;
+    if (cudaMemcpy(d_in, mel_host, in_b, cudaMemcpyHostToDevice) != cudaSuccess) rc = set_error("H2D copy failed");
+    if (!rc) rc = voc_forward(h, d_in, B, T, d_out, nullptr);
+    if (!rc && cudaMemcpy(out_host, d_out, out_b, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_error("D2H copy failed");
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+long long usb_vocoder_launch_count(const usb_vocoder* h) { return h ? h->launches : 0; }
+size_t usb_vocoder_workspace_bytes(const usb_vocoder* h) { return h ? h->arena_bytes : 0; }
+double usb_vocoder_flops_per_call(const usb_vocoder* h) { return h ? h->flops_per_call : 0; }
+
+int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, int32_t N, int32_t L, int32_t C, void* out,
+                     uint64_t stream) {
+    if (!x || !alpha || !invbeta || !out) return set_error("null argument");
+    if (C % 64 || N < 1 || L < 1) return set_error("snake activation needs C % 64 == 0");
+    ActParams p;
+    p.x = static_cast<const __half*>(x);
+    p.out = static_cast<__half*>(out);
+    p.alpha = alpha;
+    p.invbeta = invbeta;
+    p.L = L;
+    p.C = C;
+    kaiser_sinc_12(p.filt);
+    VOC_CUDA(cudaFuncSetAttribute(snake_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kActSmemBytes));
+    const dim3 grid((L + kActTL - 1) / kActTL, C / 64, N);
+    snake_act_kernel<<<grid, 256, kActSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    VOC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int usb_vocoder_filter(float* out12) {
+    if (!out12) return set_error("null argument");
+    kaiser_sinc_12(out12);
+    return 0;
+}
+
+}  // extern "C"

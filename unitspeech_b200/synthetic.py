@@ -66,3 +66,32 @@ def synthetic_inputs(B: int, T: int, n_steps: int, n_feats: int = 80, spk_emb_di
         ar = torch.arange(T).unsqueeze(0)
         mask = (ar < torch.tensor(list(lengths)).unsqueeze(1)).float().unsqueeze(1)
     return z, mask, cond, spk, noise
+
+
+# Hyper-parameters of the public 22 kHz / 80-band BigVGAN generator (the reference ships no vocoder config.json,
+# README.md:63-64 points at the public checkpoint).
+PUBLIC_VOCODER_CONFIG = dict(
+    num_mels=80, upsample_rates=[4, 4, 2, 2, 2, 2], upsample_kernel_sizes=[8, 8, 4, 4, 4, 4],
+    upsample_initial_channel=1536, resblock="1", resblock_kernel_sizes=[3, 7, 11],
+    resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], activation="snakebeta", snake_logscale=True)
+
+
+def vocoder_state(h: dict, seed: int = 4321) -> Dict[str, torch.Tensor]:
+    """Seeded generator weights in the folded (post remove_weight_norm) form: convs U(+-1/sqrt(fan_in)) so the
+    activations stay O(1), snake alpha/beta ~ N(0, 0.3) in log scale (or 1 + N(0, 0.1) linear).  The same tensors as
+    the parity harness (oracle/bigvgan_oracle.harness_params; tests/test_synthetic.py checks)."""
+    from .vocoder import param_shapes
+    g = torch.Generator().manual_seed(seed)
+    p: Dict[str, torch.Tensor] = {}
+    for name, shape in param_shapes(h).items():
+        if name.endswith(".alpha") or name.endswith(".beta"):
+            p[name] = torch.randn(shape, generator=g) * 0.3 if h.get("snake_logscale") else 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith(".weight"):
+            if name.startswith("ups."):
+                fan_in = shape[0] * shape[2] / h["upsample_rates"][int(name.split(".")[1])]
+            else:
+                fan_in = shape[1] * shape[2]
+            p[name] = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(max(fan_in, 1.0))
+        else:
+            p[name] = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+    return p
