@@ -298,6 +298,10 @@ def run_gpu_arm(args):
         breakdown = {"conv_igemm_ms": conv_ms, "gn_apply_ms": gn_ms, "attention_ms": at_ms, "other_ms": ot_ms,
                      "attention_GBps": at_bytes / (at_ms / 1e3) / 1e9 if at_ms > 0 else None,
                      "other_GBps": ot_bytes / (ot_ms / 1e3) / 1e9 if ot_ms > 0 else None}
+        # ---- optional second stage (BASELINE.json configs[3]): BigVGAN vocoder on this batch's mels
+        vocoder = None
+        if not args.no_vocoder:
+            vocoder = vocoder_leg(dev, B, T, elapsed_ms / args.steps, peaks)
         # ---- CPU baseline on this box's host cores (bounded sample)
         cpu = None
         if not args.no_cpu:
@@ -322,12 +326,58 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "breakdown_ms_per_pass": breakdown,
             "cpu_baseline": cpu,
+            "vocoder_stage": vocoder,
         }
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         _emit(line)
+
+
+def vocoder_leg(dev, B, T, decoder_ms, peaks):
+    """Times the BigVGAN stage (public 22 kHz / 80-band generator, 112.2M random-init params) on B x T mel frames and
+    reports its two kernel classes against their rooflines."""
+    from unitspeech_b200 import BigVGAN
+    from unitspeech_b200.synthetic import PUBLIC_VOCODER_CONFIG, vocoder_state
+    voc = BigVGAN(dict(PUBLIC_VOCODER_CONFIG))
+    voc.load_state_dict(vocoder_state(PUBLIC_VOCODER_CONFIG, seed=1))
+    voc.to(dev).eval()
+    voc.max_frames_per_call = max(8192, T)
+    mel = torch.randn(B, N_FEATS, T, device=dev) * 2 - 4
+    for _ in range(2):
+        wav = voc(mel)
+    torch.cuda.synchronize(dev)
+    assert torch.isfinite(wav).all(), "non-finite audio from the CUDA vocoder"
+    l0 = voc.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 3
+    e0.record()
+    for _ in range(iters):
+        voc(mel)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    launches = (voc.launch_count - l0) // iters
+    voc.set_profiling(True)
+    voc(mel)
+    torch.cuda.synchronize(dev)
+    prof = voc.get_profile()
+    voc.set_profiling(False)
+    cm, cw, cn = prof["conv_igemm"]
+    am, aw, an = prof["snake_act"]
+    return {
+        "workload": f"BigVGAN 22 kHz/80-band generator (112.2M params, random init), {B} x {T} mel frames -> {B} x {T * 256} samples",
+        "ms": ms, "mel_frames_per_s": B * T / ms * 1e3, "audio_seconds_per_s": B * T * 256 / 22050.0 / ms * 1e3,
+        "gpu_launches": launches,
+        "pipeline_mel_frames_per_s": B * T / (decoder_ms + ms) * 1e3,
+        "conv": {"kernel": "conv_igemm (1-D taps, H = 1)", "bound": "tensor", "ms": cm, "launches": cn,
+                 "achieved": cw / cm / 1e9, "peak": peaks["tensor"], "unit": "TFLOP/s (channels padded to 64)",
+                 "frac": cw / cm / 1e9 / peaks["tensor"]},
+        "snake_act": {"kernel": "snake_act_kernel (up x2 + Snake + low-pass + down x2 fused)", "bound": "hbm", "ms": am,
+                      "launches": an, "achieved": aw / am / 1e6, "peak": peaks["hbm"], "unit": "GB/s (fp16 read + write)",
+                      "frac": aw / am / 1e6 / peaks["hbm"]},
+    }
 
 
 def main():
@@ -363,6 +413,7 @@ def _main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-vocoder", action="store_true", help="skip the vocoder-stage leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

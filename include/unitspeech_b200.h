@@ -159,10 +159,16 @@ long long usb_vocoder_launch_count(const usb_vocoder* h);
 size_t usb_vocoder_workspace_bytes(const usb_vocoder* h);
 /* tensor-core FLOPs (padded channel counts) of one forward at the current (B, T) plan */
 double usb_vocoder_flops_per_call(const usb_vocoder* h);
+/* per-class CUDA-event timing of the following forward calls (adds a stream sync; not for timed runs):
+ * class 0 = tcgen05 convs (work = FLOPs on padded channels), 1 = fused Snake activation (work = fp16 bytes read +
+ * written), 2 = resblock averaging (bytes) */
+int usb_vocoder_set_profiling(usb_vocoder* h, int32_t on);
+int usb_vocoder_get_profile(usb_vocoder* h, double* ms3, double* work3, long long* launches3);
 /* Activation1d (alias_free_torch/act.py:23-28) on NLC fp16: x, out (N, L, C) dev, C % 64 == 0; alpha (C) dev =
- * snake frequency, invbeta (C) dev = 1 / (beta + 1e-9), both already exp'd when the parameters are log-scale. */
-int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, int32_t N, int32_t L, int32_t C, void* out,
-                     uint64_t stream);
+ * snake frequency, invbeta (C) dev = 1 / (beta + 1e-9), both already exp'd when the parameters are log-scale;
+ * channels [c_real, C) are layout padding and are written as zeros. */
+int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, int32_t N, int32_t L, int32_t C,
+                     int32_t c_real, void* out, uint64_t stream);
 /* kaiser_sinc_filter1d(0.25, 0.3, 12) as the library computes it (alias_free_torch/filter.py:28-57) */
 int usb_vocoder_filter(float* out12);
 

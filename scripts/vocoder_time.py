@@ -37,6 +37,16 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
     frames = a.batch * a.frames
+    voc.set_profiling(True)
+    voc(mel)
+    torch.cuda.synchronize()
+    prof = voc.get_profile()
+    voc.set_profiling(False)
+    cm, cw, cn = prof["conv_igemm"]
+    am, aw, an = prof["snake_act"]
+    om, ow, on = prof["other"]
+    print(json.dumps({"conv_ms": cm, "conv_tflops_padded": cw / cm / 1e9, "conv_launches": cn, "act_ms": am,
+                      "act_GBps": aw / am / 1e6, "act_launches": an, "other_ms": om, "other_GBps": ow / om / 1e6}))
     print(json.dumps({"vocoder_ms": ms, "mel_frames_per_s": frames / ms * 1e3, "audio_s_per_s": frames * 256 / 22050 / ms * 1e3,
                       "tensor_tflops": voc.flops_per_call / ms / 1e9, "launches_per_call": (voc.launch_count - l0) // a.iters,
                       "workspace_gb": voc.workspace_bytes / 2 ** 30, "finite": bool(torch.isfinite(out).all())}))

@@ -41,8 +41,9 @@ def _report(name, out, ref):
     return float(d.max()), float(d.mean())
 
 
-@pytest.mark.parametrize("N,L,C", [(1, 1, 64), (2, 5, 64), (1, 64, 128), (2, 200, 64), (1, 777, 192)])
-def test_snake_activation_kernel(N, L, C):
+@pytest.mark.parametrize("N,L,C,Cr", [(1, 1, 64, 64), (2, 5, 64, 24), (1, 64, 128, 96), (2, 200, 64, 48), (1, 777, 192, 192),
+                                       (1, 130, 64, 8)])
+def test_snake_activation_kernel(N, L, C, Cr):
     from unitspeech_b200 import abi
     lib = abi.load_library()
     g = torch.Generator().manual_seed(L * 7 + C)
@@ -52,13 +53,16 @@ def test_snake_activation_kernel(N, L, C):
     filt = V.kaiser_sinc_filter1d(0.25, 0.3, 12)
     ref = V.activation1d(p, "a", x, filt, dict(activation="snakebeta", snake_logscale=True))
     xd = x.permute(0, 2, 1).contiguous().cuda().half()
+    xd[:, :, Cr:] = float("nan")             # padding channels may hold anything: they must not be read
     out = torch.full_like(xd, float("nan"))
     al, ib = torch.exp(alpha).cuda(), (1.0 / (torch.exp(beta) + 1e-9)).cuda()
-    abi.check(lib.usb_op_snake_act(xd.data_ptr(), al.data_ptr(), ib.data_ptr(), N, L, C, out.data_ptr(),
+    abi.check(lib.usb_op_snake_act(xd.data_ptr(), al.data_ptr(), ib.data_ptr(), N, L, C, Cr, out.data_ptr(),
                                    int(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     got = out.float().cpu().permute(0, 2, 1)
     assert torch.isfinite(got).all()
+    assert float(got[:, Cr:].abs().max()) == 0.0 if Cr < C else True
+    got, ref = got[:, :Cr], ref[:, :Cr]
     err = (got - ref).abs()
     assert float(err.max()) <= 4e-3 * max(1.0, float(ref.abs().max())), float(err.max())
 
@@ -136,3 +140,29 @@ def test_vocoder_errors_are_loud():
     v2 = BigVGAN(bad).cuda()
     with pytest.raises(abi.UsbError):
         v2(torch.zeros(1, 80, 8).cuda())
+
+
+def test_decoder_then_vocoder_pipeline_matches_oracle_pipeline():
+    """inference.py:128-141: decoder -> de-normalise -> vocoder -> clamp, both stages on the CUDA path vs both oracles."""
+    from oracle import unitspeech_oracle as O
+    from unitspeech_b200 import UnitSpeech, denormalize_mel
+    params = O.harness_params(dim=64, dim_mults=(1, 2), seed=1234)
+    B, T, n = 2, 16, 4
+    z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=3, scale=1.0 / 512, lengths=[16, 12])
+    y_ref = torch.cat([O.reverse_diffusion(params, z[b:b + 1], mask[b:b + 1], cond[b:b + 1], spk[b:b + 1], n, 1.0, 1.0,
+                                           noise=noise[:, b:b + 1], dim=64, dim_mults=(1, 2)) for b in range(B)])
+    h = dict(V.PUBLIC_22KHZ_80BAND, upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=128)
+    vp = V.harness_params(h)
+    mel_min, mel_max = torch.full((80, 1), -11.5), torch.full((80, 1), 2.0)
+    wav_ref = V.bigvgan_forward(vp, (y_ref + 1) / 2 * (mel_max - mel_min) + mel_min, h).squeeze(1).clamp(-1, 1)
+
+    dec = UnitSpeech(80, 64, (1, 2), spk_emb_dim=256)
+    dec.load_state_dict(params)
+    dec = dec.cuda().eval()
+    voc = _vocoder(h)
+    y = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, text_gradient_scale=1.0, spk_gradient_scale=1.0,
+            noise=noise.cuda())
+    wav = voc(denormalize_mel(y, mel_min.cuda(), mel_max.cuda())).squeeze(1).clamp(-1, 1).cpu()
+    assert wav.shape == (B, T * 8)
+    mx, mn = _report("pipeline", wav, wav_ref)
+    assert mx <= MAX_ABS and mn <= MEAN_ABS

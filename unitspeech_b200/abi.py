@@ -83,7 +83,9 @@ SIGNATURES = {
     "usb_vocoder_launch_count": (c_int64, [c_void_p]),
     "usb_vocoder_workspace_bytes": (ctypes.c_size_t, [c_void_p]),
     "usb_vocoder_flops_per_call": (c_double, [c_void_p]),
-    "usb_op_snake_act": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_uint64]),
+    "usb_vocoder_set_profiling": (c_int32, [c_void_p, c_int32]),
+    "usb_vocoder_get_profile": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)]),
+    "usb_op_snake_act": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_uint64]),
     "usb_vocoder_filter": (c_int32, [POINTER(c_float)]),
 }
 

@@ -40,17 +40,19 @@ namespace usb {
 // ---------------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kActTL = 64;                    // output samples per block
+constexpr int kActTL = 56;                    // output samples per block
 constexpr int kActXRows = kActTL + 12;        // input rows t0-6 .. t0+TL+5
 constexpr int kActSRows = 2 * kActTL + 10;    // 2x-rate rows 2*t0-5 .. 2*t0+2*TL+4
-constexpr int kActSmemBytes = (kActXRows + kActSRows) * 64 * 4;
+constexpr int kActSItems = (kActSRows + 3) / 4;   // phase-2 work items of four 2x-rate rows (31: one round of 32 row slots)
+constexpr int kActSmemBytes = (kActXRows + 4 * kActSItems) * 64 * 4;   // 48 KB
 
 struct ActParams {
     const __half* x;       // [N][L][C]
     __half* out;           // [N][L][C]
     const float* alpha;    // [C] frequency a (already exp'd for log-scale parameters); 0 in padding channels
     const float* invbeta;  // [C] 1 / (b + 1e-9); 0 in padding channels
-    int L, C;
+    int L, C;              // C = padded channel count (multiple of 64)
+    int Creal;             // channels that carry data; [Creal, C) is written as zeros
     float filt[12];        // kaiser_sinc_filter1d(0.25, 0.3, 12) -- shared by the up- and the down-sampler
 };
 
@@ -58,37 +60,47 @@ struct ActParams {
 // threads of a row read/write contiguous float4s
 __device__ __forceinline__ int act_sidx(int row, int cv, int half) { return row * 64 + half * 32 + cv * 4; }
 
-__device__ __forceinline__ float sin_reduced(float v) {
-    const float k = rintf(v * 0.15915494309189535f);
-    float r = fmaf(-k, 6.2831854820251465f, v);       // 2*pi split in two fp32 terms
-    r = fmaf(-k, -1.7484556000744883e-7f, r);
-    return __sinf(r);
-}
-
 // Activation1d.forward (alias_free_torch/act.py:23-28) fused:
 //   u[2m]   = 2 * sum_{q=-3..2} f[5-2q] * x[clamp(m+q)]        (UpSample1d, resample.py:26-33)
 //   u[2m+1] = 2 * sum_{q=-2..3} f[6-2q] * x[clamp(m+q)]
 //   s[i]    = u[i] + invbeta * sin(alpha * u[i])^2             (activations.py:47-59,107-120)
 //   out[t]  = sum_{k=0..11} f[k] * s[clamp(2t+k-5)]            (LowPassFilter1d stride 2, filter.py:84-95)
-__global__ void __launch_bounds__(256) snake_act_kernel(const ActParams p) {
+__global__ void __launch_bounds__(256, 3) snake_act_kernel(const ActParams p) {
     extern __shared__ float act_smem[];
     float* xs = act_smem;
-    float* ss = act_smem + kActXRows * 64;
+    float* ss = act_smem + kActXRows * 64;      // 4 * kActSItems rows (the last two are computed but never read)
     const int tid = threadIdx.x;
-    const int cv = tid & 7, r = tid >> 3;
+    // only the real channels of this 64-channel slab are computed (padding channels are written as zeros): the
+    // block's threads are laid out as (rows x ncv) with ncv = 8-channel vectors that hold real channels
+    const int creal = min(64, p.Creal - static_cast<int>(blockIdx.y) * 64);
+    const int ncv = (creal + 7) >> 3;
     const int t0 = blockIdx.x * kActTL;
-    const int c0 = blockIdx.y * 64 + cv * 8;
     const long long nbase = static_cast<long long>(blockIdx.z) * p.L;
-
-    for (int row = r; row < kActXRows; row += 32) {
-        int t = t0 - 6 + row;
-        t = t < 0 ? 0 : (t > p.L - 1 ? p.L - 1 : t);
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.x + (nbase + t) * p.C + c0));
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-        const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]), d = __half22float2(h2[3]);
-        *reinterpret_cast<float4*>(xs + act_sidx(row, cv, 0)) = make_float4(a.x, a.y, b.x, b.y);
-        *reinterpret_cast<float4*>(xs + act_sidx(row, cv, 1)) = make_float4(c.x, c.y, d.x, d.y);
+    if (ncv < 8) {
+        const int npad = 8 - ncv;
+        for (int idx = tid; idx < kActTL * npad; idx += 256) {
+            const int t = t0 + idx / npad;
+            if (t < p.L)
+                *reinterpret_cast<uint4*>(p.out + (nbase + t) * p.C + blockIdx.y * 64 + (ncv + idx % npad) * 8) =
+                    make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (ncv <= 0) return;
     }
+    const int R = 256 / ncv;                 // rows processed in parallel
+    const int cv = tid % ncv, r = tid / ncv;
+    const bool active = r < R;
+    const int c0 = blockIdx.y * 64 + cv * 8;
+
+    if (active)
+        for (int row = r; row < kActXRows; row += R) {
+            int t = t0 - 6 + row;
+            t = t < 0 ? 0 : (t > p.L - 1 ? p.L - 1 : t);
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.x + (nbase + t) * p.C + c0));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+            const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]), d = __half22float2(h2[3]);
+            *reinterpret_cast<float4*>(xs + act_sidx(row, cv, 0)) = make_float4(a.x, a.y, b.x, b.y);
+            *reinterpret_cast<float4*>(xs + act_sidx(row, cv, 1)) = make_float4(c.x, c.y, d.x, d.y);
+        }
     float al[8], ib[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -97,49 +109,109 @@ __global__ void __launch_bounds__(256) snake_act_kernel(const ActParams p) {
     }
     __syncthreads();
 
-    for (int ii = r; ii < kActSRows; ii += 32) {
-        int i = 2 * t0 - 5 + ii;
-        i = i < 0 ? 0 : (i > 2 * p.L - 1 ? 2 * p.L - 1 : i);
-        const int m = i >> 1, odd = i & 1;
-        // first contributing input row: x[m-3] (even) or x[m-2] (odd); filter taps 11,9,..,1 (even) or 10,8,..,0 (odd)
-        const int row0 = m - 3 + odd - (t0 - 6);
-        float u[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // phase 2: the 2x-rate signal after the Snake non-linearity, four rows per item.  Rows i0 (odd), i0+1, i0+2, i0+3
+    // read the seven input rows m0-2 .. m0+4 (m0 = i0 >> 1): each shared-memory row is loaded once per item.
+    if (active)
+        for (int it = r; it < kActSItems; it += R) {
+            const int ii0 = 4 * it;
+            const int i0 = 2 * t0 - 5 + ii0;
+            float u[4][8];
+            if (i0 >= 0 && i0 + 3 <= 2 * p.L - 1) {
+                const int rowb = (i0 >> 1) - 2 - (t0 - 6);
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const float w = 2.f * (odd ? p.filt[10 - 2 * j] : p.filt[11 - 2 * j]);
-            const float4 lo = *reinterpret_cast<const float4*>(xs + act_sidx(row0 + j, cv, 0));
-            const float4 hi = *reinterpret_cast<const float4*>(xs + act_sidx(row0 + j, cv, 1));
-            u[0] = fmaf(w, lo.x, u[0]); u[1] = fmaf(w, lo.y, u[1]); u[2] = fmaf(w, lo.z, u[2]); u[3] = fmaf(w, lo.w, u[3]);
-            u[4] = fmaf(w, hi.x, u[4]); u[5] = fmaf(w, hi.y, u[5]); u[6] = fmaf(w, hi.z, u[6]); u[7] = fmaf(w, hi.w, u[7]);
-        }
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float sn = sin_reduced(al[j] * u[j]);
-            u[j] = fmaf(ib[j] * sn, sn, u[j]);
+                    for (int j = 0; j < 8; ++j) u[q][j] = 0.f;
+#pragma unroll
+                for (int xr = 0; xr < 7; ++xr) {
+                    const float4 lo = *reinterpret_cast<const float4*>(xs + act_sidx(rowb + xr, cv, 0));
+                    const float4 hi = *reinterpret_cast<const float4*>(xs + act_sidx(rowb + xr, cv, 1));
+                    const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                    // row q uses x[first_q + j] with tap f[10 - 2j] (odd rows 0, 2) or f[11 - 2j] (even rows 1, 3);
+                    // first_q - (m0 - 2) = 0, 0, 1, 1
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = xr - (q >> 1);
+                        if (j >= 0 && j < 6) {
+                            const float w = 2.f * ((q & 1) ? p.filt[11 - 2 * j] : p.filt[10 - 2 * j]);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) u[q][c] = fmaf(w, xv[c], u[q][c]);
+                        }
+                    }
+                }
+            } else {
+                // block edges of the signal: rows are clamped individually (replicate padding of the low-pass filter)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int i = i0 + q;
+                    i = i < 0 ? 0 : (i > 2 * p.L - 1 ? 2 * p.L - 1 : i);
+                    const int m = i >> 1, odd = i & 1;
+                    const int row0 = m - 3 + odd - (t0 - 6);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) u[q][c] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const float w = 2.f * (odd ? p.filt[10 - 2 * j] : p.filt[11 - 2 * j]);
+                        const float4 lo = *reinterpret_cast<const float4*>(xs + act_sidx(row0 + j, cv, 0));
+                        const float4 hi = *reinterpret_cast<const float4*>(xs + act_sidx(row0 + j, cv, 1));
+                        u[q][0] = fmaf(w, lo.x, u[q][0]); u[q][1] = fmaf(w, lo.y, u[q][1]);
+                        u[q][2] = fmaf(w, lo.z, u[q][2]); u[q][3] = fmaf(w, lo.w, u[q][3]);
+                        u[q][4] = fmaf(w, hi.x, u[q][4]); u[q][5] = fmaf(w, hi.y, u[q][5]);
+                        u[q][6] = fmaf(w, hi.z, u[q][6]); u[q][7] = fmaf(w, hi.w, u[q][7]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    // MUFU.SIN reduces its argument itself (x / 2pi in fp32): absolute error ~|x| * 2^-24, far below
+                    // the fp16 storage of the result for the |alpha * u| < 1e3 seen here
+                    const float sn = __sinf(al[j] * u[q][j]);
+                    u[q][j] = fmaf(ib[j] * sn, sn, u[q][j]);
+                }
+                *reinterpret_cast<float4*>(ss + act_sidx(ii0 + q, cv, 0)) = make_float4(u[q][0], u[q][1], u[q][2], u[q][3]);
+                *reinterpret_cast<float4*>(ss + act_sidx(ii0 + q, cv, 1)) = make_float4(u[q][4], u[q][5], u[q][6], u[q][7]);
+            }
         }
-        *reinterpret_cast<float4*>(ss + act_sidx(ii, cv, 0)) = make_float4(u[0], u[1], u[2], u[3]);
-        *reinterpret_cast<float4*>(ss + act_sidx(ii, cv, 1)) = make_float4(u[4], u[5], u[6], u[7]);
-    }
     __syncthreads();
 
-    for (int tt = r; tt < kActTL; tt += 32) {
-        const int t = t0 + tt;
-        if (t >= p.L) break;
-        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // phase 3: low-pass + decimation, two outputs per item: 14 shared rows feed 2 x 12 taps
+    if (active)
+        for (int it = r; it < kActTL / 2; it += R) {
+            const int tt = 2 * it;
+            const int t = t0 + tt;
+            if (t >= p.L) break;
+            float o[2][8];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            const float w = p.filt[k];
-            const float4 lo = *reinterpret_cast<const float4*>(ss + act_sidx(2 * tt + k, cv, 0));
-            const float4 hi = *reinterpret_cast<const float4*>(ss + act_sidx(2 * tt + k, cv, 1));
-            o[0] = fmaf(w, lo.x, o[0]); o[1] = fmaf(w, lo.y, o[1]); o[2] = fmaf(w, lo.z, o[2]); o[3] = fmaf(w, lo.w, o[3]);
-            o[4] = fmaf(w, hi.x, o[4]); o[5] = fmaf(w, hi.y, o[5]); o[6] = fmaf(w, hi.z, o[6]); o[7] = fmaf(w, hi.w, o[7]);
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[q][c] = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 14; ++rr) {
+                const float4 lo = *reinterpret_cast<const float4*>(ss + act_sidx(2 * tt + rr, cv, 0));
+                const float4 hi = *reinterpret_cast<const float4*>(ss + act_sidx(2 * tt + rr, cv, 1));
+                const float sv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int k = rr - 2 * q;
+                    if (k >= 0 && k < 12) {
+                        const float w = p.filt[k];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) o[q][c] = fmaf(w, sv[c], o[q][c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (t + q >= p.L) break;
+                uint4 pk;
+                __half2* h2 = reinterpret_cast<__half2*>(&pk);
+                h2[0] = __floats2half2_rn(o[q][0], o[q][1]); h2[1] = __floats2half2_rn(o[q][2], o[q][3]);
+                h2[2] = __floats2half2_rn(o[q][4], o[q][5]); h2[3] = __floats2half2_rn(o[q][6], o[q][7]);
+                *reinterpret_cast<uint4*>(p.out + (nbase + t + q) * p.C + c0) = pk;
+            }
         }
-        uint4 pk;
-        __half2* h2 = reinterpret_cast<__half2*>(&pk);
-        h2[0] = __floats2half2_rn(o[0], o[1]); h2[1] = __floats2half2_rn(o[2], o[3]);
-        h2[2] = __floats2half2_rn(o[4], o[5]); h2[3] = __floats2half2_rn(o[6], o[7]);
-        *reinterpret_cast<uint4*>(p.out + (nbase + t) * p.C + c0) = pk;
-    }
 }
 
 // mel (B, M, T) fp32 -> [B][T][Cp] fp16, zero padded channels
@@ -275,7 +347,7 @@ struct VocConvW {
 struct VocActW {
     float* alpha = nullptr;
     float* invbeta = nullptr;
-    int C = 0;
+    int C = 0, Creal = 0;
 };
 
 struct VocOp {
@@ -323,6 +395,11 @@ struct usb_vocoder {
     std::vector<VocOp> ops;
     long long launches = 0;
     double flops_per_call = 0;
+    // optional per-class timing of the next forward calls: 0 conv (tensor), 1 snake activation (HBM), 2 other
+    bool profiling = false;
+    double prof_ms[3] = {0, 0, 0};
+    double prof_work[3] = {0, 0, 0};    // conv: padded FLOPs; activation / other: algorithmic bytes (fp16 read + write)
+    long long prof_launches[3] = {0, 0, 0};
 };
 
 namespace usb {
@@ -415,6 +492,7 @@ static int voc_load_act(usb_vocoder* h, const std::string& prefix, int C, VocAct
     if (is_beta) VOC_TRY(voc_get(h, prefix + ".act.beta", {C}, &pb));
     else pb = pa;
     a.C = pad64(C);
+    a.Creal = C;
     std::vector<float> al(a.C, 0.f), ib(a.C, 0.f);
     for (int c = 0; c < C; ++c) {
         // activations.py:54-59,113-120: exp() in log-scale mode, then 1 / (beta + 1e-9); same fp32 operations
@@ -508,6 +586,7 @@ static void voc_push_act(usb_vocoder* h, const VocActW& a, const __half* x, __ha
     op.act.invbeta = a.invbeta;
     op.act.L = L;
     op.act.C = a.C;
+    op.act.Creal = a.Creal;
     memcpy(op.act.filt, h->filt, sizeof h->filt);
     h->ops.push_back(op);
 }
@@ -600,6 +679,13 @@ static int voc_forward(usb_vocoder* h, const float* mel, int B, int T, float* ou
         mel_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(mel, h->melp, B, h->cfg.num_mels, T, Cp);
         h->launches++;
     }
+    std::vector<cudaEvent_t> evs;
+    if (h->profiling) {
+        evs.resize(h->ops.size() + 1);
+        for (cudaEvent_t& e : evs) VOC_CUDA(cudaEventCreate(&e));
+        VOC_CUDA(cudaEventRecord(evs[0], s));
+    }
+    size_t op_i = 0;
     for (const VocOp& op : h->ops) {
         switch (op.type) {
             case VocOp::CONV: {
@@ -619,6 +705,23 @@ static int voc_forward(usb_vocoder* h, const float* mel, int B, int T, float* ou
             default: break;
         }
         h->launches++;
+        ++op_i;
+        if (h->profiling) VOC_CUDA(cudaEventRecord(evs[op_i], s));
+    }
+    if (h->profiling) {
+        VOC_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < h->ops.size(); ++i) {
+            const VocOp& op = h->ops[i];
+            float ms = 0.f;
+            VOC_CUDA(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
+            const int cls = op.type == VocOp::CONV ? 0 : (op.type == VocOp::ACT ? 1 : 2);
+            h->prof_ms[cls] += ms;
+            h->prof_launches[cls]++;
+            if (cls == 0) h->prof_work[0] += op.flops;
+            else if (cls == 1) h->prof_work[1] += 4.0 * op.N * op.act.L * op.act.Creal;
+            else h->prof_work[2] += static_cast<double>(op.n8) * 8 * (op.mode == 0 ? 6 : (op.mode == 1 ? 10 : (op.mode == 2 ? 8 : 4)));
+        }
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
     }
     {
         const long long n = static_cast<long long>(B) * h->final_L;
@@ -721,10 +824,31 @@ long long usb_vocoder_launch_count(const usb_vocoder* h) { return h ? h->launche
 size_t usb_vocoder_workspace_bytes(const usb_vocoder* h) { return h ? h->arena_bytes : 0; }
 double usb_vocoder_flops_per_call(const usb_vocoder* h) { return h ? h->flops_per_call : 0; }
 
-int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, int32_t N, int32_t L, int32_t C, void* out,
-                     uint64_t stream) {
+int usb_vocoder_set_profiling(usb_vocoder* h, int32_t on) {
+    if (!h) return set_error("null argument");
+    h->profiling = on != 0;
+    for (int i = 0; i < 3; ++i) {
+        h->prof_ms[i] = 0;
+        h->prof_work[i] = 0;
+        h->prof_launches[i] = 0;
+    }
+    return 0;
+}
+
+int usb_vocoder_get_profile(usb_vocoder* h, double* ms3, double* work3, long long* launches3) {
+    if (!h || !ms3 || !work3 || !launches3) return set_error("null argument");
+    for (int i = 0; i < 3; ++i) {
+        ms3[i] = h->prof_ms[i];
+        work3[i] = h->prof_work[i];
+        launches3[i] = h->prof_launches[i];
+    }
+    return 0;
+}
+
+int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, int32_t N, int32_t L, int32_t C,
+                     int32_t c_real, void* out, uint64_t stream) {
     if (!x || !alpha || !invbeta || !out) return set_error("null argument");
-    if (C % 64 || N < 1 || L < 1) return set_error("snake activation needs C % 64 == 0");
+    if (C % 64 || N < 1 || L < 1 || c_real < 1 || c_real > C) return set_error("snake activation needs C % 64 == 0 and 1 <= c_real <= C");
     ActParams p;
     p.x = static_cast<const __half*>(x);
     p.out = static_cast<__half*>(out);
@@ -732,6 +856,7 @@ int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, in
     p.invbeta = invbeta;
     p.L = L;
     p.C = C;
+    p.Creal = c_real;
     kaiser_sinc_12(p.filt);
     VOC_CUDA(cudaFuncSetAttribute(snake_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kActSmemBytes));
     const dim3 grid((L + kActTL - 1) / kActTL, C / 64, N);

@@ -183,6 +183,18 @@ class BigVGAN(nn.Module):
     def flops_per_call(self) -> float:
         return float(abi.load_library().usb_vocoder_flops_per_call(self._handle)) if self._handle is not None else 0.0
 
+    def set_profiling(self, on: bool) -> None:
+        """Per-kernel-class CUDA-event timing of the next forward calls (adds a sync; not for timed runs)."""
+        if self._handle is None:
+            raise abi.UsbError("run one forward before profiling")
+        abi.check(abi.load_library().usb_vocoder_set_profiling(self._handle, int(bool(on))))
+
+    def get_profile(self):
+        """{class: (ms, algorithmic work, launches)} accumulated since set_profiling(True)."""
+        ms, work, n = (ctypes.c_double * 3)(), (ctypes.c_double * 3)(), (ctypes.c_int64 * 3)()
+        abi.check(abi.load_library().usb_vocoder_get_profile(self._handle, ms, work, n))
+        return {k: (ms[i], work[i], int(n[i])) for i, k in enumerate(("conv_igemm", "snake_act", "other"))}
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
