@@ -62,6 +62,17 @@ int usb_finalize_params(usb_handle* h);
 int usb_estimator_forward(usb_handle* h, const float* x, const float* mu, const float* mask, const float* t,
                           const float* spk, float* out, int32_t Be, int32_t T, uint64_t stream);
 
+/* UnitSpeech.forward_diffusion(x0, mask, t)                                   unitspeech/unitspeech.py:376-384
+ * x0, z: (B, n_feats, T) dev; mask: (B, T) dev; t: (B,) dev.  z is the N(0,1) draw the reference makes at :381, supplied
+ * by the host.  xt_out = (x0*exp(-cn/2) + z*sqrt(1-exp(-cn)))*mask; zmask_out = z*mask (may be NULL). */
+int usb_forward_diffusion(usb_handle* h, const float* x0, const float* mask, const float* t, const float* z, float* xt_out,
+                          float* zmask_out, int32_t B, int32_t T, uint64_t stream);
+/* UnitSpeech.loss_t(x0, mask, cond, t, spk_emb) -- the fine-tuning objective    unitspeech/unitspeech.py:393-405
+ * FORWARD VALUE ONLY (no gradients: the backward pass / optimizer of fine_tune, SURVEY section 8 row a16, is not built).
+ * loss_out: dev float[1]; xt_out: (B, n_feats, T) dev or NULL. */
+int usb_loss_t(usb_handle* h, const float* x0, const float* cond, const float* mask, const float* t, const float* spk,
+               const float* z, float* loss_out, float* xt_out, int32_t B, int32_t T, uint64_t stream);
+
 /* UnitSpeech.reverse_diffusion(z, mask, cond, spk_emb, n_timesteps, tg, sg)     unitspeech/unitspeech.py:334-374
  * z, cond: (B, n_feats, T) dev; mask: (B, T) dev; spk: (B, spk_emb_dim) dev;
  * noise: (n, B, n_feats, T) dev, the per-step randn draws (:367), or NULL for all-zero noise;

@@ -352,6 +352,34 @@ def reverse_diffusion(p: Params, z: torch.Tensor, mask: torch.Tensor, cond: torc
 # parameter construction (the parity harness's "identical random-init weights")
 # ----------------------------------------------------------------------------
 
+def forward_diffusion(x0: torch.Tensor, mask: torch.Tensor, t: torch.Tensor, z: torch.Tensor,
+                      beta_min: float = 0.05, beta_max: float = 20.0):
+    """UnitSpeech.forward_diffusion (unitspeech/unitspeech.py:376-384) with the N(0,1) draw ``z`` passed in
+    (the reference draws it with torch.randn(x0.shape) at :381).  Returns (xt * mask, z * mask)."""
+    time = t.unsqueeze(-1).unsqueeze(-1)
+    cum_noise = get_noise(time, beta_min, beta_max, cumulative=True)
+    mean = x0 * torch.exp(-0.5 * cum_noise)
+    variance = 1.0 - torch.exp(-cum_noise)
+    xt = mean + z * torch.sqrt(variance)
+    return xt * mask, z * mask
+
+
+@torch.no_grad()
+def loss_t(p: Params, x0: torch.Tensor, mask: torch.Tensor, cond: torch.Tensor, t: torch.Tensor,
+           spk_emb: torch.Tensor, z: torch.Tensor, *, dim: int = 128, dim_mults: Sequence[int] = (1, 2, 4, 8),
+           beta_min: float = 0.05, beta_max: float = 20.0, pe_scale: float = 1000):
+    """UnitSpeech.loss_t (unitspeech/unitspeech.py:393-405), forward value only.  Returns (loss, xt)."""
+    xt, zm = forward_diffusion(x0, mask, t, z, beta_min, beta_max)
+    time = t.unsqueeze(-1).unsqueeze(-1)
+    cum_noise = get_noise(time, beta_min, beta_max, cumulative=True)
+    cond = cond * mask
+    est = estimator_forward(p, xt, mask, cond, t, spk_emb, dim=dim, dim_mults=dim_mults, pe_scale=pe_scale)
+    est = est * torch.sqrt(1.0 - torch.exp(-cum_noise))
+    n_feats = x0.shape[1]
+    loss = torch.sum((est + zm) ** 2) / (torch.sum(mask) * n_feats)
+    return loss, xt
+
+
 def param_shapes(n_feats: int, dim: int, dim_mults: Sequence[int], spk_emb_dim: int) -> Dict[str, Tuple[int, ...]]:
     """state_dict names and shapes of UnitSpeech — unitspeech/unitspeech.py:125-162,230-233."""
     s: Dict[str, Tuple[int, ...]] = {"text_uncon": (1, n_feats, 1), "spk_uncon": (1, 1, spk_emb_dim)}

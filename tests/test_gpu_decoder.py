@@ -6,6 +6,7 @@ Tolerance (BASELINE.json north_star): final mel max-abs <= 1e-2 and mean-abs <= 
 """
 
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -141,8 +142,6 @@ def test_argument_errors():
         dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), 1)
     with pytest.raises(ValueError):
         dec(z[..., :15].cuda(), mask[..., :15].cuda(), cond[..., :15].cuda(), spk.cuda(), 2)
-    with pytest.raises(NotImplementedError):
-        dec.compute_loss(None, None, None)
     from unitspeech_b200 import abi
     with pytest.raises(abi.UsbError):
         UnitSpeech(80, 48, (1, 2), spk_emb_dim=256).cuda()(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), 2)
@@ -236,3 +235,56 @@ def test_execute_text_to_speech_matches_reference_glue():
     assert torch.equal(y_enc, cond_y[:, :, :int(y_len.max())])
     mx, mn = _errs(y_dec, ref)
     assert mx <= MAX_TOL and mn <= MEAN_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fine-tuning objective, forward value (forward half)
+# ---------------------------------------------------------------------------------------------------------------------
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+
+
+@pytest.mark.parametrize("name", ["loss_d64", "loss_full"])
+def test_loss_t_matches_reference_golden_and_oracle(golden_dir, name):
+    from make_golden_loss import LOSS_CASES, loss_inputs
+    dim, mults, B, T, lengths, ts, s = LOSS_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=s)
+    x0, mask, cond, spk = loss_inputs(B, T, lengths)
+    t = torch.tensor(ts)
+    dec = _decoder(dim, mults, params)
+    torch.manual_seed(77)                       # same global-RNG draw as the reference's forward_diffusion (CPU tensors in)
+    loss, xt = dec.loss_t(x0, mask, cond, t, spk)
+    assert not loss.requires_grad and loss.dim() == 0
+    assert float((xt - torch.from_numpy(g["xt"])).abs().max()) <= 1e-5
+    rel = abs(float(loss) - float(g["loss"])) / float(g["loss"])
+    print(f"{name}: loss {float(loss):.6f} reference {float(g['loss']):.6f} rel {rel:.2e}")
+    assert rel <= 2e-3
+    # forward_diffusion alone, same draw
+    torch.manual_seed(77)
+    xt2, zm = dec.forward_diffusion(x0, mask, t)
+    torch.manual_seed(77)
+    z = torch.randn(x0.shape)
+    assert torch.equal(xt2, xt) and torch.equal(zm, z * mask)
+    # device tensors in -> device tensors out, and repeatable given the generator state
+    torch.cuda.manual_seed(5)
+    l1, _ = dec.loss_t(x0.cuda(), mask.cuda(), cond.cuda(), t.cuda(), spk.cuda())
+    torch.cuda.manual_seed(5)
+    l2, _ = dec.loss_t(x0.cuda(), mask.cuda(), cond.cuda(), t.cuda(), spk.cuda())
+    assert l1.is_cuda and torch.equal(l1, l2)
+
+
+@pytest.mark.parametrize("name", ["finetune_d64", "finetune_d64_short"])
+def test_fine_tune_objective_matches_reference_golden(golden_dir, name):
+    import random
+    from make_golden_loss import FT_CASES, FT_OUT_SCALE, finetune_inputs
+    dim, mults, B, Lt, T, y_lengths, seg = FT_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=FT_OUT_SCALE)
+    cond_x, y, y_mask, yl, attn, spk = finetune_inputs(B, Lt, T, y_lengths)
+    dec = _decoder(dim, mults, params)
+    random.seed(5)
+    torch.manual_seed(78)
+    loss = dec.fine_tune(cond_x, y, y_mask, yl, T, attn, spk, seg, 80)
+    rel = abs(float(loss) - float(g["loss"])) / float(g["loss"])
+    print(f"{name}: loss {float(loss):.6f} reference {float(g['loss']):.6f} rel {rel:.2e}")
+    assert rel <= 2e-3

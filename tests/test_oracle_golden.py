@@ -83,3 +83,20 @@ def test_closed_form_step_equals_op_for_op():
 def test_n_timesteps_one_rejected():
     with pytest.raises(ValueError):
         O.schedule_tables(1, 0.05, 20.0)
+
+
+@pytest.mark.parametrize("name", ["loss_d64", "loss_full"])
+def test_oracle_loss_t_matches_reference(golden_dir, name):
+    """oracle.loss_t / forward_diffusion vs UnitSpeech.loss_t of the unmodified reference (make_golden_loss.py)."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden_loss import LOSS_CASES, loss_inputs
+    dim, mults, B, T, lengths, ts, s = LOSS_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=s)
+    x0, mask, cond, spk = loss_inputs(B, T, lengths)
+    torch.manual_seed(77)
+    z = torch.randn(x0.shape)
+    loss, xt = O.loss_t(params, x0, mask, cond, torch.tensor(ts), spk, z, dim=dim, dim_mults=mults)
+    assert np.abs(xt.numpy() - g["xt"]).max() <= 1e-6
+    assert abs(float(loss) - float(g["loss"])) <= 2e-5 * float(g["loss"])

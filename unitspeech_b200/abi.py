@@ -59,6 +59,8 @@ SIGNATURES = {
     "usb_load_param": (c_int32, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int32]),
     "usb_finalize_params": (c_int32, [c_void_p]),
     "usb_estimator_forward": (c_int32, [c_void_p] + [c_void_p] * 6 + [c_int32, c_int32, c_uint64]),
+    "usb_forward_diffusion": (c_int32, [c_void_p] + [c_void_p] * 6 + [c_int32, c_int32, c_uint64]),
+    "usb_loss_t": (c_int32, [c_void_p] + [c_void_p] * 8 + [c_int32, c_int32, c_uint64]),
     "usb_reverse_diffusion": (c_int32, [c_void_p] + [c_void_p] * 7 + [c_int32, c_float, c_float, c_void_p, c_void_p,
                                                                     c_int32, c_int32, c_uint64]),
     "usb_reverse_diffusion_host": (c_int32, [c_void_p] + [c_void_p] * 7 + [c_int32, c_float, c_float, c_void_p,

@@ -524,4 +524,92 @@ int launch_gather_rows(const float* src, const int* idx, float* dst, int N, int 
     return (int)cudaGetLastError();
 }
 
+// =====================================================================================================================
+// training objective, forward value (UnitSpeech.forward_diffusion / loss_t, unitspeech/unitspeech.py:376-405)
+// =====================================================================================================================
+// xt = (x0 * exp(-cn/2) + z * sqrt(1 - exp(-cn))) * mask, zm = z * mask, mu = cond * mask,
+// cn = beta_min * t + 0.5 * (beta_max - beta_min) * t^2 (get_noise, cumulative)
+__global__ void forward_diffusion_kernel(const float* __restrict__ x0, const float* __restrict__ z,
+                                         const float* __restrict__ cond, const float* __restrict__ mask,
+                                         const float* __restrict__ t, float beta_min, float beta_max,
+                                         float* __restrict__ xt, float* __restrict__ zm, float* __restrict__ mu, int B,
+                                         int F, int T) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * F * T) return;
+    const int b = static_cast<int>(i / (static_cast<long long>(F) * T));
+    const int w = static_cast<int>(i % T);
+    const float tb = __ldg(t + b);
+    const float cn = beta_min * tb + 0.5f * (beta_max - beta_min) * (tb * tb);
+    const float m = __ldg(mask + static_cast<long long>(b) * T + w);
+    const float zz = z[i];
+    xt[i] = (x0[i] * expf(-0.5f * cn) + zz * sqrtf(1.0f - expf(-cn))) * m;
+    if (zm) zm[i] = zz * m;
+    if (mu) mu[i] = cond[i] * m;
+}
+int launch_forward_diffusion(const float* x0, const float* z, const float* cond, const float* mask, const float* t,
+                             float beta_min, float beta_max, float* xt, float* zm, float* mu, int B, int F, int T,
+                             cudaStream_t s) {
+    const long long total = static_cast<long long>(B) * F * T;
+    forward_diffusion_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x0, z, cond, mask, t, beta_min,
+                                                                                       beta_max, xt, zm, mu, B, F, T);
+    return (int)cudaGetLastError();
+}
+
+// loss = sum((score * sqrt(1 - exp(-cn)) + zm)^2) / (sum(mask) * F): fixed-shape two-stage reduction in double
+// (block partials in a fixed order, then one block), so the value does not depend on scheduling.
+constexpr int kLossBlocks = 256;
+__global__ void __launch_bounds__(256) loss_partial_kernel(const float* __restrict__ score, const float* __restrict__ zm,
+                                                           const float* __restrict__ mask, const float* __restrict__ t,
+                                                           float beta_min, float beta_max, double* __restrict__ partial,
+                                                           int B, int F, int T) {
+    __shared__ double red[2][256];
+    const long long total = static_cast<long long>(B) * F * T;
+    const long long mtotal = static_cast<long long>(B) * T;
+    double acc = 0.0, macc = 0.0;
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += 256LL * kLossBlocks) {
+        const int b = static_cast<int>(i / (static_cast<long long>(F) * T));
+        const float tb = __ldg(t + b);
+        const float cn = beta_min * tb + 0.5f * (beta_max - beta_min) * (tb * tb);
+        const float v = score[i] * sqrtf(1.0f - expf(-cn)) + zm[i];
+        acc += static_cast<double>(v * v);
+    }
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < mtotal; i += 256LL * kLossBlocks)
+        macc += static_cast<double>(mask[i]);
+    red[0][threadIdx.x] = acc;
+    red[1][threadIdx.x] = macc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + s];
+            red[1][threadIdx.x] += red[1][threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = red[0][0];
+        partial[2 * blockIdx.x + 1] = red[1][0];
+    }
+}
+__global__ void __launch_bounds__(256) loss_final_kernel(const double* __restrict__ partial, float* __restrict__ loss, int F) {
+    __shared__ double red[2][256];
+    red[0][threadIdx.x] = partial[2 * threadIdx.x];
+    red[1][threadIdx.x] = partial[2 * threadIdx.x + 1];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + s];
+            red[1][threadIdx.x] += red[1][threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = static_cast<float>(red[0][0] / (red[1][0] * F));
+}
+int launch_diffusion_loss(const float* score, const float* zm, const float* mask, const float* t, float beta_min,
+                          float beta_max, double* partial, float* loss, int B, int F, int T, cudaStream_t s) {
+    static_assert(kLossBlocks == 256, "loss_final_kernel reduces exactly 256 partials");
+    loss_partial_kernel<<<kLossBlocks, 256, 0, s>>>(score, zm, mask, t, beta_min, beta_max, partial, B, F, T);
+    loss_final_kernel<<<1, 256, 0, s>>>(partial, loss, F);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace usb

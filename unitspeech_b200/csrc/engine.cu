@@ -418,6 +418,8 @@ struct usb_handle {
     Plan plan;
     float* tpart_buf = nullptr;   // sampler: [n_steps] t, [n_steps][dim+S] u, [n_steps][J] time part
     size_t tpart_cap = 0;
+    float* loss_buf = nullptr;    // loss_t: xt, z*mask, cond*mask, score ([B][n_feats][T] each) + 512 doubles of partials
+    size_t loss_cap = 0;
     long long launches = 0;
     // optional per-kernel-class timing (bench.py roofline): events around every launch of a profiled call
     bool profiling = false;
@@ -1023,6 +1025,32 @@ static int estimator_forward(usb_handle* h, const float* x, const float* mu, con
     return 0;
 }
 
+// UnitSpeech.forward_diffusion / loss_t (unitspeech/unitspeech.py:376-405), forward value only
+static int loss_t(usb_handle* h, const float* x0, const float* cond, const float* mask, const float* t, const float* spk,
+                  const float* z, float* loss_out, float* xt_out, int B, int T, cudaStream_t s) {
+    USB_TRY(check_ready(h));
+    const int F = h->cfg.n_feats;
+    const size_t n = static_cast<size_t>(B) * F * T;
+    const size_t need = 4 * n * sizeof(float) + 512 * sizeof(double);
+    if (need > h->loss_cap) {
+        USB_CUDA(cudaDeviceSynchronize());
+        if (h->loss_buf) cudaFree(h->loss_buf);
+        h->loss_buf = nullptr;
+        h->loss_cap = 0;
+        USB_CUDA(cudaMalloc(&h->loss_buf, need));
+        h->loss_cap = need;
+    }
+    double* partial = reinterpret_cast<double*>(h->loss_buf);       // first: keeps the doubles 8-byte aligned
+    float* xt = h->loss_buf + 1024;
+    float *zm = xt + n, *mu = zm + n, *score = mu + n;
+    USB_LAUNCH(h, launch_forward_diffusion(x0, z, cond, mask, t, h->cfg.beta_min, h->cfg.beta_max, xt, zm, mu, B, F, T, s));
+    USB_TRY(estimator_forward(h, xt, mu, mask, t, spk, score, B, T, s));
+    h->launches++;
+    USB_LAUNCH(h, launch_diffusion_loss(score, zm, mask, t, h->cfg.beta_min, h->cfg.beta_max, partial, loss_out, B, F, T, s));
+    if (xt_out) USB_CUDA(cudaMemcpyAsync(xt_out, xt, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
 static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, const float* mask, const float* spk,
                              const float* noise, const float* coef, const float* t_steps, int n_steps, float tg,
                              float sg, float* out, float* trace, int B, int T, cudaStream_t s) {
@@ -1167,6 +1195,7 @@ void usb_destroy(usb_handle* h) {
     for (void* p : h->dev_allocs) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->tpart_buf) cudaFree(h->tpart_buf);
+    if (h->loss_buf) cudaFree(h->loss_buf);
     delete h;
 }
 
@@ -1194,6 +1223,22 @@ int usb_finalize_params(usb_handle* h) {
 int usb_estimator_forward(usb_handle* h, const float* x, const float* mu, const float* mask, const float* t,
                           const float* spk, float* out, int32_t Be, int32_t T, uint64_t stream) {
     return estimator_forward(h, x, mu, mask, t, spk, out, Be, T, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int usb_forward_diffusion(usb_handle* h, const float* x0, const float* mask, const float* t, const float* z, float* xt_out,
+                          float* zmask_out, int32_t B, int32_t T, uint64_t stream) {
+    if (!h || !x0 || !mask || !t || !z || !xt_out) return fail("null argument");
+    if (B < 1 || T < 1) return fail("B and T must be positive");
+    USB_CUDA(cudaSetDevice(h->cfg.device));
+    USB_LAUNCH(h, launch_forward_diffusion(x0, z, nullptr, mask, t, h->cfg.beta_min, h->cfg.beta_max, xt_out, zmask_out,
+                                           nullptr, B, h->cfg.n_feats, T, reinterpret_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int usb_loss_t(usb_handle* h, const float* x0, const float* cond, const float* mask, const float* t, const float* spk,
+               const float* z, float* loss_out, float* xt_out, int32_t B, int32_t T, uint64_t stream) {
+    if (!h || !x0 || !cond || !mask || !t || !spk || !z || !loss_out) return fail("null argument");
+    return loss_t(h, x0, cond, mask, t, spk, z, loss_out, xt_out, B, T, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int usb_reverse_diffusion(usb_handle* h, const float* z, const float* cond, const float* mask, const float* spk,

@@ -107,4 +107,12 @@ int launch_attn_context(const AttnParams& p, cudaStream_t s);
 int launch_downsample_mask(const float* src, float* dst, int N, int Wsrc, int Wdst, cudaStream_t s);
 int launch_gather_rows(const float* src, const int* idx, float* dst, int N, int len, cudaStream_t s);
 
+// ---- training objective, forward value (unitspeech/unitspeech.py:376-405); zm / mu may be null
+int launch_forward_diffusion(const float* x0, const float* z, const float* cond, const float* mask, const float* t,
+                             float beta_min, float beta_max, float* xt, float* zm, float* mu, int B, int F, int T,
+                             cudaStream_t s);
+// partial: 512 doubles of scratch; loss: device scalar
+int launch_diffusion_loss(const float* score, const float* zm, const float* mask, const float* t, float beta_min,
+                          float beta_max, double* partial, float* loss, int B, int F, int T, cudaStream_t s);
+
 }  // namespace usb

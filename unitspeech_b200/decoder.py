@@ -17,7 +17,8 @@ Differences from the reference, all deliberate:
   * tensors may live on the CPU: the call then goes through the host-buffer entry of the library (copies included)
     and returns a CPU tensor;
   * ``n_timesteps=1`` raises ValueError (the reference crashes with an indexing error).
-The training-side methods (``compute_loss``, ``fine_tune``) are not part of this path and raise NotImplementedError.
+``forward_diffusion`` / ``loss_t`` / ``compute_loss`` / ``fine_tune`` evaluate the fine-tuning objective on the same
+kernels (forward value only: no autograd graph, no optimizer -- SURVEY section 8 row a16 is not built).
 """
 
 from __future__ import annotations
@@ -363,12 +364,79 @@ class UnitSpeech(torch.nn.Module):
         decoder_outputs = decoder_outputs[:, :, :y_max_length]
         return encoder_outputs, decoder_outputs, attn[:, :, :y_max_length]
 
-    # ------------------------------------------------------------------ out of this path
-    def compute_loss(self, *a, **k):
-        raise NotImplementedError("compute_loss (training) is outside the reverse-diffusion path of unitspeech_b200")
+    # ------------------------------------------------------------------ training objective (forward value only)
+    def _dev_tensors(self, like, *tensors):
+        self._ensure_handle(like)
+        dev = torch.device("cuda", self._handle_device)
+        return dev, [_f32c(t).to(dev) for t in tensors]
 
-    def fine_tune(self, *a, **k):
-        raise NotImplementedError("fine_tune (training) is outside the reverse-diffusion path of unitspeech_b200")
+    @torch.no_grad()
+    def forward_diffusion(self, x0, mask, t):
+        """UnitSpeech.forward_diffusion (unitspeech/unitspeech.py:376-384): returns (xt * mask, z * mask); z is drawn
+        with torch.randn(x0.shape) from x0's device generator exactly like the reference (:381)."""
+        lib = abi.load_library()
+        B, F, T = x0.shape
+        z = torch.randn(x0.shape, dtype=x0.dtype, device=x0.device, requires_grad=False)
+        dev, (xd, md, td, zd) = self._dev_tensors(x0, x0, mask.reshape(B, T), t.reshape(B), z)
+        xt, zm = torch.empty_like(xd), torch.empty_like(xd)
+        with torch.cuda.device(dev):
+            abi.check(lib.usb_forward_diffusion(self._handle, xd.data_ptr(), md.data_ptr(), td.data_ptr(), zd.data_ptr(),
+                                                xt.data_ptr(), zm.data_ptr(), B, T, self._stream(dev.index)))
+        return xt.to(x0.device), zm.to(x0.device)
+
+    @torch.no_grad()
+    def loss_t(self, x0, mask, cond, t, spk_emb):
+        """UnitSpeech.loss_t (unitspeech/unitspeech.py:393-405) -> (loss, xt).  Forward value only: the returned loss
+        carries no autograd graph (the backward pass / optimizer step of fine-tuning is not built)."""
+        lib = abi.load_library()
+        B, F, T = x0.shape
+        if T % (2 ** (len(self.dim_mults) - 1)):
+            raise ValueError("T must be a multiple of 2**(len(dim_mults)-1) (use fix_len_compatibility)")
+        z = torch.randn(x0.shape, dtype=x0.dtype, device=x0.device, requires_grad=False)
+        dev, (xd, md, cd, td, sd, zd) = self._dev_tensors(x0, x0, mask.reshape(B, T), cond, t.reshape(B),
+                                                         spk_emb.reshape(B, self.spk_emb_dim), z)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        xt = torch.empty_like(xd)
+        with torch.cuda.device(dev):
+            abi.check(lib.usb_loss_t(self._handle, xd.data_ptr(), cd.data_ptr(), md.data_ptr(), td.data_ptr(),
+                                     sd.data_ptr(), zd.data_ptr(), loss.data_ptr(), xt.data_ptr(), B, T,
+                                     self._stream(dev.index)))
+        return loss.to(x0.device), xt.to(x0.device)
+
+    @torch.no_grad()
+    def compute_loss(self, x0, mask, cond, spk_emb=None, offset=1e-5):
+        """UnitSpeech.compute_loss (unitspeech/unitspeech.py:407-411): t ~ U(offset, 1 - offset) per utterance."""
+        t = torch.rand(x0.shape[0], dtype=x0.dtype, device=x0.device, requires_grad=False)
+        t = torch.clamp(t, offset, 1.0 - offset)
+        return self.loss_t(x0, mask, cond, t, spk_emb)
+
+    @torch.no_grad()
+    def fine_tune(self, cond_x, y, y_mask, y_lengths, y_max_length, attn, spk_emb, segment_size, n_feats):
+        """UnitSpeech.fine_tune (unitspeech/unitspeech.py:452-492): random segment crop (Python `random`, as the
+        reference), alignment of the encoder output to the crop, then the diffusion loss.  Returns the loss VALUE; it
+        cannot be back-propagated (see loss_t)."""
+        import random
+        if y_max_length < segment_size:
+            pad_size = segment_size - y_max_length
+            y = torch.cat([y, torch.zeros_like(y)[:, :, :pad_size]], dim=-1)
+            y_mask = torch.cat([y_mask, torch.zeros_like(y_mask)[:, :, :pad_size]], dim=-1)
+        max_offset = (y_lengths - segment_size).clamp(0)
+        out_offset = [random.choice(range(0, int(end))) if int(end) > 0 else 0 for end in max_offset.cpu().numpy()]
+        attn_cut = torch.zeros(attn.shape[0], attn.shape[1], segment_size, dtype=attn.dtype, device=attn.device)
+        y_cut = torch.zeros(y.shape[0], n_feats, segment_size, dtype=y.dtype, device=y.device)
+        y_cut_lengths = []
+        for i, lower in enumerate(out_offset):
+            cut_len = segment_size + int((y_lengths[i] - segment_size).clamp(None, 0))
+            y_cut_lengths.append(cut_len)
+            y_cut[i, :, :cut_len] = y[i, :, lower:lower + cut_len]
+            attn_cut[i, :, :cut_len] = attn[i, :, lower:lower + cut_len]
+        y_cut_mask = sequence_mask(torch.LongTensor(y_cut_lengths)).unsqueeze(1).to(y_mask)
+        if y_cut_mask.shape[-1] < segment_size:
+            y_cut_mask = torch.nn.functional.pad(y_cut_mask, (0, segment_size - y_cut_mask.shape[-1]))
+        cond_y = torch.matmul(attn_cut.squeeze(1).transpose(1, 2).contiguous(), cond_x.transpose(1, 2).contiguous())
+        cond_y = cond_y.transpose(1, 2).contiguous() * y_cut_mask
+        diff_loss, _ = self.compute_loss(y_cut, y_cut_mask, cond_y, spk_emb=spk_emb)
+        return diff_loss
 
 
 def denormalize_mel(y: torch.Tensor, mel_min: torch.Tensor, mel_max: torch.Tensor) -> torch.Tensor:
