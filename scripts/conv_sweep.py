@@ -10,6 +10,7 @@ SHAPES = {  # name: kind, N, H, W, C0, C1, Cout, stats
     "l2_512": (0, 48, 20, 128, 512, 0, 512, 1),
     "l3_1024": (0, 48, 10, 64, 1024, 0, 1024, 1),
     "u2_512to128": (0, 48, 40, 256, 256, 256, 128, 1),
+    "u3_256to128": (0, 48, 80, 512, 128, 128, 128, 1),
     "qkv_l0": (2, 48, 80, 512, 128, 0, 384, 0),
     "up_l1": (3, 48, 40, 256, 128, 0, 128, 0),
     "qkv_l1": (2, 48, 40, 256, 256, 0, 384, 0),
@@ -36,7 +37,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         run_one(sys.argv[2:])
     else:
-        configs = [{}, {"USB_DBG_FLAGS": "2"}] if os.environ.get("SWEEP") == "epi" else [{}, {"USB_NO_SWAP_AB": "1"}] if os.environ.get("SWEEP") == "swap" else [{}, {"USB_DBG_FLAGS": "1"}, {"USB_DBG_FLAGS": "2"}, {"USB_DBG_FLAGS": "3"}, {"USB_DBG_FLAGS": "4"},
+        configs = [{"USB_NO_HALO": "1"}, {}, {"USB_DBG_STAGES": "6"}, {"USB_DBG_STAGES": "5"}, {"USB_DBG_FLAGS": "2"},
+                   {"USB_NO_HALO": "1", "USB_DBG_FLAGS": "2"}] if os.environ.get("SWEEP") == "halo" else [{}, {"USB_DBG_FLAGS": "2"}] if os.environ.get("SWEEP") == "epi" else [{}, {"USB_NO_SWAP_AB": "1"}] if os.environ.get("SWEEP") == "swap" else [{}, {"USB_DBG_FLAGS": "1"}, {"USB_DBG_FLAGS": "2"}, {"USB_DBG_FLAGS": "3"}, {"USB_DBG_FLAGS": "4"},
                    {"USB_DBG_FLAGS": "6"}, {"USB_DBG_FLAGS": "7"},
                    {"USB_DBG_STAGES": "3"}, {"USB_DBG_STAGES": "4"}, {"USB_DBG_BH": "2"}, {"USB_DBG_BH": "4"},
                    {"USB_DBG_BH": "8"}, {"USB_DBG_BH": "1"}]

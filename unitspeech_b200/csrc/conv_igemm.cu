@@ -576,6 +576,253 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// =====================================================================================================================
+// Halo-reuse variant of the swapped-operand kernel for 3x3 stride-1 convs (Hm % 8 == 0, Cout % 128 == 0).
+// A tile is 8 image rows x 32 columns (256 pixels on the MMA N axis, column index = x*8 + y).  For every 64-channel
+// K chunk the activation tile is loaded ONCE with its one-pixel halo -- a TMA box {64 ch, HY rows, 34 columns} of a
+// (c, y, x, n) view, so shared-memory rows are ordered column by column, HY rows per column -- and the nine taps are
+// nine UMMA descriptors into that buffer: start row dx*HY + dy, 8-row groups HY rows apart (one group = the 8 rows
+// of one image column).  Activation traffic from L2 drops from 9 x 32 KB to 43.5 KB (HY = 10) per chunk; only the
+// 16 KB weight tiles still stream per tap through the stage ring.
+// =====================================================================================================================
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0,
+                       const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_out, int total_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];        // weight stages
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t hfull_bar[2];       // halo buffers
+    __shared__ __align__(8) uint64_t hempty_bar[2];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float mask_s[2][16];    // per epilogue group: output mask of its 16 columns (0 outside the image)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t kWBytes = 16384u;
+    const uint32_t hy = static_cast<uint32_t>(p.halo_hy);
+    const uint32_t halo_tx = 34u * hy * 128u;                      // bytes one halo load delivers
+    const uint32_t halo_bytes = (halo_tx + 1023u) & ~1023u;        // buffer pitch (1024-aligned for the swizzle)
+    const uint32_t w_base = tiles_base + 2u * halo_bytes;
+    const int stages = p.stages;
+    const int chunks = p.chunks0 + p.chunks1;
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t hfull0 = smem_u32(&hfull_bar[0]), hempty0 = smem_u32(&hempty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a0);
+        tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&hfull_bar[i], 1);
+            mbar_init(&hempty_bar[i], 1);
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], kConvEpilogueThreads);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&tmem_base_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ---------------------------------------------------- TMA producer
+        int stage = 0, hb = 0;
+        uint32_t phase = 0, hphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles_n;
+            int r = tile / p.n_tiles_n;
+            const int tx = r % p.tiles_x; r /= p.tiles_x;
+            const int ty = r % p.tiles_y;
+            const int n = r / p.tiles_y;
+            for (int cc = 0; cc < chunks; ++cc) {
+                const bool src1 = cc >= p.chunks0;
+                mbar_wait_a(hempty0 + hb * 8, hphase ^ 1u, 120 + hb);
+                if (elect_one()) {
+                    const uint32_t fb = hfull0 + hb * 8;
+                    mbar_arrive_expect_tx_a(fb, halo_tx);
+                    tma_load_4d_a(tiles_base + hb * halo_bytes, src1 ? &map_a1 : &map_a0, fb,
+                                  (src1 ? cc - p.chunks0 : cc) * kConvBK, ty * 8 - 1, tx * 32 - 1, n);
+                }
+                __syncwarp();
+                if (++hb == 2) { hb = 0; hphase ^= 1u; }
+                for (int t = 0; t < 9; ++t) {
+                    mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 100 + stage);
+                    if (elect_one()) {
+                        const uint32_t fb = full0 + stage * 8;
+                        mbar_arrive_expect_tx_a(fb, kWBytes);
+                        tma_load_3d_a(w_base + stage * kWBytes, &map_b, fb, (t * chunks + cc) * kConvBK, nt * 128, 0);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------- MMA issuer: D[ch][px] += W[ch][k] * X[px][k]^T
+        const uint32_t idesc = umma_idesc_f16(256u);
+        const uint32_t desc_hi_w = static_cast<uint32_t>(umma_desc_sw128(0) >> 32);
+        int stage = 0, hb = 0;
+        uint32_t phase = 0, hphase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait_a(tempty0 + as * 8, aphase ^ 1u, 200 + as);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as) * 256u;
+            for (int cc = 0; cc < chunks; ++cc) {
+                mbar_wait_a(hfull0 + hb * 8, hphase, 320 + hb);
+                const uint32_t hbase = tiles_base + hb * halo_bytes;
+                for (int t = 0; t < 9; ++t) {
+                    mbar_wait_a(full0 + stage * 8, phase, 300 + stage);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int dy = t / 3, dx = t - dy * 3;      // tap (kh, kw): input pixel (y + kh - 1, x + kw - 1)
+                        const uint32_t xaddr = hbase + (static_cast<uint32_t>(dx) * hy + dy) * 128u;
+                        const uint64_t db0 = umma_desc_sw128_ex(xaddr, hy * 128u, p.halo_boff ? (xaddr >> 7) : 0u);
+                        const uint32_t w_lo = ((w_base + stage * kWBytes) & 0x3FFFFu) >> 4;
+#pragma unroll
+                        for (int k = 0; k < kConvBK / 16; ++k) {
+                            const uint64_t da = (static_cast<uint64_t>(desc_hi_w) << 32) | (w_lo + 2u * k);
+                            tc_mma_f16(tmem_d, da, db0 + 2u * k, idesc, (cc | t | k) != 0 ? 1u : 0u);
+                        }
+                        tc_commit_a(empty0 + stage * 8);
+                        if (t == 8) {
+                            tc_commit_a(hempty0 + hb * 8);
+                            if (cc == chunks - 1) tc_commit_a(tfull0 + as * 8);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+                if (++hb == 2) { hb = 0; hphase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------- epilogue: thread = output channel, columns = pixels
+        const int ew = warp & 3;
+        const int grp = (warp - 4) >> 2;          // columns [128*grp, 128*grp + 128) = image columns 16*grp .. 16*grp+15
+        const int c = ew * 32 + lane;
+        const int cpg = p.stats ? p.Cout / p.groups : 16;
+        // per-warp staging: 32 pixel rows x 32 channels (64 B rows, 64-byte swizzle) = 2 KB, stored by the warp's own TMA
+        // (box {32 ch, 8 rows, 4 columns})
+        const uint32_t warp_buf = w_base + stages * kWBytes + static_cast<uint32_t>(grp * 4 + ew) * 2048u;
+        uint32_t sbase[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            sbase[q] = warp_buf + ((static_cast<uint32_t>(lane >> 3) ^ static_cast<uint32_t>(q)) << 4) +
+                       static_cast<uint32_t>(lane & 7) * 2u;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int nt = tile % p.n_tiles_n;
+            int r = tile / p.n_tiles_n;
+            const int tx = r % p.tiles_x; r /= p.tiles_x;
+            const int ty = r % p.tiles_y;
+            const int n = r / p.tiles_y;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int x0 = tx * 32 + grp * 16;    // first image column of this group
+            mbar_wait_a(tfull0 + as * 8, aphase, 400 + as);
+            tc_fence_after();
+            const int wlim = p.Wm - x0;           // columns with index >= wlim lie outside the image
+            if (wlim <= 0 || (p.dbg_flags & 2)) {
+                tc_fence_before();
+                mbar_arrive_a(tempty0 + as * 8);
+                continue;
+            }
+            const int cg = nt * 128 + c;
+            const float bias = p.bias ? __ldg(p.bias + cg) : 0.f;
+            long long* stats_n = p.stats ? p.stats + static_cast<long long>(n) * p.groups * 2 : nullptr;
+            const float* mrow = p.mask ? p.mask + static_cast<long long>(n) * p.mask_stride : nullptr;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
+            float s = 0.f, ss = 0.f;
+            const bool full = wlim >= 16;
+            if (mrow) {
+                const int et = lane + ew * 32;
+                if (et < 16) mask_s[grp][et] = et < wlim ? __ldg(mrow + x0 + et) : 0.f;
+                named_bar_sync(1 + grp, 128);
+            }
+            for (int hc = 0; hc < 4; ++hc) {
+                // 32 accumulator columns = image columns 4*hc .. 4*hc+3 of the group, 8 rows each
+                if (hc * 4 >= wlim) {             // the rest of the group lies right of the image
+                    if (hc == 3) {
+                        tc_fence_before();
+                        mbar_arrive_a(tempty0 + as * 8);
+                    }
+                    continue;
+                }
+                uint32_t v0[32];
+                tmem_ld_32x32(taddr + grp * 128 + hc * 32, v0);
+                tmem_ld_wait();
+                if (hc == 3) {
+                    tc_fence_before();
+                    mbar_arrive_a(tempty0 + as * 8);
+                }
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float f = __uint_as_float(v0[j]) + bias;
+                    const int xl = hc * 4 + (j >> 3);
+                    if (stats_n) {
+                        if (full || xl < wlim) {
+                            s += f;
+                            ss = fmaf(f, f, ss);
+                        }
+                    }
+                    if (mrow) f *= mask_s[grp][xl];
+                    unsigned short hbits;
+                    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hbits) : "f"(f));
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(sbase[(j >> 1) & 3] + j * 64), "h"(hbits) : "memory");
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d_a(&map_out, warp_buf, nt * 128 + ew * 32, ty * 8, x0 + hc * 4, n);
+                    tma_store_commit();
+                }
+            }
+            if (mrow) named_bar_sync(1 + grp, 128);
+            if (stats_n) {
+                const int span = cpg < 32 ? cpg : 32;
+                for (int o = span >> 1; o > 0; o >>= 1) {
+                    s += __shfl_xor_sync(0xffffffffu, s, o);
+                    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                }
+                if ((lane & (span - 1)) == 0) {
+                    long long* dst = stats_n + (cg / cpg) * 2;
+                    atomicAdd(reinterpret_cast<unsigned long long*>(dst),
+                              static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(dst + 1),
+                              static_cast<unsigned long long>(__float2ll_rn(ss * kStatSqScale)));
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                       const CUtensorMap& out, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
@@ -585,9 +832,20 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         if (e != cudaSuccess) return static_cast<int>(e);
         e = cudaFuncSetAttribute(conv_igemm_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
+        e = cudaFuncSetAttribute(conv_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
     long long total = static_cast<long long>(p.phases) * p.N * p.tiles_y * p.tiles_x * p.n_tiles_n;
+    if (p.halo) {
+        if (total <= 0 || total > 0x7fffffffLL) return static_cast<int>(cudaErrorInvalidValue);
+        const size_t halo_bytes = (static_cast<size_t>(34) * p.halo_hy * 128 + 1023) / 1024 * 1024;
+        const size_t smem = 1024 + 2 * halo_bytes + static_cast<size_t>(p.stages) * 16384 + 16384;
+        if (smem > static_cast<size_t>(kConvSmemBytes) || p.stages > 8) return static_cast<int>(cudaErrorInvalidValue);
+        const int grid = static_cast<int>(total < num_sms ? total : num_sms);
+        conv_igemm_halo_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));
+        return static_cast<int>(cudaGetLastError());
+    }
     if (p.swap_ab) total = static_cast<long long>(p.phases) * ((p.patches_per_phase + 1) / 2) * p.n_tiles_n;
     if (total <= 0 || total > 0x7fffffffLL) return static_cast<int>(cudaErrorInvalidValue);
     const int grid = static_cast<int>(total < num_sms ? total : num_sms);

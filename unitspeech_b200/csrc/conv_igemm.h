@@ -49,6 +49,11 @@ struct ConvParams {
     int swap_ab;               // 1: swapped-operand kernel: channels on the MMA M axis, two 128-pixel patches on N
     int patches_per_phase;     // N * tiles_y * tiles_x
     int dbg_flags;             // experiments only: 1 = skip B loads, 2 = skip epilogue math/stores, 4 = skip A loads
+    // halo-reuse kernel (3x3 stride-1, Hm % 8 == 0, Cout % 128 == 0): tiles of 8 rows x 32 columns, the activation
+    // tile is loaded once per 64-channel chunk with its 1-pixel halo and the nine taps are descriptor offsets into it
+    int halo;                  // 1: use conv_igemm_halo_kernel (tiles_y = Hm/8, tiles_x = ceil(Wm/32))
+    int halo_hy;               // rows per column of the shared-memory halo tile: 10 (dense) or 16 (power-of-two stride)
+    int halo_boff;             // 1: put (start_address >> 7) & 7 into the descriptor's base-offset field
     ConvTap tap[kConvMaxTaps];
     // epilogue: v = acc + bias[c]; stats (sum, sumsq per (n, group)) on v; v = v*res_scale + res; v *= mask
     const float* bias;         // [Cout] or null

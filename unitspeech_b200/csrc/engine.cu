@@ -100,6 +100,17 @@ static int make_act_map(CUtensorMap* m, const __half* base, int N, int H, int W,
     return encode_map(m, base, 5, dims, strides, box, box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// 4-D activation view (c, y, x, n) of the same tensor: rows before columns, so a box lands in shared memory column
+// by column (conv_igemm_halo_kernel)
+static int make_act_map_yx(CUtensorMap* m, const __half* base, int N, int H, int W, int Ctot, int Cview, int box_c,
+                           int box_y, int box_x) {
+    const cuuint64_t e = 2;
+    cuuint64_t dims[4] = {(cuuint64_t)Cview, (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)W * Ctot * e, (cuuint64_t)Ctot * e, (cuuint64_t)H * W * Ctot * e};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_y, (cuuint32_t)box_x, 1};
+    return encode_map(m, base, 4, dims, strides, box, box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 // weights [Z][Cout][K] fp16, K contiguous
 static int make_w_map(CUtensorMap* m, const __half* base, int Z, int Cout, int K, int BN) {
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, (cuuint64_t)Z};
@@ -263,10 +274,29 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
                 p.oy_off[ph * 2 + pw] = (int8_t)ph;
                 p.ox_off[ph * 2 + pw] = (int8_t)pw;
             }
+    const int K = p.taps * (C0 + (in1 ? C1 : 0));
+    // halo-reuse kernel for the 3x3 stride-1 convs of the levels whose height is a multiple of 8 (levels 0 and 1)
+    // (USB_NO_HALO=1 falls back to the per-tap loads of the swapped kernel; USB_HALO_HY / USB_HALO_BOFF are the
+    // experiment knobs that established the layout: dense 10-row columns, descriptor base-offset field left 0)
+    static const bool halo_mode = getenv("USB_NO_HALO") == nullptr;
+    if (halo_mode && p.swap_ab && kind == K3S1 && H % 8 == 0 && b_batch_mode == 0) {
+        p.halo = 1;
+        p.halo_hy = getenv("USB_HALO_HY") ? atoi(getenv("USB_HALO_HY")) : 10;
+        if (p.halo_hy != 10 && p.halo_hy != 16) return fail("USB_HALO_HY must be 10 or 16");
+        p.halo_boff = getenv("USB_HALO_BOFF") ? atoi(getenv("USB_HALO_BOFF")) : 0;
+        p.stages = p.halo_hy == 10 ? 7 : 4;
+        if (const char* e = getenv("USB_DBG_STAGES")) p.stages = atoi(e);
+        p.tiles_y = H / 8;
+        p.tiles_x = (W + 31) / 32;
+        USB_TRY(make_act_map_yx(&op.a0, in0, N, H, W, C0tot, C0, 64, p.halo_hy, 34));
+        if (in1) USB_TRY(make_act_map_yx(&op.a1, in1, N, H, W, C1tot, C1, 64, p.halo_hy, 34));
+        else op.a1 = op.a0;
+        USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, 128));
+        return make_act_map_yx(&op.o, out, N, H, W, Cout, Cout, 32, 8, 4);
+    }
     USB_TRY(make_act_map(&op.a0, in0, N, H, W, C0tot, C0, kind == K3S2, p.BH, p.BW));
     if (in1) USB_TRY(make_act_map(&op.a1, in1, N, H, W, C1tot, C1, false, p.BH, p.BW));
     else op.a1 = op.a0;
-    const int K = p.taps * (C0 + (in1 ? C1 : 0));
     USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, p.BN));
     // output tile store: plain view, or the parity view of the upsampled tensor for the transposed conv;
     // the swapped kernel stores 64-pixel sub-blocks (64 / BW image rows) per TMA
