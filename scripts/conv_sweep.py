@@ -11,6 +11,10 @@ SHAPES = {  # name: kind, N, H, W, C0, C1, Cout, stats
     "l3_1024": (0, 48, 10, 64, 1024, 0, 1024, 1),
     "u2_512to128": (0, 48, 40, 256, 256, 256, 128, 1),
     "u3_256to128": (0, 48, 80, 512, 128, 128, 128, 1),
+    "down_l0": (1, 48, 80, 512, 128, 0, 128, 0),
+    "down_l1": (1, 48, 40, 256, 256, 0, 256, 0),
+    "up_l2": (3, 48, 20, 128, 256, 0, 256, 0),
+    "l3_512": (0, 48, 10, 64, 512, 0, 512, 1),
     "qkv_l0": (2, 48, 80, 512, 128, 0, 384, 0),
     "up_l1": (3, 48, 40, 256, 128, 0, 128, 0),
     "qkv_l1": (2, 48, 40, 256, 256, 0, 384, 0),

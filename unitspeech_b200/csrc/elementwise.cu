@@ -359,40 +359,57 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalParams p, int pix
     const float* mk = p.mask + static_cast<long long>(b) * p.W;
     const int p_begin = blockIdx.x * pix_per_block;
     const int p_end = min(p.P, p_begin + pix_per_block);
-    // every lane of a pixel group must run the same number of iterations (shuffles below)
-    const int iters = (p_end - p_begin + lanes - 1) / lanes;
+    // every lane of a pixel group must run the same number of iterations (shuffles below); U pixels x nb branches of
+    // 16-byte loads are issued before any of them is consumed (the kernel is a pure HBM stream of `raw`)
+    constexpr int U = 4;
+    const int iters = (p_end - p_begin + lanes * U - 1) / (lanes * U);
     for (int it = 0; it < iters; ++it) {
-        const int pix = p_begin + it * lanes + pl;
-        const bool ok = pix < p_end;
-        const float m = ok ? __ldg(mk + pix % p.W) : 0.f;
-        float sc[3] = {0.f, 0.f, 0.f};
+        uint4 rv[U][3];
+        float m[U];
+        int pixs[U];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (k < p.nb) {
-                float dot = 0.f;
-                if (ok) {
-                    const long long o = (static_cast<long long>(k * p.B + b) * p.P + pix) * C + tq * 8;
-                    float v[8];
-                    unpack8(ldg_stream(reinterpret_cast<const uint4*>(p.raw + o)), v);
+        for (int u = 0; u < U; ++u) {
+            pixs[u] = p_begin + (it * U + u) * lanes + pl;
+            const bool ok = pixs[u] < p_end;
+            m[u] = ok ? __ldg(mk + pixs[u] % p.W) : 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dot += wf[i] * (mish_fast(v[i] * a[k][i] + sh[k][i]) * m);
-                }
-                for (int o = TP >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-                sc[k] = (dot + bf) * m;
+            for (int k = 0; k < 3; ++k) {
+                rv[u][k] = make_uint4(0u, 0u, 0u, 0u);
+                if (k < p.nb && ok)
+                    rv[u][k] = ldg_stream(reinterpret_cast<const uint4*>(
+                        p.raw + (static_cast<long long>(k * p.B + b) * p.P + pixs[u]) * C + tq * 8));
             }
         }
-        if (ok && tq == 0) {
-            const long long q = static_cast<long long>(b) * p.P + pix;
-            if (p.xt == nullptr) {
-                for (int k = 0; k < p.nb; ++k) p.score[(static_cast<long long>(k * p.B + b)) * p.P + pix] = sc[k];
-            } else {
-                const float sf = sc[p.nb - 1];
-                float score = sf;
-                if (p.nb >= 2) score = score + p.a0 * (sf - sc[0]);
-                if (p.nb >= 3) score = score + p.a1 * (sf - sc[1]);
-                const float nz = p.noise ? p.noise[q] : 0.f;
-                p.xt[q] = (p.c_x * p.xt[q] + p.c_s * score + p.sigma * nz) * m;
-                if (p.score) p.score[q] = score;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pix = pixs[u];
+            const bool ok = pix < p_end;
+            float sc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (k < p.nb) {
+                    float dot = 0.f;
+                    float v[8];
+                    unpack8(rv[u][k], v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dot += wf[i] * (mish_fast(v[i] * a[k][i] + sh[k][i]) * m[u]);
+                    for (int o = TP >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                    sc[k] = (dot + bf) * m[u];
+                }
+            }
+            if (ok && tq == 0) {
+                const long long q = static_cast<long long>(b) * p.P + pix;
+                if (p.xt == nullptr) {
+                    for (int k = 0; k < p.nb; ++k) p.score[(static_cast<long long>(k * p.B + b)) * p.P + pix] = sc[k];
+                } else {
+                    const float sf = sc[p.nb - 1];
+                    float score = sf;
+                    if (p.nb >= 2) score = score + p.a0 * (sf - sc[0]);
+                    if (p.nb >= 3) score = score + p.a1 * (sf - sc[1]);
+                    const float nz = p.noise ? p.noise[q] : 0.f;
+                    p.xt[q] = (p.c_x * p.xt[q] + p.c_s * score + p.sigma * nz) * m[u];
+                    if (p.score) p.score[q] = score;
+                }
             }
         }
     }

@@ -44,7 +44,16 @@ constexpr int kActTL = 56;                    // output samples per block
 constexpr int kActXRows = kActTL + 12;        // input rows t0-6 .. t0+TL+5
 constexpr int kActSRows = 2 * kActTL + 10;    // 2x-rate rows 2*t0-5 .. 2*t0+2*TL+4
 constexpr int kActSItems = (kActSRows + 3) / 4;   // phase-2 work items of four 2x-rate rows (31: one round of 32 row slots)
-constexpr int kActSmemBytes = (kActXRows + 4 * kActSItems) * 64 * 4;   // 48 KB
+constexpr int kActSmemBytes = (kActXRows + 4 * kActSItems) * 64 * 4;   // 48 KB at vb = 8
+
+static inline int act_vb(int creal) {
+    const int nvec = (creal + 7) / 8;
+    if (nvec % 8 == 0) return 8;
+    for (int vb = 8; vb >= 5; --vb)
+        if (nvec % vb == 0) return vb;
+    return nvec < 8 ? nvec : 8;
+}
+static inline size_t act_smem_bytes(int vb) { return static_cast<size_t>(kActXRows + 4 * kActSItems) * vb * 8 * 4; }
 
 struct ActParams {
     const __half* x;       // [N][L][C]
@@ -53,13 +62,12 @@ struct ActParams {
     const float* invbeta;  // [C] 1 / (b + 1e-9); 0 in padding channels
     int L, C;              // C = padded channel count (multiple of 64)
     int Creal;             // channels that carry data; [Creal, C) is written as zeros
+    int vb;                // 8-channel vectors per block (blockDim = 32 * vb)
     float filt[12];        // kaiser_sinc_filter1d(0.25, 0.3, 12) -- shared by the up- and the down-sampler
 };
 
-// shared-memory element (row, vector cv of 8 channels, j in 0..7): two 128-byte halves per row so that the eight
-// threads of a row read/write contiguous float4s
-__device__ __forceinline__ int act_sidx(int row, int cv, int half) { return row * 64 + half * 32 + cv * 4; }
-
+// shared-memory element (row, vector cv of 8 channels, j in 0..7): two halves per row (channels 0-3 and 4-7 of every
+// vector) so that the threads of a row read/write contiguous float4s (act_sidx, defined inside the kernel)
 // Activation1d.forward (alias_free_torch/act.py:23-28) fused:
 //   u[2m]   = 2 * sum_{q=-3..2} f[5-2q] * x[clamp(m+q)]        (UpSample1d, resample.py:26-33)
 //   u[2m+1] = 2 * sum_{q=-2..3} f[6-2q] * x[clamp(m+q)]
@@ -68,28 +76,30 @@ __device__ __forceinline__ int act_sidx(int row, int cv, int half) { return row 
 __global__ void __launch_bounds__(256, 3) snake_act_kernel(const ActParams p) {
     extern __shared__ float act_smem[];
     float* xs = act_smem;
-    float* ss = act_smem + kActXRows * 64;      // 4 * kActSItems rows (the last two are computed but never read)
     const int tid = threadIdx.x;
-    // only the real channels of this 64-channel slab are computed (padding channels are written as zeros): the
-    // block's threads are laid out as (rows x ncv) with ncv = 8-channel vectors that hold real channels
-    const int creal = min(64, p.Creal - static_cast<int>(blockIdx.y) * 64);
-    const int ncv = (creal + 7) >> 3;
+    // a block covers `vb` 8-channel vectors (blockDim = 32 * vb, shared-memory rows of vb * 8 floats): vb = 8 for the
+    // wide stages, 6 / 3 for the 96-, 48- and 24-channel stages, so every thread has work; only real channels are
+    // computed, the layout-padding channels [Creal, C) are written as zeros by the last slab
+    const int vb = p.vb;
+    const int nvec = (p.Creal + 7) >> 3;
+    const int ncv = min(vb, nvec - static_cast<int>(blockIdx.y) * vb);
     const int t0 = blockIdx.x * kActTL;
     const long long nbase = static_cast<long long>(blockIdx.z) * p.L;
-    if (ncv < 8) {
-        const int npad = 8 - ncv;
-        for (int idx = tid; idx < kActTL * npad; idx += 256) {
+    if (blockIdx.y == gridDim.y - 1) {
+        const int npad = (p.C >> 3) - nvec;
+        for (int idx = tid; idx < kActTL * npad; idx += blockDim.x) {
             const int t = t0 + idx / npad;
             if (t < p.L)
-                *reinterpret_cast<uint4*>(p.out + (nbase + t) * p.C + blockIdx.y * 64 + (ncv + idx % npad) * 8) =
-                    make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.out + (nbase + t) * p.C + (nvec + idx % npad) * 8) = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (ncv <= 0) return;
     }
-    const int R = 256 / ncv;                 // rows processed in parallel
+    const int R = blockDim.x / ncv;          // rows processed in parallel (32 when ncv == vb)
     const int cv = tid % ncv, r = tid / ncv;
     const bool active = r < R;
-    const int c0 = blockIdx.y * 64 + cv * 8;
+    const int c0 = (blockIdx.y * vb + cv) * 8;
+    float* ss = act_smem + kActXRows * vb * 8;  // 4 * kActSItems rows (the last two are computed but never read)
+    const int pitch = vb * 8, hoff = vb * 4;
+#define act_sidx(row, cv_, half) ((row) * pitch + (half) * hoff + (cv_) * 4)
 
     if (active)
         for (int row = r; row < kActXRows; row += R) {
@@ -213,6 +223,8 @@ __global__ void __launch_bounds__(256, 3) snake_act_kernel(const ActParams p) {
             }
         }
 }
+
+#undef act_sidx
 
 // mel (B, M, T) fp32 -> [B][T][Cp] fp16, zero padded channels
 __global__ void mel_pack_kernel(const float* __restrict__ mel, __half* __restrict__ out, int B, int M, int T, int Cp) {
@@ -587,6 +599,7 @@ static void voc_push_act(usb_vocoder* h, const VocActW& a, const __half* x, __ha
     op.act.L = L;
     op.act.C = a.C;
     op.act.Creal = a.Creal;
+    op.act.vb = act_vb(a.Creal);
     memcpy(op.act.filt, h->filt, sizeof h->filt);
     h->ops.push_back(op);
 }
@@ -694,8 +707,9 @@ static int voc_forward(usb_vocoder* h, const float* mel, int B, int T, float* ou
                 break;
             }
             case VocOp::ACT: {
-                const dim3 grid((op.act.L + kActTL - 1) / kActTL, op.act.C / 64, op.N);
-                snake_act_kernel<<<grid, 256, kActSmemBytes, s>>>(op.act);
+                const int nvec = (op.act.Creal + 7) / 8;
+                const dim3 grid((op.act.L + kActTL - 1) / kActTL, (nvec + op.act.vb - 1) / op.act.vb, op.N);
+                snake_act_kernel<<<grid, 32 * op.act.vb, act_smem_bytes(op.act.vb), s>>>(op.act);
                 break;
             }
             case VocOp::ACCUM:
@@ -857,10 +871,12 @@ int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, in
     p.L = L;
     p.C = C;
     p.Creal = c_real;
+    p.vb = act_vb(c_real);
     kaiser_sinc_12(p.filt);
     VOC_CUDA(cudaFuncSetAttribute(snake_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kActSmemBytes));
-    const dim3 grid((L + kActTL - 1) / kActTL, C / 64, N);
-    snake_act_kernel<<<grid, 256, kActSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    const int nvec = (c_real + 7) / 8;
+    const dim3 grid((L + kActTL - 1) / kActTL, (nvec + p.vb - 1) / p.vb, N);
+    snake_act_kernel<<<grid, 32 * p.vb, act_smem_bytes(p.vb), reinterpret_cast<cudaStream_t>(stream)>>>(p);
     VOC_CUDA(cudaGetLastError());
     return 0;
 }
