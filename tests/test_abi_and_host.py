@@ -22,7 +22,8 @@ def lib():
 
 
 def _header_functions():
-    text = open(os.path.join(ROOT, "include", "unitspeech_b200.h")).read()
+    text = "".join(open(os.path.join(ROOT, "include", f)).read() for f in sorted(os.listdir(os.path.join(ROOT, "include")))
+                   if f.endswith(".h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(usb_[a-z0-9_]+)\s*\(", text)))
 

@@ -1,4 +1,4 @@
-"""ctypes binding of libunitspeech_b200.so (declared in include/unitspeech_b200.h).
+"""ctypes binding of libunitspeech_b200.so (declared in include/unitspeech_b200.h and include/unitspeech_b200_train.h).
 
 There is no fallback: if the shared library is missing or fails to load, importing the decoder raises.
 """
@@ -89,6 +89,34 @@ SIGNATURES = {
     "usb_vocoder_get_profile": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)]),
     "usb_op_snake_act": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_uint64]),
     "usb_vocoder_filter": (c_int32, [POINTER(c_float)]),
+    # ---- fine-tune step, operator level (include/unitspeech_b200_train.h)
+    "usb_t_pack_conv": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_uint64]),
+    "usb_t_conv": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                             c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_int32, c_void_p, c_uint64]),
+    "usb_t_first_conv": (c_int32, [c_void_p] + [c_void_p] * 11 + [c_int32] * 4 + [c_uint64]),
+    "usb_t_gn_apply": (c_int32, [c_void_p] + [c_void_p] * 5 + [c_int64] + [c_void_p] * 3 + [c_int32] * 4 + [c_uint64]),
+    "usb_t_embed": (c_int32, [c_void_p] + [c_void_p] * 11 + [c_int32, c_int32, c_uint64]),
+    "usb_t_attn_scratch_bytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "usb_t_attn_context": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_int32, c_int32, c_int32, c_int32, c_uint64]),
+    "usb_t_final": (c_int32, [c_void_p] + [c_void_p] * 8 + [c_int32] * 4 + [c_uint64]),
+    "usb_t_loss": (c_int32, [c_void_p] + [c_void_p] * 6 + [c_int32, c_int32, c_uint64]),
+    "usb_t_loss_grad": (c_int32, [c_void_p] + [c_void_p] * 4 + [c_float] + [c_void_p] * 2 + [c_int32, c_int32, c_uint64]),
+    "usb_t_gn_bwd": (c_int32, [c_void_p] + [c_void_p] * 15 + [c_int64, c_void_p] + [c_int32] * 4 + [c_uint64]),
+    "usb_t_colsum": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_uint64]),
+    "usb_t_add": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_uint64]),
+    "usb_t_wgrad": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32] + [c_int32] * 7 + [c_void_p, c_int32,
+                                                                                                        c_uint64]),
+    "usb_t_first_conv_wgrad": (c_int32, [c_void_p] + [c_void_p] * 8 + [c_int32] * 4 + [c_uint64]),
+    "usb_t_attn_bwd_small": (c_int32, [c_void_p] + [c_void_p] * 11 + [c_int32] * 3 + [c_uint64]),
+    "usb_t_attn_bwd_dkv": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int32, c_int32, c_int32, c_uint64]),
+    "usb_t_embed_bwd": (c_int32, [c_void_p] + [c_void_p] * 17 + [c_int32, c_int32, c_uint64]),
+    "usb_t_dot": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_uint64]),
+    "usb_t_sumsq": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_uint64]),
+    "usb_t_adam": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                             c_int32, c_void_p, c_float, c_float, c_void_p, c_uint64]),
 }
 
 _lib = None

@@ -246,6 +246,11 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnParams p, int
                  exp2f_ftz((ph[c * kPartStride + kDh * kDh + tid] - M) * kLog2e);
         M_s[tid] = M;
         S_s[tid] = S;
+        if (p.stat_out) {
+            float* so = p.stat_out + (static_cast<long long>(n) * p.heads + h) * 2 * kDh;
+            so[tid] = M;
+            so[kDh + tid] = S;
+        }
     }
     __syncthreads();
     float* o = ctx_out + (static_cast<long long>(n) * p.heads + h) * kDh * kDh;
@@ -348,7 +353,7 @@ int launch_attn_context(const AttnParams& p, cudaStream_t s) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     // merged context lives behind the partials in the same scratch buffer
-    float* ctx = p.part + static_cast<long long>(p.N) * p.heads * nchunks * kPartStride;
+    float* ctx = p.ctx_out ? p.ctx_out : p.part + static_cast<long long>(p.N) * p.heads * nchunks * kPartStride;
     dim3 g2(p.heads, p.N);
     attn_merge_kernel<<<g2, 256, 0, s>>>(p, nchunks, ctx);
     e = cudaGetLastError();

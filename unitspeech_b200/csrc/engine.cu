@@ -15,8 +15,10 @@
 #include <cuda_runtime.h>
 
 #include "../../include/unitspeech_b200.h"
+#include "../../include/unitspeech_b200_train.h"
 #include "conv_igemm.h"
 #include "kernels.h"
+#include "train.h"
 
 namespace usb {
 
@@ -122,7 +124,11 @@ static int make_w_map(CUtensorMap* m, const __half* base, int Z, int Cout, int K
 // ---------------------------------------------------------------------------------------------------------------
 // weights
 // ---------------------------------------------------------------------------------------------------------------
-enum ConvKind { K3S1 = 0, K3S2 = 1, K1 = 2, KT4 = 3 };
+// K3S2D / KT4D are the data-gradient convolutions of the fine-tune step: the transposed 3x3/s2 conv as four phase convs of
+// 2x2 (zero-padded) taps, and the 4x4/s2 conv over the output gradient of the ConvTranspose (train.h: launch_pack_conv)
+enum ConvKind { K3S1 = 0, K3S2 = 1, K1 = 2, KT4 = 3, K3S2D = 4, KT4D = 5 };
+static inline bool kind_up(int kind) { return kind == KT4 || kind == K3S2D; }      // output 2H x 2W, four phases
+static inline bool kind_down(int kind) { return kind == K3S2 || kind == KT4D; }    // parity-split input, output H/2 x W/2
 constexpr int kAttnChunk = 2048;   // positions per attention partial block (upper bound)
 // positions per partial block: ~16 chunks per sample so small levels still fill the GPU, multiples of 64
 static inline int attn_chunk_for(int P) {
@@ -136,7 +142,9 @@ struct ConvW {
     int Cout = 0, Cin = 0, K = 0, Z = 1, kind = K3S1;
 };
 
-static inline int taps_of(int kind) { return kind == K3S1 || kind == K3S2 ? 9 : (kind == K1 ? 1 : 4); }
+static inline int taps_of(int kind) {
+    return kind == K3S1 || kind == K3S2 ? 9 : (kind == K1 ? 1 : (kind == KT4D ? 16 : 4));
+}
 
 // reference layout -> [Z][Cout][tap*Cin + ci] fp16
 static void pack_conv_host(int kind, const float* w, int Cout, int Cin, std::vector<__half>& out) {
@@ -168,7 +176,7 @@ static void pack_conv_host(int kind, const float* w, int Cout, int Cin, std::vec
 
 static void fill_taps(int kind, int Ctot0, ConvParams& p) {
     p.taps = taps_of(kind);
-    p.phases = kind == KT4 ? 4 : 1;
+    p.phases = kind_up(kind) ? 4 : 1;
     memset(p.tap, 0, sizeof p.tap);
     if (kind == K3S1) {
         for (int kh = 0; kh < 3; ++kh)
@@ -196,6 +204,26 @@ static void fill_taps(int kind, int Ctot0, ConvParams& p) {
                         t.dy = (int8_t)(ph == 0 ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0));
                         t.dx = (int8_t)(pw == 0 ? (b == 0 ? 0 : -1) : (b == 0 ? 1 : 0));
                     }
+    } else if (kind == K3S2D) {
+        // d_in[2a'+ph] = sum over kh with 2*yo + kh - 1 = 2a'+ph: ph 0 -> kh 1 (yo = a'); ph 1 -> kh 0 (yo = a'+1), kh 2 (yo = a')
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw)
+                for (int a = 0; a < 2; ++a)
+                    for (int b = 0; b < 2; ++b) {
+                        ConvTap& t = p.tap[(ph * 2 + pw) * 4 + a * 2 + b];
+                        t.dy = (int8_t)(ph == 1 && a == 0 ? 1 : 0);
+                        t.dx = (int8_t)(pw == 1 && b == 0 ? 1 : 0);
+                    }
+    } else if (kind == KT4D) {
+        // input row 2*yo + kh - 1 of the 2H-row gradient: kh 0 -> odd row yo-1; 1 -> even row yo; 2 -> odd row yo; 3 -> even row yo+1
+        for (int kh = 0; kh < 4; ++kh)
+            for (int kw = 0; kw < 4; ++kw) {
+                ConvTap& t = p.tap[kh * 4 + kw];
+                t.dy = (int8_t)(kh == 0 ? -1 : (kh == 3 ? 1 : 0));
+                t.p = (int8_t)((kh & 1) ? 0 : 1);
+                t.dx = (int8_t)(kw == 0 ? -1 : (kw == 3 ? 1 : 0));
+                t.c = (int16_t)((kw & 1) ? 0 : Ctot0);
+            }
     }
 }
 
@@ -215,14 +243,14 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
                       const ConvEpilogue& ep, __half* out) {
     USB_TRY(load_encode_fn());
     if (C0 % 64 || C1 % 64 || Cout % 64) return fail("conv channels must be multiples of 64");
-    if (kind == K3S2 && (H % 2 || W % 2 || in1 != nullptr || C0 != C0tot)) return fail("bad stride-2 conv geometry");
-    if (kind == K3S2 && 2 * C0tot > 32767) return fail("stride-2 conv too wide");
+    if (kind_down(kind) && (H % 2 || W % 2 || in1 != nullptr || C0 != C0tot)) return fail("bad stride-2 conv geometry");
+    if (kind_down(kind) && 2 * C0tot > 32767) return fail("stride-2 conv too wide");
     ConvParams& p = op.p;
     memset(&p, 0, sizeof p);
     fill_taps(kind, C0tot, p);
     p.N = N;
-    p.Hm = kind == K3S2 ? H / 2 : H;
-    p.Wm = kind == K3S2 ? W / 2 : W;
+    p.Hm = kind_down(kind) ? H / 2 : H;
+    p.Wm = kind_down(kind) ? W / 2 : W;
     int BH = 1;
     while (BH < 16 && p.Hm % (BH * 2) == 0) BH *= 2;
     // swapped-operand kernel (see conv_igemm.cu) for every 3x3 / strided / transposed conv whose Cout is a multiple of 128
@@ -260,15 +288,15 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     p.res = ep.res;
     p.res_scale = ep.res_scale;
     p.mask = ep.mask;
-    const int Hout = kind == K3S2 ? H / 2 : (kind == KT4 ? 2 * H : H);
-    const int Wout = kind == K3S2 ? W / 2 : (kind == KT4 ? 2 * W : W);
+    const int Hout = kind_down(kind) ? H / 2 : (kind_up(kind) ? 2 * H : H);
+    const int Wout = kind_down(kind) ? W / 2 : (kind_up(kind) ? 2 * W : W);
     p.mask_stride = Wout;
-    p.out_c_phase_mul = kind == KT4 ? Cout : 0;
+    p.out_c_phase_mul = kind_up(kind) ? Cout : 0;
     p.o_sx = Cout;
     p.o_sy = (long long)Wout * Cout;
     p.o_sn = (long long)Hout * Wout * Cout;
-    p.oy_mul = p.ox_mul = kind == KT4 ? 2 : 1;
-    if (kind == KT4)
+    p.oy_mul = p.ox_mul = kind_up(kind) ? 2 : 1;
+    if (kind_up(kind))
         for (int ph = 0; ph < 2; ++ph)
             for (int pw = 0; pw < 2; ++pw) {
                 p.oy_off[ph * 2 + pw] = (int8_t)ph;
@@ -294,17 +322,17 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
         USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, 128));
         return make_act_map_yx(&op.o, out, N, H, W, Cout, Cout, 32, 8, 4);
     }
-    USB_TRY(make_act_map(&op.a0, in0, N, H, W, C0tot, C0, kind == K3S2, p.BH, p.BW));
+    USB_TRY(make_act_map(&op.a0, in0, N, H, W, C0tot, C0, kind_down(kind), p.BH, p.BW));
     if (in1) USB_TRY(make_act_map(&op.a1, in1, N, H, W, C1tot, C1, false, p.BH, p.BW));
     else op.a1 = op.a0;
     USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, p.BN));
     // output tile store: plain view, or the parity view of the upsampled tensor for the transposed conv;
     // the swapped kernel stores 64-pixel sub-blocks (64 / BW image rows) per TMA
     if (p.swap_ab)   // per-warp stores: 64 pixels x 32 channels (64-byte rows, SWIZZLE_64B)
-        USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BW >= 64 ? 1 : 64 / p.BW,
+        USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind_up(kind), p.BW >= 64 ? 1 : 64 / p.BW,
                              p.BW >= 64 ? 64 : p.BW, 32));
     else   // per-warp stores: 32 pixels (one TMEM lane quarter) x 64 channels
-        USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind == KT4, p.BW >= 32 ? 1 : 32 / p.BW,
+        USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind_up(kind), p.BW >= 32 ? 1 : 32 / p.BW,
                              p.BW >= 32 ? 32 : p.BW));
     return 0;
 }
@@ -1456,6 +1484,277 @@ int usb_op_attn_context(usb_handle* h, const void* qkv, const float* wo, void* w
     cudaFree(part);
     if (e) return fail(std::string("attention launch: ") + cudaGetErrorString((cudaError_t)e));
     if (se != cudaSuccess) return fail(std::string("attention kernel: ") + cudaGetErrorString(se));
+    return 0;
+}
+
+// ===================================================================================================================
+// fine-tune step, operator level (include/unitspeech_b200_train.h).  Everything is enqueued on `stream`; no hidden
+// synchronisation, no allocation.  The Python host (unitspeech_b200/training.py) owns all buffers.
+// ===================================================================================================================
+#define USB_T_BEGIN()                                         \
+    if (!h) return fail("null handle");                       \
+    USB_CUDA(cudaSetDevice(h->cfg.device));                   \
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream)
+
+int usb_t_pack_conv(usb_handle* h, int32_t kind, const float* w, int32_t Cout, int32_t Cin, int32_t ci0, int32_t ci1,
+                    void* fwd, void* dgrad, uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_pack_conv(kind, w, Cout, Cin, ci0, ci1, static_cast<__half*>(fwd), static_cast<__half*>(dgrad), s));
+    return 0;
+}
+
+int usb_t_conv(usb_handle* h, int32_t kind, const void* in0, int32_t C0tot, int32_t C0, const void* in1, int32_t C1tot,
+               int32_t C1, int32_t N, int32_t H, int32_t W, const void* w, int32_t wZ, int32_t b_batch_mode, int32_t Cout,
+               const float* bias, const float* mask, const void* res, const float* res_scale, int64_t* stats, int32_t groups,
+               void* out, uint64_t stream) {
+    USB_T_BEGIN();
+    if (kind < 0 || kind > 5) return fail("bad conv kind");
+    ConvEpilogue ep;
+    ep.bias = bias; ep.stats = reinterpret_cast<long long*>(stats); ep.groups = groups > 0 ? groups : 8;
+    ep.res = static_cast<const __half*>(res); ep.res_scale = res_scale; ep.mask = mask;
+    ConvOp op;
+    USB_TRY(build_conv(op, kind, static_cast<const __half*>(in0), C0tot, C0, static_cast<const __half*>(in1), C1tot, C1, N, H, W,
+                       static_cast<const __half*>(w), wZ, b_batch_mode, Cout, ep, static_cast<__half*>(out)));
+    USB_LAUNCH(h, launch_conv_igemm(op.p, op.a0, op.a1, op.b, op.o, h->num_sms, s));
+    return 0;
+}
+
+int usb_t_first_conv(usb_handle* h, const float* x, const float* mu, const int32_t* rows, const float* mask, const float* w3,
+                     const float* b3, const float* w1, const float* b1, void* raw, void* res, int64_t* stats, int32_t N,
+                     int32_t H, int32_t W, int32_t C, uint64_t stream) {
+    USB_T_BEGIN();
+    FirstConvParams f;
+    memset(&f, 0, sizeof f);
+    f.x = x; f.cond = mu; f.x_row = rows; f.mu_row = rows; f.mask = mask; f.w3 = w3; f.b3 = b3; f.w1 = w1; f.b1 = b1;
+    f.raw = static_cast<__half*>(raw); f.res = static_cast<__half*>(res); f.stats = reinterpret_cast<long long*>(stats);
+    f.N = N; f.H = H; f.W = W; f.C = C; f.groups = h->cfg.groups;
+    USB_LAUNCH(h, launch_first_conv(f, s));
+    return 0;
+}
+
+int usb_t_gn_apply(usb_handle* h, const void* raw, const int64_t* stats, const float* gamma, const float* beta,
+                   const float* addvec, int64_t addvec_stride, const void* res, const float* mask, void* out, int32_t N,
+                   int32_t H, int32_t W, int32_t C, uint64_t stream) {
+    USB_T_BEGIN();
+    GnApplyParams p;
+    p.raw = static_cast<const __half*>(raw); p.stats = reinterpret_cast<const long long*>(stats); p.gamma = gamma; p.beta = beta;
+    p.addvec = addvec; p.addvec_stride = addvec_stride; p.res = static_cast<const __half*>(res); p.mask = mask;
+    p.out = static_cast<__half*>(out); p.N = N; p.P = H * W; p.W = W; p.C = C; p.groups = h->cfg.groups; p.eps = 1e-5f; p.dbg = 0;
+    USB_LAUNCH(h, launch_gn_apply(p, h->num_sms, s));
+    return 0;
+}
+
+int usb_t_embed(usb_handle* h, const float* t, const float* spk, const float* freqs, const float* w0, const float* b0,
+                const float* w2, const float* b2, const float* wcat, const float* bcat, float* u, float* e, int32_t N,
+                int32_t J, uint64_t stream) {
+    USB_T_BEGIN();
+    EmbedParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.t = t; ep.spk = spk; ep.freqs = freqs; ep.w0 = w0; ep.b0 = b0; ep.w2 = w2; ep.b2 = b2; ep.wcat = wcat; ep.bcat = bcat;
+    ep.u = u; ep.e = e; ep.N = N; ep.dim = h->cfg.dim; ep.S = h->cfg.spk_emb_dim; ep.J = J; ep.pe_scale = h->cfg.pe_scale;
+    USB_LAUNCH(h, launch_embed(ep, s));
+    h->launches++;
+    return 0;
+}
+
+int64_t usb_t_attn_scratch_bytes(int32_t N, int32_t heads, int32_t P) {
+    return static_cast<int64_t>(attn_scratch_bytes(N, heads, P, attn_chunk_for(P)));
+}
+
+int usb_t_attn_context(usb_handle* h, const void* qkv, int32_t ld, int32_t koff, int32_t voff, const float* wo, float* scratch,
+                       void* weff, float* ctx_out, float* stat_out, int32_t N, int32_t P, int32_t C, int32_t heads,
+                       uint64_t stream) {
+    USB_T_BEGIN();
+    AttnParams ap;
+    memset(&ap, 0, sizeof ap);
+    ap.qkv = static_cast<const __half*>(qkv); ap.ld = ld; ap.koff = koff; ap.voff = voff; ap.wo = wo; ap.part = scratch;
+    ap.weff = static_cast<__half*>(weff); ap.ctx_out = ctx_out; ap.stat_out = stat_out; ap.N = N; ap.P = P; ap.C = C;
+    ap.heads = heads; ap.chunk = attn_chunk_for(P);
+    USB_LAUNCH(h, launch_attn_context(ap, s));
+    h->launches += 2;
+    return 0;
+}
+
+int usb_t_final(usb_handle* h, const void* raw, const int64_t* stats, const float* gamma, const float* beta, const float* wf,
+                const float* bf, const float* mask, float* score, int32_t N, int32_t H, int32_t W, int32_t C, uint64_t stream) {
+    USB_T_BEGIN();
+    FinalParams f;
+    memset(&f, 0, sizeof f);
+    f.raw = static_cast<const __half*>(raw); f.stats = reinterpret_cast<const long long*>(stats); f.gamma = gamma; f.beta = beta;
+    f.wf = wf; f.bf = bf; f.mask = mask; f.B = N; f.nb = 1; f.P = H * W; f.W = W; f.C = C; f.groups = h->cfg.groups; f.eps = 1e-5f;
+    f.score = score;
+    USB_LAUNCH(h, launch_final(f, h->num_sms, s));
+    return 0;
+}
+
+int usb_t_loss(usb_handle* h, const float* score, const float* zm, const float* mask, const float* t, double* partial,
+               float* loss, int32_t B, int32_t T, uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_diffusion_loss(score, zm, mask, t, h->cfg.beta_min, h->cfg.beta_max, partial, loss, B, h->cfg.n_feats, T, s));
+    h->launches++;
+    return 0;
+}
+
+int usb_t_loss_grad(usb_handle* h, const float* score, const float* zm, const float* mask, const float* t, float loss_scale,
+                    float* msum, float* dscore, int32_t B, int32_t T, uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_loss_grad(score, zm, mask, t, h->cfg.beta_min, h->cfg.beta_max, loss_scale, msum, dscore, B,
+                                   h->cfg.n_feats, T, s));
+    h->launches++;
+    return 0;
+}
+
+int usb_t_gn_bwd(usb_handle* h, const void* raw, const int64_t* stats, const float* gamma, const float* beta, const void* dy0,
+                 const void* dy1, const float* dys, const float* wvec, const float* mask, float* scratch, void* d_raw,
+                 float* dbias, float* dgamma, float* dbeta, float* d_emb, int64_t emb_stride, float* d_wvec, int32_t N,
+                 int32_t H, int32_t W, int32_t C, uint64_t stream) {
+    USB_T_BEGIN();
+    const int G = h->cfg.groups;
+    GnBwdParams p;
+    memset(&p, 0, sizeof p);
+    p.raw = static_cast<const __half*>(raw); p.stats = reinterpret_cast<const long long*>(stats); p.gamma = gamma; p.beta = beta;
+    p.dy0 = static_cast<const __half*>(dy0); p.dy1 = static_cast<const __half*>(dy1); p.dys = dys; p.wvec = wvec; p.mask = mask;
+    p.sums = scratch;                                   // [3][N][C]
+    float* gsums = scratch + static_cast<size_t>(3) * N * C;   // [N][G][2]
+    p.gsums = gsums;
+    p.d_raw = static_cast<__half*>(d_raw); p.dbias = dbias; p.N = N; p.P = H * W; p.W = W; p.C = C; p.groups = G; p.eps = 1e-5f;
+    if ((dy0 == nullptr) == (dys == nullptr)) return fail("gn_bwd needs exactly one of dy0 / dys");
+    USB_CUDA(cudaMemsetAsync(scratch, 0, static_cast<size_t>(3) * N * C * sizeof(float), s));
+    USB_LAUNCH(h, launch_gn_bwd_reduce(p, h->num_sms, s));
+    USB_LAUNCH(h, launch_gn_bwd_finalize(p.sums, gamma, gsums, dgamma, dbeta, d_emb, emb_stride, d_wvec, N, C, G, s));
+    USB_LAUNCH(h, launch_gn_bwd_apply(p, h->num_sms, s));
+    return 0;
+}
+
+int usb_t_colsum(usb_handle* h, const void* t, int32_t ld, int32_t N, int32_t P, int32_t C, float* out, int64_t out_stride_n,
+                 uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_colsum(static_cast<const __half*>(t), ld, N, P, C, out, out_stride_n, h->num_sms, s));
+    return 0;
+}
+
+int usb_t_add(usb_handle* h, const void* a, const void* b, const void* c, void* out, int64_t n, uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_add_h(static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<const __half*>(c),
+                               static_cast<__half*>(out), n, s));
+    return 0;
+}
+
+// weight gradient of a convolution of the given kind, written in the reference's parameter layout.
+// dy: output gradient (N, Hout, Wout, ldy) of which Cout channels are used; x: layer input (N, H, W, ldx) of which
+// Cs = channels [0, Cs) are used and land in the [ci0, ci0 + Cs) slice of the Cin_total input channels of dW.
+// per_sample != 0 (kind 2 only): dW is (N, Cout, Cs), one matrix per sample.
+int usb_t_wgrad(usb_handle* h, int32_t kind, const void* dy, int32_t ldy, const void* x, int32_t ldx, int32_t N, int32_t H,
+                int32_t W, int32_t Cout, int32_t Cs, int32_t ci0, int32_t Cin_total, float* dW, int32_t per_sample,
+                uint64_t stream) {
+    USB_T_BEGIN();
+    if (kind < 0 || kind > 3) return fail("bad conv kind");
+    if (per_sample && kind != K1) return fail("per-sample weight gradients are 1x1 only");
+    WgradParams p;
+    memset(&p, 0, sizeof p);
+    p.A = static_cast<const __half*>(dy); p.B = static_cast<const __half*>(x); p.lda = ldy; p.ldb = ldx;
+    p.N = N; p.Cout = Cout; p.Cin = Cs; p.a_mul = p.b_mul = 1;
+    p.Hb = H; p.Wb = W;
+    if (kind == K3S1 || kind == K1) {
+        p.Ha = H; p.Wa = W; p.Hi = H; p.Wi = W;
+    } else if (kind == K3S2) {
+        p.Ha = H / 2; p.Wa = W / 2; p.Hi = H / 2; p.Wi = W / 2; p.b_mul = 2;
+    } else {
+        p.Ha = 2 * H; p.Wa = 2 * W; p.Hi = H; p.Wi = W; p.a_mul = 2;
+    }
+    if (kind == KT4) {   // (Cin, Cout, 4, 4)
+        p.taps = 16; p.s_co = 16; p.s_ci = static_cast<long long>(Cout) * 16;
+        for (int kh = 0; kh < 4; ++kh)
+            for (int kw = 0; kw < 4; ++kw) {
+                const int t = kh * 4 + kw;
+                p.ady[t] = (int8_t)(kh - 1); p.adx[t] = (int8_t)(kw - 1); p.tap_off[t] = t;
+            }
+        p.dW = dW + static_cast<long long>(ci0) * Cout * 16;
+    } else if (kind == K1) {
+        p.taps = 1; p.s_co = per_sample ? Cs : Cin_total; p.s_ci = 1;
+        p.s_n = per_sample ? static_cast<long long>(Cout) * Cs : 0;
+        p.dW = dW + (per_sample ? 0 : ci0);
+    } else {             // (Cout, Cin, 3, 3)
+        p.taps = 9; p.s_co = static_cast<long long>(Cin_total) * 9; p.s_ci = 9;
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                const int t = kh * 3 + kw;
+                p.bdy[t] = (int8_t)(kh - 1); p.bdx[t] = (int8_t)(kw - 1); p.tap_off[t] = t;
+            }
+        p.dW = dW + static_cast<long long>(ci0) * 9;
+    }
+    USB_LAUNCH(h, launch_wgrad(p, h->num_sms, s));
+    return 0;
+}
+
+int usb_t_first_conv_wgrad(usb_handle* h, const void* d_raw, const void* d_res0, const void* d_res1, const float* x,
+                           const float* mu, const float* mask, float* dW3, float* dW1, int32_t N, int32_t H, int32_t W,
+                           int32_t C, uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_first_conv_wgrad(static_cast<const __half*>(d_raw), static_cast<const __half*>(d_res0),
+                                          static_cast<const __half*>(d_res1), x, mu, mask, dW3, dW1, N, H, W, C, h->num_sms, s));
+    return 0;
+}
+
+int usb_t_attn_bwd_small(usb_handle* h, const float* G, const float* cs, const float* wo, const float* bo, const float* g,
+                         const float* ctx, float* dwo, float* dbo, float* dg, float* dctx, void* weffT, int32_t N, int32_t C,
+                         int32_t heads, uint64_t stream) {
+    USB_T_BEGIN();
+    AttnBwdParams p;
+    memset(&p, 0, sizeof p);
+    p.G = G; p.cs = cs; p.wo = wo; p.bo = bo; p.g = g; p.ctx = ctx; p.dwo = dwo; p.dbo = dbo; p.dg = dg; p.dctx = dctx;
+    p.weffT = static_cast<__half*>(weffT); p.N = N; p.C = C; p.heads = heads;
+    USB_CUDA(cudaMemsetAsync(dctx, 0, static_cast<size_t>(N) * heads * 32 * 32 * sizeof(float), s));
+    USB_LAUNCH(h, launch_attn_bwd_small(p, s));
+    return 0;
+}
+
+int usb_t_attn_bwd_dkv(usb_handle* h, const void* qkv, int32_t ld, int32_t koff, int32_t voff, const float* ms,
+                       const float* ctx, const float* dctx, void* dkv, int32_t N, int32_t P, int32_t heads, uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_attn_bwd_dkv(static_cast<const __half*>(qkv), ld, koff, voff, ms, ctx, dctx, static_cast<__half*>(dkv),
+                                      N, P, heads, h->num_sms, s));
+    return 0;
+}
+
+int usb_t_embed_bwd(usb_handle* h, const float* t, const float* spk, const float* freqs, const float* w0, const float* b0,
+                    const float* w2, const float* b2, const float* wcat, const float* u, const float* dE, float* du,
+                    float* dw0, float* db0, float* dw2, float* db2, float* dwcat, float* dbcat, int32_t N, int32_t J,
+                    uint64_t stream) {
+    USB_T_BEGIN();
+    EmbedBwdParams p;
+    memset(&p, 0, sizeof p);
+    p.t = t; p.spk = spk; p.freqs = freqs; p.w0 = w0; p.b0 = b0; p.w2 = w2; p.b2 = b2; p.wcat = wcat; p.u = u; p.dE = dE;
+    p.du = du; p.dw0 = dw0; p.db0 = db0; p.dw2 = dw2; p.db2 = db2; p.dwcat = dwcat; p.dbcat = dbcat; p.N = N;
+    p.dim = h->cfg.dim; p.S = h->cfg.spk_emb_dim; p.J = J; p.pe_scale = h->cfg.pe_scale;
+    USB_LAUNCH(h, launch_embed_bwd(p, s));
+    h->launches += 2;
+    return 0;
+}
+
+int usb_t_dot(usb_handle* h, const float* a, const float* b, int64_t n, float* out, uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_dot(a, b, n, out, s));
+    return 0;
+}
+
+int usb_t_sumsq(usb_handle* h, const float* g, int64_t n, double* out, uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_sumsq(g, n, out, s));
+    return 0;
+}
+
+int usb_t_adam(usb_handle* h, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+               float eps, int32_t step, const double* sumsq, float inv_scale, float max_norm, int32_t* skipped,
+               uint64_t stream) {
+    USB_T_BEGIN();
+    if (step < 1) return fail("Adam step counts from 1");
+    AdamParams a;
+    a.p = p; a.g = g; a.m = m; a.v = v; a.n = n; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+    a.bc1 = static_cast<float>(1.0 - std::pow(static_cast<double>(beta1), step));
+    a.bc2 = static_cast<float>(1.0 - std::pow(static_cast<double>(beta2), step));
+    a.sumsq = sumsq; a.inv_scale = inv_scale; a.max_norm = max_norm; a.skipped = skipped;
+    USB_LAUNCH(h, launch_adam(a, h->num_sms, s));
     return 0;
 }
 

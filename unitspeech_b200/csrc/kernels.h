@@ -97,6 +97,9 @@ struct AttnParams {
     const float* g;        // Rezero scalar (device)
     const float* bo;       // [C] to_out bias
     float* bprime;         // [C] g * b_o
+    // training path: keep the merged context and the softmax statistics for the backward pass (null otherwise)
+    float* ctx_out;        // [N][heads][32][32] merged, normalised context (default: behind the partials in `part`)
+    float* stat_out;       // [N][heads][2][32]: per channel max (natural-log domain) and normaliser
     int N, P, C, heads, chunk;   // dh = 32, hidden = heads*32
 };
 int attn_chunks(int P, int chunk);

@@ -1,0 +1,149 @@
+// Launchers of the backward / optimizer kernels of the speaker-adaptation (fine-tune) step:
+// UnitSpeech.fine_tune -> compute_loss -> loss_t (unitspeech/unitspeech.py:393-411,452-492) followed by
+// loss.backward(), clip_grad_norm_(max_norm=1) and Adam (finetune.py:81,159-165).
+//
+// Conventions: activations and activation gradients are NHWC fp16 ([row n][pixel p = y*W + x][channel]);
+// activation gradients carry the loss scale S (the objective is multiplied by S before differentiation so the
+// fp16 gradients stay in range); parameter gradients are fp32, in the reference's parameter layouts, also scaled by
+// S -- the optimizer kernel divides by S.  All parameter-gradient outputs ACCUMULATE (+=, atomics).
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace usb {
+
+// ---- GroupNorm + Mish backward (Block, unitspeech.py:46-55; ResnetBlock :70-75)
+//   forward: y = (Mish(GN(raw)) + emb[n][c] [+ res]) * m.   dy = (dy0 [+ dy1]) * m  or  dy = dys[n][p] * wvec[c] * m.
+//   reduce: sums[0][n][c] = sum_p dg, sums[1][n][c] = sum_p dg * xhat, dg = dy * Mish'(GN(raw)),
+//           sums[2][n][c] = sum_p dy (embedding gradient)   or, in the scalar-dy mode, sum_p dys*m * Mish(GN(raw))*m
+//   apply:  d_raw = rstd * (gamma * dg - (S1 + xhat * S2) / (cpg * P));  dbias[c] += sum_{n,p} d_raw
+struct GnBwdParams {
+    const __half* raw;        // [N][P][C] conv output (GroupNorm input)
+    const long long* stats;   // [N][groups][2] fixed point (conv_igemm.h)
+    const float* gamma;       // [C]
+    const float* beta;        // [C]
+    const __half* dy0;        // [N][P][C] or null (scalar-dy mode)
+    const __half* dy1;        // [N][P][C] second contribution or null
+    const float* dys;         // scalar-dy mode: [N][P] fp32
+    const float* wvec;        // scalar-dy mode: [C]
+    const float* mask;        // [N][W]
+    float* sums;              // [3][N][C] fp32 (zeroed by the caller before `reduce`)
+    const float* gsums;       // [N][groups][2]: S1 = sum_c gamma*sums0, S2 = sum_c gamma*sums1 (apply)
+    __half* d_raw;            // [N][P][C] (apply)
+    float* dbias;             // [C] += (apply), or null
+    int N, P, W, C, groups;
+    float eps;
+};
+int launch_gn_bwd_reduce(const GnBwdParams& p, int num_sms, cudaStream_t s);
+// gsums from sums; dgamma[c] += sum_n sums1, dbeta[c] += sum_n sums0; if d_emb: d_emb[n*emb_stride + c] = sums2[n][c];
+// if d_wvec: d_wvec[c] += sum_n sums2[n][c]
+int launch_gn_bwd_finalize(const float* sums, const float* gamma, float* gsums, float* dgamma, float* dbeta, float* d_emb,
+                           long long emb_stride, float* d_wvec, int N, int C, int groups, cudaStream_t s);
+int launch_gn_bwd_apply(const GnBwdParams& p, int num_sms, cudaStream_t s);
+
+// ---- out[c] (+ n*out_stride_n) += sum_p t[n][p][c]  (bias gradients; per-sample sums when out_stride_n != 0)
+int launch_colsum(const __half* t, int ld, int N, int P, int C, float* out, long long out_stride_n, int num_sms,
+                  cudaStream_t s);
+// ---- out = a + b (+ c), fp16, n8 = element count / 8
+int launch_add_h(const __half* a, const __half* b, const __half* c, __half* out, long long n, cudaStream_t s);
+
+// ---- weight gradient of a convolution: for tap t
+//   dW[co*s_co + ci*s_ci + tap_off[t] + n*s_n] += sum_{(n, y, x) in the iteration image}
+//       A[n][y*a_mul + ady[t]][x*a_mul + adx[t]][co] * B[n][y*b_mul + bdy[t]][x*b_mul + bdx[t]][ci]
+// (out-of-range pixels contribute zero = conv padding).  A = output gradient, B = layer input, both NHWC fp16 with
+// row strides lda / ldb.  s_n != 0: one gradient matrix per sample (LinearAttention per-sample weights).
+constexpr int kWgradMaxTaps = 16;
+struct WgradParams {
+    const __half* A;   // [N][Ha][Wa][lda]
+    const __half* B;   // [N][Hb][Wb][ldb]
+    int lda, ldb, Ha, Wa, Hb, Wb;
+    int N, Hi, Wi;     // iteration image (per sample)
+    int a_mul, b_mul;
+    int taps;
+    int8_t ady[kWgradMaxTaps], adx[kWgradMaxTaps], bdy[kWgradMaxTaps], bdx[kWgradMaxTaps];
+    int Cout, Cin;     // channels taken from A / B
+    float* dW;
+    long long s_co, s_ci, s_n;
+    int tap_off[kWgradMaxTaps];
+    int ksplit;        // pixel-range splits per sample (filled by the launcher)
+};
+int launch_wgrad(WgradParams& p, int num_sms, cudaStream_t s);
+
+// ---- input conv of downs.0.0 (2 -> C, 3x3) and its 1x1 res_conv: weight gradients only (unitspeech.py:170,49,66)
+//   dW3[co][ci][kh][kw] += sum d_raw[n][p][co] * in[ci][n][y+kh-1][x+kw-1],  dW1[co][ci] += sum d_res[n][p][co] * in[ci][n][p]
+//   in[0] = mu * m, in[1] = x * m
+int launch_first_conv_wgrad(const __half* d_raw, const __half* d_res0, const __half* d_res1, const float* x, const float* mu,
+                            const float* mask, float* dW3, float* dW1, int N, int H, int W, int C, int num_sms,
+                            cudaStream_t s);
+
+// ---- LinearAttention backward (unitspeech.py:78-96,36-43,99-106)
+struct AttnBwdParams {
+    const float* G;        // [N][C][hidden] = sum_p d_out[n][p][c] * q[n][p][j]
+    const float* cs;       // [N][C] = sum_p d_out[n][p][c]
+    const float* wo;       // [C][hidden]
+    const float* bo;       // [C]
+    const float* g;        // Rezero scalar
+    const float* ctx;      // [N][heads][32][32]
+    float* dwo;            // [C][hidden] +=
+    float* dbo;            // [C] +=
+    float* dg;             // [1] +=
+    float* dctx;           // [N][heads][32][32] (zeroed by the caller), +=
+    __half* weffT;         // [N][hidden][C] = fp16(g * Weff[n][c][j]) : per-sample weight of the dq 1x1 conv
+    int N, C, heads;
+};
+int launch_attn_bwd_small(const AttnBwdParams& p, cudaStream_t s);
+// dkv[n][p][h*32+d] = dk, dkv[n][p][hidden + h*32+e] = dv from k, v (qkv[.., koff..], qkv[.., voff..]), softmax
+// statistics ms[n][h][2][32] (max, sum), ctx and dctx
+int launch_attn_bwd_dkv(const __half* qkv, int ld, int koff, int voff, const float* ms, const float* ctx, const float* dctx,
+                        __half* dkv, int N, int P, int heads, int num_sms, cudaStream_t s);
+
+// ---- time / speaker embedding backward (unitspeech.py:109-121,133-134,165-168,61)
+struct EmbedBwdParams {
+    const float* t;        // [N]
+    const float* spk;      // [N][S]
+    const float* freqs;    // [dim/2]
+    const float* w0;       // [4*dim][dim]
+    const float* b0;
+    const float* w2;       // [dim][4*dim]
+    const float* b2;
+    const float* wcat;     // [J][dim+S]
+    const float* u;        // [N][dim+S] forward value Mish(cat(time_mlp(t), spk))
+    const float* dE;       // [N][J]
+    float* du;             // [N][dim+S] scratch (zeroed by the launcher)
+    float *dw0, *db0, *dw2, *db2, *dwcat, *dbcat;   // +=
+    int N, dim, S, J;
+    float pe_scale;
+};
+int launch_embed_bwd(const EmbedBwdParams& p, cudaStream_t s);
+
+// ---- objective gradient: dscore[n][p] = S * 2 (score * sd_n + zm) * sd_n / (sum(mask) * F), sd_n = sqrt(1 - exp(-cum_noise(t_n)))
+//      (unitspeech.py:402-404); msum: device scalar scratch
+int launch_loss_grad(const float* score, const float* zm, const float* mask, const float* t, float beta_min, float beta_max,
+                     float loss_scale, float* msum, float* dscore, int B, int F, int T, cudaStream_t s);
+// out[0] += sum_i a[i] * (b ? b[i] : 1)   (final_conv bias gradient)
+int launch_dot(const float* a, const float* b, long long n, float* out, cudaStream_t s);
+
+// ---- fp32 reference-layout weights -> fp16 GEMM operands, forward and data-gradient orientations
+// kind (engine.cu ConvKind): 0 3x3/s1, 1 3x3/s2, 2 1x1, 3 ConvTranspose 4x4/s2.  Either output may be null.
+//   fwd:   0,1: [Cout][9][Cin]; 2: [Cout][Cin]; 3: [4 phases][Cout][4][Cin]
+//   dgrad: 0: [Cin][9 (flipped)][Cout]; 1: [4 phases][Cin][4 (zero padded)][Cout]; 2: [Cin][Cout]; 3: [Cin][16][Cout]
+// ci0/ci1: the [ci0, ci1) slice of the input channels (skip-concat halves); the packed Cin is ci1 - ci0.
+int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int ci1, __half* fwd, __half* dgrad,
+                     cudaStream_t s);
+
+// ---- clip_grad_norm_ + Adam (finetune.py:81,163-165; torch.optim.Adam defaults betas (0.9, 0.999), eps 1e-8)
+int launch_sumsq(const float* g, long long n, double* out, cudaStream_t s);   // out[0] += sum g^2
+struct AdamParams {
+    float* p; const float* g; float* m; float* v;
+    long long n;
+    float lr, beta1, beta2, eps;
+    float bc1, bc2;           // 1 - beta^step
+    const double* sumsq;      // sum of squares of the scaled gradients
+    float inv_scale;          // 1 / loss scale
+    float max_norm;           // <= 0: no clipping
+    int* skipped;             // += 1 when the gradients are not finite (the step is skipped)
+};
+int launch_adam(const AdamParams& p, int num_sms, cudaStream_t s);
+
+}  // namespace usb

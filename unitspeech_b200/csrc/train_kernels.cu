@@ -1,0 +1,1018 @@
+// Backward and optimizer kernels of the fine-tune step (see train.h for the conventions and reference citations).
+// Streaming kernels follow the layout of elementwise.cu (one channel octet per thread, 16-byte accesses); the weight
+// gradient is a split-K GEMM over pixels on warp-level tensor cores (mma.sync m16n8k16, fp16 operands, fp32
+// accumulation, ldmatrix.trans because both operands are stored pixel-major = K-major rows of channels).
+#include <cmath>
+#include <cstring>
+
+#include "conv_igemm.h"
+#include "train.h"
+
+namespace usb {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 v = __half22float2(h[i]);
+        f[2 * i] = v.x;
+        f[2 * i + 1] = v.y;
+    }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    o.x = pack2(f[0], f[1]);
+    o.y = pack2(f[2], f[3]);
+    o.z = pack2(f[4], f[5]);
+    o.w = pack2(f[6], f[7]);
+    return o;
+}
+__device__ __forceinline__ uint4 ldg16(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__device__ __forceinline__ void group_moments(const long long* stats, int n, int groups, int g, double count, float eps,
+                                              float& mean, float& rstd) {
+    const double s = static_cast<double>(stats[(static_cast<long long>(n) * groups + g) * 2]) /
+                     static_cast<double>(kStatSumScale);
+    const double ss = static_cast<double>(stats[(static_cast<long long>(n) * groups + g) * 2 + 1]) /
+                      static_cast<double>(kStatSqScale);
+    const double mu = s / count;
+    double var = ss / count - mu * mu;
+    var = var < 0.0 ? 0.0 : var;
+    mean = static_cast<float>(mu);
+    rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// Mish(x) = x tanh(softplus(x)) and its derivative tanh(sp) + x (1 - tanh^2(sp)) sigmoid(x), with
+// tanh(sp) = w / (w + 2), w = e^x (e^x + 2)  (softplus threshold 20 as the reference, unitspeech.py:13-15)
+__device__ __forceinline__ void mish_fwd_bwd(float x, float& y, float& dy) {
+    const float e = __expf(fminf(x, 20.f));
+    const float w = e * (e + 2.f);
+    const float inv = 1.f / (w + 2.f);
+    const float th = w * inv;
+    const float sig = e / (1.f + e);
+    y = x * th;
+    dy = th + x * (4.f * (w + 1.f) * inv) * inv * sig;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// pixels per block so that the grid has about `waves` blocks per SM
+inline int pix_per_block(int P, int N, int lanes, int num_sms, int waves) {
+    long long want = (long long)num_sms * waves;
+    long long per_n = (want + N - 1) / N;
+    if (per_n < 1) per_n = 1;
+    int ppb = (int)((P + per_n - 1) / per_n);
+    ppb = ((ppb + lanes - 1) / lanes) * lanes;
+    if (ppb < lanes * 4) ppb = lanes * 4;
+    return ppb;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// GroupNorm + Mish backward
+// =====================================================================================================================
+struct GnThreadConst {
+    float a[8], b[8], xa[8], xb[8];
+};
+
+__device__ __forceinline__ void gn_thread_const(const GnBwdParams& p, int n, int tq, const float* s_mean, const float* s_rstd,
+                                                GnThreadConst& k) {
+    const int cpg = p.C / p.groups;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = tq * 8 + i;
+        const int g = c / cpg;
+        k.a[i] = s_rstd[g] * __ldg(p.gamma + c);
+        k.b[i] = __ldg(p.beta + c) - s_mean[g] * k.a[i];
+        k.xa[i] = s_rstd[g];
+        k.xb[i] = -s_mean[g] * s_rstd[g];
+    }
+}
+
+// dy for 8 channels of one pixel (masked); SCALAR: dys * wvec
+template <bool SCALAR>
+__device__ __forceinline__ void load_dy(const GnBwdParams& p, long long off, long long pixoff, const float (&wv)[8], float m,
+                                        float (&dy)[8], float& dys_m) {
+    if (SCALAR) {
+        dys_m = __ldg(p.dys + pixoff) * m;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dy[i] = dys_m * wv[i];
+    } else {
+        unpack8(ldg16(p.dy0 + off), dy);
+        if (p.dy1) {
+            float d1[8];
+            unpack8(ldg16(p.dy1 + off), d1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dy[i] += d1[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dy[i] *= m;
+        dys_m = 0.f;
+    }
+}
+
+template <bool SCALAR>
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p, int ppb, int TP) {
+    __shared__ float s_mean[8], s_rstd[8];
+    __shared__ float red[3 * 2048];
+    const int n = blockIdx.y;
+    const int tq = threadIdx.x % TP, pl = threadIdx.x / TP, lanes = blockDim.x / TP;
+    const int C = p.C, cpg = C / p.groups;
+    if (threadIdx.x < p.groups)
+        group_moments(p.stats, n, p.groups, threadIdx.x, static_cast<double>(p.P) * cpg, p.eps, s_mean[threadIdx.x],
+                      s_rstd[threadIdx.x]);
+    __syncthreads();
+    GnThreadConst k;
+    gn_thread_const(p, n, tq, s_mean, s_rstd, k);
+    float wv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[i] = SCALAR ? __ldg(p.wvec + tq * 8 + i) : 0.f;
+    float a0[8], a1[8], a2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = a2[i] = 0.f;
+    const float* mk = p.mask + static_cast<long long>(n) * p.W;
+    const int p_begin = blockIdx.x * ppb, p_end = min(p.P, p_begin + ppb);
+    for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
+        const long long pixoff = static_cast<long long>(n) * p.P + pix;
+        const long long off = pixoff * C + tq * 8;
+        const float m = __ldg(mk + pix % p.W);
+        float v[8], dy[8], dys_m;
+        unpack8(ldg16(p.raw + off), v);
+        load_dy<SCALAR>(p, off, pixoff, wv, m, dy, dys_m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float y, d;
+            mish_fwd_bwd(fmaf(v[i], k.a[i], k.b[i]), y, d);
+            const float dg = dy[i] * d;
+            a0[i] += dg;
+            a1[i] = fmaf(dg, fmaf(v[i], k.xa[i], k.xb[i]), a1[i]);
+            a2[i] += SCALAR ? dys_m * (y * m) : dy[i];
+        }
+    }
+    // reduce the pixel lanes of the block, one atomic per (block, channel, sum)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        red[0 * 2048 + pl * C + tq * 8 + i] = a0[i];
+        red[1 * 2048 + pl * C + tq * 8 + i] = a1[i];
+        red[2 * 2048 + pl * C + tq * 8 + i] = a2[i];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 3 * C; idx += blockDim.x) {
+        const int kk = idx / C, c = idx % C;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[kk * 2048 + l * C + c];
+        atomicAdd(p.sums + (static_cast<long long>(kk) * p.N + n) * C + c, s);
+    }
+}
+
+template <bool SCALAR>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p, int ppb, int TP) {
+    __shared__ float s_mean[8], s_rstd[8];
+    __shared__ float red[2048];
+    const int n = blockIdx.y;
+    const int tq = threadIdx.x % TP, pl = threadIdx.x / TP, lanes = blockDim.x / TP;
+    const int C = p.C, cpg = C / p.groups;
+    if (threadIdx.x < p.groups)
+        group_moments(p.stats, n, p.groups, threadIdx.x, static_cast<double>(p.P) * cpg, p.eps, s_mean[threadIdx.x],
+                      s_rstd[threadIdx.x]);
+    __syncthreads();
+    GnThreadConst k;
+    gn_thread_const(p, n, tq, s_mean, s_rstd, k);
+    float wv[8], k1[8], k2[8], acc[8];
+    const float invM = 1.f / (static_cast<float>(p.P) * cpg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = tq * 8 + i, g = c / cpg;
+        wv[i] = SCALAR ? __ldg(p.wvec + c) : 0.f;
+        const float* gs = p.gsums + (static_cast<long long>(n) * p.groups + g) * 2;
+        k1[i] = k.xa[i] * __ldg(gs) * invM;
+        k2[i] = k.xa[i] * __ldg(gs + 1) * invM;
+        acc[i] = 0.f;
+    }
+    const float* mk = p.mask + static_cast<long long>(n) * p.W;
+    const int p_begin = blockIdx.x * ppb, p_end = min(p.P, p_begin + ppb);
+    for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
+        const long long pixoff = static_cast<long long>(n) * p.P + pix;
+        const long long off = pixoff * C + tq * 8;
+        const float m = __ldg(mk + pix % p.W);
+        float v[8], dy[8], dr[8], dys_m;
+        unpack8(ldg16(p.raw + off), v);
+        load_dy<SCALAR>(p, off, pixoff, wv, m, dy, dys_m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float y, d;
+            mish_fwd_bwd(fmaf(v[i], k.a[i], k.b[i]), y, d);
+            const float xh = fmaf(v[i], k.xa[i], k.xb[i]);
+            dr[i] = fmaf(k.a[i], dy[i] * d, -fmaf(xh, k2[i], k1[i]));
+            acc[i] += dr[i];
+        }
+        *reinterpret_cast<uint4*>(p.d_raw + off) = pack8(dr);
+    }
+    if (p.dbias == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl * C + tq * 8 + i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[l * C + c];
+        atomicAdd(p.dbias + c, s);
+    }
+}
+
+static int gn_geometry(const GnBwdParams& p, int& TP, int& lanes) {
+    TP = p.C / 8;
+    if (p.C % 8 || TP < 1 || TP > 256 || (TP & (TP - 1)) || p.C % p.groups || p.groups > 8) return 1;
+    lanes = 256 / TP;
+    return 0;
+}
+
+int launch_gn_bwd_reduce(const GnBwdParams& p, int num_sms, cudaStream_t s) {
+    int TP, lanes;
+    if (gn_geometry(p, TP, lanes)) return (int)cudaErrorInvalidValue;
+    const int ppb = pix_per_block(p.P, p.N, lanes, num_sms, 4);
+    dim3 grid((p.P + ppb - 1) / ppb, p.N);
+    if (p.dys) gn_bwd_reduce_kernel<true><<<grid, 256, 0, s>>>(p, ppb, TP);
+    else gn_bwd_reduce_kernel<false><<<grid, 256, 0, s>>>(p, ppb, TP);
+    return (int)cudaGetLastError();
+}
+
+int launch_gn_bwd_apply(const GnBwdParams& p, int num_sms, cudaStream_t s) {
+    int TP, lanes;
+    if (gn_geometry(p, TP, lanes)) return (int)cudaErrorInvalidValue;
+    const int ppb = pix_per_block(p.P, p.N, lanes, num_sms, 4);
+    dim3 grid((p.P + ppb - 1) / ppb, p.N);
+    if (p.dys) gn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>(p, ppb, TP);
+    else gn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>(p, ppb, TP);
+    return (int)cudaGetLastError();
+}
+
+// grid N: group sums for `apply`, affine gradients, embedding gradient rows
+__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* sums, const float* gamma, float* gsums, float* dgamma,
+                                                              float* dbeta, float* d_emb, long long emb_stride, float* d_wvec,
+                                                              int N, int C, int groups) {
+    __shared__ float sg[8][2];
+    const int n = blockIdx.x, cpg = C / groups;
+    if (threadIdx.x < 16) sg[threadIdx.x >> 1][threadIdx.x & 1] = 0.f;
+    __syncthreads();
+    const float* s0 = sums + (0LL * N + n) * C;
+    const float* s1 = sums + (1LL * N + n) * C;
+    const float* s2 = sums + (2LL * N + n) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float g = __ldg(gamma + c), A = s0[c], B = s1[c];
+        atomicAdd(&sg[c / cpg][0], g * A);
+        atomicAdd(&sg[c / cpg][1], g * B);
+        if (dgamma) atomicAdd(dgamma + c, B);
+        if (dbeta) atomicAdd(dbeta + c, A);
+        if (d_emb) d_emb[static_cast<long long>(n) * emb_stride + c] = s2[c];
+        if (d_wvec) atomicAdd(d_wvec + c, s2[c]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * groups) gsums[(static_cast<long long>(n) * groups) * 2 + threadIdx.x] = sg[threadIdx.x >> 1][threadIdx.x & 1];
+}
+
+int launch_gn_bwd_finalize(const float* sums, const float* gamma, float* gsums, float* dgamma, float* dbeta, float* d_emb,
+                           long long emb_stride, float* d_wvec, int N, int C, int groups, cudaStream_t s) {
+    if (groups > 8 || C % groups) return (int)cudaErrorInvalidValue;
+    gn_bwd_finalize_kernel<<<N, 256, 0, s>>>(sums, gamma, gsums, dgamma, dbeta, d_emb, emb_stride, d_wvec, N, C, groups);
+    return (int)cudaGetLastError();
+}
+
+// =====================================================================================================================
+// column sums / adds
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) colsum_kernel(const __half* t, int ld, int P, int C, float* out, long long out_stride_n,
+                                                     int ppb, int TP) {
+    __shared__ float red[2048];
+    const int n = blockIdx.y;
+    const int tq = threadIdx.x % TP, pl = threadIdx.x / TP, lanes = blockDim.x / TP;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int p_begin = blockIdx.x * ppb, p_end = min(P, p_begin + ppb);
+    for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
+        float v[8];
+        unpack8(ldg16(t + (static_cast<long long>(n) * P + pix) * ld + tq * 8), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl * C + tq * 8 + i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[l * C + c];
+        atomicAdd(out + n * out_stride_n + c, s);
+    }
+}
+
+int launch_colsum(const __half* t, int ld, int N, int P, int C, float* out, long long out_stride_n, int num_sms,
+                  cudaStream_t s) {
+    const int TP = C / 8;
+    if (C % 8 || ld % 8 || TP < 1 || TP > 256 || (TP & (TP - 1))) return (int)cudaErrorInvalidValue;
+    const int lanes = 256 / TP;
+    const int ppb = pix_per_block(P, N, lanes, num_sms, 4);
+    dim3 grid((P + ppb - 1) / ppb, N);
+    colsum_kernel<<<grid, 256, 0, s>>>(t, ld, P, C, out, out_stride_n, ppb, TP);
+    return (int)cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) add_h_kernel(const uint4* a, const uint4* b, const uint4* c, uint4* out, long long n8) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float x[8], y[8];
+        unpack8(__ldg(a + i), x);
+        unpack8(__ldg(b + i), y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] += y[k];
+        if (c) {
+            unpack8(__ldg(c + i), y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] += y[k];
+        }
+        out[i] = pack8(x);
+    }
+}
+
+int launch_add_h(const __half* a, const __half* b, const __half* c, __half* out, long long n, cudaStream_t s) {
+    if (n % 8) return (int)cudaErrorInvalidValue;
+    const long long n8 = n / 8;
+    long long blocks = (n8 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    add_h_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                                  reinterpret_cast<const uint4*>(c), reinterpret_cast<uint4*>(out), n8);
+    return (int)cudaGetLastError();
+}
+
+// =====================================================================================================================
+// weight gradient: split-K GEMM over pixels on mma.sync
+// =====================================================================================================================
+namespace {
+constexpr int kWgTileM = 128, kWgTileN = 128, kWgTileK = 32;
+constexpr int kWgRowHalfs = 136;                       // 128 + 8 pad: 272-byte rows keep ldmatrix conflict-free
+constexpr int kWgOperandBytes = kWgTileK * kWgRowHalfs * 2;   // 8704
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+}  // namespace
+
+// grid.x = tap * tiles_m * tiles_n, grid.y = segment * ksplit.  A segment is one sample (s_n != 0) or the whole batch.
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p, int tiles_m, int tiles_n) {
+    __shared__ __align__(16) unsigned char sm[2 * 2 * kWgOperandBytes];   // [stage][A, B]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int bx = blockIdx.x;
+    const int tn = bx % tiles_n; bx /= tiles_n;
+    const int tm = bx % tiles_m;
+    const int tap = bx / tiles_m;
+    const int m0 = tm * kWgTileM, n0 = tn * kWgTileN;
+    const int seg = blockIdx.y / p.ksplit, part = blockIdx.y % p.ksplit;
+    const int HW = p.Hi * p.Wi;
+    const long long seg_pixels = p.s_n != 0 ? HW : static_cast<long long>(p.N) * HW;
+    long long per = (seg_pixels + p.ksplit - 1) / p.ksplit;
+    per = ((per + kWgTileK - 1) / kWgTileK) * kWgTileK;
+    const long long g_begin = seg * seg_pixels + part * per;
+    long long g_end = g_begin + per;
+    if (g_end > (seg + 1) * seg_pixels) g_end = (seg + 1) * seg_pixels;
+    const int ady = p.ady[tap], adx = p.adx[tap], bdy = p.bdy[tap], bdx = p.bdx[tap];
+
+    const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(sm));
+    const int vcol = tid & 15, vrow = tid >> 4;   // 16-byte vector column (8 channels), rows vrow and vrow + 16
+    const bool a_ch_ok = m0 + vcol * 8 < p.Cout, b_ch_ok = n0 + vcol * 8 < p.Cin;
+
+    auto issue = [&](long long g0, int stage) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = vrow + r * 16;
+            const long long gp = g0 + row;
+            const bool in = gp < g_end;
+            const long long gq = in ? gp : g_begin;
+            const int n = static_cast<int>(gq / HW);
+            const int pix = static_cast<int>(gq - static_cast<long long>(n) * HW);
+            const int y = pix / p.Wi, x = pix - y * p.Wi;
+            const int ya = y * p.a_mul + ady, xa = x * p.a_mul + adx;
+            const int yb = y * p.b_mul + bdy, xb = x * p.b_mul + bdx;
+            const bool va = in && a_ch_ok && ya >= 0 && ya < p.Ha && xa >= 0 && xa < p.Wa;
+            const bool vb = in && b_ch_ok && yb >= 0 && yb < p.Hb && xb >= 0 && xb < p.Wb;
+            const __half* pa = va ? p.A + ((static_cast<long long>(n) * p.Ha + ya) * p.Wa + xa) * p.lda + m0 + vcol * 8 : p.A;
+            const __half* pb = vb ? p.B + ((static_cast<long long>(n) * p.Hb + yb) * p.Wb + xb) * p.ldb + n0 + vcol * 8 : p.B;
+            const uint32_t so = stage * 2 * kWgOperandBytes + (row * kWgRowHalfs + vcol * 8) * 2;
+            cp_async16(sbase + so, pa, va);
+            cp_async16(sbase + so + kWgOperandBytes, pb, vb);
+        }
+        cp_async_commit();
+    };
+
+    const int wm = warp & 3, wn = warp >> 2;   // warp tile: 32 (M) x 64 (N)
+    float acc[2][8][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+    const int lm_r = lane & 7, lm_j = lane >> 3;
+
+    int stage = 0;
+    if (g_begin < g_end) issue(g_begin, 0);
+    for (long long g0 = g_begin; g0 < g_end; g0 += kWgTileK, stage ^= 1) {
+        if (g0 + kWgTileK < g_end) {
+            issue(g0 + kWgTileK, stage ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const uint32_t sa = sbase + stage * 2 * kWgOperandBytes, sb = sa + kWgOperandBytes;
+#pragma unroll
+        for (int ks = 0; ks < kWgTileK / 16; ++ks) {
+            uint32_t a[2][4], b[8][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int prow = ks * 16 + (lm_j >> 1) * 8 + lm_r, col = wm * 32 + mt * 16 + (lm_j & 1) * 8;
+                ldmatrix_x4_trans(sa + (prow * kWgRowHalfs + col) * 2, a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+            }
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                const int prow = ks * 16 + (lm_j & 1) * 8 + lm_r, col = wn * 64 + np * 16 + (lm_j >> 1) * 8;
+                ldmatrix_x4_trans(sb + (prow * kWgRowHalfs + col) * 2, b[2 * np][0], b[2 * np][1], b[2 * np + 1][0],
+                                  b[2 * np + 1][1]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) mma_16816(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b[nt][0], b[nt][1]);
+        }
+        __syncthreads();   // the other stage is refilled by the next iteration's cp.async
+    }
+
+    float* out = p.dW + p.tap_off[tap] + (p.s_n != 0 ? seg * p.s_n : 0);
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int co = m0 + wm * 32 + mt * 16 + g + (i >= 2 ? 8 : 0);
+                const int ci = n0 + wn * 64 + nt * 8 + 2 * t + (i & 1);
+                if (co < p.Cout && ci < p.Cin) atomicAdd(out + co * p.s_co + ci * p.s_ci, acc[mt][nt][i]);
+            }
+}
+
+int launch_wgrad(WgradParams& p, int num_sms, cudaStream_t s) {
+    if (p.Cout % 8 || p.Cin % 8 || p.lda % 8 || p.ldb % 8 || p.taps < 1 || p.taps > kWgradMaxTaps) return (int)cudaErrorInvalidValue;
+    const int tiles_m = (p.Cout + kWgTileM - 1) / kWgTileM, tiles_n = (p.Cin + kWgTileN - 1) / kWgTileN;
+    const long long tiles = static_cast<long long>(tiles_m) * tiles_n * p.taps;
+    const int nseg = p.s_n != 0 ? p.N : 1;
+    const long long seg_pixels = static_cast<long long>(p.Hi) * p.Wi * (p.s_n != 0 ? 1 : p.N);
+    long long ks = (2LL * num_sms + tiles * nseg - 1) / (tiles * nseg);
+    const long long max_ks = (seg_pixels + 4 * kWgTileK - 1) / (4 * kWgTileK);   // at least 128 pixels per split
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+    p.ksplit = static_cast<int>(ks);
+    dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(nseg * ks));
+    wgrad_kernel<<<grid, 256, 0, s>>>(p, tiles_m, tiles_n);
+    return (int)cudaGetLastError();
+}
+
+// =====================================================================================================================
+// input conv weight gradients (Cin = 2)
+// =====================================================================================================================
+// One block = one image-row segment of 64 pixels of one sample; blockDim = C (thread = output channel).
+__global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const __half* __restrict__ d_raw, const __half* __restrict__ d_res0,
+                                                               const __half* __restrict__ d_res1, const float* __restrict__ x,
+                                                               const float* __restrict__ mu, const float* __restrict__ mask,
+                                                               float* dW3, float* dW1, int H, int W, int C, int segs) {
+    __shared__ float in_s[2][3][66];
+    int b = blockIdx.x;
+    const int seg = b % segs; b /= segs;
+    const int y = b % H;
+    const int n = b / H;
+    const int x0 = seg * 64;
+    for (int i = threadIdx.x; i < 2 * 3 * 66; i += blockDim.x) {
+        const int ci = i / (3 * 66), r = (i / 66) % 3, cx = i % 66;
+        const int yy = y + r - 1, xx = x0 + cx - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float* src = ci == 0 ? mu : x;
+            v = __ldg(src + (static_cast<long long>(n) * H + yy) * W + xx) * __ldg(mask + static_cast<long long>(n) * W + xx);
+        }
+        in_s[ci][r][cx] = v;
+    }
+    __syncthreads();
+    const int co = threadIdx.x;
+    float a3[18], a1[2];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) a3[i] = 0.f;
+    a1[0] = a1[1] = 0.f;
+    const int xe = min(64, W - x0);
+    for (int px = 0; px < xe; ++px) {
+        const long long off = ((static_cast<long long>(n) * H + y) * W + x0 + px) * C + co;
+        const float dr = __half2float(d_raw[off]);
+        float ds = __half2float(d_res0[off]);
+        if (d_res1) ds += __half2float(d_res1[off]);
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) a3[ci * 9 + kh * 3 + kw] = fmaf(dr, in_s[ci][kh][px + kw], a3[ci * 9 + kh * 3 + kw]);
+            a1[ci] = fmaf(ds, in_s[ci][1][px + 1], a1[ci]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) atomicAdd(dW3 + co * 18 + i, a3[i]);
+    atomicAdd(dW1 + co * 2, a1[0]);
+    atomicAdd(dW1 + co * 2 + 1, a1[1]);
+}
+
+int launch_first_conv_wgrad(const __half* d_raw, const __half* d_res0, const __half* d_res1, const float* x, const float* mu,
+                            const float* mask, float* dW3, float* dW1, int N, int H, int W, int C, int num_sms,
+                            cudaStream_t s) {
+    (void)num_sms;
+    if (C > 256 || C % 32) return (int)cudaErrorInvalidValue;
+    const int segs = (W + 63) / 64;
+    first_conv_wgrad_kernel<<<N * H * segs, C, 0, s>>>(d_raw, d_res0, d_res1, x, mu, mask, dW3, dW1, H, W, C, segs);
+    return (int)cudaGetLastError();
+}
+
+// =====================================================================================================================
+// LinearAttention backward
+// =====================================================================================================================
+namespace {
+constexpr int kDh = 32;
+constexpr int kRows = 32;       // output channels per block of attn_bwd_small
+constexpr int kCtxLd = 36;
+}  // namespace
+
+// grid (ceil(C/32), N), 256 threads; hidden = heads*32 <= 128
+__global__ void __launch_bounds__(256) attn_bwd_small_kernel(const AttnBwdParams p) {
+    extern __shared__ __align__(16) float smf[];
+    const int heads = p.heads, hidden = heads * kDh;
+    float* ctx = smf;                                  // [hidden][36]
+    float* wos = ctx + hidden * kCtxLd;                // [32][hidden]
+    float* gt = wos + kRows * hidden;                  // [32][hidden]
+    float* wt = gt + kRows * hidden;                   // [32][hidden + 1]
+    __shared__ float red_s[8];
+    const int n = blockIdx.y, tid = threadIdx.x;
+    const int co0 = blockIdx.x * kRows;
+    const float* cn = p.ctx + static_cast<long long>(n) * hidden * kDh;
+    for (int i = tid; i < hidden * kDh; i += 256) ctx[(i >> 5) * kCtxLd + (i & 31)] = cn[i];
+    for (int i = tid; i < kRows * hidden; i += 256) {
+        const int co = co0 + i / hidden, k = i % hidden;
+        const bool ok = co < p.C;
+        wos[i] = ok ? __ldg(p.wo + static_cast<long long>(co) * hidden + k) : 0.f;
+        gt[i] = ok ? __ldg(p.G + (static_cast<long long>(n) * p.C + co) * hidden + k) : 0.f;
+    }
+    __syncthreads();
+    const float g = __ldg(p.g);
+    float dg_part = 0.f;
+    const int wld = hidden + 1;
+    // Weff tile, its fp16 transpose for the dq conv, and the Rezero gradient
+    for (int i = tid; i < kRows * hidden; i += 256) {
+        const int r = i / hidden, k = i % hidden, h = k / kDh, d = k % kDh;
+        float a = 0.f;
+#pragma unroll 8
+        for (int e = 0; e < kDh; ++e) a = fmaf(wos[r * hidden + h * kDh + e], ctx[(h * kDh + d) * kCtxLd + e], a);
+        wt[r * wld + k] = a;
+        dg_part = fmaf(a, gt[i], dg_part);
+        const int co = co0 + r;
+        if (co < p.C) p.weffT[(static_cast<long long>(n) * hidden + k) * p.C + co] = __float2half_rn(g * a);
+    }
+    for (int r = tid; r < kRows; r += 256) {
+        const int co = co0 + r;
+        if (co < p.C) {
+            const float c = __ldg(p.cs + static_cast<long long>(n) * p.C + co);
+            dg_part = fmaf(__ldg(p.bo + co), c, dg_part);
+            atomicAdd(p.dbo + co, g * c);
+        }
+    }
+    dg_part = warp_sum(dg_part);
+    if ((tid & 31) == 0) red_s[tid >> 5] = dg_part;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red_s[w];
+        atomicAdd(p.dg, s);
+    }
+    // dWo[co][h*32+e] += g * sum_d G[co][h*32+d] ctx[h][d][e]
+    for (int i = tid; i < kRows * hidden; i += 256) {
+        const int r = i / hidden, k = i % hidden, h = k / kDh, e = k % kDh;
+        const int co = co0 + r;
+        if (co >= p.C) continue;
+        float a = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < kDh; ++d) a = fmaf(gt[r * hidden + h * kDh + d], ctx[(h * kDh + d) * kCtxLd + e], a);
+        atomicAdd(p.dwo + static_cast<long long>(co) * hidden + k, g * a);
+    }
+    // dctx[n][h][d][e] += g * sum_{co in tile} G[co][h*32+d] Wo[co][h*32+e]
+    for (int i = tid; i < hidden * kDh; i += 256) {
+        const int hd = i >> 5, e = i & 31, h = hd / kDh;
+        float a = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < kRows; ++r) a = fmaf(gt[r * hidden + hd], wos[r * hidden + h * kDh + e], a);
+        atomicAdd(p.dctx + static_cast<long long>(n) * hidden * kDh + i, g * a);
+    }
+}
+
+int launch_attn_bwd_small(const AttnBwdParams& p, cudaStream_t s) {
+    if (p.heads < 1 || p.heads > 4) return (int)cudaErrorInvalidValue;
+    const int hidden = p.heads * kDh;
+    const size_t smem = (static_cast<size_t>(hidden) * kCtxLd + 2 * kRows * hidden + kRows * (hidden + 1)) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    dim3 grid((p.C + kRows - 1) / kRows, p.N);
+    attn_bwd_small_kernel<<<grid, 256, smem, s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// grid (blocks over positions, N), 256 threads = 8 warps; warp w serves head w % heads; heads must divide 8
+__global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const __half* __restrict__ qkv, int ld, int koff, int voff,
+                                                           const float* __restrict__ ms, const float* __restrict__ ctx,
+                                                           const float* __restrict__ dctx, __half* __restrict__ dkv, int P,
+                                                           int heads, int ppb) {
+    const int n = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = warp % heads, sub = warp / heads, nsub = 8 / heads;
+    const int hidden = heads * kDh;
+    const float* dc = dctx + (static_cast<long long>(n) * heads + h) * kDh * kDh;
+    const float* cc = ctx + (static_cast<long long>(n) * heads + h) * kDh * kDh;
+    float dcol[kDh], drow[kDh];
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < kDh; ++i) {
+        dcol[i] = __ldg(dc + i * kDh + lane);          // dctx[d = i][e = lane]
+        drow[i] = __ldg(dc + lane * kDh + i);          // dctx[d = lane][e = i]
+        r = fmaf(drow[i], __ldg(cc + lane * kDh + i), r);
+    }
+    const float M = __ldg(ms + ((static_cast<long long>(n) * heads + h) * 2) * kDh + lane);
+    const float invS = 1.f / __ldg(ms + ((static_cast<long long>(n) * heads + h) * 2 + 1) * kDh + lane);
+    const int p_begin = blockIdx.x * ppb, p_end = min(P, p_begin + ppb);
+    for (int pos = p_begin + sub; pos < p_end; pos += nsub) {
+        const long long row = static_cast<long long>(n) * P + pos;
+        const float k = __half2float(qkv[row * ld + koff + h * kDh + lane]);
+        const float v = __half2float(qkv[row * ld + voff + h * kDh + lane]);
+        const float ksm = __expf(k - M) * invS;
+        float dv = 0.f, dks = 0.f;
+#pragma unroll
+        for (int i = 0; i < kDh; ++i) {
+            dv = fmaf(__shfl_sync(0xffffffffu, ksm, i), dcol[i], dv);
+            dks = fmaf(drow[i], __shfl_sync(0xffffffffu, v, i), dks);
+        }
+        const float dk = ksm * (dks - r);
+        dkv[row * (2 * hidden) + h * kDh + lane] = __float2half_rn(dk);
+        dkv[row * (2 * hidden) + hidden + h * kDh + lane] = __float2half_rn(dv);
+    }
+}
+
+int launch_attn_bwd_dkv(const __half* qkv, int ld, int koff, int voff, const float* ms, const float* ctx, const float* dctx,
+                        __half* dkv, int N, int P, int heads, int num_sms, cudaStream_t s) {
+    if (heads < 1 || heads > 8 || 8 % heads) return (int)cudaErrorInvalidValue;
+    const int nsub = 8 / heads;
+    const int ppb = pix_per_block(P, N, nsub, num_sms, 8);
+    dim3 grid((P + ppb - 1) / ppb, N);
+    attn_bwd_dkv_kernel<<<grid, 256, 0, s>>>(qkv, ld, koff, voff, ms, ctx, dctx, dkv, P, heads, ppb);
+    return (int)cudaGetLastError();
+}
+
+// =====================================================================================================================
+// embedding backward
+// =====================================================================================================================
+__device__ __forceinline__ float mish_precise_f(float x) {
+    const float sp = x > 20.f ? x : log1pf(expf(x));
+    return x * tanhf(sp);
+}
+__device__ __forceinline__ float mish_grad_precise(float x) {
+    const float sp = x > 20.f ? x : log1pf(expf(x));
+    const float th = tanhf(sp);
+    const float sig = 1.f / (1.f + expf(-x));
+    return th + x * (1.f - th * th) * sig;
+}
+
+// warp per output row j of the stacked Linears: dwcat[j][:] += sum_n dE[n][j] u[n][:], dbcat[j] += sum_n dE[n][j]
+__global__ void __launch_bounds__(256) embed_bwd_wcat_kernel(const EmbedBwdParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= p.J) return;
+    const int K = p.dim + p.S;
+    float db = 0.f;
+    for (int n = 0; n < p.N; ++n) db += p.dE[static_cast<long long>(n) * p.J + j];
+    if (lane == 0) atomicAdd(p.dbcat + j, db);
+    for (int k = lane; k < K; k += 32) {
+        float a = 0.f;
+        for (int n = 0; n < p.N; ++n) a = fmaf(p.dE[static_cast<long long>(n) * p.J + j], p.u[static_cast<long long>(n) * K + k], a);
+        atomicAdd(p.dwcat + static_cast<long long>(j) * K + k, a);
+    }
+}
+
+// du[n][k] += sum_{j in slice} dE[n][j] wcat[j][k]; grid (ceil(K/128), N, slices)
+__global__ void __launch_bounds__(128) embed_bwd_du_kernel(const EmbedBwdParams p, int jslice) {
+    const int K = p.dim + p.S;
+    const int k = blockIdx.x * 128 + threadIdx.x, n = blockIdx.y;
+    if (k >= K) return;
+    const int j0 = blockIdx.z * jslice, j1 = min(p.J, j0 + jslice);
+    float a = 0.f;
+    for (int j = j0; j < j1; ++j) a = fmaf(__ldg(p.dE + static_cast<long long>(n) * p.J + j), __ldg(p.wcat + static_cast<long long>(j) * K + k), a);
+    atomicAdd(p.du + static_cast<long long>(n) * K + k, a);
+}
+
+// block per row n: recompute the time MLP, then its gradients (the speaker embedding is an input, no gradient)
+__global__ void __launch_bounds__(256) embed_bwd_time_kernel(const EmbedBwdParams p) {
+    extern __shared__ float sm[];   // e[dim], h0[4dim], hm[4dim], tm[dim], dtm[dim], dh0[4dim]
+    const int dim = p.dim, D4 = 4 * dim;
+    float* e = sm;
+    float* h0 = e + dim;
+    float* hm = h0 + D4;
+    float* tm = hm + D4;
+    float* dtm = tm + dim;
+    float* dh0 = dtm + dim;
+    const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = dim + p.S;
+    const int half = dim / 2;
+    const float ts = p.pe_scale * p.t[n];
+    for (int j = threadIdx.x; j < half; j += blockDim.x) {
+        const float arg = ts * p.freqs[j];
+        e[j] = sinf(arg);
+        e[j + half] = cosf(arg);
+    }
+    __syncthreads();
+    for (int i = warp; i < D4; i += 8) {
+        float acc = 0.f;
+        for (int j = lane; j < dim; j += 32) acc += p.w0[static_cast<long long>(i) * dim + j] * e[j];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            h0[i] = acc + p.b0[i];
+            hm[i] = mish_precise_f(h0[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = warp; i < dim; i += 8) {
+        float acc = 0.f;
+        for (int j = lane; j < D4; j += 32) acc += p.w2[static_cast<long long>(i) * D4 + j] * hm[j];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            tm[i] = acc + p.b2[i];
+            dtm[i] = p.du[static_cast<long long>(n) * K + i] * mish_grad_precise(tm[i]);
+            atomicAdd(p.db2 + i, dtm[i]);
+        }
+    }
+    __syncthreads();
+    // dW2[i][j] += dtm[i] hm[j];  dhm[j] = sum_i W2[i][j] dtm[i]
+    for (int idx = threadIdx.x; idx < dim * D4; idx += blockDim.x) {
+        const int i = idx / D4, j = idx % D4;
+        atomicAdd(p.dw2 + idx, dtm[i] * hm[j]);
+    }
+    for (int j = threadIdx.x; j < D4; j += blockDim.x) {
+        float a = 0.f;
+        for (int i = 0; i < dim; ++i) a = fmaf(p.w2[static_cast<long long>(i) * D4 + j], dtm[i], a);
+        dh0[j] = a * mish_grad_precise(h0[j]);
+        atomicAdd(p.db0 + j, dh0[j]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < D4 * dim; idx += blockDim.x) {
+        const int j = idx / dim, k = idx % dim;
+        atomicAdd(p.dw0 + idx, dh0[j] * e[k]);
+    }
+}
+
+int launch_embed_bwd(const EmbedBwdParams& p, cudaStream_t s) {
+    const int K = p.dim + p.S;
+    cudaError_t e = cudaMemsetAsync(p.du, 0, static_cast<size_t>(p.N) * K * sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+    embed_bwd_wcat_kernel<<<(p.J + 7) / 8, 256, 0, s>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const int slices = 16;
+    const int jslice = (p.J + slices - 1) / slices;
+    dim3 g2((K + 127) / 128, p.N, slices);
+    embed_bwd_du_kernel<<<g2, 128, 0, s>>>(p, jslice);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    embed_bwd_time_kernel<<<p.N, 256, static_cast<size_t>(15) * p.dim * sizeof(float), s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// =====================================================================================================================
+// objective gradient
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) sum_f_kernel(const float* a, const float* b, long long n, float* out) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        s += a[i] * (b ? b[i] : 1.f);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(out, t);
+    }
+}
+
+int launch_dot(const float* a, const float* b, long long n, float* out, cudaStream_t s) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    sum_f_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, b, n, out);
+    return (int)cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ score, const float* __restrict__ zm,
+                                                        const float* __restrict__ t, float beta_min, float beta_max,
+                                                        float loss_scale, const float* __restrict__ msum, float* __restrict__ dscore,
+                                                        int F, int T, long long total) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int b = static_cast<int>(i / (static_cast<long long>(F) * T));
+    const float tt = t[b];
+    const float cum = beta_min * tt + 0.5f * (beta_max - beta_min) * tt * tt;   // get_noise(cumulative=True), :204-209
+    const float sd = sqrtf(1.f - expf(-cum));
+    const float denom = msum[0] * static_cast<float>(F);
+    dscore[i] = loss_scale * 2.f * (score[i] * sd + zm[i]) * sd / denom;
+}
+
+int launch_loss_grad(const float* score, const float* zm, const float* mask, const float* t, float beta_min, float beta_max,
+                     float loss_scale, float* msum, float* dscore, int B, int F, int T, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(msum, 0, sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+    int rc = launch_dot(mask, nullptr, static_cast<long long>(B) * T, msum, s);
+    if (rc) return rc;
+    const long long total = static_cast<long long>(B) * F * T;
+    loss_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(score, zm, t, beta_min, beta_max, loss_scale, msum, dscore, F,
+                                                                     T, total);
+    return (int)cudaGetLastError();
+}
+
+// =====================================================================================================================
+// weight packing
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) pack_fwd_kernel(int kind, const float* __restrict__ w, int Cout, int Cin, int ci0, int Cs,
+                                                       __half* __restrict__ out, long long total) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float v;
+    if (kind == 0 || kind == 1) {          // [Cout][9][Cs]
+        const int ci = static_cast<int>(i % Cs);
+        const int t = static_cast<int>((i / Cs) % 9);
+        const int co = static_cast<int>(i / (9LL * Cs));
+        v = w[(static_cast<long long>(co) * Cin + ci0 + ci) * 9 + t];
+    } else if (kind == 2) {                // [Cout][Cs]
+        const int ci = static_cast<int>(i % Cs);
+        const int co = static_cast<int>(i / Cs);
+        v = w[static_cast<long long>(co) * Cin + ci0 + ci];
+    } else {                               // [ph*2+pw][Cout][a*2+b][Cs] from (Cin, Cout, 4, 4)
+        const int ci = static_cast<int>(i % Cs);
+        const int ab = static_cast<int>((i / Cs) % 4);
+        const int co = static_cast<int>((i / (4LL * Cs)) % Cout);
+        const int phase = static_cast<int>(i / (4LL * Cs * Cout));
+        const int ph = phase >> 1, pw = phase & 1, a = ab >> 1, b = ab & 1;
+        const int kh = ph == 0 ? (a == 0 ? 1 : 3) : (a == 0 ? 0 : 2);
+        const int kw = pw == 0 ? (b == 0 ? 1 : 3) : (b == 0 ? 0 : 2);
+        v = w[((static_cast<long long>(ci0 + ci) * Cout + co) * 4 + kh) * 4 + kw];
+    }
+    out[i] = __float2half_rn(v);
+}
+
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(int kind, const float* __restrict__ w, int Cout, int Cin, int ci0, int Cs,
+                                                         __half* __restrict__ out, long long total) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float v;
+    const int co = static_cast<int>(i % Cout);
+    if (kind == 0) {                       // [Cs][9][Cout], tap flipped
+        const int t = static_cast<int>((i / Cout) % 9);
+        const int ci = static_cast<int>(i / (9LL * Cout));
+        v = w[(static_cast<long long>(co) * Cin + ci0 + ci) * 9 + (8 - t)];
+    } else if (kind == 2) {                // [Cs][Cout]
+        const int ci = static_cast<int>(i / Cout);
+        v = w[static_cast<long long>(co) * Cin + ci0 + ci];
+    } else if (kind == 1) {                // [ph*2+pw][Cs][a*2+b][Cout]: transposed 3x3/s2 as four phase convs
+        const int ab = static_cast<int>((i / Cout) % 4);
+        const int ci = static_cast<int>((i / (4LL * Cout)) % Cs);
+        const int phase = static_cast<int>(i / (4LL * Cout * Cs));
+        const int ph = phase >> 1, pw = phase & 1, a = ab >> 1, b = ab & 1;
+        const int kh = ph == 0 ? (a == 0 ? 1 : -1) : (a == 0 ? 0 : 2);
+        const int kw = pw == 0 ? (b == 0 ? 1 : -1) : (b == 0 ? 0 : 2);
+        v = (kh < 0 || kw < 0) ? 0.f : w[(static_cast<long long>(co) * Cin + ci0 + ci) * 9 + kh * 3 + kw];
+    } else {                               // [Cs][16][Cout] from (Cin, Cout, 4, 4): 4x4/s2 conv over the output gradient
+        const int t = static_cast<int>((i / Cout) % 16);
+        const int ci = static_cast<int>(i / (16LL * Cout));
+        v = w[(static_cast<long long>(ci0 + ci) * Cout + co) * 16 + t];
+    }
+    out[i] = __float2half_rn(v);
+}
+
+int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int ci1, __half* fwd, __half* dgrad, cudaStream_t s) {
+    if (kind < 0 || kind > 3 || ci0 < 0 || ci1 > Cin || ci1 <= ci0) return (int)cudaErrorInvalidValue;
+    const int Cs = ci1 - ci0;
+    const int taps_f = kind == 2 ? 1 : (kind == 3 ? 16 : 9);
+    const int taps_d = kind == 2 ? 1 : (kind == 0 ? 9 : 16);
+    if (fwd) {
+        const long long total = static_cast<long long>(Cout) * Cs * taps_f;
+        pack_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(kind, w, Cout, Cin, ci0, Cs, fwd, total);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (dgrad) {
+        const long long total = static_cast<long long>(Cout) * Cs * taps_d;
+        pack_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(kind, w, Cout, Cin, ci0, Cs, dgrad, total);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+// =====================================================================================================================
+// clip_grad_norm_ + Adam
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* out) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float v = g[i];
+        s += static_cast<double>(v) * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(out, t);
+    }
+}
+
+int launch_sumsq(const float* g, long long n, double* out, cudaStream_t s) {
+    long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    sumsq_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, n, out);
+    return (int)cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamParams p) {
+    const double ssq = *p.sumsq;
+    const float norm = static_cast<float>(sqrt(ssq)) * p.inv_scale;
+    if (!isfinite(norm)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && p.skipped) atomicAdd(p.skipped, 1);
+        return;
+    }
+    float coef = p.inv_scale;
+    if (p.max_norm > 0.f) coef *= fminf(1.f, p.max_norm / (norm + 1e-6f));   // torch.nn.utils.clip_grad_norm_
+    const float step = p.lr / p.bc1, rs2 = rsqrtf(p.bc2);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float g = p.g[i] * coef;
+        const float m = p.beta1 * p.m[i] + (1.f - p.beta1) * g;
+        const float v = p.beta2 * p.v[i] + (1.f - p.beta2) * g * g;
+        p.m[i] = m;
+        p.v[i] = v;
+        p.p[i] -= step * m / (sqrtf(v) * rs2 + p.eps);
+    }
+}
+
+int launch_adam(const AdamParams& p, int num_sms, cudaStream_t s) {
+    long long blocks = (p.n + 256 * 4 - 1) / (256 * 4);
+    if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;
+    if (blocks < 1) blocks = 1;
+    adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace usb
