@@ -68,7 +68,7 @@ int usb_estimator_forward(usb_handle* h, const float* x, const float* mu, const 
 int usb_forward_diffusion(usb_handle* h, const float* x0, const float* mask, const float* t, const float* z, float* xt_out,
                           float* zmask_out, int32_t B, int32_t T, uint64_t stream);
 /* UnitSpeech.loss_t(x0, mask, cond, t, spk_emb) -- the fine-tuning objective    unitspeech/unitspeech.py:393-405
- * FORWARD VALUE ONLY (no gradients: the backward pass / optimizer of fine_tune, SURVEY section 8 row a16, is not built).
+ * Forward value (one fused call); gradients and the optimizer step are the operator-level entries of unitspeech_b200_train.h.
  * loss_out: dev float[1]; xt_out: (B, n_feats, T) dev or NULL. */
 int usb_loss_t(usb_handle* h, const float* x0, const float* cond, const float* mask, const float* t, const float* spk,
                const float* z, float* loss_out, float* xt_out, int32_t B, int32_t T, uint64_t stream);

@@ -380,6 +380,35 @@ def loss_t(p: Params, x0: torch.Tensor, mask: torch.Tensor, cond: torch.Tensor, 
     return loss, xt
 
 
+def loss_t_grads(p: Params, x0, mask, cond, t, spk_emb, z, **kw):
+    """loss_t (unitspeech/unitspeech.py:393-405) followed by ``loss.backward()`` (finetune.py:163): returns
+    (loss value, {name: dloss/dparam}); parameters the objective does not touch (text_uncon, spk_uncon) get zeros."""
+    q = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    with torch.enable_grad():
+        loss, _ = loss_t.__wrapped__(q, x0, mask, cond, t, spk_emb, z, **kw)
+        loss.backward()
+    return float(loss.detach()), {k: (v.grad.detach() if v.grad is not None else torch.zeros_like(v)) for k, v in q.items()}
+
+
+def clip_and_adam(p: Params, grads: Params, state: Dict[str, Dict[str, torch.Tensor]], step: int, lr: float = 2e-5,
+                  betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0):
+    """torch.nn.utils.clip_grad_norm_(max_norm) + one torch.optim.Adam step (finetune.py:81,164-165), restated on plain
+    tensors.  ``state`` holds exp_avg / exp_avg_sq per name (created on first use); ``step`` counts from 1.
+    Returns (new params, total gradient norm before clipping)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0) if max_norm and max_norm > 0 else torch.tensor(1.0)
+    out: Params = {}
+    bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+    for k, w in p.items():
+        g = grads[k] * coef
+        st = state.setdefault(k, {"m": torch.zeros_like(w), "v": torch.zeros_like(w)})
+        st["m"] = betas[0] * st["m"] + (1 - betas[0]) * g
+        st["v"] = betas[1] * st["v"] + (1 - betas[1]) * g * g
+        denom = st["v"].sqrt() / math.sqrt(bc2) + eps
+        out[k] = w - (lr / bc1) * st["m"] / denom
+    return out, float(total)
+
+
 def param_shapes(n_feats: int, dim: int, dim_mults: Sequence[int], spk_emb_dim: int) -> Dict[str, Tuple[int, ...]]:
     """state_dict names and shapes of UnitSpeech — unitspeech/unitspeech.py:125-162,230-233."""
     s: Dict[str, Tuple[int, ...]] = {"text_uncon": (1, n_feats, 1), "spk_uncon": (1, 1, spk_emb_dim)}

@@ -253,7 +253,8 @@ def test_loss_t_matches_reference_golden_and_oracle(golden_dir, name):
     t = torch.tensor(ts)
     dec = _decoder(dim, mults, params)
     torch.manual_seed(77)                       # same global-RNG draw as the reference's forward_diffusion (CPU tensors in)
-    loss, xt = dec.loss_t(x0, mask, cond, t, spk)
+    with torch.no_grad():                       # forward value through the fused usb_loss_t entry
+        loss, xt = dec.loss_t(x0, mask, cond, t, spk)
     assert not loss.requires_grad and loss.dim() == 0
     assert float((xt - torch.from_numpy(g["xt"])).abs().max()) <= 1e-5
     rel = abs(float(loss) - float(g["loss"])) / float(g["loss"])
@@ -266,11 +267,17 @@ def test_loss_t_matches_reference_golden_and_oracle(golden_dir, name):
     z = torch.randn(x0.shape)
     assert torch.equal(xt2, xt) and torch.equal(zm, z * mask)
     # device tensors in -> device tensors out, and repeatable given the generator state
-    torch.cuda.manual_seed(5)
-    l1, _ = dec.loss_t(x0.cuda(), mask.cuda(), cond.cuda(), t.cuda(), spk.cuda())
-    torch.cuda.manual_seed(5)
-    l2, _ = dec.loss_t(x0.cuda(), mask.cuda(), cond.cuda(), t.cuda(), spk.cuda())
+    with torch.no_grad():
+        torch.cuda.manual_seed(5)
+        l1, _ = dec.loss_t(x0.cuda(), mask.cuda(), cond.cuda(), t.cuda(), spk.cuda())
+        torch.cuda.manual_seed(5)
+        l2, _ = dec.loss_t(x0.cuda(), mask.cuda(), cond.cuda(), t.cuda(), spk.cuda())
     assert l1.is_cuda and torch.equal(l1, l2)
+    # with autograd enabled the same call goes through the fine-tune engine and carries a graph
+    torch.manual_seed(77)
+    l3, xt3 = dec.loss_t(x0, mask, cond, t, spk)
+    assert l3.requires_grad and abs(float(l3) - float(loss)) <= 1e-3 * float(loss)
+    assert float((xt3 - xt).abs().max()) <= 1e-6
 
 
 @pytest.mark.parametrize("name", ["finetune_d64", "finetune_d64_short"])

@@ -1,0 +1,174 @@
+"""Fine-tune step on the CUDA path against the oracle's autograd and against gradients /
+Adam trajectories of the unmodified reference (tests/golden/grads_*.npz).
+
+Tolerances (activations and activation gradients are fp16 with fp32 accumulation, parameters and gradients fp32):
+  per-parameter gradient: relative L2 error <= 2e-2 and cosine >= 0.999 vs the oracle's fp32 autograd;
+  loss per iteration: relative 5e-3 vs the reference; total gradient norm: relative 2e-2;
+  per-parameter |w_K - w_0| after K Adam steps: relative 5e-2 vs the reference (the first Adam steps move every element
+  by ~lr * sign(g), so the distance is insensitive to the fp16 noise on near-zero gradients; directions are checked by
+  cosine >= 0.95 against the oracle's run)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unitspeech_oracle as O
+from train_cases import CASES, FULL_KEYS, case_inputs, projection, reference_z
+
+pytestmark = pytest.mark.gpu
+
+GRAD_REL, GRAD_COS = 2e-2, 0.999
+
+
+def _tuner(dim, mults, params, **kw):
+    from unitspeech_b200 import FineTuner
+    ft = FineTuner(dim=dim, dim_mults=mults, **kw)
+    ft.load_state_dict(params)
+    return ft
+
+
+@pytest.mark.parametrize("name", ["grads_d64", "grads_full"])
+def test_gradients_match_oracle_autograd_and_reference_golden(golden_dir, name):
+    dim, mults, B, T, lengths, ts, s, lr, K = CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=s)
+    x0, mask, cond, spk = case_inputs(B, T, lengths)
+    t = torch.tensor(ts)
+    z = reference_z(x0.shape, 0)
+    ref_loss, ref = O.loss_t_grads(params, x0, mask, cond, t, spk, z, dim=dim, dim_mults=mults)
+    ft = _tuner(dim, mults, params)
+    ft.zero_grad()
+    loss = float(ft.forward(x0, mask, cond, t, spk, z))
+    ft.backward()
+    torch.cuda.synchronize()
+    assert loss == pytest.approx(float(gold["losses"][0]), rel=5e-3)
+    got = {k: v.cpu() for k, v in ft.unscaled_grads().items()}
+    worst = (0.0, "")
+    # one-element parameters (the Rezero gains .fn.g) are sums of cancelling terms: their error is measured against the
+    # norm of the vector of all of them instead of against each (possibly tiny) value
+    scalars = [k for k, r in ref.items() if r.numel() == 1 and k.endswith(".fn.g")]
+    g_scale = float(torch.stack([ref[k].reshape(()) for k in scalars]).norm())
+    for k, r in ref.items():
+        g = got[k]
+        nr = float(r.norm())
+        if nr == 0.0:
+            assert float(g.abs().max()) == 0.0, k
+            continue
+        if k in scalars:
+            assert abs(float(g) - float(r)) <= GRAD_REL * g_scale, f"{k}: {float(g):.5e} vs {float(r):.5e} (scale {g_scale:.3e})"
+            assert abs(float(g) - float(gold["gp/" + k]) / float(projection(k, g.shape))) <= GRAD_REL * g_scale, k
+            continue
+        rel = float((g - r).norm()) / nr
+        cos = float(torch.dot(g.reshape(-1), r.reshape(-1)) / (g.norm() * r.norm()))
+        worst = max(worst, (rel, k))
+        assert rel <= GRAD_REL and cos >= GRAD_COS, f"{k}: rel {rel:.3e} cos {cos:.5f}"
+        # the reference's own numbers: norm and a seeded projection of every gradient, a few gradients in full
+        assert float(g.norm()) == pytest.approx(float(gold["gn/" + k]), rel=GRAD_REL), k
+        gp = float((g.double() * projection(k, g.shape).double()).sum())
+        assert gp == pytest.approx(float(gold["gp/" + k]), abs=GRAD_REL * float(gold["gn/" + k]) * 8 + 1e-7), k
+    for k in FULL_KEYS:
+        if "gf/" + k in gold.files:
+            r = torch.from_numpy(gold["gf/" + k])
+            assert float((got[k] - r).norm()) <= GRAD_REL * float(r.norm()) + 1e-8, k
+    print(f"{name}: loss {loss:.6f} (oracle {ref_loss:.6f}); worst gradient rel error {worst[0]:.2e} ({worst[1]})")
+    ft.close()
+
+
+@pytest.mark.parametrize("name", ["grads_d64", "grads_full"])
+def test_clip_and_adam_trajectory_matches_reference(golden_dir, name):
+    dim, mults, B, T, lengths, ts, s, lr, K = CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=s)
+    x0, mask, cond, spk = case_inputs(B, T, lengths)
+    t = torch.tensor(ts)
+    ft = _tuner(dim, mults, params, lr=lr, max_norm=1.0)
+    p_or, state = dict(params), {}
+    for i in range(K):
+        z = reference_z(x0.shape, i)
+        loss = float(ft.train_step(x0, mask, cond, t, spk, z))
+        assert loss == pytest.approx(float(gold["losses"][i]), rel=5e-3), i
+        assert ft.grad_norm() == pytest.approx(float(gold["norms"][i]), rel=2e-2), i
+        _, g = O.loss_t_grads(p_or, x0, mask, cond, t, spk, z, dim=dim, dim_mults=mults)
+        p_or, _ = O.clip_and_adam(p_or, g, state, i + 1, lr=lr)
+    assert int(ft.skipped) == 0
+    new = {k: v.cpu() for k, v in ft.state_dict().items()}
+    for k in params:
+        d = new[k] - params[k]
+        want = float(gold["dw/" + k])
+        if want == 0.0:
+            assert float(d.abs().max()) == 0.0, k
+            continue
+        assert float(d.double().norm()) == pytest.approx(want, rel=5e-2), k
+        do = p_or[k] - params[k]
+        cos = float(torch.dot(d.reshape(-1), do.reshape(-1)) / (d.norm() * do.norm()))
+        assert cos >= 0.95, f"{k}: update cosine {cos:.4f}"
+    ft.close()
+
+
+def test_reference_loop_runs_unchanged_on_the_module(golden_dir):
+    """decoder.zero_grad(); loss = decoder.loss_t(...); loss.backward(); clip_grad_norm_; optimizer.step()  (finetune.py:131-165)"""
+    from unitspeech_b200 import UnitSpeech
+    name = "grads_d64"
+    dim, mults, B, T, lengths, ts, s, lr, K = CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=s)
+    dec = UnitSpeech(80, dim, mults, spk_emb_dim=256)
+    dec.load_state_dict(params, strict=True)
+    dec = dec.cuda().train()
+    opt = torch.optim.Adam(params=dec.parameters(), lr=lr)
+    x0, mask, cond, spk = case_inputs(B, T, lengths)
+    t = torch.tensor(ts)
+    for i in range(K):
+        dec.zero_grad()
+        torch.manual_seed(77 + i)                  # CPU inputs: loss_t draws z = randn(x0.shape) like the reference (:381)
+        loss, _ = dec.loss_t(x0, mask, cond, t, spk)
+        assert loss.requires_grad
+        loss.backward()
+        total = torch.nn.utils.clip_grad_norm_(dec.parameters(), max_norm=1)
+        opt.step()
+        assert float(loss) == pytest.approx(float(gold["losses"][i]), rel=5e-3), i
+        assert float(total) == pytest.approx(float(gold["norms"][i]), rel=2e-2), i
+    for k, v in dec.named_parameters():
+        want = float(gold["dw/" + k])
+        if want > 0:
+            assert float((v.detach().cpu().double() - params[k].double()).norm()) == pytest.approx(want, rel=5e-2), k
+    # the updated weights are what the sampler sees next
+    dec.eval()
+    with torch.no_grad():
+        l_after, _ = dec.loss_t(x0, mask, cond, t, spk)
+    assert torch.isfinite(l_after)
+
+
+def test_fused_finetuner_reduces_the_objective():
+    """The all-in-library loop (UnitSpeech.fused_finetuner().fine_tune) on a synthetic utterance with a fixed crop/noise
+    stream: the smoothed objective goes down and no step is skipped."""
+    import random
+    from unitspeech_b200 import UnitSpeech
+    from unitspeech_b200.util import sequence_mask
+    dim, mults = 64, (1, 2)
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=4.0)
+    dec = UnitSpeech(80, dim, mults, spk_emb_dim=256)
+    dec.load_state_dict(params, strict=True)
+    dec = dec.cuda()
+    g = torch.Generator().manual_seed(3)
+    B, Lt, T, seg = 2, 9, 48, 32
+    cond_x = torch.randn(B, 80, Lt, generator=g).clamp(-1, 1).cuda()
+    y = (torch.randn(B, 80, T, generator=g) * 0.5).clamp(-1, 1).cuda()
+    yl = torch.LongTensor([48, 41]).cuda()
+    y_mask = sequence_mask(yl, T).unsqueeze(1).float()
+    attn = torch.zeros(B, Lt, T, device="cuda")
+    for b in range(B):
+        for j in range(int(yl[b])):
+            attn[b, min(Lt - 1, j * Lt // int(yl[b])), j] = 1.0
+    spk = torch.randn(B, 1, 256, generator=g)
+    spk = (spk / spk.norm(dim=-1, keepdim=True)).cuda()
+    ft = dec.fused_finetuner(lr=1e-3)
+    random.seed(0)
+    torch.manual_seed(0)
+    losses = [float(ft.fine_tune(cond_x, y * y_mask, y_mask, yl, T, attn, spk, seg, 80)) for _ in range(40)]
+    assert int(ft.skipped) == 0 and all(np.isfinite(losses))
+    assert np.mean(losses[-10:]) < 0.8 * np.mean(losses[:10]), (np.mean(losses[:10]), np.mean(losses[-10:]))
+    dec.load_state_dict(ft.state_dict())
+    ft.close()

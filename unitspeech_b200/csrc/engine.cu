@@ -1650,6 +1650,71 @@ int usb_t_wgrad(usb_handle* h, int32_t kind, const void* dy, int32_t ldy, const 
     USB_T_BEGIN();
     if (kind < 0 || kind > 3) return fail("bad conv kind");
     if (per_sample && kind != K1) return fail("per-sample weight gradients are 1x1 only");
+    // output addressing in the reference's parameter layout
+    long long s_co, s_ci, s_n = 0;
+    int taps, tap_off[kWgradMaxTaps] = {0};
+    float* dWo = dW;
+    if (kind == KT4) {   // (Cin, Cout, 4, 4)
+        taps = 16; s_co = 16; s_ci = static_cast<long long>(Cout) * 16;
+        for (int t = 0; t < 16; ++t) tap_off[t] = t;
+        dWo = dW + static_cast<long long>(ci0) * Cout * 16;
+    } else if (kind == K1) {
+        taps = 1; s_co = per_sample ? Cs : Cin_total; s_ci = 1;
+        s_n = per_sample ? static_cast<long long>(Cout) * Cs : 0;
+        dWo = dW + (per_sample ? 0 : ci0);
+    } else {             // (Cout, Cin, 3, 3)
+        taps = 9; s_co = static_cast<long long>(Cin_total) * 9; s_ci = 9;
+        for (int t = 0; t < 9; ++t) tap_off[t] = t;
+        dWo = dW + static_cast<long long>(ci0) * 9;
+    }
+    static const bool use_mma_sync = getenv("USB_WGRAD_MMA") != nullptr;
+    if (!use_mma_sync && Cout % 64 == 0 && Cs % 64 == 0 && ldy % 8 == 0 && ldx % 8 == 0) {
+        // tcgen05 path: iteration image = the smaller of the two images; the other side is addressed through the
+        // parity-split view with the forward conv's tap table
+        WgradTcParams q;
+        memset(&q, 0, sizeof q);
+        const int Hi = kind == K3S2 ? H / 2 : H, Wi = kind == K3S2 ? W / 2 : W;
+        int bestBH = 0, bestBW = 0;
+        double best = -1.0;
+        for (int bh = 1; bh <= Hi && bh <= 128; ++bh) {
+            if (Hi % bh) continue;
+            for (int bw = 1; bw <= 128; bw *= 2) {
+                const int kp = bh * bw;
+                if (kp % 16 || kp > 128 || kp < 32) continue;
+                const double eff = static_cast<double>(Wi) / (((Wi + bw - 1) / bw) * bw) + 1e-4 * kp;
+                if (eff > best) { best = eff; bestBH = bh; bestBW = bw; }
+            }
+        }
+        if (bestBH == 0) return fail("wgrad: no pixel tiling for this image");
+        q.N = N; q.BH = bestBH; q.BW = bestBW; q.tiles_y = Hi / bestBH; q.tiles_x = (Wi + bestBW - 1) / bestBW;
+        q.taps = taps;
+        for (int t = 0; t < taps; ++t) {
+            q.tap_off[t] = tap_off[t];
+            if (kind == K3S1) {
+                q.btap[t].dy = (int8_t)(t / 3 - 1); q.btap[t].dx = (int8_t)(t % 3 - 1);
+            } else if (kind == K3S2) {
+                const int kh = t / 3, kw = t % 3;
+                q.btap[t].dy = (int8_t)(kh == 0 ? -1 : 0); q.btap[t].p = (int8_t)(kh == 1 ? 0 : 1);
+                q.btap[t].dx = (int8_t)(kw == 0 ? -1 : 0); q.btap[t].c = (int16_t)(kw == 1 ? 0 : ldx);
+            } else if (kind == KT4) {
+                const int kh = t / 4, kw = t % 4;
+                q.atap[t].dy = (int8_t)(kh == 0 ? -1 : (kh == 3 ? 1 : 0)); q.atap[t].p = (int8_t)((kh & 1) ? 0 : 1);
+                q.atap[t].dx = (int8_t)(kw == 0 ? -1 : (kw == 3 ? 1 : 0)); q.atap[t].c = (int16_t)((kw & 1) ? 0 : ldy);
+            }
+        }
+        if ((kind == K3S2 && (ldx != Cs || 2 * ldx > 32767)) || (kind == KT4 && (ldy != Cout || 2 * ldy > 32767)))
+            return fail("wgrad: strided convs need dense tensors");
+        q.Cout = Cout; q.Cin = Cs; q.n_tile = Cs <= 128 ? 128 : 256;
+        q.tiles_m = (Cout + 127) / 128; q.tiles_n = (Cs + q.n_tile - 1) / q.n_tile;
+        q.dW = dWo; q.s_co = s_co; q.s_ci = s_ci; q.s_n = s_n;
+        CUtensorMap ma, mb;
+        USB_TRY(load_encode_fn());
+        const int Hy = kind == K3S2 ? H / 2 : (kind == KT4 ? 2 * H : H), Wy = kind == K3S2 ? W / 2 : (kind == KT4 ? 2 * W : W);
+        USB_TRY(make_act_map(&ma, static_cast<const __half*>(dy), N, Hy, Wy, ldy, Cout, kind == KT4, q.BH, q.BW));
+        USB_TRY(make_act_map(&mb, static_cast<const __half*>(x), N, H, W, ldx, Cs, kind == K3S2, q.BH, q.BW));
+        USB_LAUNCH(h, launch_wgrad_tc(q, ma, mb, h->num_sms, s));
+        return 0;
+    }
     WgradParams p;
     memset(&p, 0, sizeof p);
     p.A = static_cast<const __half*>(dy); p.B = static_cast<const __half*>(x); p.lda = ldy; p.ldb = ldx;
@@ -1662,26 +1727,11 @@ int usb_t_wgrad(usb_handle* h, int32_t kind, const void* dy, int32_t ldy, const 
     } else {
         p.Ha = 2 * H; p.Wa = 2 * W; p.Hi = H; p.Wi = W; p.a_mul = 2;
     }
-    if (kind == KT4) {   // (Cin, Cout, 4, 4)
-        p.taps = 16; p.s_co = 16; p.s_ci = static_cast<long long>(Cout) * 16;
-        for (int kh = 0; kh < 4; ++kh)
-            for (int kw = 0; kw < 4; ++kw) {
-                const int t = kh * 4 + kw;
-                p.ady[t] = (int8_t)(kh - 1); p.adx[t] = (int8_t)(kw - 1); p.tap_off[t] = t;
-            }
-        p.dW = dW + static_cast<long long>(ci0) * Cout * 16;
-    } else if (kind == K1) {
-        p.taps = 1; p.s_co = per_sample ? Cs : Cin_total; p.s_ci = 1;
-        p.s_n = per_sample ? static_cast<long long>(Cout) * Cs : 0;
-        p.dW = dW + (per_sample ? 0 : ci0);
-    } else {             // (Cout, Cin, 3, 3)
-        p.taps = 9; p.s_co = static_cast<long long>(Cin_total) * 9; p.s_ci = 9;
-        for (int kh = 0; kh < 3; ++kh)
-            for (int kw = 0; kw < 3; ++kw) {
-                const int t = kh * 3 + kw;
-                p.bdy[t] = (int8_t)(kh - 1); p.bdx[t] = (int8_t)(kw - 1); p.tap_off[t] = t;
-            }
-        p.dW = dW + static_cast<long long>(ci0) * 9;
+    p.taps = taps; p.s_co = s_co; p.s_ci = s_ci; p.s_n = s_n; p.dW = dWo;
+    for (int t = 0; t < taps; ++t) {
+        p.tap_off[t] = tap_off[t];
+        if (kind == KT4) { p.ady[t] = (int8_t)(t / 4 - 1); p.adx[t] = (int8_t)(t % 4 - 1); }
+        else if (kind != K1) { p.bdy[t] = (int8_t)(t / 3 - 1); p.bdx[t] = (int8_t)(t % 3 - 1); }
     }
     USB_LAUNCH(h, launch_wgrad(p, h->num_sms, s));
     return 0;

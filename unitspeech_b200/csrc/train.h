@@ -147,3 +147,24 @@ struct AdamParams {
 int launch_adam(const AdamParams& p, int num_sms, cudaStream_t s);
 
 }  // namespace usb
+
+// ---- weight gradient on the 5th-generation tensor cores (wgrad_tc.cu)
+//   D[co][ci] (TMEM, fp32) += sum over a chunk of BH x BW pixels of dY[p][co] * X[p + tap][ci]: both operands are
+//   pixel-major tiles ([pixel][64 channels], 128-byte rows, SWIZZLE_128B) exactly as TMA writes them, consumed as
+//   MN-major UMMA operands (the GEMM K axis is the pixel axis).  One CTA = one (tap, 128 x n_tile) tile of dW over a
+//   range of pixel chunks; partial sums are added to dW with fp32 reductions.
+#include <cuda.h>
+#include "conv_igemm.h"
+namespace usb {
+struct WgradTcParams {
+    int N, BH, BW, tiles_y, tiles_x;   // iteration image tiling (per sample); kp = BH * BW pixels per chunk (multiple of 16)
+    int taps;
+    ConvTap atap[kWgradMaxTaps], btap[kWgradMaxTaps];   // per-tap load offsets of dY (A) and X (B)
+    int Cout, Cin, n_tile, tiles_m, tiles_n;
+    float* dW;
+    long long s_co, s_ci, s_n;
+    int tap_off[kWgradMaxTaps];
+    int ksplit, stages;
+};
+int launch_wgrad_tc(WgradTcParams& p, const CUtensorMap& map_a, const CUtensorMap& map_b, int num_sms, cudaStream_t s);
+}  // namespace usb

@@ -18,7 +18,9 @@ Differences from the reference, all deliberate:
     and returns a CPU tensor;
   * ``n_timesteps=1`` raises ValueError (the reference crashes with an indexing error).
 ``forward_diffusion`` / ``loss_t`` / ``compute_loss`` / ``fine_tune`` evaluate the fine-tuning objective on the same
-kernels (forward value only: no autograd graph, no optimizer -- SURVEY section 8 row a16 is not built).
+kernels; with autograd enabled the loss back-propagates through the CUDA backward pass (unitspeech_b200/training.py), so the
+reference's fine-tune loop (finetune.py:131-165) runs unchanged, and ``fused_finetuner()`` is the all-in-library fast path
+(backward + clip_grad_norm_ + Adam).
 """
 
 from __future__ import annotations
@@ -152,6 +154,7 @@ class UnitSpeech(torch.nn.Module):
         self._handle_device = None
         self._weights_version = 0
         self._synced_version = -1
+        self._tuner = None
 
     # ------------------------------------------------------------------ reference conveniences (unitspeech/base.py)
     @property
@@ -364,7 +367,7 @@ class UnitSpeech(torch.nn.Module):
         decoder_outputs = decoder_outputs[:, :, :y_max_length]
         return encoder_outputs, decoder_outputs, attn[:, :, :y_max_length]
 
-    # ------------------------------------------------------------------ training objective (forward value only)
+    # ------------------------------------------------------------------ training objective
     def _dev_tensors(self, like, *tensors):
         self._ensure_handle(like)
         dev = torch.device("cuda", self._handle_device)
@@ -384,59 +387,116 @@ class UnitSpeech(torch.nn.Module):
                                                 xt.data_ptr(), zm.data_ptr(), B, T, self._stream(dev.index)))
         return xt.to(x0.device), zm.to(x0.device)
 
-    @torch.no_grad()
+    def _wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _ensure_tuner(self, like: Optional[torch.Tensor] = None):
+        """The fine-tune engine (unitspeech_b200/training.py) behind loss.backward(): created on first use, its fp32
+        master copy refreshed from the module parameters before every forward (the caller's optimizer updates the
+        module parameters in place)."""
+        from .training import FineTuner
+        dev = self._device_index(like)
+        if self._tuner is None or self._tuner.dev.index != dev:
+            self._tuner = FineTuner(n_feats=self.n_feats, dim=self.dim, dim_mults=self.dim_mults, beta_min=self.beta_min,
+                                    beta_max=self.beta_max, pe_scale=self.pe_scale, spk_emb_dim=self.spk_emb_dim, device=dev)
+        self._tuner.load_state_dict(dict(self.state_dict()), strict=True)
+        return self._tuner
+
+    def fused_finetuner(self, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, loss_scale=8192.0):
+        """Fast path of the fine-tune loop (finetune.py:131-165): returns a FineTuner holding a copy of this decoder's
+        weights whose ``fine_tune(...)`` runs zero_grad + loss + backward + clip_grad_norm_ + Adam entirely in the CUDA
+        library (two launches for clip + Adam over all parameters).  Copy the result back with
+        ``decoder.load_state_dict(tuner.state_dict())``."""
+        from .training import FineTuner
+        ft = FineTuner(n_feats=self.n_feats, dim=self.dim, dim_mults=self.dim_mults, beta_min=self.beta_min,
+                       beta_max=self.beta_max, pe_scale=self.pe_scale, spk_emb_dim=self.spk_emb_dim, lr=lr, betas=betas, eps=eps,
+                       max_norm=max_norm, loss_scale=loss_scale, device=self._device_index())
+        ft.load_state_dict(dict(self.state_dict()), strict=True)
+        return ft
+
     def loss_t(self, x0, mask, cond, t, spk_emb):
-        """UnitSpeech.loss_t (unitspeech/unitspeech.py:393-405) -> (loss, xt).  Forward value only: the returned loss
-        carries no autograd graph (the backward pass / optimizer step of fine-tuning is not built)."""
-        lib = abi.load_library()
+        """UnitSpeech.loss_t (unitspeech/unitspeech.py:393-405) -> (loss, xt).  With autograd enabled and trainable
+        parameters the returned loss back-propagates through the CUDA backward pass into ``parameter.grad`` (so the
+        reference loop ``loss.backward(); clip_grad_norm_(...); optimizer.step()`` works unchanged, finetune.py:163-165);
+        under ``torch.no_grad()`` it is the forward value only."""
         B, F, T = x0.shape
         if T % (2 ** (len(self.dim_mults) - 1)):
             raise ValueError("T must be a multiple of 2**(len(dim_mults)-1) (use fix_len_compatibility)")
         z = torch.randn(x0.shape, dtype=x0.dtype, device=x0.device, requires_grad=False)
-        dev, (xd, md, cd, td, sd, zd) = self._dev_tensors(x0, x0, mask.reshape(B, T), cond, t.reshape(B),
-                                                         spk_emb.reshape(B, self.spk_emb_dim), z)
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        xt = torch.empty_like(xd)
-        with torch.cuda.device(dev):
-            abi.check(lib.usb_loss_t(self._handle, xd.data_ptr(), cd.data_ptr(), md.data_ptr(), td.data_ptr(),
-                                     sd.data_ptr(), zd.data_ptr(), loss.data_ptr(), xt.data_ptr(), B, T,
-                                     self._stream(dev.index)))
-        return loss.to(x0.device), xt.to(x0.device)
+        if self._wants_grad():
+            ft = self._ensure_tuner(x0)
+            names = [k for k, _ in self.named_parameters()]
+            loss = _DiffusionLoss.apply(ft, names, x0, mask, cond, t, spk_emb, z, *[p for _, p in self.named_parameters()])
+            return loss.to(x0.device), ft.xt.detach().clone().to(x0.device)
+        with torch.no_grad():
+            lib = abi.load_library()
+            dev, (xd, md, cd, td, sd, zd) = self._dev_tensors(x0, x0, mask.reshape(B, T), cond, t.reshape(B),
+                                                             spk_emb.reshape(B, self.spk_emb_dim), z)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            xt = torch.empty_like(xd)
+            with torch.cuda.device(dev):
+                abi.check(lib.usb_loss_t(self._handle, xd.data_ptr(), cd.data_ptr(), md.data_ptr(), td.data_ptr(),
+                                         sd.data_ptr(), zd.data_ptr(), loss.data_ptr(), xt.data_ptr(), B, T,
+                                         self._stream(dev.index)))
+            return loss.to(x0.device), xt.to(x0.device)
 
-    @torch.no_grad()
     def compute_loss(self, x0, mask, cond, spk_emb=None, offset=1e-5):
         """UnitSpeech.compute_loss (unitspeech/unitspeech.py:407-411): t ~ U(offset, 1 - offset) per utterance."""
         t = torch.rand(x0.shape[0], dtype=x0.dtype, device=x0.device, requires_grad=False)
         t = torch.clamp(t, offset, 1.0 - offset)
         return self.loss_t(x0, mask, cond, t, spk_emb)
 
-    @torch.no_grad()
     def fine_tune(self, cond_x, y, y_mask, y_lengths, y_max_length, attn, spk_emb, segment_size, n_feats):
         """UnitSpeech.fine_tune (unitspeech/unitspeech.py:452-492): random segment crop (Python `random`, as the
-        reference), alignment of the encoder output to the crop, then the diffusion loss.  Returns the loss VALUE; it
-        cannot be back-propagated (see loss_t)."""
-        import random
-        if y_max_length < segment_size:
-            pad_size = segment_size - y_max_length
-            y = torch.cat([y, torch.zeros_like(y)[:, :, :pad_size]], dim=-1)
-            y_mask = torch.cat([y_mask, torch.zeros_like(y_mask)[:, :, :pad_size]], dim=-1)
-        max_offset = (y_lengths - segment_size).clamp(0)
-        out_offset = [random.choice(range(0, int(end))) if int(end) > 0 else 0 for end in max_offset.cpu().numpy()]
-        attn_cut = torch.zeros(attn.shape[0], attn.shape[1], segment_size, dtype=attn.dtype, device=attn.device)
-        y_cut = torch.zeros(y.shape[0], n_feats, segment_size, dtype=y.dtype, device=y.device)
-        y_cut_lengths = []
-        for i, lower in enumerate(out_offset):
-            cut_len = segment_size + int((y_lengths[i] - segment_size).clamp(None, 0))
-            y_cut_lengths.append(cut_len)
-            y_cut[i, :, :cut_len] = y[i, :, lower:lower + cut_len]
-            attn_cut[i, :, :cut_len] = attn[i, :, lower:lower + cut_len]
-        y_cut_mask = sequence_mask(torch.LongTensor(y_cut_lengths)).unsqueeze(1).to(y_mask)
-        if y_cut_mask.shape[-1] < segment_size:
-            y_cut_mask = torch.nn.functional.pad(y_cut_mask, (0, segment_size - y_cut_mask.shape[-1]))
-        cond_y = torch.matmul(attn_cut.squeeze(1).transpose(1, 2).contiguous(), cond_x.transpose(1, 2).contiguous())
-        cond_y = cond_y.transpose(1, 2).contiguous() * y_cut_mask
+        reference), alignment of the encoder output to the crop, then the diffusion loss (see loss_t for gradients)."""
+        y_cut, y_cut_mask, cond_y = crop_segments(cond_x, y, y_mask, y_lengths, y_max_length, attn, segment_size, n_feats)
         diff_loss, _ = self.compute_loss(y_cut, y_cut_mask, cond_y, spk_emb=spk_emb)
         return diff_loss
+
+
+class _DiffusionLoss(torch.autograd.Function):
+    """loss_t with the CUDA backward pass behind torch.autograd: the parameters are inputs of the node, so
+    ``loss.backward()`` accumulates into ``parameter.grad`` like the reference's eager graph."""
+
+    @staticmethod
+    def forward(ctx, ft, names, x0, mask, cond, t, spk_emb, z, *params):
+        loss = ft.forward(x0, mask, cond, t, spk_emb, z)
+        ctx.ft, ctx.names, ctx.devs = ft, names, [p.device for p in params]
+        return loss.detach().clone().reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ft = ctx.ft
+        ft.zero_grad()
+        ft.backward()
+        scale = grad_out.to(ft.dev, torch.float32) / ft.loss_scale
+        grads = tuple((ft.grads[k] * scale).to(d) for k, d in zip(ctx.names, ctx.devs))
+        return (None,) * 8 + grads
+
+
+def crop_segments(cond_x, y, y_mask, y_lengths, y_max_length, attn, segment_size, n_feats):
+    """The segment crop + alignment half of UnitSpeech.fine_tune (unitspeech/unitspeech.py:453-487)."""
+    import random
+    if y_max_length < segment_size:
+        pad_size = segment_size - y_max_length
+        y = torch.cat([y, torch.zeros_like(y)[:, :, :pad_size]], dim=-1)
+        y_mask = torch.cat([y_mask, torch.zeros_like(y_mask)[:, :, :pad_size]], dim=-1)
+    max_offset = (y_lengths - segment_size).clamp(0)
+    out_offset = [random.choice(range(0, int(end))) if int(end) > 0 else 0 for end in max_offset.cpu().numpy()]
+    attn_cut = torch.zeros(attn.shape[0], attn.shape[1], segment_size, dtype=attn.dtype, device=attn.device)
+    y_cut = torch.zeros(y.shape[0], n_feats, segment_size, dtype=y.dtype, device=y.device)
+    y_cut_lengths = []
+    for i, lower in enumerate(out_offset):
+        cut_len = segment_size + int((y_lengths[i] - segment_size).clamp(None, 0))
+        y_cut_lengths.append(cut_len)
+        y_cut[i, :, :cut_len] = y[i, :, lower:lower + cut_len]
+        attn_cut[i, :, :cut_len] = attn[i, :, lower:lower + cut_len]
+    y_cut_mask = sequence_mask(torch.LongTensor(y_cut_lengths)).unsqueeze(1).to(y_mask)
+    if y_cut_mask.shape[-1] < segment_size:
+        y_cut_mask = torch.nn.functional.pad(y_cut_mask, (0, segment_size - y_cut_mask.shape[-1]))
+    cond_y = torch.matmul(attn_cut.squeeze(1).transpose(1, 2).contiguous(), cond_x.transpose(1, 2).contiguous())
+    cond_y = cond_y.transpose(1, 2).contiguous() * y_cut_mask
+    return y_cut, y_cut_mask, cond_y
 
 
 def denormalize_mel(y: torch.Tensor, mel_min: torch.Tensor, mel_max: torch.Tensor) -> torch.Tensor:

@@ -616,5 +616,17 @@ class FineTuner:
         self.optimizer_step()
         return loss
 
+    def fine_tune(self, cond_x, y, y_mask, y_lengths, y_max_length, attn, spk_emb, segment_size, n_feats, offset=1e-5):
+        """One iteration of the reference loop (finetune.py:131-165) with the signature of UnitSpeech.fine_tune
+        (unitspeech/unitspeech.py:452-492): crop, align, t ~ U(offset, 1-offset) and z ~ N(0,1) in the reference's RNG
+        order (compute_loss :408 then forward_diffusion :381), then zero_grad + loss + backward + clip + Adam.
+        Returns the loss (device scalar) evaluated before the update."""
+        from .decoder import crop_segments
+        y_cut, y_cut_mask, cond_y = crop_segments(cond_x, y, y_mask, y_lengths, y_max_length, attn, segment_size, n_feats)
+        t = torch.rand(y_cut.shape[0], dtype=y_cut.dtype, device=y_cut.device)
+        t = torch.clamp(t, offset, 1.0 - offset)
+        z = torch.randn(y_cut.shape, dtype=y_cut.dtype, device=y_cut.device)
+        return self.train_step(y_cut, y_cut_mask, cond_y, t, spk_emb, z)
+
     def unscaled_grads(self) -> Dict[str, torch.Tensor]:
         return {k: v / self.loss_scale for k, v in self.grads.items()}
