@@ -302,6 +302,12 @@ def run_gpu_arm(args):
         vocoder = None
         if not args.no_vocoder:
             vocoder = vocoder_leg(dev, B, T, elapsed_ms / args.steps, peaks)
+        # ---- optional: speaker-adaptive fine-tuning step (BASELINE.json configs[4])
+        finetune = None
+        if not args.no_finetune:
+            dec._release()            # frees the sampler's workspace before the training buffers are allocated
+            torch.cuda.empty_cache()
+            finetune = finetune_leg(dev, params, peaks, with_cpu=not args.no_cpu)
         # ---- CPU baseline on this box's host cores (bounded sample)
         cpu = None
         if not args.no_cpu:
@@ -327,12 +333,75 @@ def run_gpu_arm(args):
             "roofline": roofline, "roofline_hbm": roofline_hbm, "breakdown_ms_per_pass": breakdown,
             "cpu_baseline": cpu,
             "vocoder_stage": vocoder,
+            "finetune_stage": finetune,
         }
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         _emit(line)
+
+
+def finetune_leg(dev, params, peaks, with_cpu=True, B=8, T=176, iters=30):
+    """BASELINE.json configs[4]: one fine-tune iteration = zero_grad + diffusion loss forward + backward + clip_grad_norm_ +
+    Adam (finetune.py:131-165) on 8 crops of 176 frames (fix_len_compatibility(2 * 22050 // 256)), lr 2e-5, timed with CUDA
+    events over `iters` CUDA-graph replays; the oracle's autograd step on the host cores is timed beside it."""
+    from unitspeech_b200 import FineTuner, abi
+    ft = FineTuner(lr=2e-5, device=dev.index)
+    sd = {k: (v * (4.0 * 512) if k.startswith("estimator.final_conv") else v) for k, v in params.items()}   # O(1) score output
+    ft.load_state_dict(sd)
+    g = torch.Generator().manual_seed(11)
+    x0 = (torch.randn(B, N_FEATS, T, generator=g) * 0.5).clamp(-1, 1).to(dev)
+    cond = torch.randn(B, N_FEATS, T, generator=g).clamp(-1, 1).to(dev)
+    mask = torch.ones(B, 1, T, device=dev)
+    spk = torch.randn(B, 1, SPK, generator=g)
+    spk = (spk / spk.norm(dim=-1, keepdim=True)).to(dev)
+    zs = torch.randn(4, B, N_FEATS, T, generator=g).to(dev)
+    ts = torch.rand(4, B, generator=g).clamp(1e-5, 1 - 1e-5).to(dev)
+    first = float(ft.train_step(x0, mask, cond, ts[0], spk, zs[0]))
+    for i in range(1, 6):
+        ft.train_step(x0, mask, cond, ts[i % 4], spk, zs[i % 4])
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        ft.train_step(x0, mask, cond, ts[i % 4], spk, zs[i % 4])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    last = float(ft.loss)
+    assert int(ft.skipped) == 0 and last == last, "fine-tune step produced non-finite gradients"
+    # launches per iteration: counted on one eager (non-graph) step, the graph replays the same sequence
+    ft.use_cuda_graph = False
+    ft._graphs.clear()
+    l0 = int(abi.load_library().usb_launch_count(ft.h))
+    ft.train_step(x0, mask, cond, ts[0], spk, zs[0])
+    torch.cuda.synchronize(dev)
+    launches = int(abi.load_library().usb_launch_count(ft.h)) - l0
+    flop = 3.0 * CONV_FLOP_PER_FRAME_EVAL * B * T          # forward + data gradient + weight gradient of every conv
+    out = {
+        "workload": f"fine-tune iteration: {B} crops x {T} frames, U-Net forward + backward of the diffusion loss, "
+                    f"clip_grad_norm_(1) + Adam(lr 2e-5) over 119.1M fp32 parameters (BASELINE.json configs[4])",
+        "ms_per_iter": ms, "iters_per_s": 1e3 / ms, "seconds_per_500_iters": ms * 0.5, "gpu_launches_per_iter": launches,
+        "loss_first": first, "loss_after": last,
+        "conv_fwd_bwd": {"bound": "tensor", "achieved": flop / ms / 1e9, "peak": peaks["tensor"], "unit": "TFLOP/s over the whole iteration",
+                         "frac": flop / ms / 1e9 / peaks["tensor"]},
+    }
+    ft.close()
+    if with_cpu:
+        from oracle import unitspeech_oracle as O
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        Bc = 2
+        cpu = lambda v: v[:Bc].cpu()  # noqa: E731
+        p_cpu = {k: v.cpu() for k, v in sd.items()}
+        t0 = time.perf_counter()
+        _, grads = O.loss_t_grads(p_cpu, cpu(x0), cpu(mask), cpu(cond), ts[0][:Bc].cpu(), cpu(spk), zs[0][:Bc].cpu())
+        O.clip_and_adam(p_cpu, grads, {}, 1)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / (dt * B / Bc), "unit": "iters/s", "cores": threads, "kind": "port",
+                               "sample": f"one oracle iteration (autograd + clip + Adam) on {Bc} of the {B} crops ({dt:.1f} s), scaled x{B // Bc}"}
+    return out
 
 
 def vocoder_leg(dev, B, T, decoder_ms, peaks):
@@ -414,6 +483,7 @@ def _main():
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-vocoder", action="store_true", help="skip the vocoder-stage leg")
+    ap.add_argument("--no-finetune", action="store_true", help="skip the fine-tune-iteration leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

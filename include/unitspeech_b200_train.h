@@ -119,11 +119,13 @@ int usb_t_dot(usb_handle* h, const float* a, const float* b, int64_t n, float* o
 
 /* clip_grad_norm_(max_norm) + torch.optim.Adam step over flat fp32 buffers               finetune.py:81,163-165
  * sumsq[0] += sum g^2; usb_t_adam: g' = g * inv_scale * min(1, max_norm / (||g|| * inv_scale + 1e-6)); a non-finite
- * norm skips the step and increments *skipped. */
+ * norm skips the step and increments *skipped.  step counts from 1; with step_dev != NULL the step number is read from
+ * the device counter (*step_dev + 1) and the counter is advanced after the update, so a captured CUDA graph of a whole
+ * training step can be replayed. */
 int usb_t_sumsq(usb_handle* h, const float* g, int64_t n, double* out, uint64_t stream);
 int usb_t_adam(usb_handle* h, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-               float eps, int32_t step, const double* sumsq, float inv_scale, float max_norm, int32_t* skipped,
-               uint64_t stream);
+               float eps, int32_t step, int32_t* step_dev, const double* sumsq, float inv_scale, float max_norm,
+               int32_t* skipped, uint64_t stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from unitspeech_b200.training import FineTuner, _p  # noqa: E402
+from unitspeech_b200.training import FineTuner, _p, to_reference_layout  # noqa: E402
 
 ft = FineTuner(dim=64, dim_mults=(1, 2))
 dev = ft.dev
@@ -41,11 +41,13 @@ def run(kind, N, H, W, Cin, Cout, ci0=0, Cs=None, per_sample=False):
     else:
         ref = torch.autograd.grad(y, w, dy.to(dev))[0]
         shape = (Cin, Cout, 4, 4) if kind == 3 else (Cout, Cin, ref.shape[2], ref.shape[3])
-        out = torch.zeros(shape, device=dev)
+        out = torch.zeros(shape, device=dev).reshape(-1)      # training layout (forward operand order)
     a, b = nhwc16(dy), nhwc16(x)
     ft.B = N
     ft.call("usb_t_wgrad", kind, _p(a), Cout, _p(b), Cs, N, H, W, Cout, Cs, ci0, Cin, _p(out), 1 if per_sample else 0)
     torch.cuda.synchronize()
+    if not per_sample:
+        out = to_reference_layout(kind, out, shape)
     got = out if per_sample else (out[ci0:ci0 + Cs] if kind == 3 else out[:, ci0:ci0 + Cs])
     err = float((got - ref).norm() / ref.norm())
     other = float(out.norm() ** 2 - got.norm() ** 2)

@@ -71,7 +71,8 @@ def test_gradients_match_oracle_autograd_and_reference_golden(golden_dir, name):
     for k in FULL_KEYS:
         if "gf/" + k in gold.files:
             r = torch.from_numpy(gold["gf/" + k])
-            assert float((got[k] - r).norm()) <= GRAD_REL * float(r.norm()) + 1e-8, k
+            scale = g_scale if k in scalars else float(r.norm())
+            assert float((got[k] - r).norm()) <= GRAD_REL * scale + 1e-8, k
     print(f"{name}: loss {loss:.6f} (oracle {ref_loss:.6f}); worst gradient rel error {worst[0]:.2e} ({worst[1]})")
     ft.close()
 

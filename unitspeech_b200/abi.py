@@ -116,7 +116,7 @@ SIGNATURES = {
     "usb_t_dot": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_uint64]),
     "usb_t_sumsq": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_uint64]),
     "usb_t_adam": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
-                             c_int32, c_void_p, c_float, c_float, c_void_p, c_uint64]),
+                             c_int32, c_void_p, c_void_p, c_float, c_float, c_void_p, c_uint64]),
 }
 
 _lib = None

@@ -1615,13 +1615,11 @@ int usb_t_gn_bwd(usb_handle* h, const void* raw, const int64_t* stats, const flo
     p.raw = static_cast<const __half*>(raw); p.stats = reinterpret_cast<const long long*>(stats); p.gamma = gamma; p.beta = beta;
     p.dy0 = static_cast<const __half*>(dy0); p.dy1 = static_cast<const __half*>(dy1); p.dys = dys; p.wvec = wvec; p.mask = mask;
     p.sums = scratch;                                   // [3][N][C]
-    float* gsums = scratch + static_cast<size_t>(3) * N * C;   // [N][G][2]
-    p.gsums = gsums;
+    p.dgamma = dgamma; p.dbeta = dbeta; p.d_emb = d_emb; p.emb_stride = emb_stride; p.d_wvec = d_wvec;
     p.d_raw = static_cast<__half*>(d_raw); p.dbias = dbias; p.N = N; p.P = H * W; p.W = W; p.C = C; p.groups = G; p.eps = 1e-5f;
     if ((dy0 == nullptr) == (dys == nullptr)) return fail("gn_bwd needs exactly one of dy0 / dys");
     USB_CUDA(cudaMemsetAsync(scratch, 0, static_cast<size_t>(3) * N * C * sizeof(float), s));
     USB_LAUNCH(h, launch_gn_bwd_reduce(p, h->num_sms, s));
-    USB_LAUNCH(h, launch_gn_bwd_finalize(p.sums, gamma, gsums, dgamma, dbeta, d_emb, emb_stride, d_wvec, N, C, G, s));
     USB_LAUNCH(h, launch_gn_bwd_apply(p, h->num_sms, s));
     return 0;
 }
@@ -1650,22 +1648,24 @@ int usb_t_wgrad(usb_handle* h, int32_t kind, const void* dy, int32_t ldy, const 
     USB_T_BEGIN();
     if (kind < 0 || kind > 3) return fail("bad conv kind");
     if (per_sample && kind != K1) return fail("per-sample weight gradients are 1x1 only");
-    // output addressing in the reference's parameter layout
-    long long s_co, s_ci, s_n = 0;
+    // output addressing in the training layout (train.h: launch_pack_conv), input channels contiguous
+    long long s_co, s_ci = 1, s_n = 0;
     int taps, tap_off[kWgradMaxTaps] = {0};
-    float* dWo = dW;
-    if (kind == KT4) {   // (Cin, Cout, 4, 4)
-        taps = 16; s_co = 16; s_ci = static_cast<long long>(Cout) * 16;
-        for (int t = 0; t < 16; ++t) tap_off[t] = t;
-        dWo = dW + static_cast<long long>(ci0) * Cout * 16;
+    float* dWo = dW + ci0;
+    if (kind == KT4) {   // [phase][Cout][a*2+b][Cin]; tap (kh, kw): kh 1,3 -> phase row 0 (a = 0,1), kh 0,2 -> phase row 1
+        taps = 16; s_co = 4LL * Cin_total;
+        for (int kh = 0; kh < 4; ++kh)
+            for (int kw = 0; kw < 4; ++kw) {
+                const int ph = (kh & 1) ? 0 : 1, a = kh >> 1, pw = (kw & 1) ? 0 : 1, b = kw >> 1;
+                tap_off[kh * 4 + kw] = static_cast<int>((static_cast<long long>(ph * 2 + pw) * Cout * 4 + (a * 2 + b)) * Cin_total);
+            }
     } else if (kind == K1) {
-        taps = 1; s_co = per_sample ? Cs : Cin_total; s_ci = 1;
+        taps = 1; s_co = per_sample ? Cs : Cin_total;
         s_n = per_sample ? static_cast<long long>(Cout) * Cs : 0;
-        dWo = dW + (per_sample ? 0 : ci0);
-    } else {             // (Cout, Cin, 3, 3)
-        taps = 9; s_co = static_cast<long long>(Cin_total) * 9; s_ci = 9;
-        for (int t = 0; t < 9; ++t) tap_off[t] = t;
-        dWo = dW + static_cast<long long>(ci0) * 9;
+        if (per_sample) dWo = dW;
+    } else {             // [Cout][9][Cin]
+        taps = 9; s_co = 9LL * Cin_total;
+        for (int t = 0; t < 9; ++t) tap_off[t] = t * Cin_total;
     }
     static const bool use_mma_sync = getenv("USB_WGRAD_MMA") != nullptr;
     if (!use_mma_sync && Cout % 64 == 0 && Cs % 64 == 0 && ldy % 8 == 0 && ldx % 8 == 0) {
@@ -1795,14 +1795,15 @@ int usb_t_sumsq(usb_handle* h, const float* g, int64_t n, double* out, uint64_t 
 }
 
 int usb_t_adam(usb_handle* h, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-               float eps, int32_t step, const double* sumsq, float inv_scale, float max_norm, int32_t* skipped,
-               uint64_t stream) {
+               float eps, int32_t step, int32_t* step_dev, const double* sumsq, float inv_scale, float max_norm,
+               int32_t* skipped, uint64_t stream) {
     USB_T_BEGIN();
-    if (step < 1) return fail("Adam step counts from 1");
+    if (step < 1 && !step_dev) return fail("Adam step counts from 1");
     AdamParams a;
     a.p = p; a.g = g; a.m = m; a.v = v; a.n = n; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
-    a.bc1 = static_cast<float>(1.0 - std::pow(static_cast<double>(beta1), step));
-    a.bc2 = static_cast<float>(1.0 - std::pow(static_cast<double>(beta2), step));
+    a.bc1 = static_cast<float>(1.0 - std::pow(static_cast<double>(beta1), step > 0 ? step : 1));
+    a.bc2 = static_cast<float>(1.0 - std::pow(static_cast<double>(beta2), step > 0 ? step : 1));
+    a.step_dev = step_dev;
     a.sumsq = sumsq; a.inv_scale = inv_scale; a.max_norm = max_norm; a.skipped = skipped;
     USB_LAUNCH(h, launch_adam(a, h->num_sms, s));
     return 0;

@@ -4,8 +4,8 @@
 //
 // Conventions: activations and activation gradients are NHWC fp16 ([row n][pixel p = y*W + x][channel]);
 // activation gradients carry the loss scale S (the objective is multiplied by S before differentiation so the
-// fp16 gradients stay in range); parameter gradients are fp32, in the reference's parameter layouts, also scaled by
-// S -- the optimizer kernel divides by S.  All parameter-gradient outputs ACCUMULATE (+=, atomics).
+// fp16 gradients stay in range); parameter gradients are fp32, in the training layout of launch_pack_conv (conv weights)
+// or the reference's layout (everything else), also scaled by S -- the optimizer kernel divides by S.  All parameter-gradient outputs ACCUMULATE (+=, atomics).
 #pragma once
 #include <cstdint>
 #include <cuda_fp16.h>
@@ -29,17 +29,16 @@ struct GnBwdParams {
     const float* wvec;        // scalar-dy mode: [C]
     const float* mask;        // [N][W]
     float* sums;              // [3][N][C] fp32 (zeroed by the caller before `reduce`)
-    const float* gsums;       // [N][groups][2]: S1 = sum_c gamma*sums0, S2 = sum_c gamma*sums1 (apply)
     __half* d_raw;            // [N][P][C] (apply)
     float* dbias;             // [C] += (apply), or null
+    // emitted by `apply` from the sums: dgamma[c] += sum_n sums1, dbeta[c] += sum_n sums0,
+    // d_emb[n*emb_stride + c] = sums2[n][c], d_wvec[c] += sum_n sums2[n][c]  (any may be null)
+    float *dgamma, *dbeta, *d_emb, *d_wvec;
+    long long emb_stride;
     int N, P, W, C, groups;
     float eps;
 };
 int launch_gn_bwd_reduce(const GnBwdParams& p, int num_sms, cudaStream_t s);
-// gsums from sums; dgamma[c] += sum_n sums1, dbeta[c] += sum_n sums0; if d_emb: d_emb[n*emb_stride + c] = sums2[n][c];
-// if d_wvec: d_wvec[c] += sum_n sums2[n][c]
-int launch_gn_bwd_finalize(const float* sums, const float* gamma, float* gsums, float* dgamma, float* dbeta, float* d_emb,
-                           long long emb_stride, float* d_wvec, int N, int C, int groups, cudaStream_t s);
 int launch_gn_bwd_apply(const GnBwdParams& p, int num_sms, cudaStream_t s);
 
 // ---- out[c] (+ n*out_stride_n) += sum_p t[n][p][c]  (bias gradients; per-sample sums when out_stride_n != 0)
@@ -124,11 +123,12 @@ int launch_loss_grad(const float* score, const float* zm, const float* mask, con
 // out[0] += sum_i a[i] * (b ? b[i] : 1)   (final_conv bias gradient)
 int launch_dot(const float* a, const float* b, long long n, float* out, cudaStream_t s);
 
-// ---- fp32 reference-layout weights -> fp16 GEMM operands, forward and data-gradient orientations
-// kind (engine.cu ConvKind): 0 3x3/s1, 1 3x3/s2, 2 1x1, 3 ConvTranspose 4x4/s2.  Either output may be null.
-//   fwd:   0,1: [Cout][9][Cin]; 2: [Cout][Cin]; 3: [4 phases][Cout][4][Cin]
-//   dgrad: 0: [Cin][9 (flipped)][Cout]; 1: [4 phases][Cin][4 (zero padded)][Cout]; 2: [Cin][Cout]; 3: [Cin][16][Cout]
-// ci0/ci1: the [ci0, ci1) slice of the input channels (skip-concat halves); the packed Cin is ci1 - ci0.
+// ---- fp32 master weights -> fp16 GEMM operands.  The master copy (and its gradient / Adam state) is kept in the
+// TRAINING LAYOUT = the forward operand layout: kinds 0,1 (3x3): [Cout][9][Cin]; 2 (1x1): [Cout][Cin];
+// 3 (ConvTranspose 4x4/s2): [4 phases][Cout][4 taps][Cin] (phase / tap order of pack_conv_host in engine.cu).
+//   fwd:   plain fp32 -> fp16 cast (needs the whole input-channel range)
+//   dgrad: 0: [Cs][9 (flipped)][Cout]; 1: [4 phases][Cs][4 (zero padded)][Cout]; 2: [Cs][Cout]; 3: [Cs][16][Cout]
+// ci0/ci1: the [ci0, ci1) slice of the input channels (skip-concat halves), Cs = ci1 - ci0.  Either output may be null.
 int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int ci1, __half* fwd, __half* dgrad,
                      cudaStream_t s);
 
@@ -138,7 +138,9 @@ struct AdamParams {
     float* p; const float* g; float* m; float* v;
     long long n;
     float lr, beta1, beta2, eps;
-    float bc1, bc2;           // 1 - beta^step
+    float bc1, bc2;           // 1 - beta^step (host-computed; ignored when step_dev is set)
+    int* step_dev;            // device step counter or null: the step number is *step_dev + 1, and the counter is
+                              // incremented after a non-skipped update (so a captured CUDA graph can be replayed)
     const double* sumsq;      // sum of squares of the scaled gradients
     float inv_scale;          // 1 / loss scale
     float max_norm;           // <= 0: no clipping

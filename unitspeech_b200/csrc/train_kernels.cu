@@ -177,9 +177,12 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p,
     }
 }
 
+// The prologue of every block folds the reduce kernel's sums into the two per-group scalars; block 0 of each sample
+// also emits the affine / embedding / final-conv gradients (the former finalize kernel).
 template <bool SCALAR>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p, int ppb, int TP) {
     __shared__ float s_mean[8], s_rstd[8];
+    __shared__ float sg[8][2];
     __shared__ float red[2048];
     const int n = blockIdx.y;
     const int tq = threadIdx.x % TP, pl = threadIdx.x / TP, lanes = blockDim.x / TP;
@@ -187,6 +190,25 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p, 
     if (threadIdx.x < p.groups)
         group_moments(p.stats, n, p.groups, threadIdx.x, static_cast<double>(p.P) * cpg, p.eps, s_mean[threadIdx.x],
                       s_rstd[threadIdx.x]);
+    if (threadIdx.x < 16) sg[threadIdx.x >> 1][threadIdx.x & 1] = 0.f;
+    __syncthreads();
+    {
+        const float* s0 = p.sums + (0LL * p.N + n) * C;
+        const float* s1 = p.sums + (1LL * p.N + n) * C;
+        const float* s2 = p.sums + (2LL * p.N + n) * C;
+        const bool emit = blockIdx.x == 0;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float g = __ldg(p.gamma + c), A = s0[c], B = s1[c];
+            atomicAdd(&sg[c / cpg][0], g * A);
+            atomicAdd(&sg[c / cpg][1], g * B);
+            if (emit) {
+                if (p.dgamma) atomicAdd(p.dgamma + c, B);
+                if (p.dbeta) atomicAdd(p.dbeta + c, A);
+                if (p.d_emb) p.d_emb[static_cast<long long>(n) * p.emb_stride + c] = s2[c];
+                if (p.d_wvec) atomicAdd(p.d_wvec + c, s2[c]);
+            }
+        }
+    }
     __syncthreads();
     GnThreadConst k;
     gn_thread_const(p, n, tq, s_mean, s_rstd, k);
@@ -196,9 +218,8 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p, 
     for (int i = 0; i < 8; ++i) {
         const int c = tq * 8 + i, g = c / cpg;
         wv[i] = SCALAR ? __ldg(p.wvec + c) : 0.f;
-        const float* gs = p.gsums + (static_cast<long long>(n) * p.groups + g) * 2;
-        k1[i] = k.xa[i] * __ldg(gs) * invM;
-        k2[i] = k.xa[i] * __ldg(gs + 1) * invM;
+        k1[i] = k.xa[i] * sg[g][0] * invM;
+        k2[i] = k.xa[i] * sg[g][1] * invM;
         acc[i] = 0.f;
     }
     const float* mk = p.mask + static_cast<long long>(n) * p.W;
@@ -255,37 +276,6 @@ int launch_gn_bwd_apply(const GnBwdParams& p, int num_sms, cudaStream_t s) {
     dim3 grid((p.P + ppb - 1) / ppb, p.N);
     if (p.dys) gn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>(p, ppb, TP);
     else gn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>(p, ppb, TP);
-    return (int)cudaGetLastError();
-}
-
-// grid N: group sums for `apply`, affine gradients, embedding gradient rows
-__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* sums, const float* gamma, float* gsums, float* dgamma,
-                                                              float* dbeta, float* d_emb, long long emb_stride, float* d_wvec,
-                                                              int N, int C, int groups) {
-    __shared__ float sg[8][2];
-    const int n = blockIdx.x, cpg = C / groups;
-    if (threadIdx.x < 16) sg[threadIdx.x >> 1][threadIdx.x & 1] = 0.f;
-    __syncthreads();
-    const float* s0 = sums + (0LL * N + n) * C;
-    const float* s1 = sums + (1LL * N + n) * C;
-    const float* s2 = sums + (2LL * N + n) * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float g = __ldg(gamma + c), A = s0[c], B = s1[c];
-        atomicAdd(&sg[c / cpg][0], g * A);
-        atomicAdd(&sg[c / cpg][1], g * B);
-        if (dgamma) atomicAdd(dgamma + c, B);
-        if (dbeta) atomicAdd(dbeta + c, A);
-        if (d_emb) d_emb[static_cast<long long>(n) * emb_stride + c] = s2[c];
-        if (d_wvec) atomicAdd(d_wvec + c, s2[c]);
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * groups) gsums[(static_cast<long long>(n) * groups) * 2 + threadIdx.x] = sg[threadIdx.x >> 1][threadIdx.x & 1];
-}
-
-int launch_gn_bwd_finalize(const float* sums, const float* gamma, float* gsums, float* dgamma, float* dbeta, float* d_emb,
-                           long long emb_stride, float* d_wvec, int N, int C, int groups, cudaStream_t s) {
-    if (groups > 8 || C % groups) return (int)cudaErrorInvalidValue;
-    gn_bwd_finalize_kernel<<<N, 256, 0, s>>>(sums, gamma, gsums, dgamma, dbeta, d_emb, emb_stride, d_wvec, N, C, groups);
     return (int)cudaGetLastError();
 }
 
@@ -878,78 +868,94 @@ int launch_loss_grad(const float* score, const float* zm, const float* mask, con
 }
 
 // =====================================================================================================================
-// weight packing
+// weight packing: the fp32 master weights are kept in the forward operand layout ("training layout"), so the forward
+// fp16 operand is a plain cast and the data-gradient operand a set of per-tap matrix transposes
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) pack_fwd_kernel(int kind, const float* __restrict__ w, int Cout, int Cin, int ci0, int Cs,
-                                                       __half* __restrict__ out, long long total) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    float v;
-    if (kind == 0 || kind == 1) {          // [Cout][9][Cs]
-        const int ci = static_cast<int>(i % Cs);
-        const int t = static_cast<int>((i / Cs) % 9);
-        const int co = static_cast<int>(i / (9LL * Cs));
-        v = w[(static_cast<long long>(co) * Cin + ci0 + ci) * 9 + t];
-    } else if (kind == 2) {                // [Cout][Cs]
-        const int ci = static_cast<int>(i % Cs);
-        const int co = static_cast<int>(i / Cs);
-        v = w[static_cast<long long>(co) * Cin + ci0 + ci];
-    } else {                               // [ph*2+pw][Cout][a*2+b][Cs] from (Cin, Cout, 4, 4)
-        const int ci = static_cast<int>(i % Cs);
-        const int ab = static_cast<int>((i / Cs) % 4);
-        const int co = static_cast<int>((i / (4LL * Cs)) % Cout);
-        const int phase = static_cast<int>(i / (4LL * Cs * Cout));
-        const int ph = phase >> 1, pw = phase & 1, a = ab >> 1, b = ab & 1;
-        const int kh = ph == 0 ? (a == 0 ? 1 : 3) : (a == 0 ? 0 : 2);
-        const int kw = pw == 0 ? (b == 0 ? 1 : 3) : (b == 0 ? 0 : 2);
-        v = w[((static_cast<long long>(ci0 + ci) * Cout + co) * 4 + kh) * 4 + kw];
+__global__ void __launch_bounds__(256) cast_h_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n4) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        uint2 o;
+        o.x = pack2(v.x, v.y);
+        o.y = pack2(v.z, v.w);
+        dst[i] = o;
     }
-    out[i] = __float2half_rn(v);
 }
 
-__global__ void __launch_bounds__(256) pack_dgrad_kernel(int kind, const float* __restrict__ w, int Cout, int Cin, int ci0, int Cs,
-                                                         __half* __restrict__ out, long long total) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    float v;
-    const int co = static_cast<int>(i % Cout);
-    if (kind == 0) {                       // [Cs][9][Cout], tap flipped
-        const int t = static_cast<int>((i / Cout) % 9);
-        const int ci = static_cast<int>(i / (9LL * Cout));
-        v = w[(static_cast<long long>(co) * Cin + ci0 + ci) * 9 + (8 - t)];
-    } else if (kind == 2) {                // [Cs][Cout]
-        const int ci = static_cast<int>(i / Cout);
-        v = w[static_cast<long long>(co) * Cin + ci0 + ci];
-    } else if (kind == 1) {                // [ph*2+pw][Cs][a*2+b][Cout]: transposed 3x3/s2 as four phase convs
-        const int ab = static_cast<int>((i / Cout) % 4);
-        const int ci = static_cast<int>((i / (4LL * Cout)) % Cs);
-        const int phase = static_cast<int>(i / (4LL * Cout * Cs));
-        const int ph = phase >> 1, pw = phase & 1, a = ab >> 1, b = ab & 1;
-        const int kh = ph == 0 ? (a == 0 ? 1 : -1) : (a == 0 ? 0 : 2);
-        const int kw = pw == 0 ? (b == 0 ? 1 : -1) : (b == 0 ? 0 : 2);
-        v = (kh < 0 || kw < 0) ? 0.f : w[(static_cast<long long>(co) * Cin + ci0 + ci) * 9 + kh * 3 + kw];
-    } else {                               // [Cs][16][Cout] from (Cin, Cout, 4, 4): 4x4/s2 conv over the output gradient
-        const int t = static_cast<int>((i / Cout) % 16);
-        const int ci = static_cast<int>(i / (16LL * Cout));
-        v = w[(static_cast<long long>(ci0 + ci) * Cout + co) * 16 + t];
+struct PackDgradParams {
+    const float* src;
+    __half* dst;
+    int Cout, Cs, ci0;
+    long long s_src_co, s_dst_ci;
+    int n;                       // destination tap slots
+    long long src_off[16];       // < 0: the slot is zero (padding tap of the transposed 3x3/s2 conv)
+    long long dst_off[16];
+};
+
+// grid (ceil(Cs/32), ceil(Cout/32), slots), block (32, 8): dst[ci][co] = src[co][ci] per slot through a padded smem tile
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const PackDgradParams p) {
+    __shared__ float tile[32][33];
+    const int slot = blockIdx.z;
+    const int ci_b = blockIdx.x * 32, co_b = blockIdx.y * 32;
+    const long long so = p.src_off[slot];
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int co = co_b + j, ci = ci_b + threadIdx.x;
+        float v = 0.f;
+        if (so >= 0 && co < p.Cout && ci < p.Cs) v = __ldg(p.src + co * p.s_src_co + so + p.ci0 + ci);
+        tile[j][threadIdx.x] = v;
     }
-    out[i] = __float2half_rn(v);
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int ci = ci_b + j, co = co_b + threadIdx.x;
+        if (ci < p.Cs && co < p.Cout) p.dst[ci * p.s_dst_ci + p.dst_off[slot] + co] = __float2half_rn(tile[threadIdx.x][j]);
+    }
 }
 
 int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int ci1, __half* fwd, __half* dgrad, cudaStream_t s) {
     if (kind < 0 || kind > 3 || ci0 < 0 || ci1 > Cin || ci1 <= ci0) return (int)cudaErrorInvalidValue;
     const int Cs = ci1 - ci0;
     const int taps_f = kind == 2 ? 1 : (kind == 3 ? 16 : 9);
-    const int taps_d = kind == 2 ? 1 : (kind == 0 ? 9 : 16);
     if (fwd) {
-        const long long total = static_cast<long long>(Cout) * Cs * taps_f;
-        pack_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(kind, w, Cout, Cin, ci0, Cs, fwd, total);
+        if (ci0 != 0 || ci1 != Cin) return (int)cudaErrorInvalidValue;
+        const long long total = static_cast<long long>(Cout) * Cin * taps_f;
+        if (total % 4) return (int)cudaErrorInvalidValue;
+        long long blocks = (total / 4 + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        cast_h_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(w), reinterpret_cast<uint2*>(fwd), total / 4);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
     if (dgrad) {
-        const long long total = static_cast<long long>(Cout) * Cs * taps_d;
-        pack_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(kind, w, Cout, Cin, ci0, Cs, dgrad, total);
+        PackDgradParams p;
+        memset(&p, 0, sizeof p);
+        p.src = w; p.dst = dgrad; p.Cout = Cout; p.Cs = Cs; p.ci0 = ci0;
+        if (kind == 0) {            // [Cout][9][Cin] -> [Cs][9 flipped][Cout]
+            p.n = 9; p.s_src_co = 9LL * Cin; p.s_dst_ci = 9LL * Cout;
+            for (int t = 0; t < 9; ++t) { p.src_off[t] = static_cast<long long>(8 - t) * Cin; p.dst_off[t] = static_cast<long long>(t) * Cout; }
+        } else if (kind == 2) {     // [Cout][Cin] -> [Cs][Cout]
+            p.n = 1; p.s_src_co = Cin; p.s_dst_ci = Cout;
+        } else if (kind == 1) {     // [Cout][9][Cin] -> [phase][Cs][a*2+b][Cout], transposed 3x3/s2 as four phase convs
+            p.n = 16; p.s_src_co = 9LL * Cin; p.s_dst_ci = 4LL * Cout;
+            for (int phase = 0; phase < 4; ++phase)
+                for (int ab = 0; ab < 4; ++ab) {
+                    const int ph = phase >> 1, pw = phase & 1, a = ab >> 1, b = ab & 1;
+                    const int kh = ph == 0 ? (a == 0 ? 1 : -1) : (a == 0 ? 0 : 2);
+                    const int kw = pw == 0 ? (b == 0 ? 1 : -1) : (b == 0 ? 0 : 2);
+                    p.src_off[phase * 4 + ab] = (kh < 0 || kw < 0) ? -1 : static_cast<long long>(kh * 3 + kw) * Cin;
+                    p.dst_off[phase * 4 + ab] = (static_cast<long long>(phase) * Cs * 4 + ab) * Cout;
+                }
+        } else {                    // [phase][Cout][a*2+b][Cin] -> [Cs][kh*4+kw][Cout]: 4x4/s2 conv over the output gradient
+            p.n = 16; p.s_src_co = 4LL * Cin; p.s_dst_ci = 16LL * Cout;
+            for (int kh = 0; kh < 4; ++kh)
+                for (int kw = 0; kw < 4; ++kw) {
+                    const int ph = (kh & 1) ? 0 : 1, a = kh >> 1 ? 1 : 0;      // kh 1,3 -> phase 0 (a = 0,1); kh 0,2 -> phase 1 (a = 0,1)
+                    const int pw = (kw & 1) ? 0 : 1, b = kw >> 1 ? 1 : 0;
+                    p.src_off[kh * 4 + kw] = (static_cast<long long>(ph * 2 + pw) * Cout * 4 + (a * 2 + b)) * Cin;
+                    p.dst_off[kh * 4 + kw] = static_cast<long long>(kh * 4 + kw) * Cout;
+                }
+        }
+        dim3 grid((Cs + 31) / 32, (Cout + 31) / 32, p.n), block(32, 8);
+        pack_dgrad_kernel<<<grid, block, 0, s>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
@@ -995,7 +1001,13 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamParams p) {
     }
     float coef = p.inv_scale;
     if (p.max_norm > 0.f) coef *= fminf(1.f, p.max_norm / (norm + 1e-6f));   // torch.nn.utils.clip_grad_norm_
-    const float step = p.lr / p.bc1, rs2 = rsqrtf(p.bc2);
+    float bc1 = p.bc1, bc2 = p.bc2;
+    if (p.step_dev) {
+        const double st = static_cast<double>(*p.step_dev + 1);
+        bc1 = static_cast<float>(1.0 - pow(static_cast<double>(p.beta1), st));
+        bc2 = static_cast<float>(1.0 - pow(static_cast<double>(p.beta2), st));
+    }
+    const float step = p.lr / bc1, rs2 = rsqrtf(bc2);
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float g = p.g[i] * coef;
@@ -1007,11 +1019,16 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamParams p) {
     }
 }
 
+__global__ void adam_step_inc_kernel(int* step_dev, const double* sumsq) {
+    if (isfinite(static_cast<float>(sqrt(*sumsq)))) *step_dev += 1;
+}
+
 int launch_adam(const AdamParams& p, int num_sms, cudaStream_t s) {
     long long blocks = (p.n + 256 * 4 - 1) / (256 * 4);
     if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;
     if (blocks < 1) blocks = 1;
     adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
+    if (p.step_dev) adam_step_inc_kernel<<<1, 1, 0, s>>>(p.step_dev, p.sumsq);
     return (int)cudaGetLastError();
 }
 

@@ -139,10 +139,20 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap map_a
             tmem_ld_32x32(taddr + cb, v);
             tmem_ld_wait();
             if (co < p.Cout) {
+                if (p.s_ci == 1 && n0 + cb + 32 <= p.Cin) {   // contiguous input channels: 16-byte vector reductions
+                    float* o = out + n0 + cb;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int ci = n0 + cb + j;
-                    if (ci < p.Cin) atomicAdd(out + ci * p.s_ci, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(v[j])),
+                                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                                     "f"(__uint_as_float(v[j + 3]))
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int ci = n0 + cb + j;
+                        if (ci < p.Cin) atomicAdd(out + ci * p.s_ci, __uint_as_float(v[j]));
+                    }
                 }
             }
         }

@@ -470,7 +470,7 @@ class _DiffusionLoss(torch.autograd.Function):
         ft.zero_grad()
         ft.backward()
         scale = grad_out.to(ft.dev, torch.float32) / ft.loss_scale
-        grads = tuple((ft.grads[k] * scale).to(d) for k, d in zip(ctx.names, ctx.devs))
+        grads = tuple((ft.grad_reference(k) * scale).to(d) for k, d in zip(ctx.names, ctx.devs))
         return (None,) * 8 + grads
 
 

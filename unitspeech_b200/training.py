@@ -26,6 +26,36 @@ K3S1, K3S2, K1, KT4, K3S2D, KT4D = 0, 1, 2, 3, 4, 5
 _HID, _HEADS = 128, 4
 
 
+_KH = torch.tensor([[1, 3], [0, 2]])   # ConvTranspose 4x4/s2: kernel row used by output phase ph, tap a (engine.cu pack_conv_host)
+
+
+def to_train_layout(kind: int, w: torch.Tensor) -> torch.Tensor:
+    """Reference conv weight -> training layout (= forward GEMM operand layout, input channels contiguous):
+    3x3 (Cout, Cin, 3, 3) -> (Cout, 3, 3, Cin); ConvTranspose (Cin, Cout, 4, 4) -> (ph, pw, Cout, a, b, Cin); 1x1 unchanged."""
+    if kind in (K3S1, K3S2):
+        return w.permute(0, 2, 3, 1).contiguous()
+    if kind == KT4:
+        kh = _KH.to(w.device)
+        x = w[:, :, kh[:, None, :, None], kh[None, :, None, :]]          # (Cin, Cout, ph, pw, a, b)
+        return x.permute(2, 3, 1, 4, 5, 0).contiguous()
+    return w
+
+
+def to_reference_layout(kind: int, t: torch.Tensor, shape) -> torch.Tensor:
+    """Inverse of to_train_layout; ``shape`` is the reference shape."""
+    if kind in (K3S1, K3S2):
+        co, ci = shape[0], shape[1]
+        return t.reshape(co, 3, 3, ci).permute(0, 3, 1, 2).contiguous()
+    if kind == KT4:
+        ci, co = shape[0], shape[1]
+        kh = _KH.to(t.device)
+        x = t.reshape(2, 2, co, 2, 2, ci).permute(5, 2, 0, 1, 3, 4)      # (Cin, Cout, ph, pw, a, b)
+        out = torch.empty(ci, co, 4, 4, dtype=t.dtype, device=t.device)
+        out[:, :, kh[:, None, :, None], kh[None, :, None, :]] = x
+        return out
+    return t.reshape(shape).clone()
+
+
 def _p(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -100,6 +130,7 @@ class _Conv:
     def __init__(self, ft: "FineTuner", key: str, kind: int, cout: int, cin: int, has_bias: bool = True,
                  splits: Optional[Sequence[Tuple[int, int]]] = None, need_dgrad: bool = True):
         self.key, self.kind, self.cout, self.cin = key, kind, cout, cin
+        ft.layout_kind[key + ".weight"] = kind        # stored in the training layout (to_train_layout)
         self.w, self.dw = ft.params[key + ".weight"], ft.grads[key + ".weight"]
         self.b = ft.params[key + ".bias"] if has_bias else None
         self.db = ft.grads[key + ".bias"] if has_bias else None
@@ -122,7 +153,7 @@ class FineTuner:
 
     def __init__(self, n_feats=80, dim=128, dim_mults=(1, 2, 4, 8), beta_min=0.05, beta_max=20.0, pe_scale=1000,
                  spk_emb_dim=256, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, loss_scale=8192.0, device=0,
-                 _trace_calls: Optional[list] = None):
+                 use_cuda_graph: bool = True, _trace_calls: Optional[list] = None):
         self.lib = abi.load_library()
         # _trace_calls (tests only): record the ABI call sequence on CPU buffers instead of launching anything --
         # it checks the host-side graph walk and computes nothing
@@ -137,7 +168,9 @@ class FineTuner:
         self.L = len(self.dim_mults)
         self.C = [dim * m for m in self.dim_mults]
         self.lr, self.betas, self.eps, self.max_norm, self.loss_scale = lr, betas, eps, max_norm, float(loss_scale)
-        self.step_count = 0
+        self.use_cuda_graph = bool(use_cuda_graph) and _trace_calls is None
+        self._graphs: Dict[Tuple[int, int], "torch.cuda.CUDAGraph"] = {}
+        self._eager_steps: Dict[Tuple[int, int], int] = {}
         cfg = abi.UsbConfig()
         cfg.n_feats, cfg.dim, cfg.n_mults = n_feats, dim, self.L
         for i, m in enumerate(self.dim_mults):
@@ -155,8 +188,9 @@ class FineTuner:
         self.nparams = total
         mk = lambda: torch.zeros(total, dtype=torch.float32, device=self.dev)  # noqa: E731
         self.P, self.G, self.M, self.V = mk(), mk(), mk(), mk()
-        self.params: Dict[str, torch.Tensor] = {}
+        self.params: Dict[str, torch.Tensor] = {}     # flat views; conv weights of layout_kind are in the training layout
         self.grads: Dict[str, torch.Tensor] = {}
+        self.layout_kind: Dict[str, int] = {}
         off = 0
         for k, shp in self.shapes.items():
             n = int(torch.Size(shp).numel())
@@ -165,6 +199,7 @@ class FineTuner:
             off += al(n)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.skipped = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)   # optimizer steps taken (device counter)
         half = dim // 2
         import math
         e = math.log(10000) / (half - 1)          # SinusoidalPosEmb table, the reference's own torch expression (:116-118)
@@ -206,11 +241,22 @@ class FineTuner:
                 v = state[k]
                 if tuple(v.shape) != tuple(shp):
                     raise ValueError(f"{k}: shape {tuple(v.shape)} != {tuple(shp)}")
-                self.params[k].copy_(v.detach().to(self.dev, torch.float32))
-        self._packed = False
+                v = v.detach().to(self.dev, torch.float32)
+                if k in self.layout_kind:
+                    v = to_train_layout(self.layout_kind[k], v)
+                self.params[k].view(-1).copy_(v.reshape(-1))
+        self._packed = False          # (captured graphs stay valid: they re-pack at the end of every step)
+
+    def _reference(self, k: str, flat: torch.Tensor) -> torch.Tensor:
+        return to_reference_layout(self.layout_kind[k], flat, self.shapes[k]) if k in self.layout_kind else flat.detach().clone()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
-        return {k: v.detach().clone() for k, v in self.params.items()}
+        """Reference key names, shapes and layouts."""
+        return {k: self._reference(k, v) for k, v in self.params.items()}
+
+    def grad_reference(self, k: str) -> torch.Tensor:
+        """Gradient of parameter ``k`` in the reference layout, still multiplied by the loss scale."""
+        return self._reference(k, self.grads[k])
 
     def zero_grad(self):
         self.G.zero_()
@@ -282,8 +328,11 @@ class FineTuner:
             c.pack(self)
         w3 = self.params["estimator.downs.0.0.block1.block.0.weight"]     # (C, 2, 3, 3) -> tap-major (9, 2, C)
         w1 = self.params["estimator.downs.0.0.res_conv.weight"]           # (C, 2, 1, 1) -> (2, C)
-        self.first_w3 = w3.permute(2, 3, 1, 0).reshape(18, -1).contiguous()
-        self.first_w1 = w1.reshape(-1, 2).t().contiguous()
+        if getattr(self, "first_w3", None) is None:
+            self.first_w3 = torch.empty(18, w3.shape[0], dtype=torch.float32, device=self.dev)
+            self.first_w1 = torch.empty(2, w3.shape[0], dtype=torch.float32, device=self.dev)
+        self.first_w3.view(3, 3, 2, -1).copy_(w3.permute(2, 3, 1, 0))
+        self.first_w1.copy_(w1.reshape(-1, 2).t())
         self._packed = True
 
     # ------------------------------------------------------------------------------------------------ workspace
@@ -303,6 +352,8 @@ class FineTuner:
         if T % (1 << (self.L - 1)) or T <= 0:
             raise ValueError("T must be a positive multiple of 2^(len(dim_mults)-1)")
         self._ws = {}
+        self._graphs.clear()          # graphs hold pointers into the workspace of their shape
+        self._eager_steps.clear()
         self._ws_key = (B, T)
         self.B, self.T = B, T
         self.Hs = [self.n_feats >> l for l in range(self.L)]
@@ -319,6 +370,9 @@ class FineTuner:
         self.loss_partial = torch.zeros(512, dtype=torch.float64, device=self.dev)
         self.msum = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.dev)  # noqa: E731
+        self.x0, self.mu, self.z = f(B, self.n_feats, T), f(B, self.n_feats, T), f(B, self.n_feats, T)
+        self.t, self.spk = f(B), f(B, self.S)
 
     # ------------------------------------------------------------------------------------------------ op wrappers
     def _conv(self, kind, in0, c0, in1, c1, l_in, w, wz, bmode, cout, out, bias=None, mask=None, res=None, res_scale=None,
@@ -403,18 +457,27 @@ class FineTuner:
     def forward(self, x0, mask, cond, t, spk_emb, z):
         """loss_t (unitspeech.py:393-405) with the N(0,1) draw ``z`` of forward_diffusion (:381) supplied by the caller.
         x0, cond, z: (B, n_feats, T); mask: (B, 1, T); t: (B,); spk_emb: (B, 1, S).  Returns the device loss scalar."""
+        self.set_inputs(x0, mask, cond, t, spk_emb, z)
+        return self._forward_body()
+
+    def set_inputs(self, x0, mask, cond, t, spk_emb, z):
+        """Copies one batch into the step's static device buffers (the captured CUDA graph reads them)."""
         B, F, T = x0.shape
         self._plan(B, T)
+        self.x0.copy_(x0.detach())
+        self.mu.copy_(cond.detach())
+        self.z.copy_(z.detach())
+        self.t.copy_(t.detach().reshape(B))
+        self.spk.copy_(spk_emb.detach().reshape(B, self.S))
+        self.masks[0].copy_(mask.detach().reshape(B, T))
+
+    def _forward_body(self):
+        B, F, T = self.B, self.n_feats, self.T
         if not self._packed:
             self._pack_weights()
-        f32 = lambda v: v.detach().to(self.dev, torch.float32).contiguous()  # noqa: E731
-        x0, cond, z, t = f32(x0), f32(cond), f32(z), f32(t)
-        self.masks[0].copy_(f32(mask).reshape(B, T))
+        x0, z, t = self.x0, self.z, self.t
         for l in range(1, self.L):
             self.masks[l].copy_(self.masks[l - 1][:, ::2])
-        self.spk = f32(spk_emb).reshape(B, self.S)
-        self.t = t
-        self.mu = cond
         self.xt = self._buf("xt", (B, F, T), torch.float32)
         self.zm = self._buf("zm", (B, F, T), torch.float32)
         self.call("usb_forward_diffusion", _p(x0), _p(self.masks[0]), _p(t), _p(z), _p(self.xt), _p(self.zm), B, T)
@@ -596,11 +659,10 @@ class FineTuner:
     # ------------------------------------------------------------------------------------------------ optimizer
     def optimizer_step(self):
         """clip_grad_norm_(max_norm) + Adam over all parameters in two launches (finetune.py:163-165)."""
-        self.step_count += 1
         self.sumsq.zero_()
         self.call("usb_t_sumsq", _p(self.G), self.nparams, _p(self.sumsq))
         self.call("usb_t_adam", _p(self.P), _p(self.G), _p(self.M), _p(self.V), self.nparams, self.lr, self.betas[0], self.betas[1],
-                  self.eps, self.step_count, _p(self.sumsq), 1.0 / self.loss_scale, self.max_norm if self.max_norm else 0.0,
+                  self.eps, 0, _p(self.step_dev), _p(self.sumsq), 1.0 / self.loss_scale, self.max_norm if self.max_norm else 0.0,
                   _p(self.skipped))
         self._packed = False
 
@@ -608,13 +670,42 @@ class FineTuner:
         """L2 norm of the (unscaled) gradients of the last optimizer_step (host sync)."""
         return float(self.sumsq.sqrt().item()) / self.loss_scale
 
-    def train_step(self, x0, mask, cond, t, spk_emb, z) -> torch.Tensor:
-        """zero_grad -> loss_t -> backward -> clip -> Adam.  Returns the device loss scalar (before the update)."""
+    @property
+    def step_count(self) -> int:
+        return int(self.step_dev.item())
+
+    def _step_body(self):
         self.zero_grad()
-        loss = self.forward(x0, mask, cond, t, spk_emb, z)
+        self._forward_body()
         self.backward()
         self.optimizer_step()
-        return loss
+        self._pack_weights()          # fp16 operands of the updated weights, ready for the next step / the sampler
+
+    def train_step(self, x0, mask, cond, t, spk_emb, z) -> torch.Tensor:
+        """zero_grad -> loss_t -> backward -> clip -> Adam.  Returns the device loss scalar (before the update).
+        After two eager steps per (B, T) the whole step is captured in a CUDA graph and replayed (the step is ~900 short
+        launches; replaying removes the host from the loop).  All state the graph touches lives in buffers owned by this
+        object; the Adam step number is a device counter."""
+        self.set_inputs(x0, mask, cond, t, spk_emb, z)
+        key = (self.B, self.T)
+        g = self._graphs.get(key)
+        if g is not None:
+            if not self._packed:      # weights were replaced from outside (load_state_dict) since the last step
+                self._pack_weights()
+            g.replay()
+            return self.loss
+        n = self._eager_steps.get(key, 0)
+        if not self.use_cuda_graph or n < 2:
+            self._eager_steps[key] = n + 1
+            self._step_body()
+            return self.loss
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_body()
+        self._graphs[key] = g
+        g.replay()
+        return self.loss
 
     def fine_tune(self, cond_x, y, y_mask, y_lengths, y_max_length, attn, spk_emb, segment_size, n_feats, offset=1e-5):
         """One iteration of the reference loop (finetune.py:131-165) with the signature of UnitSpeech.fine_tune
@@ -629,4 +720,4 @@ class FineTuner:
         return self.train_step(y_cut, y_cut_mask, cond_y, t, spk_emb, z)
 
     def unscaled_grads(self) -> Dict[str, torch.Tensor]:
-        return {k: v / self.loss_scale for k, v in self.grads.items()}
+        return {k: self.grad_reference(k) / self.loss_scale for k in self.grads}
