@@ -92,6 +92,15 @@ int usb_reverse_diffusion_host(usb_handle* h, const float* z, const float* cond,
                                const float* t_steps_host, int32_t n_steps, float text_scale, float spk_scale,
                                float* out, int32_t B, int32_t T, uint64_t stream);
 
+/* Front-end glue of UnitSpeech.execute_text_to_speech on the device            unitspeech/unitspeech.py:421-441
+ * (durations -> y_lengths, y_mask, generate_path, cond_y = path^T cond_x) for a caller-fixed frame capacity T, so the
+ * reference's host round trip int(y_lengths.max()) (:428) disappears.  All pointers dev.  w_ceil: (B, Tx) = ceil(w) *
+ * length_scale, already multiplied by x_mask; x_mask: (B, Tx); cond_x: (B, n_feats, Tx).  Outputs: y_lengths (B) int64 =
+ * clamp_min(sum, 1); y_mask (B, T); attn (B, Tx, T) the 0/1 alignment path; cond_y (B, n_feats, T). */
+int usb_align_expand(usb_handle* h, const float* w_ceil, const float* x_mask, const float* cond_x, int32_t B, int32_t Tx,
+                     int32_t n_feats, int32_t T, int64_t* y_lengths, float* y_mask, float* attn, float* cond_y,
+                     uint64_t stream);
+
 /* bytes of device workspace the handle holds for (Be, T); 0 if that shape has not been planned yet */
 int64_t usb_workspace_bytes(usb_handle* h);
 /* number of kernels launched by the handle since creation (bench.py's gpu_launches) */

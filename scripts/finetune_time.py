@@ -26,7 +26,7 @@ def main():
     T = int(sys.argv[3]) if len(sys.argv) > 3 else 176
     dec = UnitSpeech(80, 128, (1, 2, 4, 8), spk_emb_dim=256)
     sd = random_init_state_dict(dec, seed=1234, out_scale=4.0)
-    ft = FineTuner(lr=2e-5)
+    ft = FineTuner(lr=2e-5, use_cuda_graph=not os.environ.get('FT_NO_GRAPH'))
     ft.load_state_dict(sd)
     g = torch.Generator().manual_seed(0)
     x0 = (torch.randn(B, 80, T, generator=g) * 0.5).clamp(-1, 1).cuda()

@@ -237,6 +237,44 @@ def test_execute_text_to_speech_matches_reference_glue():
     assert mx <= MAX_TOL and mn <= MEAN_TOL
 
 
+def test_on_device_front_end_matches_reference_glue():
+    """execute_text_to_speech(max_frames=...): the durations -> mask / path / cond_y glue in one
+    kernel at a fixed frame capacity, against the reference's torch glue (unitspeech.py:421-441) on a ragged batch."""
+    from unitspeech_b200 import fix_len_compatibility, generate_path, sequence_mask
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=1234, out_scale=1.0 / 32)
+    dec = _decoder(64, (1, 2), p)
+    enc, dur = _StubEncoder().cuda(), _StubDuration().cuda()
+    tokens = torch.tensor([[3, 7, 11, 2, 40, 5, 9], [8, 1, 30, 4, 0, 0, 0]]).cuda()
+    lengths = torch.tensor([7, 4]).cuda()
+    spk = torch.nn.functional.normalize(torch.randn(2, 1, 256, generator=torch.Generator().manual_seed(4)), dim=-1).cuda()
+    n = 3
+    with torch.no_grad():
+        cond_x, x, x_mask = enc(tokens, lengths)
+        w_ceil = torch.ceil(torch.exp(dur(x, x_mask)) * x_mask)
+        y_len = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+        T = fix_len_compatibility(int(y_len.max()), 1)
+        y_mask = sequence_mask(y_len, T).unsqueeze(1).to(x_mask.dtype)
+        path = generate_path(w_ceil.squeeze(1), (x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)).squeeze(1))
+        cond_y = torch.matmul(path.transpose(1, 2), cond_x.transpose(1, 2)).transpose(1, 2).contiguous()
+    noise = torch.randn(n, 2, 80, T, generator=torch.Generator().manual_seed(9)).cuda() / 32
+    torch.manual_seed(5)
+    y_enc, y_dec, attn = dec.execute_text_to_speech(tokens, lengths, spk, enc, dur, num_downsamplings_in_unet=1,
+                                                    diffusion_steps=n, text_gradient_scale=1.0, spk_gradient_scale=1.0,
+                                                    noise=noise, max_frames=T)
+    assert torch.equal(dec.last_y_lengths, y_len)
+    assert torch.equal(y_enc, cond_y) and torch.equal(attn.squeeze(1), path)
+    torch.manual_seed(5)
+    z = torch.randn_like(cond_y)
+    want = dec.forward(z, y_mask, cond_y, spk, n_timesteps=n, text_gradient_scale=1.0, spk_gradient_scale=1.0, noise=noise)
+    assert torch.equal(y_dec, want)
+    # a larger capacity only appends masked (zero) frames
+    torch.manual_seed(5)
+    y_enc2, y_dec2, attn2 = dec.execute_text_to_speech(tokens, lengths, spk, enc, dur, num_downsamplings_in_unet=1,
+                                                       diffusion_steps=n, max_frames=T + 6)
+    assert y_dec2.shape[-1] == T + 6 and float(y_dec2[:, :, T:].abs().max()) == 0.0 and float(y_enc2[:, :, T:].abs().max()) == 0.0
+    assert torch.equal(attn2[..., :T].squeeze(1), path) and float(attn2[..., T:].abs().max()) == 0.0
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # fine-tuning objective, forward value (SURVEY section 8 row a16, forward half)
 # ---------------------------------------------------------------------------------------------------------------------

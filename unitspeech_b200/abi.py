@@ -65,6 +65,8 @@ SIGNATURES = {
                                                                     c_int32, c_int32, c_uint64]),
     "usb_reverse_diffusion_host": (c_int32, [c_void_p] + [c_void_p] * 7 + [c_int32, c_float, c_float, c_void_p,
                                                                          c_int32, c_int32, c_uint64]),
+    "usb_align_expand": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_uint64]),
     "usb_workspace_bytes": (c_int64, [c_void_p]),
     "usb_launch_count": (c_int64, [c_void_p]),
     "usb_set_profiling": (c_int32, [c_void_p, c_int32]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libunitspeech_b200.so")
-SOURCES = ["conv_igemm.cu", "elementwise.cu", "attention.cu", "engine.cu", "vocoder.cu", "train_kernels.cu", "wgrad_tc.cu"]
+SOURCES = ["conv_igemm.cu", "elementwise.cu", "attention.cu", "engine.cu", "vocoder.cu", "train_kernels.cu", "wgrad_tc.cu", "frontend.cu"]
 HEADERS = ["ptx.cuh", "conv_igemm.h", "kernels.h", "train.h", os.path.join("..", "..", "include", "unitspeech_b200.h"),
            os.path.join("..", "..", "include", "unitspeech_b200_train.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

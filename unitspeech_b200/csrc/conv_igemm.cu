@@ -499,13 +499,14 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                 continue;
             }
             const int wlim = p.Wm - pc.x0;        // pixels with tx >= wlim lie outside the image
+            const int hlim = p.Hm - pc.y0;        // rows >= hlim too (patch heights need not divide the image height)
             const int cg = nt * 128 + c;          // global output channel
             const float bias = p.bias ? __ldg(p.bias + cg) : 0.f;
             long long* stats_n = p.stats ? p.stats + static_cast<long long>(pc.n) * p.groups * 2 : nullptr;
             const float* mrow = p.mask ? p.mask + static_cast<long long>(pc.n) * p.mask_stride + p.ox_off[ph] : nullptr;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
             float s = 0.f, ss = 0.f;
-            const bool full = wlim >= p.BW;       // every pixel column of the patch lies inside the image
+            const bool full = wlim >= p.BW && hlim >= p.BH;   // every pixel of the patch lies inside the image
             if (mrow) {
                 const int et = lane + ew * 32;    // any 128 threads of the group cover BW <= 128 columns
                 if (et < p.BW) mask_s[grp][et] = et < wlim ? __ldg(mrow + (pc.x0 + et) * p.ox_mul) : 0.f;
@@ -530,7 +531,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                         if (full) {
                             s += f;
                             ss = fmaf(f, f, ss);
-                        } else if (((pb + j) & (p.BW - 1)) < wlim) {
+                        } else if (((pb + j) & (p.BW - 1)) < wlim && ((pb + j) >> bw_shift) < hlim) {
                             s += f;
                             ss = fmaf(f, f, ss);
                         }

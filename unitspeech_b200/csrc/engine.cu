@@ -257,9 +257,22 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     static const bool allow_swap = getenv("USB_NO_SWAP_AB") == nullptr;
     static const bool swap_k1 = getenv("USB_SWAP_K1") != nullptr;
     p.swap_ab = (allow_swap && Cout % 128 == 0 && (kind != K1 || swap_k1) && ep.res == nullptr && b_batch_mode != 2) ? 1 : 0;
+    // The swapped-operand kernel masks rows as well as columns, so its patch height need not divide the image height:
+    // pick the 128-pixel patch shape that wastes the fewest pixels (e.g. a 10 x 22 level-3 image: 4 x 32 patches cover
+    // it at 57 % instead of 34 % for 2 x 64); keep the dividing shape unless the gain is above 5 %.
+    const bool halo_candidate = kind == K3S1 && H % 8 == 0 && b_batch_mode == 0 && getenv("USB_NO_HALO") == nullptr;
+    if (p.swap_ab && !halo_candidate) {
+        auto eff = [&](int bh) {
+            const int bw = 128 / bh;
+            return (double)p.Hm * p.Wm / ((double)((p.Hm + bh - 1) / bh) * bh * ((p.Wm + bw - 1) / bw) * bw);
+        };
+        double best = eff(BH) * 1.05;
+        for (int bh = 1; bh <= 16; bh *= 2)
+            if (eff(bh) > best) { best = eff(bh); BH = bh; }
+    }
     p.BH = BH;
     p.BW = 128 / BH;
-    p.tiles_y = p.Hm / BH;
+    p.tiles_y = (p.Hm + BH - 1) / BH;
     p.tiles_x = (p.Wm + p.BW - 1) / p.BW;
     p.patches_per_phase = N * p.tiles_y * p.tiles_x;
     p.Cout = Cout;

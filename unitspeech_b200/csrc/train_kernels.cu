@@ -54,9 +54,9 @@ __device__ __forceinline__ void group_moments(const long long* stats, int n, int
 __device__ __forceinline__ void mish_fwd_bwd(float x, float& y, float& dy) {
     const float e = __expf(fminf(x, 20.f));
     const float w = e * (e + 2.f);
-    const float inv = 1.f / (w + 2.f);
+    const float inv = __fdividef(1.f, w + 2.f);
     const float th = w * inv;
-    const float sig = e / (1.f + e);
+    const float sig = __fdividef(e, 1.f + e);
     y = x * th;
     dy = th + x * (4.f * (w + 1.f) * inv) * inv * sig;
 }
@@ -101,27 +101,44 @@ __device__ __forceinline__ void gn_thread_const(const GnBwdParams& p, int n, int
     }
 }
 
-// dy for 8 channels of one pixel (masked); SCALAR: dys * wvec
+// raw operands of one pixel's channel octet, loaded U pixels ahead of their use
+struct GnPix {
+    uint4 raw, d0, d1;
+    float m, dys;
+};
 template <bool SCALAR>
-__device__ __forceinline__ void load_dy(const GnBwdParams& p, long long off, long long pixoff, const float (&wv)[8], float m,
-                                        float (&dy)[8], float& dys_m) {
+__device__ __forceinline__ void gn_load(const GnBwdParams& p, long long off, long long pixoff, float m, GnPix& q) {
+    q.raw = ldg16(p.raw + off);
+    q.m = m;
     if (SCALAR) {
-        dys_m = __ldg(p.dys + pixoff) * m;
+        q.dys = __ldg(p.dys + pixoff);
+    } else {
+        q.d0 = ldg16(p.dy0 + off);
+        if (p.dy1) q.d1 = ldg16(p.dy1 + off);
+    }
+}
+// masked dy of the octet; SCALAR: dys * wvec
+template <bool SCALAR>
+__device__ __forceinline__ void gn_dy(const GnBwdParams& p, const GnPix& q, const float (&wv)[8], float (&dy)[8], float& dys_m) {
+    if (SCALAR) {
+        dys_m = q.dys * q.m;
 #pragma unroll
         for (int i = 0; i < 8; ++i) dy[i] = dys_m * wv[i];
     } else {
-        unpack8(ldg16(p.dy0 + off), dy);
+        unpack8(q.d0, dy);
         if (p.dy1) {
             float d1[8];
-            unpack8(ldg16(p.dy1 + off), d1);
+            unpack8(q.d1, d1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) dy[i] += d1[i];
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dy[i] *= m;
+        for (int i = 0; i < 8; ++i) dy[i] *= q.m;
         dys_m = 0.f;
     }
 }
+
+constexpr int kGnU = 4;   // pixels in flight per thread
 
 template <bool SCALAR>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p, int ppb, int TP) {
@@ -144,21 +161,32 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p,
     for (int i = 0; i < 8; ++i) a0[i] = a1[i] = a2[i] = 0.f;
     const float* mk = p.mask + static_cast<long long>(n) * p.W;
     const int p_begin = blockIdx.x * ppb, p_end = min(p.P, p_begin + ppb);
-    for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
-        const long long pixoff = static_cast<long long>(n) * p.P + pix;
-        const long long off = pixoff * C + tq * 8;
-        const float m = __ldg(mk + pix % p.W);
-        float v[8], dy[8], dys_m;
-        unpack8(ldg16(p.raw + off), v);
-        load_dy<SCALAR>(p, off, pixoff, wv, m, dy, dys_m);
+    for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += lanes * kGnU) {
+        GnPix q[kGnU];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float y, d;
-            mish_fwd_bwd(fmaf(v[i], k.a[i], k.b[i]), y, d);
-            const float dg = dy[i] * d;
-            a0[i] += dg;
-            a1[i] = fmaf(dg, fmaf(v[i], k.xa[i], k.xb[i]), a1[i]);
-            a2[i] += SCALAR ? dys_m * (y * m) : dy[i];
+        for (int u = 0; u < kGnU; ++u) {
+            const int pix = pix0 + u * lanes;
+            if (pix < p_end) {
+                const long long pixoff = static_cast<long long>(n) * p.P + pix;
+                gn_load<SCALAR>(p, pixoff * C + tq * 8, pixoff, __ldg(mk + pix % p.W), q[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kGnU; ++u) {
+            if (pix0 + u * lanes < p_end) {
+                float v[8], dy[8], dys_m;
+                unpack8(q[u].raw, v);
+                gn_dy<SCALAR>(p, q[u], wv, dy, dys_m);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float y, d;
+                    mish_fwd_bwd(fmaf(v[i], k.a[i], k.b[i]), y, d);
+                    const float dg = dy[i] * d;
+                    a0[i] += dg;
+                    a1[i] = fmaf(dg, fmaf(v[i], k.xa[i], k.xb[i]), a1[i]);
+                    a2[i] += SCALAR ? dys_m * (y * q[u].m) : dy[i];
+                }
+            }
         }
     }
     // reduce the pixel lanes of the block, one atomic per (block, channel, sum)
@@ -178,7 +206,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p,
 }
 
 // The prologue of every block folds the reduce kernel's sums into the two per-group scalars; block 0 of each sample
-// also emits the affine / embedding / final-conv gradients (the former finalize kernel).
+// also emits the affine / embedding / final-conv gradients.
 template <bool SCALAR>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p, int ppb, int TP) {
     __shared__ float s_mean[8], s_rstd[8];
@@ -197,15 +225,28 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p, 
         const float* s1 = p.sums + (1LL * p.N + n) * C;
         const float* s2 = p.sums + (2LL * p.N + n) * C;
         const bool emit = blockIdx.x == 0;
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const float g = __ldg(p.gamma + c), A = s0[c], B = s1[c];
-            atomicAdd(&sg[c / cpg][0], g * A);
-            atomicAdd(&sg[c / cpg][1], g * B);
-            if (emit) {
-                if (p.dgamma) atomicAdd(p.dgamma + c, B);
-                if (p.dbeta) atomicAdd(p.dbeta + c, A);
-                if (p.d_emb) p.d_emb[static_cast<long long>(n) * p.emb_stride + c] = s2[c];
-                if (p.d_wvec) atomicAdd(p.d_wvec + c, s2[c]);
+        const int seg = cpg < 32 ? cpg : 32;          // lanes of one warp that share a GroupNorm group (cpg is 8, 16 or >= 32)
+        for (int c0 = 0; c0 < C; c0 += blockDim.x) {  // C is a multiple of 64 and blockDim 256: whole warps stay in range together
+            const int c = c0 + threadIdx.x;
+            float ga = 0.f, gb = 0.f;
+            if (c < C) {
+                const float g = __ldg(p.gamma + c), A = s0[c], B = s1[c];
+                ga = g * A;
+                gb = g * B;
+                if (emit) {
+                    if (p.dgamma) atomicAdd(p.dgamma + c, B);
+                    if (p.dbeta) atomicAdd(p.dbeta + c, A);
+                    if (p.d_emb) p.d_emb[static_cast<long long>(n) * p.emb_stride + c] = s2[c];
+                    if (p.d_wvec) atomicAdd(p.d_wvec + c, s2[c]);
+                }
+            }
+            for (int o = seg >> 1; o > 0; o >>= 1) {
+                ga += __shfl_xor_sync(0xffffffffu, ga, o);
+                gb += __shfl_xor_sync(0xffffffffu, gb, o);
+            }
+            if (c < C && (threadIdx.x & (seg - 1)) == 0) {
+                atomicAdd(&sg[c / cpg][0], ga);
+                atomicAdd(&sg[c / cpg][1], gb);
             }
         }
     }
@@ -224,22 +265,34 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p, 
     }
     const float* mk = p.mask + static_cast<long long>(n) * p.W;
     const int p_begin = blockIdx.x * ppb, p_end = min(p.P, p_begin + ppb);
-    for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
-        const long long pixoff = static_cast<long long>(n) * p.P + pix;
-        const long long off = pixoff * C + tq * 8;
-        const float m = __ldg(mk + pix % p.W);
-        float v[8], dy[8], dr[8], dys_m;
-        unpack8(ldg16(p.raw + off), v);
-        load_dy<SCALAR>(p, off, pixoff, wv, m, dy, dys_m);
+    for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += lanes * kGnU) {
+        GnPix q[kGnU];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float y, d;
-            mish_fwd_bwd(fmaf(v[i], k.a[i], k.b[i]), y, d);
-            const float xh = fmaf(v[i], k.xa[i], k.xb[i]);
-            dr[i] = fmaf(k.a[i], dy[i] * d, -fmaf(xh, k2[i], k1[i]));
-            acc[i] += dr[i];
+        for (int u = 0; u < kGnU; ++u) {
+            const int pix = pix0 + u * lanes;
+            if (pix < p_end) {
+                const long long pixoff = static_cast<long long>(n) * p.P + pix;
+                gn_load<SCALAR>(p, pixoff * C + tq * 8, pixoff, __ldg(mk + pix % p.W), q[u]);
+            }
         }
-        *reinterpret_cast<uint4*>(p.d_raw + off) = pack8(dr);
+#pragma unroll
+        for (int u = 0; u < kGnU; ++u) {
+            const int pix = pix0 + u * lanes;
+            if (pix < p_end) {
+                float v[8], dy[8], dr[8], dys_m;
+                unpack8(q[u].raw, v);
+                gn_dy<SCALAR>(p, q[u], wv, dy, dys_m);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float y, d;
+                    mish_fwd_bwd(fmaf(v[i], k.a[i], k.b[i]), y, d);
+                    const float xh = fmaf(v[i], k.xa[i], k.xb[i]);
+                    dr[i] = fmaf(k.a[i], dy[i] * d, -fmaf(xh, k2[i], k1[i]));
+                    acc[i] += dr[i];
+                }
+                *reinterpret_cast<uint4*>(p.d_raw + (static_cast<long long>(n) * p.P + pix) * C + tq * 8) = pack8(dr);
+            }
+        }
     }
     if (p.dbias == nullptr) return;
 #pragma unroll
@@ -670,20 +723,31 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const __half* __restr
     const float M = __ldg(ms + ((static_cast<long long>(n) * heads + h) * 2) * kDh + lane);
     const float invS = 1.f / __ldg(ms + ((static_cast<long long>(n) * heads + h) * 2 + 1) * kDh + lane);
     const int p_begin = blockIdx.x * ppb, p_end = min(P, p_begin + ppb);
-    for (int pos = p_begin + sub; pos < p_end; pos += nsub) {
-        const long long row = static_cast<long long>(n) * P + pos;
-        const float k = __half2float(qkv[row * ld + koff + h * kDh + lane]);
-        const float v = __half2float(qkv[row * ld + voff + h * kDh + lane]);
-        const float ksm = __expf(k - M) * invS;
-        float dv = 0.f, dks = 0.f;
+    // two positions per iteration: their loads are issued together and the two shuffle/FMA chains interleave
+    for (int pos = p_begin + sub; pos < p_end; pos += 2 * nsub) {
+        const int pos1 = pos + nsub;
+        const bool has1 = pos1 < p_end;
+        const long long row0 = static_cast<long long>(n) * P + pos;
+        const long long row1 = static_cast<long long>(n) * P + (has1 ? pos1 : pos);
+        const float k0 = __half2float(qkv[row0 * ld + koff + h * kDh + lane]);
+        const float v0 = __half2float(qkv[row0 * ld + voff + h * kDh + lane]);
+        const float k1 = __half2float(qkv[row1 * ld + koff + h * kDh + lane]);
+        const float v1 = __half2float(qkv[row1 * ld + voff + h * kDh + lane]);
+        const float ksm0 = __expf(k0 - M) * invS, ksm1 = __expf(k1 - M) * invS;
+        float dv0 = 0.f, dks0 = 0.f, dv1 = 0.f, dks1 = 0.f;
 #pragma unroll
         for (int i = 0; i < kDh; ++i) {
-            dv = fmaf(__shfl_sync(0xffffffffu, ksm, i), dcol[i], dv);
-            dks = fmaf(drow[i], __shfl_sync(0xffffffffu, v, i), dks);
+            dv0 = fmaf(__shfl_sync(0xffffffffu, ksm0, i), dcol[i], dv0);
+            dks0 = fmaf(drow[i], __shfl_sync(0xffffffffu, v0, i), dks0);
+            dv1 = fmaf(__shfl_sync(0xffffffffu, ksm1, i), dcol[i], dv1);
+            dks1 = fmaf(drow[i], __shfl_sync(0xffffffffu, v1, i), dks1);
         }
-        const float dk = ksm * (dks - r);
-        dkv[row * (2 * hidden) + h * kDh + lane] = __float2half_rn(dk);
-        dkv[row * (2 * hidden) + hidden + h * kDh + lane] = __float2half_rn(dv);
+        dkv[row0 * (2 * hidden) + h * kDh + lane] = __float2half_rn(ksm0 * (dks0 - r));
+        dkv[row0 * (2 * hidden) + hidden + h * kDh + lane] = __float2half_rn(dv0);
+        if (has1) {
+            dkv[row1 * (2 * hidden) + h * kDh + lane] = __float2half_rn(ksm1 * (dks1 - r));
+            dkv[row1 * (2 * hidden) + hidden + h * kDh + lane] = __float2half_rn(dv1);
+        }
     }
 }
 

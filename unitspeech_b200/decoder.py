@@ -345,12 +345,22 @@ class UnitSpeech(torch.nn.Module):
     @torch.no_grad()
     def execute_text_to_speech(self, phoneme, phoneme_lengths, spk_emb, text_encoder, duration_predictor,
                                num_downsamplings_in_unet, diffusion_steps=50, length_scale=1.0,
-                               text_gradient_scale=1.0, spk_gradient_scale=1.0, noise: Optional[torch.Tensor] = None):
-        """unitspeech/unitspeech.py:414-450: encoder -> durations -> alignment -> z -> reverse diffusion -> crop."""
+                               text_gradient_scale=1.0, spk_gradient_scale=1.0, noise: Optional[torch.Tensor] = None,
+                               max_frames: Optional[int] = None):
+        """unitspeech/unitspeech.py:414-450: encoder -> durations -> alignment -> z -> reverse diffusion -> crop.
+
+        ``max_frames=None`` follows the reference exactly, including its host round trip ``int(y_lengths.max())`` (:428).
+        With ``max_frames`` (rounded up by fix_len_compatibility) the glue between the duration predictor and the sampler
+        runs in one CUDA kernel (usb_align_expand) at that fixed frame capacity and nothing synchronises with the host:
+        the three outputs come back padded to the capacity (frames past an utterance's length are zero) and the
+        per-utterance frame counts are left in ``self.last_y_lengths`` (device int64)."""
         cond_x, x, x_mask = text_encoder(phoneme, phoneme_lengths)
         logw = duration_predictor(x, x_mask, w=None, g=spk_emb, reverse=True)
         w = torch.exp(logw) * x_mask
         w_ceil = torch.ceil(w) * length_scale
+        if max_frames is not None:
+            return self._tts_on_device(cond_x, x_mask, w_ceil, spk_emb, num_downsamplings_in_unet, int(max_frames),
+                                       diffusion_steps, text_gradient_scale, spk_gradient_scale, noise)
         y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
         y_max_length = int(y_lengths.max())
         y_max_length_ = fix_len_compatibility(y_max_length, num_downsamplings_in_unet)
@@ -366,6 +376,26 @@ class UnitSpeech(torch.nn.Module):
                                        noise=noise)
         decoder_outputs = decoder_outputs[:, :, :y_max_length]
         return encoder_outputs, decoder_outputs, attn[:, :, :y_max_length]
+
+    def _tts_on_device(self, cond_x, x_mask, w_ceil, spk_emb, n_down, max_frames, diffusion_steps, tg, sg, noise):
+        lib = abi.load_library()
+        h = self._ensure_handle(cond_x)
+        dev = torch.device("cuda", self._handle_device)
+        B, F, Tx = cond_x.shape
+        T = fix_len_compatibility(max_frames, n_down)
+        wd, xm, cx = _f32c(w_ceil).to(dev).reshape(B, Tx), _f32c(x_mask).to(dev).reshape(B, Tx), _f32c(cond_x).to(dev)
+        y_lengths = torch.empty(B, dtype=torch.int64, device=dev)
+        y_mask = torch.empty(B, 1, T, dtype=torch.float32, device=dev)
+        attn = torch.empty(B, 1, Tx, T, dtype=torch.float32, device=dev)
+        cond_y = torch.empty(B, F, T, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            abi.check(lib.usb_align_expand(h, wd.data_ptr(), xm.data_ptr(), cx.data_ptr(), B, Tx, F, T, y_lengths.data_ptr(),
+                                           y_mask.data_ptr(), attn.data_ptr(), cond_y.data_ptr(), self._stream(dev.index)))
+        self.last_y_lengths = y_lengths
+        z = torch.randn_like(cond_y)
+        dec = self.forward(z, y_mask, cond_y, spk_emb.to(dev), n_timesteps=diffusion_steps, text_gradient_scale=tg,
+                           spk_gradient_scale=sg, noise=noise)
+        return cond_y, dec, attn
 
     # ------------------------------------------------------------------ training objective
     def _dev_tensors(self, like, *tensors):
