@@ -9,7 +9,7 @@
  *
  * Conventions (in addition to unitspeech_b200.h): every pointer is a DEVICE pointer; "h16" tensors are NHWC fp16
  * ((N, H, W, C), pixel p = y*W + x), everything else fp32; parameters and parameter gradients use the reference's
- * state_dict layouts; gradients ACCUMULATE into their outputs (+=); activation gradients and parameter gradients
+ * state_dict layouts, except conv weights (training layout, see usb_t_pack_conv); gradients ACCUMULATE into their outputs (+=); activation gradients and parameter gradients
  * carry the loss scale S (usb_t_loss_grad multiplies by it, usb_t_adam divides by it).  Every call only enqueues
  * work on `stream`: no synchronisation, no allocation.  Conv kinds: 0 = 3x3/s1, 1 = 3x3/s2, 2 = 1x1,
  * 3 = ConvTranspose 4x4/s2, and the data-gradient forms 4 = transposed 3x3/s2, 5 = 4x4/s2 over a ConvTranspose
@@ -24,12 +24,18 @@
 extern "C" {
 #endif
 
-/* fp32 reference-layout conv weight -> fp16 GEMM operands.  fwd (kinds 0-3): the forward operand; dgrad: the operand
- * of the data-gradient convolution (kind 0 -> run as kind 0 with flipped taps, 1 -> kind 4, 2 -> kind 2 transposed,
- * 3 -> kind 5).  [ci0, ci1) selects a slice of the input channels (skip-concat halves, unitspeech.py:192).
- * Either output may be NULL. */
+/* fp32 master conv weight -> fp16 GEMM operands.  The master copy is kept in the TRAINING LAYOUT = the forward operand
+ * layout (3x3: [Cout][9][Cin]; 1x1: [Cout][Cin]; ConvTranspose 4x4/s2: [4 phases][Cout][4 taps][Cin]); the Python host
+ * converts from / to the reference's (Cout, Cin, k, k) / (Cin, Cout, 4, 4) at load_state_dict / state_dict.
+ * fwd (kinds 0-3): plain cast; dgrad: the operand of the data-gradient convolution (kind 0 -> run as kind 0 with
+ * flipped taps, 1 -> kind 4, 2 -> kind 2 transposed, 3 -> kind 5).  [ci0, ci1) selects a slice of the input channels
+ * (skip-concat halves, unitspeech.py:192).  Either output may be NULL. */
 int usb_t_pack_conv(usb_handle* h, int32_t kind, const float* w, int32_t Cout, int32_t Cin, int32_t ci0, int32_t ci1,
                     void* fwd, void* dgrad, uint64_t stream);
+
+/* dst (fp16) = src (fp32), n a multiple of 4: refreshes the fp16 mirror of the flat master buffer -- with the conv
+ * weights kept in the forward operand layout this IS the forward pack of every conv */
+int usb_t_cast(usb_handle* h, const float* src, void* dst, int64_t n, uint64_t stream);
 
 /* Conv2d / ConvTranspose2d and their data gradients on the tcgen05 implicit-GEMM kernels   unitspeech.py:49,21,30,66,83-84
  * in0/in1: h16 (N, H, W, C*tot) of which the first C0/C1 channels are contracted (in1: second K source or NULL);
@@ -89,7 +95,7 @@ int usb_t_colsum(usb_handle* h, const void* t, int32_t ld, int32_t N, int32_t P,
                  uint64_t stream);
 int usb_t_add(usb_handle* h, const void* a, const void* b, const void* c, void* out, int64_t n, uint64_t stream);
 
-/* weight gradient of a conv of kind 0-3 in the reference's parameter layout.  dy: h16 output gradient (row stride ldy),
+/* weight gradient of a conv of kind 0-3 in the training layout (see usb_t_pack_conv).  dy: h16 output gradient (row stride ldy),
  * x: h16 layer input (N, H, W, ldx) whose channels [0, Cs) are the [ci0, ci0+Cs) slice of the Cin_total input channels.
  * per_sample (kind 2): dW is (N, Cout, Cs), one matrix per sample. */
 int usb_t_wgrad(usb_handle* h, int32_t kind, const void* dy, int32_t ldy, const void* x, int32_t ldx, int32_t N, int32_t H,

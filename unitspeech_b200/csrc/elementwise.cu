@@ -312,7 +312,9 @@ int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s) {
     const int threads = TP * lanes;
     // 64 pixels per thread for big tensors; shrink (down to 16 per thread: the per-thread prologue loads 24 affine /
     // embedding values) only while the grid would leave SMs idle
-    static const int min_ppt = getenv("USB_GN_PPT") ? atoi(getenv("USB_GN_PPT")) : 32;
+    // (small tensors -- a few samples at the low-resolution levels -- are latency-bound: let them spread further)
+    static const int env_ppt = getenv("USB_GN_PPT") ? atoi(getenv("USB_GN_PPT")) : 0;
+    const int min_ppt = env_ppt > 0 ? env_ppt : ((long long)p.N * p.P * p.C * 2 < (16ll << 20) ? 8 : 32);
     static const int min_bps = getenv("USB_GN_BPS") ? atoi(getenv("USB_GN_BPS")) : 4;
     int ppb = lanes * 64;
     while (ppb > lanes * min_ppt && (long long)((p.P + ppb - 1) / ppb) * p.N < (long long)num_sms * min_bps) ppb >>= 1;

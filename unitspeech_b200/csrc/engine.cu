@@ -1516,6 +1516,12 @@ int usb_t_pack_conv(usb_handle* h, int32_t kind, const float* w, int32_t Cout, i
     return 0;
 }
 
+int usb_t_cast(usb_handle* h, const float* src, void* dst, int64_t n, uint64_t stream) {
+    USB_T_BEGIN();
+    USB_LAUNCH(h, launch_cast_h(src, static_cast<__half*>(dst), n, s));
+    return 0;
+}
+
 int usb_t_conv(usb_handle* h, int32_t kind, const void* in0, int32_t C0tot, int32_t C0, const void* in1, int32_t C1tot,
                int32_t C1, int32_t N, int32_t H, int32_t W, const void* w, int32_t wZ, int32_t b_batch_mode, int32_t Cout,
                const float* bias, const float* mask, const void* res, const float* res_scale, int64_t* stats, int32_t groups,

@@ -129,6 +129,8 @@ int launch_dot(const float* a, const float* b, long long n, float* out, cudaStre
 //   fwd:   plain fp32 -> fp16 cast (needs the whole input-channel range)
 //   dgrad: 0: [Cs][9 (flipped)][Cout]; 1: [4 phases][Cs][4 (zero padded)][Cout]; 2: [Cs][Cout]; 3: [Cs][16][Cout]
 // ci0/ci1: the [ci0, ci1) slice of the input channels (skip-concat halves), Cs = ci1 - ci0.  Either output may be null.
+// dst = fp16(src), n a multiple of 4 (the flat master buffer -> its fp16 mirror in one launch)
+int launch_cast_h(const float* src, __half* dst, long long n, cudaStream_t s);
 int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int ci1, __half* fwd, __half* dgrad,
                      cudaStream_t s);
 

@@ -946,6 +946,15 @@ __global__ void __launch_bounds__(256) cast_h_kernel(const float4* __restrict__ 
     }
 }
 
+int launch_cast_h(const float* src, __half* dst, long long n, cudaStream_t s) {
+    if (n % 4) return (int)cudaErrorInvalidValue;
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    cast_h_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n / 4);
+    return (int)cudaGetLastError();
+}
+
 struct PackDgradParams {
     const float* src;
     __half* dst;

@@ -136,13 +136,14 @@ class _Conv:
         self.db = ft.grads[key + ".bias"] if has_bias else None
         taps_f = {K3S1: 9, K3S2: 9, K1: 1, KT4: 16}[kind]
         taps_d = {K3S1: 9, K3S2: 16, K1: 1, KT4: 16}[kind]
-        self.fwd = torch.empty(cout * cin * taps_f, dtype=torch.float16, device=ft.dev)
+        # forward operand = the fp16 mirror of the master weight (same offset in ft.P16: one cast refreshes all of them)
+        off = (self.w.data_ptr() - ft.P.data_ptr()) // 4
+        self.fwd = ft.P16[off:off + cout * cin * taps_f]
         self.splits = list(splits) if splits else [(0, cin)]
         self.dgrad = [torch.empty(cout * (c1 - c0) * taps_d, dtype=torch.float16, device=ft.dev) for c0, c1 in self.splits] \
             if need_dgrad else []
 
     def pack(self, ft: "FineTuner"):
-        ft.call("usb_t_pack_conv", self.kind, _p(self.w), self.cout, self.cin, 0, self.cin, _p(self.fwd), None)
         for (c0, c1), d in zip(self.splits, self.dgrad):
             ft.call("usb_t_pack_conv", self.kind, _p(self.w), self.cout, self.cin, c0, c1, None, _p(d))
 
@@ -188,6 +189,7 @@ class FineTuner:
         self.nparams = total
         mk = lambda: torch.zeros(total, dtype=torch.float32, device=self.dev)  # noqa: E731
         self.P, self.G, self.M, self.V = mk(), mk(), mk(), mk()
+        self.P16 = torch.zeros(total, dtype=torch.float16, device=self.dev)    # fp16 mirror of P (conv forward operands)
         self.params: Dict[str, torch.Tensor] = {}     # flat views; conv weights of layout_kind are in the training layout
         self.grads: Dict[str, torch.Tensor] = {}
         self.layout_kind: Dict[str, int] = {}
@@ -324,6 +326,7 @@ class FineTuner:
         self.dbcat = self.G[ob // 4: ob // 4 + self.J]
 
     def _pack_weights(self):
+        self.call("usb_t_cast", _p(self.P), _p(self.P16), self.nparams)
         for c in self.convs:
             c.pack(self)
         w3 = self.params["estimator.downs.0.0.block1.block.0.weight"]     # (C, 2, 3, 3) -> tap-major (9, 2, C)
