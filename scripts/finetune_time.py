@@ -28,6 +28,7 @@ def main():
     sd = random_init_state_dict(dec, seed=1234, out_scale=4.0)
     ft = FineTuner(lr=2e-5, use_cuda_graph=not os.environ.get('FT_NO_GRAPH'))
     ft.load_state_dict(sd)
+    ft.overlap_wgrad = not os.environ.get('FT_NO_OVERLAP')
     g = torch.Generator().manual_seed(0)
     x0 = (torch.randn(B, 80, T, generator=g) * 0.5).clamp(-1, 1).cuda()
     cond = torch.randn(B, 80, T, generator=g).clamp(-1, 1).cuda()

@@ -170,6 +170,8 @@ class FineTuner:
         self.C = [dim * m for m in self.dim_mults]
         self.lr, self.betas, self.eps, self.max_norm, self.loss_scale = lr, betas, eps, max_norm, float(loss_scale)
         self.use_cuda_graph = bool(use_cuda_graph) and _trace_calls is None
+        self.overlap_wgrad = True          # weight-gradient kernels on a side stream, overlapping the data-gradient chain
+        self._readers: Dict[int, "torch.cuda.Event"] = {}
         self._graphs: Dict[Tuple[int, int], "torch.cuda.CUDAGraph"] = {}
         self._eager_steps: Dict[Tuple[int, int], int] = {}
         cfg = abi.UsbConfig()
@@ -207,6 +209,7 @@ class FineTuner:
         e = math.log(10000) / (half - 1)          # SinusoidalPosEmb table, the reference's own torch expression (:116-118)
         self.freqs = torch.exp(torch.arange(half).float() * -e).to(self.dev)
         self._build_modules()
+        self.side = torch.cuda.Stream(self.dev) if self._trace is None else None
         self._ws: Dict[str, torch.Tensor] = {}
         self._ws_key = None
         self._packed = False
@@ -344,7 +347,30 @@ class FineTuner:
         if t is None:
             t = torch.empty(shape, dtype=dtype, device=self.dev)
             self._ws[name] = t
+        if self._readers and name.startswith("bw."):
+            # backward buffers are recycled: wait for side-stream kernels that still read the previous contents
+            ev = self._readers.pop(t.data_ptr(), None)
+            if ev is not None:
+                torch.cuda.current_stream(self.dev).wait_event(ev)
         return t
+
+    def _side(self, fn, *reads):
+        """Runs ``fn`` (parameter-gradient kernels: weight gradients, bias column sums) on the side stream, ordered after
+        everything enqueued so far; the buffers in ``reads`` are protected until those kernels have finished.  The data
+        gradient chain is the critical path of the backward pass and rarely fills the GPU at fine-tuning sizes."""
+        if self._trace is not None or not self.overlap_wgrad:
+            fn()
+            return
+        main = torch.cuda.current_stream(self.dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self.side.wait_event(fork)
+        with torch.cuda.stream(self.side):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self.side)
+        for t in reads:
+            self._readers[t.data_ptr()] = done
 
     def _act(self, name: str, l: int, c: int) -> torch.Tensor:
         return self._buf(f"{name}@{l}x{c}", (self.B, self.Hs[l], self.Ws[l], c))
@@ -399,12 +425,22 @@ class FineTuner:
                   self.B, raw.shape[1], raw.shape[2], C)
         return d_raw
 
-    def _wgrad(self, kind, dy, x, cout, cs, ci0, cin_total, dw, per_sample=0):
-        self.call("usb_t_wgrad", kind, _p(dy), dy.shape[3], _p(x), x.shape[3], self.B, x.shape[1], x.shape[2], cout, cs, ci0,
-                  cin_total, _p(dw), per_sample)
+    def _wgrad(self, kind, dy, x, cout, cs, ci0, cin_total, dw, per_sample=0, side=True):
+        def fn():
+            self.call("usb_t_wgrad", kind, _p(dy), dy.shape[3], _p(x), x.shape[3], self.B, x.shape[1], x.shape[2], cout, cs,
+                      ci0, cin_total, _p(dw), per_sample)
+        if side:
+            self._side(fn, dy)
+        else:
+            fn()
 
-    def _colsum(self, t, c, out, stride_n=0):
-        self.call("usb_t_colsum", _p(t), t.shape[3], self.B, t.shape[1] * t.shape[2], c, _p(out), stride_n)
+    def _colsum(self, t, c, out, stride_n=0, side=True):
+        def fn():
+            self.call("usb_t_colsum", _p(t), t.shape[3], self.B, t.shape[1] * t.shape[2], c, _p(out), stride_n)
+        if side:
+            self._side(fn, t)
+        else:
+            fn()
 
     def _add(self, a, b, out, c=None):
         self.call("usb_t_add", _p(a), _p(b), _p(c), _p(out), a.numel())
@@ -550,17 +586,18 @@ class FineTuner:
         pre, co = r["pre"], r["cout"]
         l, in0, in1, raw1, h1, raw2 = r["saved"]
         s1, s2 = self.stats[2 * i], self.stats[2 * i + 1]
-        d_raw2 = self._act("bw.d_raw", l, co)
+        d_raw2 = self._act("bw.d_raw2", l, co)     # (two buffers: the side-stream weight gradients still read d_raw2)
         self._gn_bwd(raw2, s2, pre + ".block2.block.1", l, d_raw2, r["c2"].db, dy=d_out)
         self._wgrad(K3S1, d_raw2, h1, co, co, 0, co, r["c2"].dw)
         d_h1 = self._conv_dgrad(r["c2"], 0, d_raw2, l, "bw.d_h1")
-        d_raw1 = self._act("bw.d_raw", l, co)       # d_raw2 is dead once d_h1 exists
+        d_raw1 = self._act("bw.d_raw1", l, co)
         b1 = self.grads[pre + ".block1.block.0.bias"]
         self._gn_bwd(raw1, s1, pre + ".block1.block.1", l, d_raw1, b1, dy=d_h1, d_emb=self.dE[:, r["emb_off"]:])
         if r["first"]:
-            self.call("usb_t_first_conv_wgrad", _p(d_raw1), _p(d_out), None, _p(self.xt), _p(self.mu), _p(self.masks[0]),
-                      _p(self.grads[pre + ".block1.block.0.weight"]), _p(self.grads[pre + ".res_conv.weight"]), self.B,
-                      self.Hs[0], self.Ws[0], co)
+            self._side(lambda: self.call(
+                "usb_t_first_conv_wgrad", _p(d_raw1), _p(d_out), None, _p(self.xt), _p(self.mu), _p(self.masks[0]),
+                _p(self.grads[pre + ".block1.block.0.weight"]), _p(self.grads[pre + ".res_conv.weight"]), self.B,
+                self.Hs[0], self.Ws[0], co), d_raw1, d_out)
             self._colsum(d_out, co, self.grads[pre + ".res_conv.bias"])
             return None, None
         c0 = in0.shape[3]
@@ -592,8 +629,8 @@ class FineTuner:
         Gm = self._buf(f"bw.a.G{C}", (self.B, C, _HID), torch.float32)
         cs.zero_()
         Gm.zero_()
-        self._colsum(d_out, C, cs, C)
-        self._wgrad(K1, d_out, qkv, C, _HID, 0, _HID, Gm, per_sample=1)
+        self._colsum(d_out, C, cs, C, side=False)                                   # inputs of attn_bwd_small: critical path
+        self._wgrad(K1, d_out, qkv, C, _HID, 0, _HID, Gm, per_sample=1, side=False)
         dctx = self._buf("bw.a.dctx", (self.B, _HEADS, 32, 32), torch.float32)
         weffT = self._buf(f"bw.a.weffT{C}", (self.B, _HID, C))
         self.call("usb_t_attn_bwd_small", _p(Gm), _p(cs), _p(g[pre + ".fn.fn.to_out.weight"]), _p(g[pre + ".fn.fn.to_out.bias"]),
@@ -658,6 +695,9 @@ class FineTuner:
                   _p(P[e + "mlp.2.weight"]), _p(P[e + "mlp.2.bias"]), _p(self.wcat), _p(self.u), _p(self.dE),
                   _p(self._buf("bw.du", (B, self.dim + self.S), torch.float32)), _p(G[e + "mlp.0.weight"]), _p(G[e + "mlp.0.bias"]),
                   _p(G[e + "mlp.2.weight"]), _p(G[e + "mlp.2.bias"]), _p(self.dwcat), _p(self.dbcat), B, self.J)
+        if self._trace is None and self.overlap_wgrad:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)      # join: every parameter gradient is complete
+            self._readers.clear()
 
     # ------------------------------------------------------------------------------------------------ optimizer
     def optimizer_step(self):
