@@ -337,11 +337,11 @@ def reverse_diffusion(p: Params, z: torch.Tensor, mask: torch.Tensor, cond: torc
     for i in range(n_timesteps):
         if teacher is not None:
             xt = teacher[i]
-        t = times[i] * torch.ones(B, dtype=z.dtype)
+        t = times[i] * torch.ones(B, dtype=z.dtype, device=z.device)
         idx = n_timesteps - 1 - i
         score = cfg_score(p, xt, mask, cond, t, spk_emb, text_uncon, spk_uncon,
                           text_gradient_scale, spk_gradient_scale, est)
-        nz = noise[i] if noise is not None else torch.randn(xt.shape, dtype=xt.dtype)
+        nz = noise[i] if noise is not None else torch.randn(xt.shape, dtype=xt.dtype).to(xt.device)
         xt = sampler_step(tb, idx, xt, score, nz, mask)
         if trace is not None:
             trace.append(xt.clone())
