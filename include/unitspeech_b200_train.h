@@ -33,6 +33,12 @@ extern "C" {
 int usb_t_pack_conv(usb_handle* h, int32_t kind, const float* w, int32_t Cout, int32_t Cin, int32_t ci0, int32_t ci1,
                     void* fwd, void* dgrad, uint64_t stream);
 
+/* Between usb_t_pack_begin and usb_t_pack_flush, usb_t_pack_conv only records its dgrad part; flush runs all recorded
+ * convs in ONE launch (the table is uploaded on first use -- a synchronising step -- and reused afterwards, so a captured
+ * CUDA graph replays it). */
+int usb_t_pack_begin(usb_handle* h, uint64_t stream);
+int usb_t_pack_flush(usb_handle* h, uint64_t stream);
+
 /* dst (fp16) = src (fp32), n a multiple of 4: refreshes the fp16 mirror of the flat master buffer -- with the conv
  * weights kept in the forward operand layout this IS the forward pack of every conv */
 int usb_t_cast(usb_handle* h, const float* src, void* dst, int64_t n, uint64_t stream);

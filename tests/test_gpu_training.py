@@ -173,3 +173,82 @@ def test_fused_finetuner_reduces_the_objective():
     assert np.mean(losses[-10:]) < 0.8 * np.mean(losses[:10]), (np.mean(losses[:10]), np.mean(losses[-10:]))
     dec.load_state_dict(ft.state_dict())
     ft.close()
+
+
+def test_edge_shapes_single_crop_minimal_width_and_masked_tail():
+    """B = 1, the narrowest width the 4-level U-Net accepts (T = 8 -> a 10 x 1 level-3 image) and an utterance shorter than
+    its crop (zero-padded, masked frames): gradients still match the oracle's autograd."""
+    dim, mults = 128, (1, 2, 4, 8)
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=4.0)
+    ft = _tuner(dim, mults, params)
+    for B, T, lengths, ts in ((1, 8, (8,), (0.5,)), (2, 16, (16, 5), (0.2, 0.9))):
+        x0, mask, cond, spk = case_inputs(B, T, lengths)
+        t = torch.tensor(ts)
+        z = reference_z(x0.shape, 3)
+        ref_loss, ref = O.loss_t_grads(params, x0, mask, cond, t, spk, z, dim=dim, dim_mults=mults)
+        ft.zero_grad()
+        loss = float(ft.forward(x0, mask, cond, t, spk, z))
+        ft.backward()
+        assert loss == pytest.approx(ref_loss, rel=5e-3)
+        got = {k: v.cpu() for k, v in ft.unscaled_grads().items()}
+        bad = []
+        for k, r in ref.items():
+            if r.numel() == 1 or float(r.norm()) == 0.0:
+                continue
+            rel = float((got[k] - r).norm() / r.norm())
+            if rel > GRAD_REL:
+                bad.append((k, rel))
+        assert not bad, bad[:5]
+    ft.close()
+
+
+def test_non_finite_gradients_skip_the_update():
+    """A non-finite gradient norm must leave parameters, Adam moments and the step counter untouched
+    (GradScaler semantics of the reference's fp16 path, finetune.py:156-162)."""
+    dim, mults = 64, (1, 2)
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=4.0)
+    ft = _tuner(dim, mults, params, use_cuda_graph=False)
+    x0, mask, cond, spk = case_inputs(2, 16, (16, 11))
+    t = torch.tensor([0.3, 0.7])
+    z = reference_z(x0.shape, 0)
+    ft.train_step(x0, mask, cond, t, spk, z)
+    assert ft.step_count == 1 and int(ft.skipped) == 0
+    before = ft.P.clone()
+    m_before = ft.M.clone()
+    ft.zero_grad()
+    ft.forward(x0, mask, cond, t, spk, z)
+    ft.backward()
+    ft.G[12345] = float("inf")
+    ft.optimizer_step()
+    torch.cuda.synchronize()
+    assert int(ft.skipped) == 1 and ft.step_count == 1
+    assert torch.equal(ft.P, before) and torch.equal(ft.M, m_before)
+    ft.close()
+
+
+def test_cuda_graph_replay_equals_eager_steps():
+    """The captured iteration (third step onwards) must follow the same trajectory as eager execution."""
+    dim, mults = 64, (1, 2)
+    params = O.harness_params(dim=dim, dim_mults=mults, seed=1234, out_scale=4.0)
+    x0, mask, cond, spk = case_inputs(2, 16, (16, 11))
+    t = torch.tensor([0.3, 0.7])
+    runs = []
+    for graph in (False, True):
+        ft = _tuner(dim, mults, params, lr=1e-4, use_cuda_graph=graph)
+        losses = [float(ft.train_step(x0, mask, cond, t, spk, reference_z(x0.shape, i))) for i in range(6)]
+        assert (len(ft._graphs) == 1) == graph and ft.step_count == 6
+        runs.append((losses, ft.P.clone()))
+        ft.close()
+    (l0, p0), (l1, p1) = runs
+    assert l0 == pytest.approx(l1, rel=2e-3)              # fp32 atomics reorder sums between runs
+    assert float((p0 - p1).norm() / (p0 - O_flat_norm(params, p0)).norm().clamp_min(1e-12)) < 0.2
+
+
+def O_flat_norm(params, like):
+    """Initial parameters in the FineTuner's flat order/layout (helper for the displacement comparison above)."""
+    from unitspeech_b200 import FineTuner
+    ft = FineTuner(dim=64, dim_mults=(1, 2))
+    ft.load_state_dict(params)
+    out = ft.P.clone()
+    ft.close()
+    return out

@@ -93,6 +93,8 @@ SIGNATURES = {
     "usb_vocoder_filter": (c_int32, [POINTER(c_float)]),
     # ---- fine-tune step, operator level (include/unitspeech_b200_train.h)
     "usb_t_pack_conv": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_uint64]),
+    "usb_t_pack_begin": (c_int32, [c_void_p, c_uint64]),
+    "usb_t_pack_flush": (c_int32, [c_void_p, c_uint64]),
     "usb_t_cast": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_uint64]),
     "usb_t_conv": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
                              c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

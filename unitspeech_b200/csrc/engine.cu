@@ -489,6 +489,7 @@ struct usb_handle {
     Plan plan;
     float* tpart_buf = nullptr;   // sampler: [n_steps] t, [n_steps][dim+S] u, [n_steps][J] time part
     size_t tpart_cap = 0;
+    PackBatch* pack = nullptr;    // fine-tune step: recorder of the per-conv data-gradient weight packs (train.h)
     float* loss_buf = nullptr;    // loss_t: xt, z*mask, cond*mask, score ([B][n_feats][T] each) + 512 doubles of partials
     size_t loss_cap = 0;
     long long launches = 0;
@@ -1267,6 +1268,7 @@ void usb_destroy(usb_handle* h) {
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->tpart_buf) cudaFree(h->tpart_buf);
     if (h->loss_buf) cudaFree(h->loss_buf);
+    pack_batch_destroy(h->pack);
     delete h;
 }
 
@@ -1512,7 +1514,22 @@ int usb_op_attn_context(usb_handle* h, const void* qkv, const float* wo, void* w
 int usb_t_pack_conv(usb_handle* h, int32_t kind, const float* w, int32_t Cout, int32_t Cin, int32_t ci0, int32_t ci1,
                     void* fwd, void* dgrad, uint64_t stream) {
     USB_T_BEGIN();
-    USB_LAUNCH(h, launch_pack_conv(kind, w, Cout, Cin, ci0, ci1, static_cast<__half*>(fwd), static_cast<__half*>(dgrad), s));
+    USB_LAUNCH(h, launch_pack_conv(kind, w, Cout, Cin, ci0, ci1, static_cast<__half*>(fwd), static_cast<__half*>(dgrad), s, h->pack));
+    return 0;
+}
+
+int usb_t_pack_begin(usb_handle* h, uint64_t stream) {
+    (void)stream;
+    if (!h) return fail("null handle");
+    if (!h->pack) h->pack = pack_batch_create();
+    pack_batch_begin(h->pack);
+    return 0;
+}
+
+int usb_t_pack_flush(usb_handle* h, uint64_t stream) {
+    USB_T_BEGIN();
+    if (!h->pack) return fail("usb_t_pack_flush without usb_t_pack_begin");
+    USB_LAUNCH(h, pack_batch_flush(h->pack, s));
     return 0;
 }
 

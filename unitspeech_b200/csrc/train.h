@@ -131,8 +131,24 @@ int launch_dot(const float* a, const float* b, long long n, float* out, cudaStre
 // ci0/ci1: the [ci0, ci1) slice of the input channels (skip-concat halves), Cs = ci1 - ci0.  Either output may be null.
 // dst = fp16(src), n a multiple of 4 (the flat master buffer -> its fp16 mirror in one launch)
 int launch_cast_h(const float* src, __half* dst, long long n, cudaStream_t s);
-int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int ci1, __half* fwd, __half* dgrad,
-                     cudaStream_t s);
+struct PackDgradParams {
+    const float* src;
+    __half* dst;
+    int Cout, Cs, ci0;
+    long long s_src_co, s_dst_ci;
+    int n;                       // destination tap slots
+    long long src_off[16];       // < 0: the slot is zero (padding tap of the transposed 3x3/s2 conv)
+    long long dst_off[16];
+};
+// Recorder that turns the per-conv data-gradient packs of one weight refresh into ONE launch: between begin and flush,
+// launch_pack_conv only records its dgrad part; flush uploads the table when it changed (first use) and launches.
+struct PackBatch;
+PackBatch* pack_batch_create();
+void pack_batch_destroy(PackBatch* b);
+void pack_batch_begin(PackBatch* b);
+int pack_batch_flush(PackBatch* b, cudaStream_t s);
+int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int ci1, __half* fwd, __half* dgrad, cudaStream_t s,
+                     PackBatch* batch = nullptr);
 
 // ---- clip_grad_norm_ + Adam (finetune.py:81,163-165; torch.optim.Adam defaults betas (0.9, 0.999), eps 1e-8)
 int launch_sumsq(const float* g, long long n, double* out, cudaStream_t s);   // out[0] += sum g^2

@@ -4,6 +4,7 @@
 // accumulation, ldmatrix.trans because both operands are stored pixel-major = K-major rows of channels).
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "conv_igemm.h"
 #include "train.h"
@@ -723,7 +724,10 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const __half* __restr
     const float M = __ldg(ms + ((static_cast<long long>(n) * heads + h) * 2) * kDh + lane);
     const float invS = 1.f / __ldg(ms + ((static_cast<long long>(n) * heads + h) * 2 + 1) * kDh + lane);
     const int p_begin = blockIdx.x * ppb, p_end = min(P, p_begin + ppb);
-    // two positions per iteration: their loads are issued together and the two shuffle/FMA chains interleave
+    // two positions per iteration; the two 32-vectors of each position (softmax weights, v) are broadcast to the lanes
+    // through a per-warp shared-memory row read as float4 (16 wavefronts per position instead of 64 shuffles)
+    __shared__ __align__(16) float bc[8][4][kDh];
+    float* bw = &bc[warp][0][0];
     for (int pos = p_begin + sub; pos < p_end; pos += 2 * nsub) {
         const int pos1 = pos + nsub;
         const bool has1 = pos1 < p_end;
@@ -734,13 +738,23 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const __half* __restr
         const float k1 = __half2float(qkv[row1 * ld + koff + h * kDh + lane]);
         const float v1 = __half2float(qkv[row1 * ld + voff + h * kDh + lane]);
         const float ksm0 = __expf(k0 - M) * invS, ksm1 = __expf(k1 - M) * invS;
+        __syncwarp();
+        bw[0 * kDh + lane] = ksm0;
+        bw[1 * kDh + lane] = v0;
+        bw[2 * kDh + lane] = ksm1;
+        bw[3 * kDh + lane] = v1;
+        __syncwarp();
         float dv0 = 0.f, dks0 = 0.f, dv1 = 0.f, dks1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < kDh; ++i) {
-            dv0 = fmaf(__shfl_sync(0xffffffffu, ksm0, i), dcol[i], dv0);
-            dks0 = fmaf(drow[i], __shfl_sync(0xffffffffu, v0, i), dks0);
-            dv1 = fmaf(__shfl_sync(0xffffffffu, ksm1, i), dcol[i], dv1);
-            dks1 = fmaf(drow[i], __shfl_sync(0xffffffffu, v1, i), dks1);
+        for (int i = 0; i < kDh; i += 4) {
+            const float4 a0 = *reinterpret_cast<const float4*>(bw + 0 * kDh + i);
+            const float4 b0 = *reinterpret_cast<const float4*>(bw + 1 * kDh + i);
+            const float4 a1 = *reinterpret_cast<const float4*>(bw + 2 * kDh + i);
+            const float4 b1 = *reinterpret_cast<const float4*>(bw + 3 * kDh + i);
+            dv0 = fmaf(a0.x, dcol[i], dv0); dv0 = fmaf(a0.y, dcol[i + 1], dv0); dv0 = fmaf(a0.z, dcol[i + 2], dv0); dv0 = fmaf(a0.w, dcol[i + 3], dv0);
+            dks0 = fmaf(drow[i], b0.x, dks0); dks0 = fmaf(drow[i + 1], b0.y, dks0); dks0 = fmaf(drow[i + 2], b0.z, dks0); dks0 = fmaf(drow[i + 3], b0.w, dks0);
+            dv1 = fmaf(a1.x, dcol[i], dv1); dv1 = fmaf(a1.y, dcol[i + 1], dv1); dv1 = fmaf(a1.z, dcol[i + 2], dv1); dv1 = fmaf(a1.w, dcol[i + 3], dv1);
+            dks1 = fmaf(drow[i], b1.x, dks1); dks1 = fmaf(drow[i + 1], b1.y, dks1); dks1 = fmaf(drow[i + 2], b1.z, dks1); dks1 = fmaf(drow[i + 3], b1.w, dks1);
         }
         dkv[row0 * (2 * hidden) + h * kDh + lane] = __float2half_rn(ksm0 * (dks0 - r));
         dkv[row0 * (2 * hidden) + hidden + h * kDh + lane] = __float2half_rn(dv0);
@@ -955,21 +969,9 @@ int launch_cast_h(const float* src, __half* dst, long long n, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
-struct PackDgradParams {
-    const float* src;
-    __half* dst;
-    int Cout, Cs, ci0;
-    long long s_src_co, s_dst_ci;
-    int n;                       // destination tap slots
-    long long src_off[16];       // < 0: the slot is zero (padding tap of the transposed 3x3/s2 conv)
-    long long dst_off[16];
-};
-
-// grid (ceil(Cs/32), ceil(Cout/32), slots), block (32, 8): dst[ci][co] = src[co][ci] per slot through a padded smem tile
-__global__ void __launch_bounds__(256) pack_dgrad_kernel(const PackDgradParams p) {
-    __shared__ float tile[32][33];
-    const int slot = blockIdx.z;
-    const int ci_b = blockIdx.x * 32, co_b = blockIdx.y * 32;
+// dst[ci][co] = src[co][ci] for one 32 x 32 tile of one tap slot, through a padded smem tile; block (32, 8)
+__device__ __forceinline__ void pack_dgrad_tile(const PackDgradParams& p, int bx, int by, int slot, float (&tile)[32][33]) {
+    const int ci_b = bx * 32, co_b = by * 32;
     const long long so = p.src_off[slot];
     for (int j = threadIdx.y; j < 32; j += 8) {
         const int co = co_b + j, ci = ci_b + threadIdx.x;
@@ -984,7 +986,90 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const PackDgradParams p
     }
 }
 
-int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int ci1, __half* fwd, __half* dgrad, cudaStream_t s) {
+// grid (ceil(Cs/32), ceil(Cout/32), slots)
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const PackDgradParams p) {
+    __shared__ float tile[32][33];
+    pack_dgrad_tile(p, blockIdx.x, blockIdx.y, blockIdx.z, tile);
+}
+
+// every recorded conv in one launch: block -> (entry, tile) through the prefix table of tile counts
+__global__ void __launch_bounds__(256) pack_dgrad_batch_kernel(const PackDgradParams* __restrict__ list,
+                                                               const int* __restrict__ first_block, int n_entries) {
+    __shared__ float tile[32][33];
+    __shared__ PackDgradParams p;
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {           // last entry whose first block <= blockIdx.x
+        const int mid = (lo + hi + 1) >> 1;
+        if (first_block[mid] <= static_cast<int>(blockIdx.x)) lo = mid;
+        else hi = mid - 1;
+    }
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < static_cast<int>(sizeof(PackDgradParams) / 4); i += 256)
+        reinterpret_cast<int*>(&p)[i] = reinterpret_cast<const int*>(list + lo)[i];
+    __syncthreads();
+    const int local = blockIdx.x - first_block[lo];
+    const int gx = (p.Cs + 31) / 32, gy = (p.Cout + 31) / 32;
+    pack_dgrad_tile(p, local % gx, (local / gx) % gy, local / (gx * gy), tile);
+}
+
+struct PackBatch {
+    bool recording = false;
+    std::vector<PackDgradParams> list;
+    std::vector<int> first_block;
+    PackDgradParams* d_list = nullptr;
+    int* d_first = nullptr;
+    size_t cap = 0;
+    unsigned long long hash = 0;
+    int total_blocks = 0;
+};
+PackBatch* pack_batch_create() { return new PackBatch(); }
+void pack_batch_destroy(PackBatch* b) {
+    if (!b) return;
+    if (b->d_list) cudaFree(b->d_list);
+    if (b->d_first) cudaFree(b->d_first);
+    delete b;
+}
+void pack_batch_begin(PackBatch* b) {
+    b->recording = true;
+    b->list.clear();
+}
+int pack_batch_flush(PackBatch* b, cudaStream_t s) {
+    b->recording = false;
+    if (b->list.empty()) return 0;
+    unsigned long long hsh = 1469598103934665603ull;
+    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(b->list.data());
+    for (size_t i = 0; i < b->list.size() * sizeof(PackDgradParams); ++i) hsh = (hsh ^ bytes[i]) * 1099511628211ull;
+    if (hsh != b->hash || b->d_list == nullptr) {
+        // first use (or re-planned buffers): build the block prefix table and upload; never happens inside a captured graph
+        b->first_block.assign(b->list.size() + 1, 0);
+        for (size_t i = 0; i < b->list.size(); ++i) {
+            const PackDgradParams& p = b->list[i];
+            b->first_block[i + 1] = b->first_block[i] + ((p.Cs + 31) / 32) * ((p.Cout + 31) / 32) * p.n;
+        }
+        b->total_blocks = b->first_block.back();
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return (int)e;
+        if (b->list.size() > b->cap) {
+            if (b->d_list) cudaFree(b->d_list);
+            if (b->d_first) cudaFree(b->d_first);
+            b->cap = b->list.size();
+            e = cudaMalloc(&b->d_list, b->cap * sizeof(PackDgradParams));
+            if (e != cudaSuccess) return (int)e;
+            e = cudaMalloc(&b->d_first, (b->cap + 1) * sizeof(int));
+            if (e != cudaSuccess) return (int)e;
+        }
+        e = cudaMemcpy(b->d_list, b->list.data(), b->list.size() * sizeof(PackDgradParams), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemcpy(b->d_first, b->first_block.data(), b->first_block.size() * sizeof(int), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return (int)e;
+        b->hash = hsh;
+    }
+    pack_dgrad_batch_kernel<<<b->total_blocks, dim3(32, 8), 0, s>>>(b->d_list, b->d_first, static_cast<int>(b->list.size()));
+    return (int)cudaGetLastError();
+}
+
+int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int ci1, __half* fwd, __half* dgrad, cudaStream_t s,
+                     PackBatch* batch) {
     if (kind < 0 || kind > 3 || ci0 < 0 || ci1 > Cin || ci1 <= ci0) return (int)cudaErrorInvalidValue;
     const int Cs = ci1 - ci0;
     const int taps_f = kind == 2 ? 1 : (kind == 3 ? 16 : 9);
@@ -1026,6 +1111,10 @@ int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int c
                     p.src_off[kh * 4 + kw] = (static_cast<long long>(ph * 2 + pw) * Cout * 4 + (a * 2 + b)) * Cin;
                     p.dst_off[kh * 4 + kw] = static_cast<long long>(kh * 4 + kw) * Cout;
                 }
+        }
+        if (batch && batch->recording) {   // deferred: pack_batch_flush runs every recorded conv in one launch
+            batch->list.push_back(p);
+            return 0;
         }
         dim3 grid((Cs + 31) / 32, (Cout + 31) / 32, p.n), block(32, 8);
         pack_dgrad_kernel<<<grid, block, 0, s>>>(p);

@@ -330,8 +330,10 @@ class FineTuner:
 
     def _pack_weights(self):
         self.call("usb_t_cast", _p(self.P), _p(self.P16), self.nparams)
+        self.call("usb_t_pack_begin")
         for c in self.convs:
             c.pack(self)
+        self.call("usb_t_pack_flush")
         w3 = self.params["estimator.downs.0.0.block1.block.0.weight"]     # (C, 2, 3, 3) -> tap-major (9, 2, C)
         w1 = self.params["estimator.downs.0.0.res_conv.weight"]           # (C, 2, 1, 1) -> (2, C)
         if getattr(self, "first_w3", None) is None:
