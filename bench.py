@@ -307,10 +307,10 @@ def run_gpu_arm(args):
         if not args.no_finetune:
             dec._release()            # frees the sampler's workspace before the training buffers are allocated
             torch.cuda.empty_cache()
-            finetune = finetune_leg(dev, params, peaks, with_cpu=not args.no_cpu)
+            finetune = finetune_leg(dev, params, peaks, with_cpu=not args.no_cpu and world == 1)
         # ---- CPU baseline on this box's host cores (bounded sample)
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # the CPU baseline is an N = 1 figure (torchrun also pins OMP to 1 thread)
             threads = os.cpu_count() or 1
             dt, fps, nst = cpu_sample(params, threads, diffusion_steps=12)   # ~10-20 s of CPU work
             cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
