@@ -489,6 +489,8 @@ struct usb_handle {
     Plan plan;
     float* tpart_buf = nullptr;   // sampler: [n_steps] t, [n_steps][dim+S] u, [n_steps][J] time part
     size_t tpart_cap = 0;
+    float* stage_buf = nullptr;   // usb_reverse_diffusion_host: device copies of the host inputs / output
+    size_t stage_cap = 0;
     PackBatch* pack = nullptr;    // fine-tune step: recorder of the per-conv data-gradient weight packs (train.h)
     float* loss_buf = nullptr;    // loss_t: xt, z*mask, cond*mask, score ([B][n_feats][T] each) + 512 doubles of partials
     size_t loss_cap = 0;
@@ -1269,6 +1271,7 @@ void usb_destroy(usb_handle* h) {
     if (h->tpart_buf) cudaFree(h->tpart_buf);
     if (h->loss_buf) cudaFree(h->loss_buf);
     pack_batch_destroy(h->pack);
+    if (h->stage_buf) cudaFree(h->stage_buf);
     delete h;
 }
 
@@ -1330,8 +1333,17 @@ int usb_reverse_diffusion_host(usb_handle* h, const float* z, const float* cond,
     const size_t P = (size_t)h->cfg.n_feats * T, S = h->cfg.spk_emb_dim;
     const size_t n_z = (size_t)B * P, n_mask = (size_t)B * T, n_spk = (size_t)B * S;
     const size_t n_noise = noise ? (size_t)n_steps * B * P : 0;
-    float* d = nullptr;
-    USB_CUDA(cudaMalloc(&d, (3 * n_z + n_mask + n_spk + n_noise) * sizeof(float)));
+    // device staging for the host entry, kept on the handle and grown on demand (no cudaMalloc / cudaFree per call)
+    const size_t need = (3 * n_z + n_mask + n_spk + n_noise) * sizeof(float);
+    if (need > h->stage_cap) {
+        USB_CUDA(cudaStreamSynchronize(s));
+        if (h->stage_buf) cudaFree(h->stage_buf);
+        h->stage_buf = nullptr;
+        h->stage_cap = 0;
+        USB_CUDA(cudaMalloc(&h->stage_buf, need));
+        h->stage_cap = need;
+    }
+    float* d = h->stage_buf;
     float *dz = d, *dc = dz + n_z, *dout = dc + n_z, *dm = dout + n_z, *ds = dm + n_mask, *dn = ds + n_spk;
     int rc = 0;
     auto H2D = [&](float* dst, const float* src, size_t n) {
@@ -1353,7 +1365,6 @@ int usb_reverse_diffusion_host(usb_handle* h, const float* z, const float* cond,
     } else {
         cudaStreamSynchronize(s);
     }
-    cudaFree(d);
     return rc;
 }
 

@@ -9,6 +9,7 @@ q_posterior :280-291, the update :366-370).
 
 from __future__ import annotations
 
+import functools
 import math
 from typing import Dict
 
@@ -22,8 +23,9 @@ def get_noise(t, beta_init: float, beta_term: float, cumulative: bool = False):
     return beta_init + (beta_term - beta_init) * t
 
 
+@functools.lru_cache(maxsize=32)
 def step_times(n_timesteps: int) -> torch.Tensor:
-    """t_i = (1 - (i + 0.5) h) * ones(1) in fp32 (unitspeech/unitspeech.py:361)."""
+    """t_i = (1 - (i + 0.5) h) * ones(1) in fp32 (unitspeech/unitspeech.py:361).  Cached: treat the result as read-only."""
     h = 1.0 / n_timesteps
     return torch.cat([(1.0 - (i + 0.5) * h) * torch.ones(1, dtype=torch.float32) for i in range(n_timesteps)])
 
@@ -55,8 +57,10 @@ def schedule_tables(n_timesteps: int, beta_min: float, beta_max: float) -> Dict[
     }
 
 
+@functools.lru_cache(maxsize=32)
 def step_coefficients(n_timesteps: int, beta_min: float, beta_max: float) -> torch.Tensor:
-    """(n, 3) fp32 [c_x, c_s, sigma] indexed by loop iteration i (table index n-1-i)."""
+    """(n, 3) fp32 [c_x, c_s, sigma] indexed by loop iteration i (table index n-1-i).  Cached per (n, beta_min, beta_max) --
+    ~800 tiny torch ops otherwise sit on the host-side critical path of every call; treat the result as read-only."""
     tb = schedule_tables(n_timesteps, beta_min, beta_max)
     out = torch.zeros(n_timesteps, 3, dtype=torch.float32)
     for i in range(n_timesteps):
