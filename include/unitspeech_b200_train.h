@@ -103,7 +103,8 @@ int usb_t_add(usb_handle* h, const void* a, const void* b, const void* c, void* 
 
 /* weight gradient of a conv of kind 0-3 in the training layout (see usb_t_pack_conv).  dy: h16 output gradient (row stride ldy),
  * x: h16 layer input (N, H, W, ldx) whose channels [0, Cs) are the [ci0, ci0+Cs) slice of the Cin_total input channels.
- * per_sample (kind 2): dW is (N, Cout, Cs), one matrix per sample. */
+ * per_sample bit 0 (kind 2): dW is (N, Cout, Cs), one matrix per sample; bit 1: the destination slice is known to hold
+ * zeros (fresh zero_grad), which lets a launch with one CTA per tile store its result instead of adding it. */
 int usb_t_wgrad(usb_handle* h, int32_t kind, const void* dy, int32_t ldy, const void* x, int32_t ldx, int32_t N, int32_t H,
                 int32_t W, int32_t Cout, int32_t Cs, int32_t ci0, int32_t Cin_total, float* dW, int32_t per_sample,
                 uint64_t stream);

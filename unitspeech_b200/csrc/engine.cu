@@ -1694,6 +1694,8 @@ int usb_t_wgrad(usb_handle* h, int32_t kind, const void* dy, int32_t ldy, const 
                 uint64_t stream) {
     USB_T_BEGIN();
     if (kind < 0 || kind > 3) return fail("bad conv kind");
+    const int dst_is_zero = (per_sample >> 1) & 1;   // flag bit 1: the destination slice holds zeros (fresh zero_grad)
+    per_sample &= 1;
     if (per_sample && kind != K1) return fail("per-sample weight gradients are 1x1 only");
     // output addressing in the training layout (train.h: launch_pack_conv), input channels contiguous
     long long s_co, s_ci = 1, s_n = 0;
@@ -1753,7 +1755,7 @@ int usb_t_wgrad(usb_handle* h, int32_t kind, const void* dy, int32_t ldy, const 
             return fail("wgrad: strided convs need dense tensors");
         q.Cout = Cout; q.Cin = Cs; q.n_tile = Cs <= 128 ? 128 : 256;
         q.tiles_m = (Cout + 127) / 128; q.tiles_n = (Cs + q.n_tile - 1) / q.n_tile;
-        q.dW = dWo; q.s_co = s_co; q.s_ci = s_ci; q.s_n = s_n;
+        q.dW = dWo; q.s_co = s_co; q.s_ci = s_ci; q.s_n = s_n; q.overwrite = dst_is_zero;
         CUtensorMap ma, mb;
         USB_TRY(load_encode_fn());
         const int Hy = kind == K3S2 ? H / 2 : (kind == KT4 ? 2 * H : H), Wy = kind == K3S2 ? W / 2 : (kind == KT4 ? 2 * W : W);

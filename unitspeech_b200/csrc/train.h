@@ -185,6 +185,7 @@ struct WgradTcParams {
     long long s_co, s_ci, s_n;
     int tap_off[kWgradMaxTaps];
     int ksplit, stages;
+    int overwrite;     // dW is known to be zero: a launch with one CTA per tile stores instead of adding
 };
 int launch_wgrad_tc(WgradTcParams& p, const CUtensorMap& map_a, const CUtensorMap& map_b, int num_sms, cudaStream_t s);
 }  // namespace usb

@@ -139,7 +139,15 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap map_a
             tmem_ld_32x32(taddr + cb, v);
             tmem_ld_wait();
             if (co < p.Cout) {
-                if (p.s_ci == 1 && n0 + cb + 32 <= p.Cin) {   // contiguous input channels: 16-byte vector reductions
+                if (p.s_ci == 1 && n0 + cb + 32 <= p.Cin && p.ksplit == 1 && p.overwrite) {
+                    // the only CTA of this tile and a destination known to be zero: plain 16-byte stores (fp32 reductions
+                    // resolve in L2 at a fraction of the store rate; the level-3 layers write 38 MB of gradient each)
+                    float4* o = reinterpret_cast<float4*>(out + n0 + cb);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        o[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                __uint_as_float(v[j + 3]));
+                } else if (p.s_ci == 1 && n0 + cb + 32 <= p.Cin) {   // contiguous input channels: 16-byte vector reductions
                     float* o = out + n0 + cb;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -181,7 +189,8 @@ int launch_wgrad_tc(WgradTcParams& p, const CUtensorMap& map_a, const CUtensorMa
     const long long tiles = static_cast<long long>(p.taps) * p.tiles_m * p.tiles_n;
     const int nseg = p.s_n != 0 ? p.N : 1;
     const long long seg_chunks = static_cast<long long>(p.tiles_y) * p.tiles_x * (p.s_n != 0 ? 1 : p.N);
-    long long ks = (2LL * num_sms + tiles * nseg - 1) / (tiles * nseg);
+    // split the pixel range only while the tiles alone leave SMs idle (a split multiplies the reduction traffic)
+    long long ks = (3LL * num_sms / 2) / (tiles * nseg);
     const long long max_ks = (seg_chunks + 3) / 4;   // at least four chunks per split
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;

@@ -429,8 +429,9 @@ class FineTuner:
 
     def _wgrad(self, kind, dy, x, cout, cs, ci0, cin_total, dw, per_sample=0, side=True):
         def fn():
+            # flag bit 1: every weight-gradient slice is written once per backward pass, right after zero_grad
             self.call("usb_t_wgrad", kind, _p(dy), dy.shape[3], _p(x), x.shape[3], self.B, x.shape[1], x.shape[2], cout, cs,
-                      ci0, cin_total, _p(dw), per_sample)
+                      ci0, cin_total, _p(dw), per_sample | 2)
         if side:
             self._side(fn, dy)
         else:
@@ -650,7 +651,8 @@ class FineTuner:
         return d_x
 
     def backward(self):
-        """Gradients of ``loss_scale * loss`` for every parameter, accumulated into ``self.grads``."""
+        """Gradients of ``loss_scale * loss`` of the last ``forward`` for every parameter, written into ``self.grads``.
+        Call ``zero_grad()`` before every pass: weight-gradient tiles that a single CTA produces are stored, not added."""
         B, T, L, C = self.B, self.T, self.L, self.C
         e = "estimator."
         P, G = self.params, self.grads
