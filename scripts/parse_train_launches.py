@@ -4,7 +4,7 @@ import csv
 import collections
 import sys
 
-rows = list(csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')))
+rows = [r for r in csv.reader(open(sys.argv[1])) if r and (r[0].isdigit() or r[0] == "ID")]
 hdr = rows[0]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
