@@ -135,11 +135,22 @@ def test_reference_loop_runs_unchanged_on_the_module(golden_dir):
         want = float(gold["dw/" + k])
         if want > 0:
             assert float((v.detach().cpu().double() - params[k].double()).norm()) == pytest.approx(want, rel=5e-2), k
-    # the updated weights are what the sampler sees next
+    # the updated weights are what the inference handle (sampler, fused loss) sees next: the fused forward-only loss must
+    # agree with the fine-tune engine's forward on the current parameters and differ from the loss of the initial ones
     dec.eval()
     with torch.no_grad():
+        torch.manual_seed(123)
         l_after, _ = dec.loss_t(x0, mask, cond, t, spk)
-    assert torch.isfinite(l_after)
+    torch.manual_seed(123)
+    l_engine, _ = dec.loss_t(x0, mask, cond, t, spk)
+    fresh = UnitSpeech(80, dim, mults, spk_emb_dim=256)
+    fresh.load_state_dict(params, strict=True)
+    fresh = fresh.cuda().eval()
+    with torch.no_grad():
+        torch.manual_seed(123)
+        l_init, _ = fresh.loss_t(x0, mask, cond, t, spk)
+    assert float(l_after) == pytest.approx(float(l_engine.detach()), rel=2e-3)
+    assert abs(float(l_after) - float(l_init)) > 1e-3 * float(l_init)
 
 
 def test_fused_finetuner_reduces_the_objective():

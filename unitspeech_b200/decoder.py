@@ -457,6 +457,9 @@ class UnitSpeech(torch.nn.Module):
             ft = self._ensure_tuner(x0)
             names = [k for k, _ in self.named_parameters()]
             loss = _DiffusionLoss.apply(ft, names, x0, mask, cond, t, spk_emb, z, *[p for _, p in self.named_parameters()])
+            # an optimizer is about to update the parameters in place: the sampler's copy of the weights (fp16 operands
+            # inside the library handle) must be rebuilt before the next inference call
+            self._weights_version += 1
             return loss.to(x0.device), ft.xt.detach().clone().to(x0.device)
         with torch.no_grad():
             lib = abi.load_library()
