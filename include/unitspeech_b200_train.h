@@ -89,7 +89,7 @@ int usb_t_loss_grad(usb_handle* h, const float* score, const float* zm, const fl
                     float* msum, float* dscore, int32_t B, int32_t T, uint64_t stream);
 
 /* backward of y = (Mish(GroupNorm(raw)) + emb + res) * mask: d_raw (h16), dbias (conv bias), dgamma, dbeta, and the
- * embedding gradient d_emb[n*emb_stride + c] = sum_p dy.  dy = dy0 (+ dy1), h16 -- or, for the final block, the outer
+ * embedding gradient d_emb[n*emb_stride + c] = sum_p dy.  dy = dy0, h16 (dy1 is reserved, pass NULL) -- or, for the final block, the outer
  * product dys[n][p] * wvec[c] (then d_wvec[c] += sum dys * y).  scratch: (3*N*C + N*16) floats. */
 int usb_t_gn_bwd(usb_handle* h, const void* raw, const int64_t* stats, const float* gamma, const float* beta, const void* dy0,
                  const void* dy1, const float* dys, const float* wvec, const float* mask, float* scratch, void* d_raw,

@@ -24,7 +24,7 @@ struct GnBwdParams {
     const float* gamma;       // [C]
     const float* beta;        // [C]
     const __half* dy0;        // [N][P][C] or null (scalar-dy mode)
-    const __half* dy1;        // [N][P][C] second contribution or null
+    const __half* dy1;        // must be null (reserved: a second contribution is summed by the caller with add_h)
     const float* dys;         // scalar-dy mode: [N][P] fp32
     const float* wvec;        // scalar-dy mode: [C]
     const float* mask;        // [N][W]

@@ -104,7 +104,7 @@ __device__ __forceinline__ void gn_thread_const(const GnBwdParams& p, int n, int
 
 // raw operands of one pixel's channel octet, loaded U pixels ahead of their use
 struct GnPix {
-    uint4 raw, d0, d1;
+    uint4 raw, d0;
     float m, dys;
 };
 template <bool SCALAR>
@@ -115,7 +115,6 @@ __device__ __forceinline__ void gn_load(const GnBwdParams& p, long long off, lon
         q.dys = __ldg(p.dys + pixoff);
     } else {
         q.d0 = ldg16(p.dy0 + off);
-        if (p.dy1) q.d1 = ldg16(p.dy1 + off);
     }
 }
 // masked dy of the octet; SCALAR: dys * wvec
@@ -127,12 +126,6 @@ __device__ __forceinline__ void gn_dy(const GnBwdParams& p, const GnPix& q, cons
         for (int i = 0; i < 8; ++i) dy[i] = dys_m * wv[i];
     } else {
         unpack8(q.d0, dy);
-        if (p.dy1) {
-            float d1[8];
-            unpack8(q.d1, d1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dy[i] += d1[i];
-        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) dy[i] *= q.m;
         dys_m = 0.f;
@@ -142,7 +135,7 @@ __device__ __forceinline__ void gn_dy(const GnBwdParams& p, const GnPix& q, cons
 constexpr int kGnU = 4;   // pixels in flight per thread
 
 template <bool SCALAR>
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p, int ppb, int TP) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(const GnBwdParams p, int ppb, int TP) {
     __shared__ float s_mean[8], s_rstd[8];
     __shared__ float red[3 * 2048];
     const int n = blockIdx.y;
@@ -209,7 +202,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p,
 // The prologue of every block folds the reduce kernel's sums into the two per-group scalars; block 0 of each sample
 // also emits the affine / embedding / final-conv gradients.
 template <bool SCALAR>
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p, int ppb, int TP) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const GnBwdParams p, int ppb, int TP) {
     __shared__ float s_mean[8], s_rstd[8];
     __shared__ float sg[8][2];
     __shared__ float red[2048];
@@ -307,6 +300,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p, 
 }
 
 static int gn_geometry(const GnBwdParams& p, int& TP, int& lanes) {
+    if (p.dy1 != nullptr) return 1;   // fan-in sums are materialised by the caller (usb_t_add)
     TP = p.C / 8;
     if (p.C % 8 || TP < 1 || TP > 256 || (TP & (TP - 1)) || p.C % p.groups || p.groups > 8) return 1;
     lanes = 256 / TP;
