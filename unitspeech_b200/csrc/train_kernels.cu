@@ -3,6 +3,7 @@
 // gradient is a split-K GEMM over pixels on warp-level tensor cores (mma.sync m16n8k16, fp16 operands, fp32
 // accumulation, ldmatrix.trans because both operands are stored pixel-major = K-major rows of channels).
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <vector>
 
@@ -1124,7 +1125,14 @@ int launch_pack_conv(int kind, const float* w, int Cout, int Cin, int ci0, int c
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* out) {
     __shared__ double red[8];
     double s = 0.0;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+    const long long n4 = ((reinterpret_cast<uintptr_t>(g) & 15) == 0) ? (n >> 2) : 0;   // 16-byte loads when aligned
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 v = __ldg(g4 + i);
+        s += static_cast<double>(v.x * v.x + v.y * v.y) + static_cast<double>(v.z * v.z + v.w * v.w);
+    }
+    for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float v = g[i];
         s += static_cast<double>(v) * v;
@@ -1164,15 +1172,35 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamParams p) {
         bc2 = static_cast<float>(1.0 - pow(static_cast<double>(p.beta2), st));
     }
     const float step = p.lr / bc1, rs2 = rsqrtf(bc2);
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n;
+    auto upd = [&](float& w, float g0, float& m, float& v) {
+        const float g = g0 * coef;
+        m = p.beta1 * m + (1.f - p.beta1) * g;
+        v = p.beta2 * v + (1.f - p.beta2) * g * g;
+        w -= step * m / (sqrtf(v) * rs2 + p.eps);
+    };
+    // 16-byte accesses (the flat buffers are 256-byte aligned and padded to multiples of 64 floats)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p.p) | reinterpret_cast<uintptr_t>(p.g) | reinterpret_cast<uintptr_t>(p.m) |
+                           reinterpret_cast<uintptr_t>(p.v)) & 15) == 0;
+    const long long n4 = aligned ? (p.n >> 2) : 0;
+    float4* P4 = reinterpret_cast<float4*>(p.p);
+    const float4* G4 = reinterpret_cast<const float4*>(p.g);
+    float4* M4 = reinterpret_cast<float4*>(p.m);
+    float4* V4 = reinterpret_cast<float4*>(p.v);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float g = p.g[i] * coef;
-        const float m = p.beta1 * p.m[i] + (1.f - p.beta1) * g;
-        const float v = p.beta2 * p.v[i] + (1.f - p.beta2) * g * g;
-        p.m[i] = m;
-        p.v[i] = v;
-        p.p[i] -= step * m / (sqrtf(v) * rs2 + p.eps);
+        float4 w = P4[i], m = M4[i], v = V4[i];
+        const float4 g = __ldg(G4 + i);
+        upd(w.x, g.x, m.x, v.x);
+        upd(w.y, g.y, m.y, v.y);
+        upd(w.z, g.z, m.z, v.z);
+        upd(w.w, g.w, m.w, v.w);
+        P4[i] = w;
+        M4[i] = m;
+        V4[i] = v;
     }
+    for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        upd(p.p[i], p.g[i], p.m[i], p.v[i]);
 }
 
 __global__ void adam_step_inc_kernel(int* step_dev, const double* sumsq) {
@@ -1180,7 +1208,7 @@ __global__ void adam_step_inc_kernel(int* step_dev, const double* sumsq) {
 }
 
 int launch_adam(const AdamParams& p, int num_sms, cudaStream_t s) {
-    long long blocks = (p.n + 256 * 4 - 1) / (256 * 4);
+    long long blocks = (p.n / 4 + 256 * 4 - 1) / (256 * 4);
     if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;
     if (blocks < 1) blocks = 1;
     adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
