@@ -456,18 +456,34 @@ __global__ void __launch_bounds__(256) time_mlp_kernel(const EmbedParams p) {
             e[j + half] = cosf(arg);
         }
         __syncthreads();
-        for (int i = warp; i < 4 * p.dim; i += 8) {
-            float acc = 0.f;
-            for (int j = lane; j < p.dim; j += 32) acc += p.w0[static_cast<long long>(i) * p.dim + j] * e[j];
-            acc = warp_sum_f(acc);
-            if (lane == 0) h[i] = mish_precise(acc + p.b0[i]);
+        // four output rows per warp iteration: their weight loads are in flight together (the kernel is pure latency;
+        // dim is a multiple of 32, so 4*dim and dim are multiples of 32).  Per row the summation order is unchanged.
+        for (int i0 = warp * 4; i0 < 4 * p.dim; i0 += 32) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = lane; j < p.dim; j += 32) {
+                const float ej = e[j];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] += p.w0[static_cast<long long>(i0 + r) * p.dim + j] * ej;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float a = warp_sum_f(acc[r]);
+                if (lane == 0) h[i0 + r] = mish_precise(a + p.b0[i0 + r]);
+            }
         }
         __syncthreads();
-        for (int i = warp; i < p.dim; i += 8) {
-            float acc = 0.f;
-            for (int j = lane; j < 4 * p.dim; j += 32) acc += p.w2[static_cast<long long>(i) * 4 * p.dim + j] * h[j];
-            acc = warp_sum_f(acc);
-            if (lane == 0) tm[i] = acc + p.b2[i];
+        for (int i0 = warp * 4; i0 < p.dim; i0 += 32) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = lane; j < 4 * p.dim; j += 32) {
+                const float hj = h[j];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] += p.w2[static_cast<long long>(i0 + r) * 4 * p.dim + j] * hj;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float a = warp_sum_f(acc[r]);
+                if (lane == 0) tm[i0 + r] = a + p.b2[i0 + r];
+            }
         }
         __syncthreads();
     }

@@ -807,6 +807,7 @@ __global__ void __launch_bounds__(128) embed_bwd_du_kernel(const EmbedBwdParams 
     if (k >= K) return;
     const int j0 = blockIdx.z * jslice, j1 = min(p.J, j0 + jslice);
     float a = 0.f;
+#pragma unroll 8
     for (int j = j0; j < j1; ++j) a = fmaf(__ldg(p.dE + static_cast<long long>(n) * p.J + j), __ldg(p.wcat + static_cast<long long>(j) * K + k), a);
     atomicAdd(p.du + static_cast<long long>(n) * K + k, a);
 }
@@ -831,24 +832,40 @@ __global__ void __launch_bounds__(256) embed_bwd_time_kernel(const EmbedBwdParam
         e[j + half] = cosf(arg);
     }
     __syncthreads();
-    for (int i = warp; i < D4; i += 8) {
-        float acc = 0.f;
-        for (int j = lane; j < dim; j += 32) acc += p.w0[static_cast<long long>(i) * dim + j] * e[j];
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            h0[i] = acc + p.b0[i];
-            hm[i] = mish_precise_f(h0[i]);
+    // four output rows per warp iteration: their weight loads are in flight together (the kernel is pure latency)
+    for (int i0 = warp * 4; i0 < D4; i0 += 32) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = lane; j < dim; j += 32) {
+            const float ej = e[j];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(__ldg(p.w0 + static_cast<long long>(i0 + r) * dim + j), ej, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float a = warp_sum(acc[r]);
+            if (lane == 0) {
+                h0[i0 + r] = a + p.b0[i0 + r];
+                hm[i0 + r] = mish_precise_f(h0[i0 + r]);
+            }
         }
     }
     __syncthreads();
-    for (int i = warp; i < dim; i += 8) {
-        float acc = 0.f;
-        for (int j = lane; j < D4; j += 32) acc += p.w2[static_cast<long long>(i) * D4 + j] * hm[j];
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            tm[i] = acc + p.b2[i];
-            dtm[i] = p.du[static_cast<long long>(n) * K + i] * mish_grad_precise(tm[i]);
-            atomicAdd(p.db2 + i, dtm[i]);
+    for (int i0 = warp * 4; i0 < dim; i0 += 32) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = lane; j < D4; j += 32) {
+            const float hj = hm[j];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(__ldg(p.w2 + static_cast<long long>(i0 + r) * D4 + j), hj, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float a = warp_sum(acc[r]);
+            if (lane == 0) {
+                const int i = i0 + r;
+                tm[i] = a + p.b2[i];
+                dtm[i] = p.du[static_cast<long long>(n) * K + i] * mish_grad_precise(tm[i]);
+                atomicAdd(p.db2 + i, dtm[i]);
+            }
         }
     }
     __syncthreads();
@@ -859,7 +876,8 @@ __global__ void __launch_bounds__(256) embed_bwd_time_kernel(const EmbedBwdParam
     }
     for (int j = threadIdx.x; j < D4; j += blockDim.x) {
         float a = 0.f;
-        for (int i = 0; i < dim; ++i) a = fmaf(p.w2[static_cast<long long>(i) * D4 + j], dtm[i], a);
+#pragma unroll 8
+        for (int i = 0; i < dim; ++i) a = fmaf(__ldg(p.w2 + static_cast<long long>(i) * D4 + j), dtm[i], a);
         dh0[j] = a * mish_grad_precise(h0[j]);
         atomicAdd(p.db0 + j, dh0[j]);
     }
