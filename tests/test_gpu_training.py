@@ -249,6 +249,11 @@ def test_cuda_graph_replay_equals_eager_steps():
         losses = [float(ft.train_step(x0, mask, cond, t, spk, reference_z(x0.shape, i))) for i in range(6)]
         assert (len(ft._graphs) == 1) == graph and ft.step_count == 6
         runs.append((losses, ft.P.clone()))
+        if graph:   # hyper-parameters are baked into the captured graph: changing one must drop it
+            frozen = ft.P.clone()
+            ft.lr = 0.0
+            ft.train_step(x0, mask, cond, t, spk, reference_z(x0.shape, 6))
+            assert len(ft._graphs) == 0 and torch.equal(ft.P, frozen)
         ft.close()
     (l0, p0), (l1, p1) = runs
     assert l0 == pytest.approx(l1, rel=2e-3)              # fp32 atomics reorder sums between runs

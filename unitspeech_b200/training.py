@@ -215,6 +215,15 @@ class FineTuner:
         self._packed = False
 
     # ------------------------------------------------------------------------------------------------ plumbing
+    _BAKED = ("lr", "betas", "eps", "max_norm", "loss_scale", "overlap_wgrad")
+
+    def __setattr__(self, name, value):
+        # hyper-parameters are kernel arguments baked into a captured iteration: changing one drops the captured graphs
+        if name in FineTuner._BAKED and getattr(self, "_graphs", None):
+            self._graphs.clear()
+            self._eager_steps.clear()
+        object.__setattr__(self, name, value)
+
     def close(self):
         if getattr(self, "h", None) and self._trace is None:
             torch.cuda.synchronize(self.dev)
