@@ -54,3 +54,40 @@ def test_step_call_sequence(dim, mults, B, T):
     assert c["usb_t_wgrad"] == (n_conv_params - n_attn) + n_split + n_attn + n_attn
     names = [n for n, _ in trace]
     assert names.index("usb_t_loss") < names.index("usb_t_loss_grad") < names.index("usb_t_embed_bwd") < names.index("usb_t_adam")
+
+
+def test_training_layout_round_trip_and_operand_order():
+    """Conv master weights live in the forward operand layout; the conversion is exact, invertible and matches the order
+    the kernels address (tap-major rows of contiguous input channels; ConvTranspose as four phase matrices)."""
+    from unitspeech_b200.training import K1, K3S1, K3S2, KT4, to_reference_layout, to_train_layout
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(6, 4, 3, 3, generator=g)
+    for kind in (K3S1, K3S2):
+        t = to_train_layout(kind, w)
+        assert torch.equal(to_reference_layout(kind, t.reshape(-1), w.shape), w)
+        assert t.reshape(6, 9, 4)[2, 5, 3] == w[2, 3, 5 // 3, 5 % 3]
+    w1 = torch.randn(5, 7, 1, 1, generator=g)
+    assert torch.equal(to_reference_layout(K1, to_train_layout(K1, w1).reshape(-1), w1.shape), w1)
+    wt = torch.randn(5, 7, 4, 4, generator=g)                       # ConvTranspose2d weight: (Cin, Cout, 4, 4)
+    t = to_train_layout(KT4, wt)
+    assert torch.equal(to_reference_layout(KT4, t.reshape(-1), wt.shape), wt)
+    flat = t.reshape(-1)
+    for ph in range(2):
+        for pw in range(2):
+            for a in range(2):
+                for b in range(2):
+                    kh = (1 if a == 0 else 3) if ph == 0 else (0 if a == 0 else 2)     # engine.cu pack_conv_host
+                    kw = (1 if b == 0 else 3) if pw == 0 else (0 if b == 0 else 2)
+                    assert flat[(((ph * 2 + pw) * 7 + 3) * 4 + (a * 2 + b)) * 5 + 2] == wt[2, 3, kh, kw]
+
+
+def test_state_dict_round_trip_through_the_training_layout():
+    trace = []
+    ft = FineTuner(dim=64, dim_mults=(1, 2), _trace_calls=trace)
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=7, out_scale=1.0)
+    ft.load_state_dict(p)
+    back = ft.state_dict()
+    assert list(back) == list(ft.shapes) and set(back) == set(p)
+    assert all(torch.equal(back[k], p[k]) for k in p)
+    with pytest.raises(KeyError):
+        ft.load_state_dict({k: v for k, v in p.items() if k != "text_uncon"})
