@@ -299,15 +299,24 @@ def run_gpu_arm(args):
                      "attention_GBps": at_bytes / (at_ms / 1e3) / 1e9 if at_ms > 0 else None,
                      "other_GBps": ot_bytes / (ot_ms / 1e3) / 1e9 if ot_ms > 0 else None}
         # ---- optional second stage (BASELINE.json configs[3]): BigVGAN vocoder on this batch's mels
+        # (the two optional legs below report their own failure in the JSON line instead of taking the headline down)
         vocoder = None
         if not args.no_vocoder:
-            vocoder = vocoder_leg(dev, B, T, elapsed_ms / args.steps, peaks)
+            try:
+                vocoder = vocoder_leg(dev, B, T, elapsed_ms / args.steps, peaks)
+            except Exception as exc:  # noqa: BLE001
+                print(f"vocoder leg failed: {exc!r}", file=sys.stderr)
+                vocoder = {"error": repr(exc)}
         # ---- optional: speaker-adaptive fine-tuning step (BASELINE.json configs[4])
         finetune = None
         if not args.no_finetune:
             dec._release()            # frees the sampler's workspace before the training buffers are allocated
             torch.cuda.empty_cache()
-            finetune = finetune_leg(dev, params, peaks, with_cpu=not args.no_cpu and world == 1)
+            try:
+                finetune = finetune_leg(dev, params, peaks, with_cpu=not args.no_cpu and world == 1)
+            except Exception as exc:  # noqa: BLE001
+                print(f"fine-tune leg failed: {exc!r}", file=sys.stderr)
+                finetune = {"error": repr(exc)}
         # ---- CPU baseline on this box's host cores (bounded sample)
         cpu = None
         if not args.no_cpu and world == 1:          # the CPU baseline is an N = 1 figure (torchrun also pins OMP to 1 thread)
