@@ -33,6 +33,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU reference arm (rank 0 only, the other ranks exit at once) is
+# specified to use all the host threads it can, and OpenMP reads the variable when torch is first imported
+if "reference" in sys.argv and os.environ.get("RANK", "0") == "0":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ.pop("MKL_NUM_THREADS", None)
+
 import torch  # noqa: E402
 
 METRIC = "mel frames/s of 50-step CFG reverse diffusion"
