@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 
 # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU reference arm (rank 0 only, the other ranks exit at once) is
 # specified to use all the host threads it can, and OpenMP reads the variable when torch is first imported
-if "reference" in sys.argv and os.environ.get("RANK", "0") == "0":
+if any(a in ("reference", "--impl=reference") for a in sys.argv) and os.environ.get("RANK", "0") == "0":
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     os.environ.pop("MKL_NUM_THREADS", None)
 
