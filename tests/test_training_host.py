@@ -91,3 +91,32 @@ def test_state_dict_round_trip_through_the_training_layout():
     assert all(torch.equal(back[k], p[k]) for k in p)
     with pytest.raises(KeyError):
         ft.load_state_dict({k: v for k, v in p.items() if k != "text_uncon"})
+
+
+def test_every_trainable_parameter_receives_a_gradient_writer():
+    """Graph-walk completeness without a GPU: in the recorded ABI call sequence of one backward pass, the gradient view
+    of every parameter the objective depends on is handed to some kernel (directly, or as part of the stacked
+    ResnetBlock.mlp buffers); only the CFG unconditionals (unused by loss_t, unitspeech.py:393-405) get none."""
+    import ctypes
+    trace = []
+    ft = FineTuner(dim=128, dim_mults=(1, 2, 4, 8), _trace_calls=trace)
+    ft.load_state_dict(O.harness_params(seed=3, out_scale=1.0))
+    x0, mask, cond, spk = case_inputs(2, 16, [16, 11])
+    ft.zero_grad()
+    ft.forward(x0, mask, cond, torch.tensor([0.3, 0.7]), spk, torch.randn(x0.shape))
+    n_fwd = len(trace)
+    ft.backward()
+    ptrs = set()
+    for _, args in trace[n_fwd:]:
+        for a in args:
+            if isinstance(a, ctypes.c_void_p) and a.value:
+                ptrs.add(a.value)
+    stacked = [(ft.dwcat.data_ptr(), ft.dwcat.numel() * 4), (ft.dbcat.data_ptr(), ft.dbcat.numel() * 4)]
+    assert ft.dwcat.data_ptr() in ptrs and ft.dbcat.data_ptr() in ptrs
+    missing = []
+    for k, g in ft.grads.items():
+        a = g.data_ptr()
+        if a in ptrs or any(lo <= a < lo + n for lo, n in stacked):
+            continue
+        missing.append(k)
+    assert sorted(missing) == ["spk_uncon", "text_uncon"], missing
