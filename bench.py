@@ -4,19 +4,25 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 One "step" = one full pass of the hot path over one batch: a 50-step text+speaker classifier-free-guided reverse
-diffusion (150 U-Net evaluations per utterance) of 16 utterances x 512 frames per GPU (BASELINE.json configs[1]).
-With N > 1 every rank samples its own 16 utterances (weak scaling, sharded by utterance, no collective in the step
-loop); the final mels are all-gathered with NCCL inside the timed region.
+diffusion (150 U-Net evaluations per utterance) of 32 utterances x 1000 frames per GPU -- the per-GPU shard of
+BASELINE.json configs[2] (256 utterances x 1000 frames over 8 GPUs), so `--gpus 8` IS configs[2] and smaller N are the
+same shard on fewer GPUs (weak scaling).  The job is `32 N` utterances sharded by utterance through the product's own
+`unitspeech_b200.sharding.sample_sharded` (independent sampling loops, no collective in the step loop); the mels are
+all-gathered with NCCL inside the timed region.
 
-Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same metric through the
-public API with pinned HOST tensors (H2D of z/cond/mask/spk/noise and D2H of the mels inside the timed region);
-`roofline` = the tcgen05 implicit-GEMM conv kernel (algorithmic conv FLOPs / its summed CUDA-event time, measured in a
-separate profiled pass of the same workload, against the measured bf16 GEMM peak); `cpu_baseline` = the CPU port of the
-reference algorithm (oracle/) on a bounded sample of the same workload.
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same metric over the same
+number of steps through the public API with pinned HOST tensors (H2D of z/cond/mask/spk/noise and D2H of the mels inside
+the timed region, gather included); `roofline` = the tcgen05 implicit-GEMM conv kernels (algorithmic conv FLOPs / their
+summed CUDA-event time, measured in a separate profiled pass of the same workload, against the measured bf16 GEMM peak;
+`traffic` from the committed ncu capture under profiles/); `cpu_baseline` = the unmodified reference (baseline/_ref,
+installed by scripts/install_ref.py; the oracle port only if that is absent) on a bounded sample of the same workload;
+`gpu_eager_baseline` = the same reference run eagerly by PyTorch/cuDNN on this GPU (fp32 and TF32);
+`latency_stage` = one utterance x 256 frames (the reference callers' B = 1 pattern, inference.py:128);
+`secondary_16x512` = BASELINE.json configs[1].
 
-`--impl reference` times the CPU port of the reference (oracle/unitspeech_oracle.py, pinned to the reference's outputs
-by tests/golden) on the host cores: the upstream package is a research script tree whose decoder imports need stubs
- and its path is pure PyTorch, so the oracle port is the reference arm that can travel to the GPU box.
+`--impl reference` times the reference's own CPU implementation of the path on the host cores: the UNMODIFIED
+`UnitSpeech.forward` (unitspeech/unitspeech.py:387-391) imported from baseline/_ref through oracle/ref_shim.py, one
+utterance of the same workload per step, with all host threads.
 """
 
 from __future__ import annotations
@@ -45,10 +51,18 @@ METRIC = "mel frames/s of 50-step CFG reverse diffusion"
 UNIT = "frames/s"
 N_STEPS = 50                      # diffusion steps per pass
 TG, SG = 1.0, 1.0                 # text / speaker guidance scales
-BATCH, FRAMES = 16, 512           # per-GPU batch (BASELINE.json configs[1])
+BATCH, FRAMES = 32, 1000          # per-GPU shard of BASELINE.json configs[2] (256 x 1000 over 8 GPUs)
 N_FEATS, SPK = 80, 256
 CONV_FLOP_PER_FRAME_EVAL = 647.27e6   # conv FLOPs per mel frame per estimator evaluation
+VOCODER_FLOP_PER_FRAME = 2 * 901859328.0   # BigVGAN public config, FLOPs per mel frame
 SCALE = 1.0 / 512                 # harness scale keeping the untrained sampler O(1)
+
+
+def workload_name(B: int, T: int) -> str:
+    return (f"UnitSpeech decoder (random-init pretrained_decoder architecture, 119.1M params), 50-step text+speaker CFG "
+            f"(1.0/1.0) reverse diffusion, {B} utterances x {T} frames per GPU"
+            + (" = the per-GPU shard of BASELINE.json configs[2] (256 x 1000 over 8 GPUs)" if (B, T) == (32, 1000) else "")
+            + "; sharded by utterance across GPUs")
 
 
 def _peaks():
@@ -59,6 +73,18 @@ def _peaks():
         return {"tensor": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "tensor_burst": float(p["bf16_tflops"]),
                 "hbm": float(p["hbm_gbs"]), "src": "measured"}
     return {"tensor": 1400.0, "tensor_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
+
+
+def _profile_json(name: str):
+    """Committed evidence under profiles/ (ncu-derived traffic, per-step drift) that the line quotes; None if absent."""
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        return None
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -128,30 +154,59 @@ def harness_weights(dec=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU arm (oracle port of the reference algorithm)
+# CPU arm: the unmodified reference from baseline/_ref (scripts/install_ref.py), else the oracle port
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_sample(params, threads: int, T: int = FRAMES, diffusion_steps: int = 1):
-    """One utterance x T frames x `diffusion_steps` CFG steps on the host; returns (seconds, frames/s of the 50-step job)."""
-    from oracle import unitspeech_oracle as O
-    torch.set_num_threads(threads)
-    n = max(2, diffusion_steps)
-    z, mask, cond, spk, noise = make_inputs(7, 1, T, N_STEPS)
-    # run the first `n` steps of the real 50-step schedule: same per-step cost as any other step
-    tb = O.schedule_tables(N_STEPS, 0.05, 20.0)
-    times = O.step_times(N_STEPS)
-    xt = z * mask
-    tu = params["text_uncon"].repeat(1, 1, T)
-    su = (params["spk_uncon"] / params["spk_uncon"].norm()).repeat(1, 1, 1)
-    est = lambda x_, m_, mu_, t_, s_: O.estimator_forward(params, x_, m_, mu_, t_, s_, 128, (1, 2, 4, 8))  # noqa: E731
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        for i in range(n):
-            t = times[i] * torch.ones(1)
-            score = O.cfg_score(params, xt, mask, cond, t, spk, tu, su, TG, SG, est)
-            xt = O.sampler_step(tb, N_STEPS - 1 - i, xt, score, noise[i], mask)
-    dt = time.perf_counter() - t0
-    per_step = dt / n
-    return dt, T / (N_STEPS * per_step), n
+class CpuReference:
+    """The reference decoder on the host cores.  kind "reference": the unmodified upstream class
+    (unitspeech/unitspeech.py:220) imported from baseline/_ref through oracle/ref_shim.py, called through its own
+    `forward` per utterance (B = 1 is its only correct batch, SURVEY F2) with the per-step randn draws injected;
+    kind "port": oracle/unitspeech_oracle.py (only when baseline/_ref is absent)."""
+
+    def __init__(self, params, threads: int, device: str = "cpu"):
+        from oracle import ref_shim
+        self.threads, self.device = threads, torch.device(device)
+        torch.set_num_threads(threads)
+        self.params = {k: v.to(self.device) for k, v in params.items()}
+        self.shim = ref_shim
+        if ref_shim.installed_reference_available():
+            U = ref_shim.load_reference(root=ref_shim.INSTALLED_REF)
+            dec = U.UnitSpeech(N_FEATS, 128, (1, 2, 4, 8), 0.05, 20, 1000, SPK)
+            dec.load_state_dict(params, strict=True)
+            self.dec = dec.to(self.device).eval()
+            self.kind = "reference"
+        else:
+            self.dec = None
+            self.kind = "port"
+
+    def sample(self, z, mask, cond, spk, noise, n: int, tg: float, sg: float):
+        mv = lambda a: a.to(self.device)  # noqa: E731
+        with torch.no_grad():
+            if self.dec is not None:
+                return self.shim.run_reference_per_utterance(self.dec, mv(z), mv(mask), mv(cond), mv(spk), mv(noise), n, tg, sg)
+            from oracle import unitspeech_oracle as O
+            return O.reverse_diffusion(self.params, mv(z), mv(mask), mv(cond), mv(spk), n, tg, sg, noise=mv(noise))
+
+    def timed(self, T: int, n: int, tg: float, sg: float, seed: int = 7):
+        """One utterance x T frames x n diffusion steps through the reference's public call; returns seconds."""
+        z, mask, cond, spk, noise = make_inputs(seed, 1, T, n)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = self.sample(z, mask, cond, spk, noise, n, tg, sg)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert torch.isfinite(out).all()
+        return dt
+
+
+REF_DIFFUSION_STEPS = 2     # diffusion steps per reference-arm bench step (n_timesteps = 2 is the smallest call the reference supports)
+
+
+def reference_sample_text(T: int, n: int) -> str:
+    return (f"1 utterance x {T} frames x n_timesteps={n} text+speaker CFG diffusion steps ({3 * n} U-Net evaluations) through the "
+            f"reference's UnitSpeech.forward per bench step; per-step cost is independent of n_timesteps, so "
+            f"frames/s of the 50-step job = {T} / (50 x seconds per diffusion step)")
 
 
 def run_reference_arm(args):
@@ -160,26 +215,36 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     params = harness_weights()
-    vals = []
-    ref_steps = 4   # CFG diffusion steps per bench step: ~4 s of CPU work each
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_sample(params, threads, diffusion_steps=2)
+    ref = CpuReference(params, threads)
+    T, n = args.frames, REF_DIFFUSION_STEPS
+    for _ in range(min(max(args.warmup, 0), 1)):      # one warm-up call is enough for a CPU arm (thread pool, allocator)
+        ref.timed(T, n, TG, SG)
+    per_step = []
     t_total = 0.0
-    for _ in range(args.steps):
-        dt, fps, n = cpu_sample(params, threads, diffusion_steps=ref_steps)
-        vals.append(fps)
+    for i in range(args.steps):
+        dt = ref.timed(T, n, TG, SG, seed=7 + i)
+        per_step.append(dt / n)
         t_total += dt
-    v = statistics.median(vals)
-    sample = (f"1 utterance x {FRAMES} frames x {ref_steps} of the 50 CFG diffusion steps ({3 * ref_steps} U-Net evaluations) "
-              f"per bench step, scaled to the 50-step job")
+    v = T / (N_STEPS * statistics.median(per_step))
+    sample = reference_sample_text(T, n)
+    cfg1 = None
+    if not args.no_config1:
+        # BASELINE.md section 3 / SURVEY 8(d6): BASELINE.json configs[0] exactly -- 1 utterance x 256 frames, 50 steps, no CFG,
+        # the whole call, best of 3
+        best = min(ref.timed(256, N_STEPS, 0.0, 0.0, seed=3) for _ in range(3))
+        cfg1 = {"workload": "BASELINE.json configs[0]: 1 utterance x 80 mel x 256 frames, 50 steps, no CFG, fp32 CPU, whole call",
+                "seconds_best_of_3": best, "value": 256 / best, "unit": UNIT, "rtf": best / (256 * 256 / 22050.0)}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"UnitSpeech decoder, 50-step text+speaker CFG (1.0/1.0) reverse diffusion, {BATCH} utt x {FRAMES} frames per GPU",
-                   "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args.batch, T), "batch_per_gpu": args.batch, "frames": T,
+                   "diffusion_steps": N_STEPS, "cfg_scales": [TG, SG], "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": ref.kind, "sample": sample,
+                         "install": "baseline/_ref (unmodified reference files, scripts/install_ref.py)" if ref.kind == "reference"
+                         else "oracle/unitspeech_oracle.py (baseline/_ref absent)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config1_cpu": cfg1,
         "gpu_launches": 0,
     }
     _emit(line)
@@ -188,9 +253,28 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+def _new_decoder(dev, params=None):
+    from unitspeech_b200 import UnitSpeech
+    dec = UnitSpeech(N_FEATS, 128, (1, 2, 4, 8), beta_min=0.05, beta_max=20, pe_scale=1000, spk_emb_dim=SPK)
+    params = harness_weights(dec) if params is None else params
+    dec.load_state_dict(params)
+    return dec.to(dev).eval(), params
+
+
+def _time_passes(fn, steps, sync):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    sync()
+    return e0.elapsed_time(e1), out
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
-    from unitspeech_b200 import UnitSpeech
+    from unitspeech_b200.sharding import sample_sharded, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,22 +287,22 @@ def run_gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    dec = UnitSpeech(N_FEATS, 128, (1, 2, 4, 8), beta_min=0.05, beta_max=20, pe_scale=1000, spk_emb_dim=SPK)
-    params = harness_weights(dec)
-    dec.load_state_dict(params)
-    dec = dec.to(dev).eval()
-
+    dec, params = _new_decoder(dev)
     B, T, n = args.batch, args.frames, N_STEPS
-    z, mask, cond, spk, noise = make_inputs(100 + rank, B, T, n)
-    host = [t.pin_memory() for t in (z, mask, cond, spk, noise)]
-    zd, md, cd, sd, nd = (t.to(dev) for t in (z, mask, cond, spk, noise))
-    from unitspeech_b200.sharding import gather_utterances
+    n_job = world * B                               # utterances of the whole job; this rank samples shard_range(n_job, rank, world)
+    b0, b1 = shard_range(n_job, rank, world)
+    assert b1 - b0 == B
+    # the job's small tensors exist in full on every rank (as a caller of sample_sharded holds them); the per-step noise
+    # (50x larger) only for the rank's own utterances -- sample_sharded(noise_is_local=True)
+    zj, mj, cj, sj, _ = make_inputs(100, n_job, T, 1)
+    g = torch.Generator().manual_seed(1000 + rank)
+    noise = torch.randn(n, B, N_FEATS, T, generator=g) * SCALE
+    host = [t.pin_memory() for t in (zj, mj, cj, sj, noise)]
+    zd, md, cd, sd, nd = (t.to(dev) for t in host)
 
-    def one_pass():
-        out = dec(zd, md, cd, sd, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=nd)
-        if world > 1:
-            gather_utterances(out, world * B)      # the job's mels on every rank (NCCL all_gather)
-        return out
+    def one_pass(tensors=(zd, md, cd, sd, nd)):
+        z_, m_, c_, s_, n_ = tensors
+        return sample_sharded(dec, z_, m_, c_, s_, n, TG, SG, noise=n_, noise_is_local=True)
 
     def sync():
         if world > 1:
@@ -228,54 +312,40 @@ def run_gpu_arm(args):
     for _ in range(max(args.warmup, 0)):
         out = one_pass()
     sync()
-    assert torch.isfinite(out).all(), "non-finite mel from the CUDA decoder"
+    assert out.shape[0] == n_job and torch.isfinite(out).all(), "non-finite mel from the CUDA decoder"
+    sat = dec.saturation_count()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = dec.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    e0.record()
-    for _ in range(args.steps):
-        one_pass()
-    e1.record()
-    sync()
-    elapsed_ms = e0.elapsed_time(e1)
+    elapsed_ms, _ = _time_passes(one_pass, args.steps, sync)
     launches = dec.launch_count - launches0
     clocks = sampler.finish()
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    frames_total = world * B * T * args.steps
+    elapsed_ms = max_over_ranks(elapsed_ms)
+    frames_total = n_job * T * args.steps
     value = frames_total / (elapsed_ms / 1000.0)
 
-    # ---- end-to-end through the public API with pinned host tensors (copies inside the timed region)
-    hz, hm, hc, hs, hn = host
-    for _ in range(1):
-        dec(hz, hm, hc, hs, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=hn)
-    sync()
-    e2e_steps = max(1, min(args.steps, 3))
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(e2e_steps):
-        out_h = dec(hz, hm, hc, hs, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=hn)
-    f1.record()
-    sync()
-    e2e_ms = f0.elapsed_time(f1)
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * T * e2e_steps / (float(t.item()) / 1000.0)
-    h2d = sum(x.numel() * 4 for x in host)
-    d2h = out_h.numel() * 4
+    # ---- end-to-end through the public API with pinned host tensors: H2D of the rank's inputs, D2H of its mels and the
+    # gather of the job's mels inside the timed region, over the same number of steps as `value`
+    one_pass(host)
+    e2e_ms, out_h = _time_passes(lambda: one_pass(host), args.steps, sync)
+    e2e_ms = max_over_ranks(e2e_ms)
+    e2e_value = frames_total / (e2e_ms / 1000.0)
+    h2d = sum(x[b0:b1].numel() * 4 for x in host[:4]) + host[4].numel() * 4     # per rank and step
+    d2h = B * N_FEATS * T * 4
 
     line = None
     if rank == 0:
         # ---- roofline: one profiled pass of the same workload (per-launch CUDA events on the launching stream)
         peaks = _peaks()
         dec.set_profiling(True)
-        dec(zd, md, cd, sd, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=nd)   # rank-local: no collective here
+        dec(zd[b0:b1], md[b0:b1], cd[b0:b1], sd[b0:b1], n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=nd)   # rank-local
         torch.cuda.synchronize(dev)
         prof = dec.get_profile()
         dec.set_profiling(False)
@@ -285,76 +355,141 @@ def run_gpu_arm(args):
         ot_ms, ot_bytes, ot_n = prof["other"]
         achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
         total_prof_ms = conv_ms + gn_ms + at_ms + ot_ms
+        traffic = _profile_json("r2_traffic.json") or {}
+        conv_traffic = (traffic.get(f"{B}x{T}") or {}).get("conv_igemm")
         roofline = {
-            "kernel": "conv_igemm_kernel (tcgen05.mma kind::f16, fp16 operands, fp32 TMEM accumulators)",
+            "kernel": "conv_igemm_{halo,swapped,}_kernel (tcgen05.mma kind::f16, fp16 operands, fp32 TMEM accumulators), all 60 conv launches of an evaluation",
             "bound": "tensor", "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tensor"] if achieved else None, "traffic": None,
+            "frac": achieved / peaks["tensor"] if achieved else None,
+            "traffic": conv_traffic["dram_bytes_per_launch"] if conv_traffic else None,
+            "traffic_note": (conv_traffic or {}).get("note"),
             "peak_source": f"{peaks['src']} bf16 GEMM, sustained (burst {peaks['tensor_burst']})",
             "launches_per_pass": conv_n, "ms_per_pass": conv_ms, "share_of_pass": conv_ms / total_prof_ms,
             "flop_per_launch_avg": conv_flop / max(conv_n, 1),
+            "algorithmic_bytes_per_launch_avg": (conv_traffic or {}).get("algorithmic_bytes_per_launch"),
+            "whole_step_frac": CONV_FLOP_PER_FRAME_EVAL * 3 * N_STEPS * (value / world) / 1e12 / peaks["tensor"],
             "frames_per_s_at_peak": peaks["tensor"] * 1e12 / (CONV_FLOP_PER_FRAME_EVAL * 3 * N_STEPS),
         }
         gn_gbs = gn_bytes / (gn_ms / 1e3) / 1e9 if gn_ms > 0 else None
+        gn_traffic = (traffic.get(f"{B}x{T}") or {}).get("gn_apply")
         roofline_hbm = {
             "kernel": "gn_apply_kernel (GroupNorm apply + Mish + embedding/residual + mask, fp16 in/out)",
             "bound": "hbm", "achieved": gn_gbs, "peak": peaks["hbm"], "unit": "GB/s",
-            "frac": gn_gbs / peaks["hbm"] if gn_gbs else None, "traffic": None, "launches_per_pass": gn_n,
+            "frac": gn_gbs / peaks["hbm"] if gn_gbs else None,
+            "traffic": gn_traffic["dram_bytes_per_launch"] if gn_traffic else None, "launches_per_pass": gn_n,
             "ms_per_pass": gn_ms, "share_of_pass": gn_ms / total_prof_ms,
         }
         breakdown = {"conv_igemm_ms": conv_ms, "gn_apply_ms": gn_ms, "attention_ms": at_ms, "other_ms": ot_ms,
                      "attention_GBps": at_bytes / (at_ms / 1e3) / 1e9 if at_ms > 0 else None,
                      "other_GBps": ot_bytes / (ot_ms / 1e3) / 1e9 if ot_ms > 0 else None}
-        # ---- optional second stage (BASELINE.json configs[3]): BigVGAN vocoder on this batch's mels
-        # (the two optional legs below report their own failure in the JSON line instead of taking the headline down)
-        vocoder = None
+        legs = {}
+
+        def leg(name, fn):
+            # the optional legs report their own failure in the JSON line instead of taking the headline down
+            try:
+                legs[name] = fn()
+            except Exception as exc:  # noqa: BLE001
+                print(f"{name} leg failed: {exc!r}", file=sys.stderr)
+                legs[name] = {"error": repr(exc)}
+
+        if not args.no_secondary:
+            leg("secondary_16x512", lambda: small_config_leg(dec, dev, 16, 512, 3, peaks, "BASELINE.json configs[1]"))
+            leg("latency_stage", lambda: small_config_leg(dec, dev, 1, 256, 5, peaks,
+                                                          "one utterance x 256 frames (2.97 s of speech), the reference callers' "
+                                                          "B = 1 pattern (inference.py:128)"))
         if not args.no_vocoder:
-            try:
-                vocoder = vocoder_leg(dev, B, T, elapsed_ms / args.steps, peaks)
-            except Exception as exc:  # noqa: BLE001
-                print(f"vocoder leg failed: {exc!r}", file=sys.stderr)
-                vocoder = {"error": repr(exc)}
-        # ---- optional: speaker-adaptive fine-tuning step (BASELINE.json configs[4])
-        finetune = None
+            leg("vocoder_stage", lambda: vocoder_leg(dev, 16, 512, None, peaks))
+        dec._release()            # frees the sampler's workspace before the training / eager buffers are allocated
+        torch.cuda.empty_cache()
         if not args.no_finetune:
-            dec._release()            # frees the sampler's workspace before the training buffers are allocated
-            torch.cuda.empty_cache()
-            try:
-                finetune = finetune_leg(dev, params, peaks, with_cpu=not args.no_cpu and world == 1)
-            except Exception as exc:  # noqa: BLE001
-                print(f"fine-tune leg failed: {exc!r}", file=sys.stderr)
-                finetune = {"error": repr(exc)}
-        # ---- CPU baseline on this box's host cores (bounded sample)
+            leg("finetune_stage", lambda: finetune_leg(dev, params, peaks, with_cpu=not args.no_cpu and world == 1))
+        if not args.no_eager and world == 1:
+            leg("gpu_eager_baseline", lambda: eager_leg(dev, params, T))
+        # ---- CPU baseline on this box's host cores (bounded sample; an N = 1 figure: torchrun pins OMP to 1 thread)
         cpu = None
-        if not args.no_cpu and world == 1:          # the CPU baseline is an N = 1 figure (torchrun also pins OMP to 1 thread)
+        if not args.no_cpu and world == 1:
             threads = os.cpu_count() or 1
-            dt, fps, nst = cpu_sample(params, threads, diffusion_steps=12)   # ~10-20 s of CPU work
-            cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"1 utterance x {T} frames x {nst} of the 50 CFG diffusion steps ({3 * nst} U-Net evaluations, {dt:.1f} s), scaled to the 50-step job"}
+            ref = CpuReference(params, threads)
+            ref.timed(T, REF_DIFFUSION_STEPS, TG, SG)
+            dts = [ref.timed(T, REF_DIFFUSION_STEPS, TG, SG, seed=8 + i) for i in range(3)]      # ~10-20 s of CPU work
+            fps = T / (N_STEPS * statistics.median(dts) / REF_DIFFUSION_STEPS)
+            cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": ref.kind,
+                   "sample": reference_sample_text(T, REF_DIFFUSION_STEPS) + f"; median of 3 calls ({sum(dts):.1f} s)"}
+        drift = _profile_json(f"r2_drift_T{T}.json")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": f"UnitSpeech decoder (random-init pretrained_decoder architecture, 119.1M params), "
-                                   f"50-step text+speaker CFG (1.0/1.0) reverse diffusion, {B} utterances x {T} frames "
-                                   f"per GPU (BASELINE.json configs[1]); sharded by utterance across GPUs",
-                       "batch_per_gpu": B, "frames": T, "diffusion_steps": n, "cfg_scales": [TG, SG],
-                       "estimator_evals_per_step": 3, "parallelism": f"utterance-sharded x{world}",
-                       "l2": "per-step working set (multi-GB activations, 131 MB noise) far exceeds the 126 MB L2; no explicit flush",
-                       "rtf": (elapsed_ms / 1000.0 / args.steps) / (B * T * 256 / 22050.0)},
+            "config": {"workload": workload_name(B, T),
+                       "batch_per_gpu": B, "frames": T, "job_utterances": n_job, "diffusion_steps": n, "cfg_scales": [TG, SG],
+                       "estimator_evals_per_step": 3, "parallelism": f"utterance-sharded x{world} (sample_sharded)",
+                       "l2": "per-step working set (tens of GB of activations, 0.5 GB of noise) far exceeds the 126 MB L2; no explicit flush",
+                       "rtf": (elapsed_ms / 1000.0 / args.steps) / (n_job * T * 256 / 22050.0)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": args.steps, "ms_per_step": e2e_ms / args.steps, "includes_gather": world > 1},
             "gpu_launches": launches,
+            "fp16_saturation_events": sat,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "breakdown_ms_per_pass": breakdown,
             "cpu_baseline": cpu,
-            "vocoder_stage": vocoder,
-            "finetune_stage": finetune,
+            "per_step_drift": ({"file": f"profiles/r2_drift_T{T}.json", **{k: drift[k] for k in drift if k != "per_step"}}
+                               if drift else None),
         }
+        line.update(legs)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         _emit(line)
+
+
+def small_config_leg(dec, dev, B, T, passes, peaks, what):
+    """A second workload on the same handle: ms per 50-step CFG pass (CUDA events, inputs resident) and the conv class
+    against the tensor roofline from one profiled pass."""
+    n = N_STEPS
+    z, mask, cond, spk, noise = (t.to(dev) for t in make_inputs(5, B, T, n))
+    run = lambda: dec(z, mask, cond, spk, n, text_gradient_scale=TG, spk_gradient_scale=SG, noise=noise)  # noqa: E731
+    for _ in range(2):
+        run()
+    l0 = dec.launch_count
+    ms, _ = _time_passes(run, passes, lambda: torch.cuda.synchronize(dev))
+    launches = (dec.launch_count - l0) // passes
+    ms /= passes
+    dec.set_profiling(True)
+    run()
+    torch.cuda.synchronize(dev)
+    prof = dec.get_profile()
+    dec.set_profiling(False)
+    conv_ms, conv_flop, _ = prof["conv_igemm"]
+    # the profiled pass serialises on per-launch events; the conv fraction below uses the un-profiled pass time
+    flop = CONV_FLOP_PER_FRAME_EVAL * 3 * n * B * T
+    return {"workload": f"{B} x {T} frames, 50-step text+speaker CFG: {what}", "ms_per_pass": ms,
+            "frames_per_s": B * T / ms * 1e3, "rtf": ms / 1e3 / (B * T * 256 / 22050.0), "gpu_launches_per_pass": launches,
+            "whole_pass_TFLOPs": flop / ms / 1e9, "whole_pass_frac": flop / ms / 1e9 / peaks["tensor"],
+            "conv_class_TFLOPs_profiled": conv_flop / conv_ms / 1e9 if conv_ms > 0 else None,
+            "conv_class_frac_profiled": conv_flop / conv_ms / 1e9 / peaks["tensor"] if conv_ms > 0 else None}
+
+
+def eager_leg(dev, params, T):
+    """BASELINE.md section 3 'second baseline': the reference modules run EAGERLY by PyTorch/cuDNN on this same B200
+    (per-utterance B = 1, the only batch the reference supports), fp32 (cudnn.allow_tf32 = False, the parity oracle's
+    arithmetic) and TF32 (PyTorch's default): what a user of the reference gets on this GPU today."""
+    ref = CpuReference(params, os.cpu_count() or 1, device=str(dev))
+    out = {"what": "unmodified reference (baseline/_ref) eager on this GPU" if ref.kind == "reference" else "oracle port eager on this GPU",
+           "workload": f"1 utterance x {T} frames, 50-step text+speaker CFG (1.0/1.0), whole UnitSpeech.forward call", "unit": UNIT}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ref.timed(T, 2, TG, SG)
+            dt = ref.timed(T, N_STEPS, TG, SG)
+            out[f"frames_per_s_{name}"] = T / dt
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    del ref
+    torch.cuda.empty_cache()
+    return out
 
 
 def finetune_leg(dev, params, peaks, with_cpu=True, B=8, T=176, iters=30):
@@ -454,10 +589,13 @@ def vocoder_leg(dev, B, T, decoder_ms, peaks):
         "workload": f"BigVGAN 22 kHz/80-band generator (112.2M params, random init), {B} x {T} mel frames -> {B} x {T * 256} samples",
         "ms": ms, "mel_frames_per_s": B * T / ms * 1e3, "audio_seconds_per_s": B * T * 256 / 22050.0 / ms * 1e3,
         "gpu_launches": launches,
-        "pipeline_mel_frames_per_s": B * T / (decoder_ms + ms) * 1e3,
+        "pipeline_mel_frames_per_s": B * T / (decoder_ms + ms) * 1e3 if decoder_ms else None,
         "conv": {"kernel": "conv_igemm (1-D taps, H = 1)", "bound": "tensor", "ms": cm, "launches": cn,
-                 "achieved": cw / cm / 1e9, "peak": peaks["tensor"], "unit": "TFLOP/s (channels padded to 64)",
-                 "frac": cw / cm / 1e9 / peaks["tensor"]},
+                 # algorithmic FLOPs: SURVEY 8(d4) 1.804 GFLOP per mel frame (901 859 328 MAC), not the padded channel counts
+                 "achieved": VOCODER_FLOP_PER_FRAME * B * T / cm / 1e9, "peak": peaks["tensor"], "unit": "TFLOP/s (algorithmic)",
+                 "frac": VOCODER_FLOP_PER_FRAME * B * T / cm / 1e9 / peaks["tensor"],
+                 "padded_TFLOPs": cw / cm / 1e9},
+        "whole_stage_frac": VOCODER_FLOP_PER_FRAME * B * T / ms / 1e9 / peaks["tensor"],
         "snake_act": {"kernel": "snake_act_kernel (up x2 + Snake + low-pass + down x2 fused)", "bound": "hbm", "ms": am,
                       "launches": an, "achieved": aw / am / 1e6, "peak": peaks["hbm"], "unit": "GB/s (fp16 read + write)",
                       "frac": aw / am / 1e6 / peaks["hbm"]},
@@ -499,7 +637,13 @@ def _main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-vocoder", action="store_true", help="skip the vocoder-stage leg")
     ap.add_argument("--no-finetune", action="store_true", help="skip the fine-tune-iteration leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-this-GPU baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the 16 x 512 and 1 x 256 legs")
+    ap.add_argument("--no-config1", action="store_true", help="reference arm: skip the BASELINE configs[0] whole-call timing")
+    ap.add_argument("--headline-only", action="store_true", help="only value / e2e / roofline (no optional legs, no CPU baseline)")
     args = ap.parse_args()
+    if args.headline_only:
+        args.no_cpu = args.no_vocoder = args.no_finetune = args.no_eager = args.no_secondary = True
     if args.impl == "reference":
         run_reference_arm(args)
     else:

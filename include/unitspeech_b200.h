@@ -13,7 +13,8 @@
  *    failure on the calling thread.  Nothing throws across the ABI and there is no CPU fallback;
  *  - a handle is bound to one device and is not thread-safe; all work is enqueued on the given stream
  *    (pass the integer value of a cudaStream_t, 0 = legacy default stream); no hidden synchronisation except
- *    where stated (the *_host entry, workspace growth).
+ *    where stated (the *_host entries, the first call with a new (Be, T) shape or a larger step count, which (re)allocates
+ *    workspace, usb_saturation_count, usb_set_output_denorm, and calls made while profiling is on).
  *  - batch semantics: every utterance is sampled exactly like a batch-1 call of the reference (the reference's
  *    own B>1 path is broken, unitspeech/unitspeech.py:338-347,301-305).
  */
@@ -96,10 +97,24 @@ int usb_reverse_diffusion_host(usb_handle* h, const float* z, const float* cond,
  * (durations -> y_lengths, y_mask, generate_path, cond_y = path^T cond_x) for a caller-fixed frame capacity T, so the
  * reference's host round trip int(y_lengths.max()) (:428) disappears.  All pointers dev.  w_ceil: (B, Tx) = ceil(w) *
  * length_scale, already multiplied by x_mask; x_mask: (B, Tx); cond_x: (B, n_feats, Tx).  Outputs: y_lengths (B) int64 =
- * clamp_min(sum, 1); y_mask (B, T); attn (B, Tx, T) the 0/1 alignment path; cond_y (B, n_feats, T). */
+ * min(clamp_min(sum, 1), T) -- an utterance whose durations exceed the capacity T is truncated at T (the caller can detect
+ * it as sum(w_ceil) > T without a host sync); y_mask (B, T); attn (B, Tx, T) the 0/1 alignment path; cond_y (B, n_feats, T). */
 int usb_align_expand(usb_handle* h, const float* w_ceil, const float* x_mask, const float* cond_x, int32_t B, int32_t Tx,
                      int32_t n_feats, int32_t T, int64_t* y_lengths, float* y_mask, float* attn, float* cond_y,
                      uint64_t stream);
+
+/* The mel de-normalisation contract of the callers fused into the sampler            inference.py:140
+ * mel = (y + 1) / 2 * (mel_max - mel_min) + mel_min with per-bin mel_min / mel_max (host fp32 (n_feats,), as stored in the
+ * decoder checkpoint).  While set, `out` of usb_reverse_diffusion[_host] is the de-normalised log-mel, written by the
+ * last sampler step (the `trace` stays in normalised space).  Pass NULL, NULL to switch it off.  Synchronises (small
+ * host->device copy). */
+int usb_set_output_denorm(usb_handle* h, const float* mel_min_host, const float* mel_max_host);
+
+/* fp16 range report.  Activations are stored as fp16 with a saturating pack (values beyond +-65504 are
+ * clamped, never inf).  Every conv / GroupNorm-apply epilogue thread that clamped (or exactly reached the limit) bumps a
+ * device counter; this reads it (synchronising with the handle's outstanding work) and optionally resets it.  A
+ * non-zero count means the fp16 operand format was out of range for this checkpoint / input. */
+int usb_saturation_count(usb_handle* h, int64_t* count_out, int32_t reset);
 
 /* bytes of device workspace the handle holds for (Be, T); 0 if that shape has not been planned yet */
 int64_t usb_workspace_bytes(usb_handle* h);
@@ -175,6 +190,9 @@ int usb_vocoder_finalize_params(usb_vocoder* h);
 int usb_vocoder_forward(usb_vocoder* h, const float* mel, int32_t B, int32_t T, float* out, uint64_t stream);
 /* same with host buffers: upload, run, download, synchronise */
 int usb_vocoder_forward_host(usb_vocoder* h, const float* mel_host, int32_t B, int32_t T, float* out_host);
+/* The vocoder then takes the decoder's NORMALISED mel and applies inference.py:140 while packing its input
+ * (mel_min / mel_max host fp32 (num_mels,)); NULL, NULL switches it off. */
+int usb_vocoder_set_input_denorm(usb_vocoder* h, const float* mel_min_host, const float* mel_max_host);
 long long usb_vocoder_launch_count(const usb_vocoder* h);
 size_t usb_vocoder_workspace_bytes(const usb_vocoder* h);
 /* tensor-core FLOPs (padded channel counts) of one forward at the current (B, T) plan */

@@ -1,9 +1,12 @@
-"""Import shim for running the UNMODIFIED upstream reference in the build container.
+"""Import shim for running the UNMODIFIED upstream reference.
 
-TEST INFRASTRUCTURE ONLY (golden-vector generation and oracle validation).
-The reference lives read-only at /root/reference and does not exist on the GPU
-box, so nothing in the ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call
-``load_reference()``; callers must check ``reference_available()`` first.
+TEST / BASELINE INFRASTRUCTURE ONLY (golden-vector generation, oracle validation, the CPU
+reference arm of bench.py).  The reference lives read-only at /root/reference in the build
+container and does not exist on the GPU box; scripts/install_ref.py puts the unmodified
+files of the decoder path under the git-ignored baseline/_ref/, which does travel.  Nothing
+may read /root/reference at run time on the GPU box: bench.py passes
+``root=INSTALLED_REF`` explicitly; callers must check ``reference_available()`` /
+``installed_reference_available()`` first.  The product (unitspeech_b200/) never imports this.
 
 Why a shim: unitspeech/util.py imports librosa, matplotlib, phonemizer and
 fairseq-backed modules at top level (unitspeech/util.py:8-18) and
@@ -19,11 +22,31 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("UNITSPEECH_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INSTALLED_REF = os.path.join(_REPO, "baseline", "_ref")      # scripts/install_ref.py: the unmodified files, git-ignored
+
+
+def _has_decoder(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "unitspeech", "unitspeech.py"))
+
+
+def _default_root() -> str:
+    env = os.environ.get("UNITSPEECH_REFERENCE")
+    if env:
+        return env
+    return "/root/reference" if _has_decoder("/root/reference") else INSTALLED_REF
+
+
+REF_ROOT = _default_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "unitspeech", "unitspeech.py"))
+    return _has_decoder(REF_ROOT)
+
+
+def installed_reference_available() -> bool:
+    """True when scripts/install_ref.py has put the unmodified reference under baseline/_ref (travels to the GPU box)."""
+    return _has_decoder(INSTALLED_REF)
 
 
 class _Stub(types.ModuleType):
@@ -45,13 +68,15 @@ _STUBBED = [
 ]
 
 
-def load_reference():
-    """Returns the reference module ``unitspeech.unitspeech`` (classes UnitSpeech, GradLogPEstimator2d...)."""
-    if not reference_available():
-        raise RuntimeError(f"reference not found under {REF_ROOT}")
+def load_reference(root: str = None):
+    """Returns the reference module ``unitspeech.unitspeech`` (classes UnitSpeech, GradLogPEstimator2d...), imported
+    from ``root`` (default: $UNITSPEECH_REFERENCE, /root/reference, else baseline/_ref)."""
+    root = root or REF_ROOT
+    if not _has_decoder(root):
+        raise RuntimeError(f"reference not found under {root}")
     sys.dont_write_bytecode = True
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     for name in _STUBBED:
         if name not in sys.modules:
             m = _Stub(name)

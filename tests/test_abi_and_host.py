@@ -151,3 +151,34 @@ def test_checkpoint_roundtrip_in_reference_format(tmp_path):
     assert b.iteration == 123 and torch.equal(b.spk_emb, spk)
     y = torch.rand(1, 80, 8, generator=g) * 2 - 1
     assert torch.allclose(b.denormalize(y), (y + 1) / 2 * (mx - mn) + mn)
+
+
+def test_loss_t_refuses_gradients_it_cannot_produce():
+    """the CUDA backward pass yields decoder-parameter gradients only; a caller that expects the diffusion
+    loss to reach its encoder through cond / x0 / spk_emb (train_STEP1.py:381, train_STEP2.py:299) must get an error, not a
+    silently constant loss."""
+    from unitspeech_b200 import UnitSpeech
+    dec = UnitSpeech(80, 64, (1, 2), spk_emb_dim=256)
+    x0, cond = torch.zeros(1, 80, 16), torch.zeros(1, 80, 16, requires_grad=True)
+    mask, t, spk = torch.ones(1, 1, 16), torch.tensor([0.5]), torch.zeros(1, 1, 256)
+    with pytest.raises(NotImplementedError, match="decoder parameters only"):
+        dec.loss_t(x0, mask, cond, t, spk)
+    for p in dec.parameters():
+        p.requires_grad_(False)                      # frozen decoder (train_STEP2.py) makes no difference
+    with pytest.raises(NotImplementedError):
+        dec.compute_loss(x0, mask, cond, spk_emb=spk)
+
+
+def test_installed_reference_is_the_unmodified_reference():
+    """baseline/_ref (scripts/install_ref.py) holds byte-identical copies of the reference's decoder-path files."""
+    import filecmp
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import install_ref
+    from oracle import ref_shim
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference tree not present (GPU box)")
+    assert install_ref.install(verbose=False)
+    assert ref_shim.installed_reference_available()
+    for f in install_ref.FILES:
+        assert filecmp.cmp(os.path.join("/root/reference", f), os.path.join(install_ref.DEST, f), shallow=False), f

@@ -180,6 +180,42 @@ def test_long_odd_width_utterances_and_microbatching():
     assert torch.equal(chunked, full)       # micro-batching is exact (bitwise batch invariance)
 
 
+def test_fused_mel_denormalisation_is_bit_exact():
+    """(y + 1) / 2 * (mel_max - mel_min) + mel_min (inference.py:140) fused into the last sampler step."""
+    from unitspeech_b200 import denormalize_mel
+    B, T, n, s = 2, 16, 3, 1.0 / 32
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=1234, out_scale=s)
+    z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=2, scale=s, lengths=(16, 12))
+    dec = _decoder(64, (1, 2), p)
+    g = torch.Generator().manual_seed(3)
+    mel_min = -11.0 + torch.rand(80, 1, generator=g)
+    mel_max = 1.5 + torch.rand(80, 1, generator=g)
+    args = (z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, 1.0, 1.0)
+    y = dec(*args, noise=noise.cuda())
+    fused = dec(*args, noise=noise.cuda(), denorm=(mel_min, mel_max))
+    assert torch.equal(fused, denormalize_mel(y, mel_min.cuda(), mel_max.cuda()))
+    # (1, 80, 1)-shaped ranges as scripts/finetune.py:106-107 stores them, host entry, and switching it off again
+    fused_h = dec(z, mask, cond, spk, n, 1.0, 1.0, noise=noise, denorm=(mel_min.view(1, 80, 1), mel_max.view(1, 80, 1)))
+    assert torch.equal(fused_h, fused.cpu())
+    assert torch.equal(dec(*args, noise=noise.cuda()), y)
+    with pytest.raises(ValueError):
+        dec(*args, noise=noise.cuda(), denorm=(mel_min[:10], mel_max[:10]))
+
+
+def test_fp16_saturation_is_clamped_and_reported():
+    """out-of-range activations saturate at +-65504 (never inf) and the clamp is counted."""
+    B, T, n, s = 1, 16, 2, 1.0 / 32
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=1234, out_scale=s)
+    z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=2, scale=s)
+    dec = _decoder(64, (1, 2), p)
+    out = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, 1.0, 1.0, noise=noise.cuda())
+    assert dec.saturation_count() == 0 and torch.isfinite(out).all()
+    # inputs scaled by 1e6 drive the first conv's fp16 outputs past the format's range
+    dec(z.cuda() * 1e6, mask.cuda(), cond.cuda() * 1e6, spk.cuda(), n, 1.0, 1.0, noise=noise.cuda())
+    assert dec.saturation_count() > 0
+    assert dec.saturation_count(reset=True) > 0 and dec.saturation_count() == 0
+
+
 class _StubEncoder(torch.nn.Module):
     """Deterministic stand-in for the text/unit encoder (unitspeech/encoder.py:294): (cond_x, x, x_mask)."""
 

@@ -166,3 +166,10 @@ def test_decoder_then_vocoder_pipeline_matches_oracle_pipeline():
     assert wav.shape == (B, T * 8)
     mx, mn = _report("pipeline", wav, wav_ref)
     assert mx <= MAX_ABS and mn <= MEAN_ABS
+    # the same pipeline with the de-normalisation fused on either side: into the vocoder's input pack ...
+    wav_v = voc(y, mel_min=mel_min, mel_max=mel_max).squeeze(1).clamp(-1, 1).cpu()
+    assert torch.equal(wav_v, wav)
+    # ... or into the sampler's last step
+    y_dn = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, text_gradient_scale=1.0, spk_gradient_scale=1.0,
+               noise=noise.cuda(), denorm=(mel_min, mel_max))
+    assert torch.equal(voc(y_dn).squeeze(1).clamp(-1, 1).cpu(), wav)

@@ -49,6 +49,14 @@ def _worker(rank, world, port, n_utt, q):
     ok = torch.equal(got, ref)
     b, e = shard_range(n_utt, rank, world)
     ok = ok and torch.equal(gather_utterances(ref[b:e], n_utt), ref)
+    # the per-step noise may be handed over already sharded (bench.py: only the rank's own utterances are materialised)
+    got_local = sample_sharded(dec, z, mask, cond, spk, 3, 1.0, 1.0, noise=noise[:, b:e].contiguous(), noise_is_local=True)
+    ok = ok and torch.equal(got_local, ref)
+    try:
+        sample_sharded(dec, z, mask, cond, spk, 3, 1.0, 1.0, noise=noise, noise_is_local=n_utt > 1)
+        ok = ok and n_utt <= 1
+    except ValueError:
+        pass
     # timing-style reduction used by bench.py: max over ranks
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

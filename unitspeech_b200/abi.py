@@ -67,6 +67,8 @@ SIGNATURES = {
                                                                          c_int32, c_int32, c_uint64]),
     "usb_align_expand": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_uint64]),
+    "usb_set_output_denorm": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "usb_saturation_count": (c_int32, [c_void_p, POINTER(c_int64), c_int32]),
     "usb_workspace_bytes": (c_int64, [c_void_p]),
     "usb_launch_count": (c_int64, [c_void_p]),
     "usb_set_profiling": (c_int32, [c_void_p, c_int32]),
@@ -84,6 +86,7 @@ SIGNATURES = {
     "usb_vocoder_finalize_params": (c_int32, [c_void_p]),
     "usb_vocoder_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_uint64]),
     "usb_vocoder_forward_host": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "usb_vocoder_set_input_denorm": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "usb_vocoder_launch_count": (c_int64, [c_void_p]),
     "usb_vocoder_workspace_bytes": (ctypes.c_size_t, [c_void_p]),
     "usb_vocoder_flops_per_call": (c_double, [c_void_p]),

@@ -61,7 +61,8 @@ __device__ __forceinline__ void warp_reduce_items(float (&v)[NV], int lane) {
 template <int G>
 __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
                                               int c_glob, bool valid, float m, float rs, const __half* res_row,
-                                              uint32_t stage_row, int row, long long* stats_n, int cpg, int lane) {
+                                              uint32_t stage_row, int row, long long* stats_n, int cpg, int lane,
+                                              float& amax) {
     constexpr int CPG8 = 8 / G;  // 8-column chunks per group inside the slab (G=8 -> 1, 4 -> 2, 2 -> 4, 1 -> 8)
     float acc[2 * G];
 #pragma unroll
@@ -98,10 +99,14 @@ __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const uint32_
                 f[2 * e + 1] = fmaf(f[2 * e + 1], rs, r2.y);
             }
         }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            f[e] *= m;
+            amax = fmaxf(amax, fabsf(f[e]));
+        }
         // 16-byte chunk q of row `row`, 128-byte swizzle (chunk index XOR row%8) = the layout the TMA store expects
-        sts128(stage_row + (static_cast<uint32_t>(q ^ (row & 7)) << 4), pack_f16x2_sat(f[0] * m, f[1] * m),
-               pack_f16x2_sat(f[2] * m, f[3] * m), pack_f16x2_sat(f[4] * m, f[5] * m),
-               pack_f16x2_sat(f[6] * m, f[7] * m));
+        sts128(stage_row + (static_cast<uint32_t>(q ^ (row & 7)) << 4), pack_f16x2_sat(f[0], f[1]),
+               pack_f16x2_sat(f[2], f[3]), pack_f16x2_sat(f[4], f[5]), pack_f16x2_sat(f[6], f[7]));
     }
     if (stats_n) {
         warp_reduce_items<2 * G>(acc, lane);
@@ -256,6 +261,7 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
         // (two 4 KB buffers per warp, alternating, so a store only waits for the one issued two slabs earlier)
         const uint32_t warp_buf0 = tiles_base + stages * stage_bytes + static_cast<uint32_t>(grp * 4 + ew) * 8192u;
         uint32_t buf_sel = 0;
+        float amax = 0.f;                             // largest |value| packed by this thread (saturation report)
         const int q0 = ew * 32;                       // first tile pixel of this warp
         const int wty0 = q0 >> bw_shift, wtx0 = q0 & (p.BW - 1);
         int it = 0;
@@ -298,10 +304,10 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
                 if (lane == 0) tma_store_wait_read<1>();
                 __syncwarp();
                 const __half* res_row = res_px ? res_px + c_glob : nullptr;
-                if (cpg >= 64) epilogue_slab<1>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane);
-                else if (cpg == 32) epilogue_slab<2>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane);
-                else if (cpg == 16) epilogue_slab<4>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane);
-                else epilogue_slab<8>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane);
+                if (cpg >= 64) epilogue_slab<1>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
+                else if (cpg == 32) epilogue_slab<2>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
+                else if (cpg == 16) epilogue_slab<4>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
+                else epilogue_slab<8>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
                 fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
                 __syncwarp();
                 if (lane == 0) {
@@ -311,6 +317,7 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
                 }
             }
         }
+        if (p.sat && amax >= 65504.f) atomicAdd(p.sat, 1ull);
         if (lane == 0) tma_store_wait_all<0>();
     }
 
@@ -483,6 +490,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
         for (int q = 0; q < 4; ++q)
             sbase[q] = warp_buf + ((static_cast<uint32_t>(lane >> 3) ^ static_cast<uint32_t>(q)) << 4) +
                        static_cast<uint32_t>(lane & 7) * 2u;
+        float amax = 0.f;                         // largest |value| packed by this thread (saturation report)
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int ph = tile / tiles_per_phase;
@@ -537,6 +545,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                         }
                     }
                     if (mrow) f *= mask_s[grp][(pb + j) & (p.BW - 1)];
+                    amax = fmaxf(amax, fabsf(f));
                     unsigned short hbits;
                     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hbits) : "f"(f));
                     asm volatile("st.shared.b16 [%0], %1;" ::"r"(sbase[(j >> 1) & 3] + j * 64), "h"(hbits) : "memory");
@@ -569,6 +578,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                 }
             }
         }
+        if (p.sat && amax >= 65504.f) atomicAdd(p.sat, 1ull);
         if (lane == 0) tma_store_wait_all<0>();
     }
 
@@ -730,6 +740,7 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
         for (int q = 0; q < 4; ++q)
             sbase[q] = warp_buf + ((static_cast<uint32_t>(lane >> 3) ^ static_cast<uint32_t>(q)) << 4) +
                        static_cast<uint32_t>(lane & 7) * 2u;
+        float amax = 0.f;                         // largest |value| packed by this thread (saturation report)
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int nt = tile % p.n_tiles_n;
@@ -789,6 +800,7 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
                         }
                     }
                     if (mrow) f *= mask_s[grp][xl];
+                    amax = fmaxf(amax, fabsf(f));
                     unsigned short hbits;
                     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hbits) : "f"(f));
                     asm volatile("st.shared.b16 [%0], %1;" ::"r"(sbase[(j >> 1) & 3] + j * 64), "h"(hbits) : "memory");
@@ -816,6 +828,7 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
                 }
             }
         }
+        if (p.sat && amax >= 65504.f) atomicAdd(p.sat, 1ull);
         if (lane == 0) tma_store_wait_all<0>();
     }
 

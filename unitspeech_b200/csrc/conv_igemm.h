@@ -70,6 +70,9 @@ struct ConvParams {
     int out_c_phase_mul;
     int oy_mul, ox_mul;        // yo = y*oy_mul + oy_off[phase], xo = x*ox_mul + ox_off[phase]
     int8_t oy_off[4], ox_off[4];
+    // fp16 saturation report: incremented once per epilogue thread and tile in which a value reached the
+    // fp16 limit (|v| >= 65504 before the satfinite pack); null = not reported
+    unsigned long long* sat;
 };
 
 struct ConvOp {
@@ -79,6 +82,11 @@ struct ConvOp {
 
 // engine.cu: records the thread's last error message (usb_last_error) and returns 1
 int set_error(const std::string& m);
+}  // namespace usb
+struct usb_handle;
+namespace usb {
+// engine.cu: CUDA device ordinal the handle is bound to
+int handle_device(const usb_handle* h);
 // engine.cu: parameter block + tensor maps of a 1-D (transposed) convolution over NLC fp16 tensors
 int build_conv1d(ConvOp& op, const int8_t* dx, int taps, int phases, const __half* in, int Cin, int N, int L,
                  const __half* w, int Cout, const float* bias, const __half* res, __half* out);

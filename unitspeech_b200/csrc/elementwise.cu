@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(256, HAS_RES ? 2 : 3) gn_apply_kernel(const Gn
     const int p_end = min(p.P, p_begin + pix_per_block);
     const long long base = static_cast<long long>(n) * p.P * C + tq * 8;
     int xcol = (p_begin + pl) % p.W;   // column of the thread's next pixel, advanced incrementally
+    __half2 amax2 = __float2half2_rn(0.f);   // largest |value| stored by this thread (saturation report)
     for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += lanes * U) {
         uint4 rv[U], rr[U];
         float m[U];
@@ -299,10 +300,14 @@ __global__ void __launch_bounds__(256, HAS_RES ? 2 : 3) gn_apply_kernel(const Gn
             const int pix = pix0 + u * lanes;
             if (pix < p_end) {
                 const uint4 o4 = gn_mish8<HAS_RES>(rv[u], rr[u], a, b, al, bl, ba, m[u]);
+                const __half2* oh = reinterpret_cast<const __half2*>(&o4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) amax2 = __hmax2(amax2, __habs2(oh[i]));
                 if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(p.out + base + static_cast<long long>(pix) * C) = o4;
             }
         }
     }
+    if (p.sat && fmaxf(__low2float(amax2), __high2float(amax2)) >= 65504.f) atomicAdd(p.sat, 1ull);
 }
 
 int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s) {
@@ -409,8 +414,19 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalParams p, int pix
                     if (p.nb >= 2) score = score + p.a0 * (sf - sc[0]);
                     if (p.nb >= 3) score = score + p.a1 * (sf - sc[1]);
                     const float nz = p.noise ? p.noise[q] : 0.f;
-                    p.xt[q] = (p.c_x * p.xt[q] + p.c_s * score + p.sigma * nz) * m[u];
+                    const float xn = (p.c_x * p.xt[q] + p.c_s * score + p.sigma * nz) * m[u];
+                    p.xt[q] = xn;
                     if (p.score) p.score[q] = score;
+                    if (p.out) {
+                        float o = xn;
+                        if (p.mel_min) {
+                            const int yb = pix / p.W;
+                            const float lo = __ldg(p.mel_min + yb), hi = __ldg(p.mel_max + yb);
+                            // the reference's four separate fp32 ops (no contraction into an fma): bit-identical to the torch expression
+                            o = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.f), 2.f), __fsub_rn(hi, lo)), lo);
+                        }
+                        p.out[q] = o;
+                    }
                 }
             }
         }

@@ -234,6 +234,7 @@ struct ConvEpilogue {
     const __half* res = nullptr;
     const float* res_scale = nullptr;
     const float* mask = nullptr;  // [N][Wout]
+    unsigned long long* sat = nullptr;
 };
 
 // Builds the parameter block + tensor maps of one convolution launch.
@@ -301,6 +302,7 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     p.res = ep.res;
     p.res_scale = ep.res_scale;
     p.mask = ep.mask;
+    p.sat = ep.sat;
     const int Hout = kind_down(kind) ? H / 2 : (kind_up(kind) ? 2 * H : H);
     const int Wout = kind_down(kind) ? W / 2 : (kind_up(kind) ? 2 * W : W);
     p.mask_stride = Wout;
@@ -495,6 +497,9 @@ struct usb_handle {
     float* loss_buf = nullptr;    // loss_t: xt, z*mask, cond*mask, score ([B][n_feats][T] each) + 512 doubles of partials
     size_t loss_cap = 0;
     long long launches = 0;
+    unsigned long long* sat = nullptr;   // device counter of fp16 saturation events (usb_saturation_count)
+    float* mel_range = nullptr;          // device [2][n_feats] (mel_min, mel_max) when output de-normalisation is on
+    bool denorm = false;
     // optional per-kernel-class timing (bench.py roofline): events around every launch of a profiled call
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -507,6 +512,8 @@ struct usb_handle {
 };
 
 namespace usb {
+
+int handle_device(const usb_handle* h) { return h->cfg.device; }
 
 template <typename T>
 static int upload(usb_handle* h, const T* host, size_t count, T** dev) {
@@ -789,8 +796,10 @@ static int build_plan(usb_handle* h, int Be, int T) {
                          const ConvW* w, const __half* wptr, int wZ, int bmode, int Cout, const ConvEpilogue& ep,
                          __half* out) -> int {
         pl.convs.emplace_back();
+        ConvEpilogue eps = ep;
+        eps.sat = h->sat;
         USB_TRY(build_conv(pl.convs.back(), kind, in0, C0tot, C0, in1, C1tot, C1, Be, H[l], W[l], w ? w->w : wptr,
-                           w ? w->Z : wZ, bmode, Cout, ep, out));
+                           w ? w->Z : wZ, bmode, Cout, eps, out));
         pl.ops.push_back({Op::CONV, (int)pl.convs.size() - 1});
         return 0;
     };
@@ -801,6 +810,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         p.res = res; p.mask = pl.mask[l]; p.out = out; p.N = Be; p.P = H[l] * W[l]; p.W = W[l]; p.C = Cc; p.groups = G;
         p.eps = 1e-5f;
         p.dbg = 0;
+        p.sat = h->sat;
         pl.gns.push_back(p);
         pl.ops.push_back({Op::GN, (int)pl.gns.size() - 1});
     };
@@ -929,9 +939,39 @@ static int build_plan(usb_handle* h, int Be, int T) {
 // ---------------------------------------------------------------------------------------------------------------
 // execution
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void fill_kernel(float* p, float v, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+// One launch builds everything a call needs per estimator row (no pageable-host uploads, hence no stream sync):
+// the CFG row tables (unitspeech.py:301-317: row k*B+b reads x_t of utterance b and cond of utterance b, or text_uncon when
+// k == k_tu), the speaker rows (spk_uncon/||spk_uncon|| when k == k_su, :358), and the frame masks of every level
+// (mask[..., ::2] per down-sampling, :182).  spk_rows == null: speaker rows are the caller's (estimator entry).
+struct PrepParams {
+    const float* mask;      // [B][T]
+    const float* spk;       // [B][S] or null
+    const float* spk_uncon; // [S]
+    int* x_row;
+    int* mu_row;
+    float* spk_rows;        // [Be][S] or null
+    float* mask_l[8];       // per level [Be][T >> l]
+    int B, nb, k_tu, k_su, T, S, L;
+};
+__global__ void __launch_bounds__(256) prep_rows_kernel(const PrepParams p) {
+    const int Be = p.B * p.nb;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < Be) {
+        const int k = static_cast<int>(i) / p.B, b = static_cast<int>(i) % p.B;
+        p.x_row[i] = b;
+        p.mu_row[i] = k == p.k_tu ? -1 : b;
+    }
+    if (p.spk_rows && i < static_cast<long long>(Be) * p.S) {
+        const int r = static_cast<int>(i / p.S), c = static_cast<int>(i % p.S);
+        const int k = r / p.B, b = r % p.B;
+        p.spk_rows[i] = k == p.k_su ? __ldg(p.spk_uncon + c) : __ldg(p.spk + static_cast<long long>(b) * p.S + c);
+    }
+    if (i < static_cast<long long>(Be) * p.T) {
+        const int r = static_cast<int>(i / p.T), w = static_cast<int>(i % p.T);
+        const float m = __ldg(p.mask + static_cast<long long>(r % p.B) * p.T + w);
+        for (int l = 0; l < p.L; ++l)
+            if ((w & ((1 << l) - 1)) == 0) p.mask_l[l][static_cast<long long>(r) * (p.T >> l) + (w >> l)] = m;
+    }
 }
 __global__ void mul_mask_kernel(const float* z, const float* mask, float* out, int B, int P, int W) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -989,11 +1029,20 @@ struct EstInputs {
     const float* spk_rows;    // [Be][S]
 };
 
-// masks for all levels from pl.mask[0]
-static int prepare_masks(usb_handle* h, cudaStream_t s) {
+// row tables, speaker rows and the masks of all levels for this call (one launch, see prep_rows_kernel)
+static int prepare_rows(usb_handle* h, const float* mask, const float* spk, int B, int nb, int k_tu, int k_su,
+                        bool fill_spk, cudaStream_t s) {
     Plan& pl = h->plan;
-    for (int l = 1; l < h->L; ++l)
-        USB_LAUNCH(h, launch_downsample_mask(pl.mask[l - 1], pl.mask[l], pl.Be, pl.T >> (l - 1), pl.T >> l, s));
+    PrepParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.mask = mask; pp.spk = spk; pp.spk_uncon = h->spk_uncon_normed; pp.x_row = pl.x_row; pp.mu_row = pl.mu_row;
+    pp.spk_rows = fill_spk ? pl.spk_rows : nullptr;
+    for (int l = 0; l < h->L; ++l) pp.mask_l[l] = pl.mask[l];
+    pp.B = B; pp.nb = nb; pp.k_tu = k_tu; pp.k_su = k_su; pp.T = pl.T; pp.S = h->cfg.spk_emb_dim; pp.L = h->L;
+    const long long Be = (long long)B * nb;
+    const long long total = Be * (pl.T > pp.S ? pl.T : pp.S);
+    prep_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pp);
+    USB_LAUNCH(h, (int)cudaGetLastError());
     return 0;
 }
 
@@ -1083,14 +1132,7 @@ static int estimator_forward(usb_handle* h, const float* x, const float* mu, con
                              const float* spk, float* out, int Be, int T, cudaStream_t s) {
     USB_TRY(check_ready(h));
     USB_TRY(build_plan(h, Be, T));
-    Plan& pl = h->plan;
-    std::vector<int> ident(Be);
-    for (int i = 0; i < Be; ++i) ident[i] = i;
-    USB_CUDA(cudaMemcpyAsync(pl.x_row, ident.data(), Be * sizeof(int), cudaMemcpyHostToDevice, s));
-    USB_CUDA(cudaMemcpyAsync(pl.mu_row, ident.data(), Be * sizeof(int), cudaMemcpyHostToDevice, s));
-    USB_CUDA(cudaMemcpyAsync(pl.mask[0], mask, (size_t)Be * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    USB_CUDA(cudaStreamSynchronize(s));  // `ident` is pageable host memory
-    USB_TRY(prepare_masks(h, s));
+    USB_TRY(prepare_rows(h, mask, nullptr, Be, 1, -1, -1, false, s));
     EstInputs in{x, mu, nullptr, t, spk};
     USB_TRY(run_estimator(h, in, s));
     FinalParams f = final_params(h, Be, 1);
@@ -1139,31 +1181,10 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
     Plan& pl = h->plan;
     const int S = c.spk_emb_dim, P = c.n_feats * T;
     // branch order of classifier_free_guidance (unitspeech.py:301-317): [text-uncond] [spk-uncond] full
-    std::vector<int> xrow(Be), murow(Be);
     int kb = 0, k_tu = -1, k_su = -1;
     if (use_t) k_tu = kb++;
     if (use_s) k_su = kb++;
-    for (int k = 0; k < nb; ++k)
-        for (int b = 0; b < B; ++b) {
-            xrow[k * B + b] = b;
-            murow[k * B + b] = k == k_tu ? -1 : b;
-        }
-    USB_CUDA(cudaMemcpyAsync(pl.x_row, xrow.data(), Be * sizeof(int), cudaMemcpyHostToDevice, s));
-    USB_CUDA(cudaMemcpyAsync(pl.mu_row, murow.data(), Be * sizeof(int), cudaMemcpyHostToDevice, s));
-    USB_CUDA(cudaStreamSynchronize(s));
-    for (int k = 0; k < nb; ++k) {
-        USB_CUDA(cudaMemcpyAsync(pl.mask[0] + (size_t)k * B * T, mask, (size_t)B * T * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, s));
-        if (k == k_su) {
-            for (int b = 0; b < B; ++b)
-                USB_CUDA(cudaMemcpyAsync(pl.spk_rows + ((size_t)k * B + b) * S, h->spk_uncon_normed, S * sizeof(float),
-                                         cudaMemcpyDeviceToDevice, s));
-        } else {
-            USB_CUDA(cudaMemcpyAsync(pl.spk_rows + (size_t)k * B * S, spk, (size_t)B * S * sizeof(float),
-                                     cudaMemcpyDeviceToDevice, s));
-        }
-    }
-    USB_TRY(prepare_masks(h, s));
+    USB_TRY(prepare_rows(h, mask, spk, B, nb, k_tu, k_su, true, s));
     {
         const long long tot = (long long)B * P;
         mul_mask_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(z, mask, pl.xt, B, P, T);
@@ -1203,6 +1224,12 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
         f.xt = pl.xt;
         f.noise = noise ? noise + (size_t)i * B * P : nullptr;
         f.c_x = coef[i * 3 + 0]; f.c_s = coef[i * 3 + 1]; f.sigma = coef[i * 3 + 2];
+        if (i == n_steps - 1) {
+            // the reference returns xt * mask (:373; xt is already masked by the update): the last step writes the caller's
+            // buffer directly, de-normalised to log-mel when usb_set_output_denorm is active (inference.py:140)
+            f.out = out;
+            if (h->denorm) { f.mel_min = h->mel_range; f.mel_max = h->mel_range + c.n_feats; }
+        }
         {
             // reads the final_block conv output of every CFG branch (fp16) + x_t and noise, writes x_t
             ProfScope ps(h, s, 3, (double)Be * P * c.dim * 2.0 + (double)B * P * 12.0);
@@ -1212,8 +1239,6 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
             USB_CUDA(cudaMemcpyAsync(trace + (size_t)i * B * P, pl.xt, (size_t)B * P * sizeof(float),
                                      cudaMemcpyDeviceToDevice, s));
     }
-    // the reference returns xt * mask (:373); xt is already masked by the update
-    USB_CUDA(cudaMemcpyAsync(out, pl.xt, (size_t)B * P * sizeof(float), cudaMemcpyDeviceToDevice, s));
     USB_TRY(prof_collect(h, s));
     return 0;
 }
@@ -1257,6 +1282,19 @@ int usb_create(const usb_config* cfg, usb_handle** out) {
         delete h;
         return 1;
     }
+    void* p = nullptr;
+    if (cudaMalloc(&p, sizeof(unsigned long long)) != cudaSuccess || cudaMemset(p, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        delete h;
+        return fail("cudaMalloc of the saturation counter failed");
+    }
+    h->sat = static_cast<unsigned long long*>(p);
+    h->dev_allocs.push_back(p);
+    if (cudaMalloc(&p, 2 * sizeof(float) * cfg->n_feats) != cudaSuccess) {
+        usb_destroy(h);
+        return fail("cudaMalloc of the mel range failed");
+    }
+    h->mel_range = static_cast<float*>(p);
+    h->dev_allocs.push_back(p);
     *out = h;
     return 0;
 }
@@ -1385,6 +1423,29 @@ int usb_get_profile(usb_handle* h, double* ms4, double* work4, int64_t* launches
         ms4[i] = h->prof_ms[i];
         work4[i] = h->prof_work[i];
         launches4[i] = h->prof_launches[i];
+    }
+    return 0;
+}
+
+int usb_saturation_count(usb_handle* h, int64_t* count_out, int32_t reset) {
+    if (!h || !count_out) return fail("null argument");
+    USB_CUDA(cudaSetDevice(h->cfg.device));
+    unsigned long long v = 0;
+    USB_CUDA(cudaMemcpy(&v, h->sat, sizeof v, cudaMemcpyDeviceToHost));   // synchronises with the work that reports into it
+    if (reset) USB_CUDA(cudaMemset(h->sat, 0, sizeof v));
+    *count_out = static_cast<int64_t>(v);
+    return 0;
+}
+
+int usb_set_output_denorm(usb_handle* h, const float* mel_min_host, const float* mel_max_host) {
+    if (!h) return fail("null handle");
+    if ((mel_min_host == nullptr) != (mel_max_host == nullptr)) return fail("mel_min and mel_max must be given together");
+    USB_CUDA(cudaSetDevice(h->cfg.device));
+    h->denorm = mel_min_host != nullptr;
+    if (h->denorm) {
+        const size_t n = sizeof(float) * h->cfg.n_feats;
+        USB_CUDA(cudaMemcpy(h->mel_range, mel_min_host, n, cudaMemcpyHostToDevice));
+        USB_CUDA(cudaMemcpy(h->mel_range + h->cfg.n_feats, mel_max_host, n, cudaMemcpyHostToDevice));
     }
     return 0;
 }

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256) align_expand_kernel(const float* __restri
         }
         long long yl = static_cast<long long>(static_cast<float>(s));       // .long() of the fp32 sum (:427)
         if (s < 1.0) yl = 1;                                                 // clamp_min(., 1)
+        if (yl > T) yl = T;   // frame capacity: mask / path / cond_y end at T, so the reported length does too
         ylen_s = yl;
         y_lengths[b] = yl;
     }
@@ -63,6 +64,10 @@ extern "C" int usb_align_expand(usb_handle* h, const float* w_ceil, const float*
     if (B < 1 || Tx < 1 || T < 1 || n_feats < 1) return usb::set_error("bad front-end geometry");
     const size_t smem = static_cast<size_t>(Tx) * sizeof(double);
     if (smem > 200 * 1024) return usb::set_error("too many tokens for the alignment kernel");
+    {
+        cudaError_t e = cudaSetDevice(usb::handle_device(h));
+        if (e != cudaSuccess) return usb::set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    }
     if (smem > 48 * 1024) cudaFuncSetAttribute(align_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     align_expand_kernel<<<B, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         w_ceil, x_mask, cond_x, Tx, n_feats, T, reinterpret_cast<long long*>(y_lengths), y_mask, attn, cond_y);

@@ -42,6 +42,7 @@ struct GnApplyParams {
     int N, P, W, C, groups;
     float eps;
     int dbg;               // experiments: 1 = skip Mish, 2 = skip the store
+    unsigned long long* sat = nullptr;   // fp16 saturation report (see ConvParams::sat) or null
 };
 int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s);
 
@@ -62,6 +63,11 @@ struct FinalParams {
     const float* noise;    // [B][P] or null (treated as 0)
     float c_x, c_s, sigma;
     float* score;          // estimator mode: [nb*B][P] per-row outputs; sampler mode: optional [B][P] combined score
+    // last sampler step: also write the updated x_t to the caller's buffer, optionally de-normalised to log-mel
+    // (inference.py:140: (y + 1) / 2 * (mel_max - mel_min) + mel_min with per-bin mel_min/mel_max)
+    float* out;            // [B][P] or null
+    const float* mel_min;  // [H] device or null
+    const float* mel_max;  // [H]
 };
 int launch_final(const FinalParams& p, int num_sms, cudaStream_t s);
 

@@ -226,8 +226,10 @@ __global__ void __launch_bounds__(256, 3) snake_act_kernel(const ActParams p) {
 
 #undef act_sidx
 
-// mel (B, M, T) fp32 -> [B][T][Cp] fp16, zero padded channels
-__global__ void mel_pack_kernel(const float* __restrict__ mel, __half* __restrict__ out, int B, int M, int T, int Cp) {
+// mel (B, M, T) fp32 -> [B][T][Cp] fp16, zero padded channels.  mel_min != null: `mel` is the decoder's normalised
+// output and is de-normalised on the way in, (y + 1) / 2 * (mel_max - mel_min) + mel_min (inference.py:140)
+__global__ void mel_pack_kernel(const float* __restrict__ mel, __half* __restrict__ out, int B, int M, int T, int Cp,
+                                const float* __restrict__ mel_min, const float* __restrict__ mel_max) {
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int groups = Cp / 8;
     if (idx >= static_cast<long long>(B) * groups * T) return;
@@ -239,7 +241,12 @@ __global__ void mel_pack_kernel(const float* __restrict__ mel, __half* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = cg * 8 + j;
-        h[j] = __float2half_rn(c < M ? __ldg(mel + (static_cast<long long>(b) * M + c) * T + t) : 0.f);
+        float v = c < M ? __ldg(mel + (static_cast<long long>(b) * M + c) * T + t) : 0.f;
+        if (mel_min && c < M) {
+            const float lo = __ldg(mel_min + c), hi = __ldg(mel_max + c);
+            v = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v, 1.f), 2.f), __fsub_rn(hi, lo)), lo);
+        }
+        h[j] = __float2half_rn(v);
     }
     *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * T + t) * Cp + cg * 8) = pk;
 }
@@ -407,6 +414,8 @@ struct usb_vocoder {
     std::vector<VocOp> ops;
     long long launches = 0;
     double flops_per_call = 0;
+    float* mel_range = nullptr;   // device [2][num_mels] (mel_min, mel_max) when the input is the normalised decoder output
+    bool denorm = false;
     // optional per-class timing of the next forward calls: 0 conv (tensor), 1 snake activation (HBM), 2 other
     bool profiling = false;
     double prof_ms[3] = {0, 0, 0};
@@ -689,7 +698,9 @@ static int voc_forward(usb_vocoder* h, const float* mel, int B, int T, float* ou
     {
         const int Cp = h->conv_pre.Cin;
         const long long n = static_cast<long long>(B) * (Cp / 8) * T;
-        mel_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(mel, h->melp, B, h->cfg.num_mels, T, Cp);
+        mel_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
+            mel, h->melp, B, h->cfg.num_mels, T, Cp, h->denorm ? h->mel_range : nullptr,
+            h->denorm ? h->mel_range + h->cfg.num_mels : nullptr);
         h->launches++;
     }
     std::vector<cudaEvent_t> evs;
@@ -837,6 +848,24 @@ int usb_vocoder_forward_host(usb_vocoder* h, const float* mel_host, int32_t B, i
 long long usb_vocoder_launch_count(const usb_vocoder* h) { return h ? h->launches : 0; }
 size_t usb_vocoder_workspace_bytes(const usb_vocoder* h) { return h ? h->arena_bytes : 0; }
 double usb_vocoder_flops_per_call(const usb_vocoder* h) { return h ? h->flops_per_call : 0; }
+
+int usb_vocoder_set_input_denorm(usb_vocoder* h, const float* mel_min_host, const float* mel_max_host) {
+    if (!h) return set_error("null argument");
+    if ((mel_min_host == nullptr) != (mel_max_host == nullptr)) return set_error("mel_min and mel_max must be given together");
+    VOC_CUDA(cudaSetDevice(h->cfg.device));
+    h->denorm = mel_min_host != nullptr;
+    if (!h->denorm) return 0;
+    const size_t n = sizeof(float) * h->cfg.num_mels;
+    if (!h->mel_range) {
+        void* p = nullptr;
+        VOC_CUDA(cudaMalloc(&p, 2 * n));
+        h->dev_allocs.push_back(p);
+        h->mel_range = static_cast<float*>(p);
+    }
+    VOC_CUDA(cudaMemcpy(h->mel_range, mel_min_host, n, cudaMemcpyHostToDevice));
+    VOC_CUDA(cudaMemcpy(h->mel_range + h->cfg.num_mels, mel_max_host, n, cudaMemcpyHostToDevice));
+    return 0;
+}
 
 int usb_vocoder_set_profiling(usb_vocoder* h, int32_t on) {
     if (!h) return set_error("null argument");

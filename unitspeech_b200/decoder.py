@@ -184,6 +184,7 @@ class UnitSpeech(torch.nn.Module):
         if self._handle is not None:
             abi.load_library().usb_destroy(self._handle)
             self._handle = None
+            self._denorm_key = self._denorm_handle = None
 
     def __del__(self):
         try:
@@ -241,6 +242,16 @@ class UnitSpeech(torch.nn.Module):
     def workspace_bytes(self) -> int:
         return int(abi.load_library().usb_workspace_bytes(self._handle)) if self._handle is not None else 0
 
+    def saturation_count(self, reset: bool = False) -> int:
+        """Number of kernel epilogue threads that clamped a value to the fp16 limit (+-65504) since the handle was
+        created / last reset (saturate and flag instead of emitting inf).  Non-zero means the fp16 operand
+        format was out of range for this checkpoint or input.  Synchronises with the device."""
+        if self._handle is None:
+            return 0
+        n = ctypes.c_int64(0)
+        abi.check(abi.load_library().usb_saturation_count(self._handle, ctypes.byref(n), int(bool(reset))))
+        return int(n.value)
+
     def set_profiling(self, on: bool) -> None:
         """Per-kernel-class CUDA-event timing of the next reverse_diffusion calls (adds a sync; not for timed runs)."""
         abi.check(abi.load_library().usb_set_profiling(self._ensure_handle(), int(bool(on))))
@@ -272,11 +283,15 @@ class UnitSpeech(torch.nn.Module):
     # ------------------------------------------------------------------ sampler
     @torch.no_grad()
     def reverse_diffusion(self, z, mask, cond, spk_emb, n_timesteps, text_gradient_scale=0.0, spk_gradient_scale=0.0,
-                          noise: Optional[torch.Tensor] = None, trace: bool = False):
+                          noise: Optional[torch.Tensor] = None, trace: bool = False,
+                          denorm: Optional[Sequence[torch.Tensor]] = None):
         """UnitSpeech.reverse_diffusion (unitspeech/unitspeech.py:334-374), per-utterance batch-1 semantics.
 
         z, cond: (B, n_feats, T); mask: (B, 1, T); spk_emb: (B, 1, spk_emb_dim); noise: optional (n, B, n_feats, T).
         Returns (B, n_feats, T) on z's device; with trace=True also the (n, B, n_feats, T) x_t after every step.
+        ``denorm=(mel_min, mel_max)`` (per-bin, n_feats values each, as stored in the decoder checkpoint) fuses the
+        callers' mel de-normalisation ``(y + 1) / 2 * (mel_max - mel_min) + mel_min`` (inference.py:140) into the last
+        sampler step: the returned tensor is then the log-mel the vocoder takes (the trace stays normalised).
         """
         if n_timesteps < 2:
             raise ValueError("n_timesteps must be >= 2 (the reference fails for 1)")
@@ -300,7 +315,7 @@ class UnitSpeech(torch.nn.Module):
             for b0 in range(0, B, max_b):
                 sl = slice(b0, min(B, b0 + max_b))
                 r = self.reverse_diffusion(z[sl], mask[sl], cond[sl], spk_emb[sl], n_timesteps, text_gradient_scale,
-                                           spk_gradient_scale, noise=noise[:, sl], trace=trace)
+                                           spk_gradient_scale, noise=noise[:, sl], trace=trace, denorm=denorm)
                 outs.append(r[0] if trace else r)
                 if trace:
                     traces.append(r[1])
@@ -312,6 +327,7 @@ class UnitSpeech(torch.nn.Module):
         h = self._ensure_handle(z)
         dev = torch.device("cuda", self._handle_device)
         on_host = z.device.type != "cuda"
+        self._set_denorm(h, denorm)
         with torch.cuda.device(dev):
             stream = self._stream(dev.index)
             if on_host and not trace:
@@ -336,6 +352,22 @@ class UnitSpeech(torch.nn.Module):
             tr = tr.cpu() if trace else None
         return (out, tr) if trace else out
 
+    def _set_denorm(self, h, denorm) -> None:
+        key = None
+        if denorm is not None:
+            lo, hi = (t.detach().to(torch.float32).reshape(-1).cpu().contiguous() for t in denorm)
+            if lo.numel() != self.n_feats or hi.numel() != self.n_feats:
+                raise ValueError(f"denorm=(mel_min, mel_max) must hold {self.n_feats} values each")
+            key = (lo.numpy().tobytes(), hi.numpy().tobytes())
+        if key == getattr(self, "_denorm_key", None) and getattr(self, "_denorm_handle", None) == h.value:
+            return
+        lib = abi.load_library()
+        if denorm is None:
+            abi.check(lib.usb_set_output_denorm(h, None, None))
+        else:
+            abi.check(lib.usb_set_output_denorm(h, lo.data_ptr(), hi.data_ptr()))
+        self._denorm_key, self._denorm_handle = key, h.value
+
     @torch.no_grad()
     def forward(self, z, mask, cond, spk_emb, n_timesteps, text_gradient_scale=0.0, spk_gradient_scale=0.0, **kw):
         """unitspeech/unitspeech.py:387-391."""
@@ -346,21 +378,22 @@ class UnitSpeech(torch.nn.Module):
     def execute_text_to_speech(self, phoneme, phoneme_lengths, spk_emb, text_encoder, duration_predictor,
                                num_downsamplings_in_unet, diffusion_steps=50, length_scale=1.0,
                                text_gradient_scale=1.0, spk_gradient_scale=1.0, noise: Optional[torch.Tensor] = None,
-                               max_frames: Optional[int] = None):
+                               max_frames: Optional[int] = None, denorm: Optional[Sequence[torch.Tensor]] = None):
         """unitspeech/unitspeech.py:414-450: encoder -> durations -> alignment -> z -> reverse diffusion -> crop.
 
         ``max_frames=None`` follows the reference exactly, including its host round trip ``int(y_lengths.max())`` (:428).
         With ``max_frames`` (rounded up by fix_len_compatibility) the glue between the duration predictor and the sampler
         runs in one CUDA kernel (usb_align_expand) at that fixed frame capacity and nothing synchronises with the host:
         the three outputs come back padded to the capacity (frames past an utterance's length are zero) and the
-        per-utterance frame counts are left in ``self.last_y_lengths`` (device int64)."""
+        per-utterance frame counts are left in ``self.last_y_lengths`` (device int64, capped at the capacity; utterances
+        that did not fit are flagged in ``self.last_y_overflow``, device bool)."""
         cond_x, x, x_mask = text_encoder(phoneme, phoneme_lengths)
         logw = duration_predictor(x, x_mask, w=None, g=spk_emb, reverse=True)
         w = torch.exp(logw) * x_mask
         w_ceil = torch.ceil(w) * length_scale
         if max_frames is not None:
             return self._tts_on_device(cond_x, x_mask, w_ceil, spk_emb, num_downsamplings_in_unet, int(max_frames),
-                                       diffusion_steps, text_gradient_scale, spk_gradient_scale, noise)
+                                       diffusion_steps, text_gradient_scale, spk_gradient_scale, noise, denorm)
         y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
         y_max_length = int(y_lengths.max())
         y_max_length_ = fix_len_compatibility(y_max_length, num_downsamplings_in_unet)
@@ -373,11 +406,12 @@ class UnitSpeech(torch.nn.Module):
         z = torch.randn_like(cond_y, device=cond_y.device)
         decoder_outputs = self.forward(z, y_mask, cond_y, spk_emb, n_timesteps=diffusion_steps,
                                        text_gradient_scale=text_gradient_scale, spk_gradient_scale=spk_gradient_scale,
-                                       noise=noise)
+                                       noise=noise, denorm=denorm)
         decoder_outputs = decoder_outputs[:, :, :y_max_length]
         return encoder_outputs, decoder_outputs, attn[:, :, :y_max_length]
 
-    def _tts_on_device(self, cond_x, x_mask, w_ceil, spk_emb, n_down, max_frames, diffusion_steps, tg, sg, noise):
+    def _tts_on_device(self, cond_x, x_mask, w_ceil, spk_emb, n_down, max_frames, diffusion_steps, tg, sg, noise,
+                       denorm=None):
         lib = abi.load_library()
         h = self._ensure_handle(cond_x)
         dev = torch.device("cuda", self._handle_device)
@@ -392,9 +426,11 @@ class UnitSpeech(torch.nn.Module):
             abi.check(lib.usb_align_expand(h, wd.data_ptr(), xm.data_ptr(), cx.data_ptr(), B, Tx, F, T, y_lengths.data_ptr(),
                                            y_mask.data_ptr(), attn.data_ptr(), cond_y.data_ptr(), self._stream(dev.index)))
         self.last_y_lengths = y_lengths
+        # utterances whose predicted durations exceed the frame capacity are truncated at T (device bool, no host sync)
+        self.last_y_overflow = wd.sum(dim=1) > T
         z = torch.randn_like(cond_y)
         dec = self.forward(z, y_mask, cond_y, spk_emb.to(dev), n_timesteps=diffusion_steps, text_gradient_scale=tg,
-                           spk_gradient_scale=sg, noise=noise)
+                           spk_gradient_scale=sg, noise=noise, denorm=denorm)
         return cond_y, dec, attn
 
     # ------------------------------------------------------------------ training objective
@@ -429,7 +465,11 @@ class UnitSpeech(torch.nn.Module):
         if self._tuner is None or self._tuner.dev.index != dev:
             self._tuner = FineTuner(n_feats=self.n_feats, dim=self.dim, dim_mults=self.dim_mults, beta_min=self.beta_min,
                                     beta_max=self.beta_max, pe_scale=self.pe_scale, spk_emb_dim=self.spk_emb_dim, device=dev)
-        self._tuner.load_state_dict(dict(self.state_dict()), strict=True)
+        # the optimizer updates parameters in place (tensor._version counts that); an unchanged set needs no re-upload
+        stamp = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if stamp != getattr(self._tuner, "_source_stamp", None):
+            self._tuner.load_state_dict(dict(self.state_dict()), strict=True)
+            self._tuner._source_stamp = stamp
         return self._tuner
 
     def fused_finetuner(self, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, loss_scale=8192.0):
@@ -453,6 +493,14 @@ class UnitSpeech(torch.nn.Module):
         if T % (2 ** (len(self.dim_mults) - 1)):
             raise ValueError("T must be a multiple of 2**(len(dim_mults)-1) (use fix_len_compatibility)")
         z = torch.randn(x0.shape, dtype=x0.dtype, device=x0.device, requires_grad=False)
+        if torch.is_grad_enabled() and any(isinstance(v, torch.Tensor) and v.requires_grad for v in (x0, cond, spk_emb)):
+            # the reference back-propagates through the estimator into cond / x0 / spk_emb (train_STEP1.py:381,
+            # train_STEP2.py:299 train an encoder that way); the CUDA backward pass only produces the decoder's parameter
+            # gradients, so refuse instead of silently training the caller's encoder on a constant
+            raise NotImplementedError(
+                "unitspeech_b200.UnitSpeech.loss_t computes gradients for the decoder parameters only (the fine-tuning "
+                "path, finetune.py:131-165); x0 / cond / spk_emb require grad here, which needs the reference decoder "
+                "(detach them or wrap the call in torch.no_grad())")
         if self._wants_grad():
             ft = self._ensure_tuner(x0)
             names = [k for k, _ in self.named_parameters()]
@@ -495,11 +543,17 @@ class _DiffusionLoss(torch.autograd.Function):
     def forward(ctx, ft, names, x0, mask, cond, t, spk_emb, z, *params):
         loss = ft.forward(x0, mask, cond, t, spk_emb, z)
         ctx.ft, ctx.names, ctx.devs = ft, names, [p.device for p in params]
+        ctx.generation = ft.generation
         return loss.detach().clone().reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
         ft = ctx.ft
+        if ft.generation != ctx.generation:
+            # the engine keeps ONE set of activations: a second loss_t before this backward has overwritten them
+            raise RuntimeError("unitspeech_b200: the activations of this loss were overwritten by a later loss_t / fine_tune "
+                               "call; call backward() before evaluating the next loss (gradient accumulation over several "
+                               "losses is not supported by the CUDA fine-tune engine)")
         ft.zero_grad()
         ft.backward()
         scale = grad_out.to(ft.dev, torch.float32) / ft.loss_scale

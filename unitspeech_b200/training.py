@@ -202,7 +202,8 @@ class FineTuner:
             self.grads[k] = self.G[off:off + n].view(shp)
             off += al(n)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
-        self.skipped = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.skipped = torch.zeros(1, dtype=torch.int32, device=self.dev)   # Adam steps skipped for a non-finite gradient norm
+        self.generation = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)   # optimizer steps taken (device counter)
         half = dim // 2
         import math
@@ -515,6 +516,7 @@ class FineTuner:
         """Copies one batch into the step's static device buffers (the captured CUDA graph reads them)."""
         B, F, T = x0.shape
         self._plan(B, T)
+        self.generation += 1          # stamps the activations the next backward() will read
         self.x0.copy_(x0.detach())
         self.mu.copy_(cond.detach())
         self.z.copy_(z.detach())

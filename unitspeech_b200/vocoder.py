@@ -197,8 +197,12 @@ class BigVGAN(nn.Module):
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """BigVGAN.forward (models.py:169-191).  x: (B, num_mels, T) -> (B, 1, T * hop), on x's device."""
+    def forward(self, x: torch.Tensor, mel_min: torch.Tensor = None, mel_max: torch.Tensor = None) -> torch.Tensor:
+        """BigVGAN.forward (models.py:169-191).  x: (B, num_mels, T) -> (B, 1, T * hop), on x's device.
+
+        With ``mel_min`` / ``mel_max`` (per-bin, any shape holding num_mels values, as stored in the decoder checkpoint)
+        ``x`` is the decoder's NORMALISED output and the callers' de-normalisation (inference.py:140) is applied while
+        the input is packed, i.e. ``voc(y, mel_min, mel_max) == voc((y + 1) / 2 * (mel_max - mel_min) + mel_min)``."""
         if x.dim() != 3 or x.shape[1] != self.h["num_mels"]:
             raise ValueError(f"expected (B, {self.h['num_mels']}, T) mel, got {tuple(x.shape)}")
         lib = abi.load_library()
@@ -211,6 +215,16 @@ class BigVGAN(nn.Module):
             p = next(self.parameters())
             dev = p.device.index if p.is_cuda and p.device.index is not None else torch.cuda.current_device()
         hp = self._ensure_handle(dev)
+        if (mel_min is None) != (mel_max is None):
+            raise ValueError("mel_min and mel_max must be given together")
+        if mel_min is not None:
+            lo = mel_min.detach().float().reshape(-1).cpu().contiguous()
+            hi = mel_max.detach().float().reshape(-1).cpu().contiguous()
+            if lo.numel() != M or hi.numel() != M:
+                raise ValueError(f"mel_min / mel_max must hold {M} values")
+            abi.check(lib.usb_vocoder_set_input_denorm(hp, lo.data_ptr(), hi.data_ptr()))
+        else:
+            abi.check(lib.usb_vocoder_set_input_denorm(hp, None, None))
         xf = x.detach().float().contiguous()
         out = torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=x.device)
         per = max(1, self.max_frames_per_call // max(T, 1))
