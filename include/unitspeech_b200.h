@@ -116,6 +116,20 @@ int usb_set_output_denorm(usb_handle* h, const float* mel_min_host, const float*
  * non-zero count means the fp16 operand format was out of range for this checkpoint / input. */
 int usb_saturation_count(usb_handle* h, int64_t* count_out, int32_t reset);
 
+/* Launch-bound (small) workloads: instead of ~120 host launches per diffusion step, the sampler replays ONE captured CUDA
+ * graph of a step (device step counter + per-step scalar table; cond / noise / out are staged at fixed device
+ * addresses).  mode -1 = auto (on when (CFG branches x utterances) x frames <= 12288, e.g. the reference callers'
+ * one-utterance calls, inference.py:128), 0 = off, 1 = on.  Same kernels and arguments as the eager loop: results are
+ * bit-identical.  Not used while profiling or when a trace is requested.  usb_graph_steps = steps replayed so far. */
+int usb_set_graph_mode(usb_handle* h, int32_t mode);
+int64_t usb_graph_steps(usb_handle* h);
+/* Small calls also leave most SMs idle in the level-2/3 convolutions (12-60 output tiles for 148 SMs).  In split-K mode
+ * those launches cut a tile's K range into up to 8 work items whose fp32 partial tiles are summed in split order by the
+ * CTA that finishes last (deterministic).  The split factor depends on the layer geometry only, never on the batch, so
+ * an utterance is bit-identical alone or inside a batch AS LONG AS both calls run in the same mode; results differ in
+ * the last fp32 bits between the modes.  mode -1 = auto ((CFG branches x utterances) x frames <= 3072), 0 = off, 1 = on. */
+int usb_set_splitk_mode(usb_handle* h, int32_t mode);
+
 /* bytes of device workspace the handle holds for (Be, T); 0 if that shape has not been planned yet */
 int64_t usb_workspace_bytes(usb_handle* h);
 /* number of kernels launched by the handle since creation (bench.py's gpu_launches) */

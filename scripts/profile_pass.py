@@ -1,4 +1,4 @@
-"""Short profiling workload: the bench configuration (16 utt x 512 frames, text+speaker CFG) for a few diffusion
+"""Short profiling workload: a bench configuration (--batch x --frames, text+speaker CFG) for a few diffusion
 steps, once as warm-up and once measured.  Used under ncu (launch list / --set full); prints nothing timed."""
 import argparse
 import os
@@ -15,10 +15,12 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--frames", type=int, default=512)
 ap.add_argument("--passes", type=int, default=2)
+ap.add_argument("--graph", type=int, default=0, help="sampler CUDA-graph mode: -1 auto, 0 off (plain launches for ncu), 1 on")
 a = ap.parse_args()
 dec = UnitSpeech(80, 128, (1, 2, 4, 8), spk_emb_dim=256)
 dec.load_state_dict(random_init_state_dict(dec, out_scale=1 / 512))
 dec = dec.cuda().eval()
+dec.graph_mode = a.graph
 z, mask, cond, spk, noise = (t.cuda() for t in synthetic_inputs(a.batch, a.frames, a.steps, seed=100))
 for _ in range(a.passes):
     l0 = dec.launch_count

@@ -69,6 +69,9 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_uint64]),
     "usb_set_output_denorm": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "usb_saturation_count": (c_int32, [c_void_p, POINTER(c_int64), c_int32]),
+    "usb_set_graph_mode": (c_int32, [c_void_p, c_int32]),
+    "usb_graph_steps": (c_int64, [c_void_p]),
+    "usb_set_splitk_mode": (c_int32, [c_void_p, c_int32]),
     "usb_workspace_bytes": (c_int64, [c_void_p]),
     "usb_launch_count": (c_int64, [c_void_p]),
     "usb_set_profiling": (c_int32, [c_void_p, c_int32]),

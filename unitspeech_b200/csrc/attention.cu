@@ -21,7 +21,7 @@ __device__ __forceinline__ float exp2f_ftz(float x) {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kDh = 32;                             // dim_head
 constexpr int kPartStride = kDh * kDh + 2 * kDh;    // ctx + m + s
-constexpr int kFoldRows = 32;                       // output channels per fold block
+constexpr int kFoldRows = 32;                       // output channels per fold block (8 when the launch would have few blocks)
 constexpr int kCtxLd = kDh + 4;                     // 36: float4-aligned, conflict-free row stride
 constexpr int kRowHalfs = 40;                       // 32 halfs + 8 pad: 80-byte rows make ldmatrix conflict-free
 
@@ -239,8 +239,10 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnParams p, int
     const float* ph = p.part + (static_cast<long long>(n) * p.heads + h) * nchunks * kPartStride;
     if (tid < kDh) {
         float M = -INFINITY;
+#pragma unroll 8
         for (int c = 0; c < nchunks; ++c) M = fmaxf(M, ph[c * kPartStride + kDh * kDh + tid]);
         float S = 0.f;
+#pragma unroll 8
         for (int c = 0; c < nchunks; ++c)
             S += ph[c * kPartStride + kDh * kDh + kDh + tid] *
                  exp2f_ftz((ph[c * kPartStride + kDh * kDh + tid] - M) * kLog2e);
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnParams p, int
         const int d = i >> 5;
         const float M = M_s[d];
         float a = 0.f;
+#pragma unroll 8
         for (int c = 0; c < nchunks; ++c)
             a += ph[c * kPartStride + i] * exp2f_ftz((ph[c * kPartStride + kDh * kDh + d] - M) * kLog2e);
         o[i] = a / S_s[d];
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnParams p, int
 // grid (ceil(C/32), N): Weff[n][co][h*32+d] = sum_e Wo[co][h*32+e] * ctx[n][h][d][e] for 32 output channels.
 // Plain mode writes Weff (fp16).  Fused-q mode goes on to W'[n][co][c] = g * sum_d' Weff[co][d'] Wq[d'][c] + (co == c),
 // the per-sample 1x1 weight of the whole Residual(Rezero(LinearAttention)) block, and b' = g * b_o.
+template <int kFoldRows>
 __global__ void __launch_bounds__(256) attn_fold_kernel(const AttnParams p, const float* ctx_in) {
     extern __shared__ __align__(16) float sm[];   // ctx [heads*32][36], weff tile [32][hidden + 4], Wo tile [32][hidden]
     const int n = blockIdx.y, tid = threadIdx.x;
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(256) attn_fold_kernel(const AttnParams p, cons
     __syncthreads();
     // W'[co0 + r][c] for the block's 32 rows: thread = column c, rpt rows each, Wq streamed once per thread
     const int groups = 256 / p.C;                 // C in {64, 128, 256}
-    const int rpt = kFoldRows / groups;           // rows per thread: 8, 16 or 32
+    const int rpt = kFoldRows / groups;           // rows per thread: kFoldRows / 4, / 2 or / 1
     const int c = tid % p.C, r0 = (tid / p.C) * rpt;
     const float g = __ldg(p.g);
     float acc[kFoldRows];
@@ -360,12 +364,19 @@ int launch_attn_context(const AttnParams& p, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     static bool fold_attr = false;
     if (!fold_attr) {   // ctx + Weff tile + Wo tile = 48.6 KB of dynamic shared memory
-        e = cudaFuncSetAttribute(attn_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        e = cudaFuncSetAttribute(attn_fold_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return (int)e;
         fold_attr = true;
     }
-    dim3 g3((p.C + kFoldRows - 1) / kFoldRows, p.N);
-    attn_fold_kernel<<<g3, 256, (p.heads * kDh * kCtxLd + kFoldRows * (2 * p.heads * kDh + 4)) * sizeof(float), s>>>(p, ctx);
+    // few samples: 8 output channels per block instead of 32, four times the blocks (a function of the launch shape only;
+    // every output element is computed by the same instruction sequence either way, so results do not change)
+    if (static_cast<long long>((p.C + 31) / 32) * p.N < 2 * 148) {
+        dim3 g3((p.C + 7) / 8, p.N);
+        attn_fold_kernel<8><<<g3, 256, (p.heads * kDh * kCtxLd + 8 * (2 * p.heads * kDh + 4)) * sizeof(float), s>>>(p, ctx);
+    } else {
+        dim3 g3((p.C + 31) / 32, p.N);
+        attn_fold_kernel<32><<<g3, 256, (p.heads * kDh * kCtxLd + 32 * (2 * p.heads * kDh + 4)) * sizeof(float), s>>>(p, ctx);
+    }
     return (int)cudaGetLastError();
 }
 

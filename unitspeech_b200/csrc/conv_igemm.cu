@@ -365,13 +365,16 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float mask_s[2][128];   // per epilogue group: output mask of the patch's columns (0 outside the image)
+    __shared__ int split_last_s;       // split-K: 1 when this CTA took the last ticket of its tile
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr uint32_t kWBytes = 16384u, kPBytes = 16384u, kStageBytes = kWBytes + 2 * kPBytes;
     const int stages = p.stages;
-    const int ksteps = p.taps * (p.chunks0 + p.chunks1);
+    const int ctot = p.chunks0 + p.chunks1;
+    const int ksteps_all = p.taps * ctot;
+    const int ksplit = p.ksplit > 1 ? p.ksplit : 1;      // work item = (tile, K range); total_tiles counts items
     const int pairs_per_phase = (p.patches_per_phase + 1) >> 1;
     const int tiles_per_phase = pairs_per_phase * p.n_tiles_n;
     const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
@@ -407,7 +410,8 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
         // ---------------------------------------------------- TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+            const int tile = item / ksplit, sp = item - tile * ksplit;
             const int ph = tile / tiles_per_phase;
             const int rem = tile - ph * tiles_per_phase;
             const int nt = rem % p.n_tiles_n;
@@ -415,29 +419,28 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
             const PatchCoord c0 = decode_patch(p, ph, 2 * pair), c1 = decode_patch(p, ph, 2 * pair + 1);
             const int bz = p.b_batch_mode == 1 ? ph : 0;
             const uint32_t tx_bytes = kWBytes + kPBytes + (c1.valid ? kPBytes : 0u);
-            int kcoord = 0;
-            for (int t = 0; t < p.taps; ++t) {
+            // K step ks = (tap t, source, 64-channel chunk cc) in the order the weights are packed: kcoord = ks * 64
+            const int k0 = sp * ksteps_all / ksplit, k1 = (sp + 1) * ksteps_all / ksplit;
+            int t = k0 / ctot, r = k0 - t * ctot;
+            for (int ks = k0; ks < k1; ++ks) {
                 const ConvTap tap = p.tap[ph * p.taps + t];
-                for (int src = 0; src < 2; ++src) {
-                    const int chunks = src ? p.chunks1 : p.chunks0;
-                    const CUtensorMap* ma = src ? &map_a1 : &map_a0;
-                    for (int cc = 0; cc < chunks; ++cc, kcoord += kConvBK) {
-                        mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 100 + stage);
-                        if (elect_one()) {
-                            const uint32_t sw = tiles_base + stage * kStageBytes;
-                            const uint32_t fb = full0 + stage * 8;
-                            const int cch = tap.c + cc * kConvBK;
-                            mbar_arrive_expect_tx_a(fb, tx_bytes);
-                            tma_load_3d_a(sw, &map_b, fb, kcoord, nt * 128, bz);
-                            tma_load_5d_a(sw + kWBytes, ma, fb, cch, c0.x0 + tap.dx, tap.p, c0.y0 + tap.dy, c0.n);
-                            if (c1.valid)
-                                tma_load_5d_a(sw + kWBytes + kPBytes, ma, fb, cch, c1.x0 + tap.dx, tap.p, c1.y0 + tap.dy,
-                                              c1.n);
-                        }
-                        __syncwarp();
-                        if (++stage == stages) { stage = 0; phase ^= 1u; }
-                    }
+                const bool src1 = r >= p.chunks0;
+                const CUtensorMap* ma = src1 ? &map_a1 : &map_a0;
+                const int cc = src1 ? r - p.chunks0 : r;
+                mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 100 + stage);
+                if (elect_one()) {
+                    const uint32_t sw = tiles_base + stage * kStageBytes;
+                    const uint32_t fb = full0 + stage * 8;
+                    const int cch = tap.c + cc * kConvBK;
+                    mbar_arrive_expect_tx_a(fb, tx_bytes);
+                    tma_load_3d_a(sw, &map_b, fb, ks * kConvBK, nt * 128, bz);
+                    tma_load_5d_a(sw + kWBytes, ma, fb, cch, c0.x0 + tap.dx, tap.p, c0.y0 + tap.dy, c0.n);
+                    if (c1.valid)
+                        tma_load_5d_a(sw + kWBytes + kPBytes, ma, fb, cch, c1.x0 + tap.dx, tap.p, c1.y0 + tap.dy, c1.n);
                 }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+                if (++r == ctot) { r = 0; ++t; }
             }
         }
     } else if (warp == 1) {
@@ -448,9 +451,11 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
+            const int sp = item % ksplit;
+            const int ksteps = (sp + 1) * ksteps_all / ksplit - sp * ksteps_all / ksplit;
             mbar_wait_a(tempty0 + as * 8, aphase ^ 1u, 200 + as);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as) * 256u;
@@ -492,7 +497,8 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                        static_cast<uint32_t>(lane & 7) * 2u;
         float amax = 0.f;                         // largest |value| packed by this thread (saturation report)
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++it) {
+            const int tile = item / ksplit;
             const int ph = tile / tiles_per_phase;
             const int rem = tile - ph * tiles_per_phase;
             const int nt = rem % p.n_tiles_n;
@@ -501,7 +507,35 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait_a(tfull0 + as * 8, aphase, 400 + as);
             tc_fence_after();
-            if (!pc.valid) {   // odd patch count: the second half of the last pair holds no image
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
+            if (ksplit > 1) {
+                // ---- split-K: park this item's fp32 partial tile ([px][ch]: a warp stores 128 contiguous bytes per pixel),
+                // take a ticket; only the CTA holding the last ticket goes on to reduce + epilogue
+                if (pc.valid) {
+                    float* part = p.kpart + ((static_cast<long long>(item) * 2 + grp) * 128) * 128 + c;
+                    for (int hc = 0; hc < 2; ++hc) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld_32x32(taddr + grp * 128 + hc * 64, v0);
+                        tmem_ld_32x32(taddr + grp * 128 + hc * 64 + 32, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 64; ++j)
+                            __stcg(part + (hc * 64 + j) * 128, __uint_as_float(j < 32 ? v0[j] : v1[j - 32]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_a(tempty0 + as * 8);
+                __threadfence();
+                named_bar_sync(3, kConvEpilogueThreads);
+                if (threadIdx.x == 4 * 32) split_last_s = atomicAdd(p.ktick + tile, 1) == ksplit - 1 ? 1 : 0;
+                named_bar_sync(3, kConvEpilogueThreads);
+                const bool last = split_last_s != 0;
+                named_bar_sync(3, kConvEpilogueThreads);      // split_last_s may be rewritten by the next item
+                if (!last) continue;
+                __threadfence();
+                if (threadIdx.x == 4 * 32) p.ktick[tile] = 0;  // ready for the next launch
+                if (!pc.valid) continue;
+            } else if (!pc.valid) {   // odd patch count: the second half of the last pair holds no image
                 tc_fence_before();
                 mbar_arrive_a(tempty0 + as * 8);
                 continue;
@@ -512,7 +546,6 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
             const float bias = p.bias ? __ldg(p.bias + cg) : 0.f;
             long long* stats_n = p.stats ? p.stats + static_cast<long long>(pc.n) * p.groups * 2 : nullptr;
             const float* mrow = p.mask ? p.mask + static_cast<long long>(pc.n) * p.mask_stride + p.ox_off[ph] : nullptr;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
             float s = 0.f, ss = 0.f;
             const bool full = wlim >= p.BW && hlim >= p.BH;   // every pixel of the patch lies inside the image
             if (mrow) {
@@ -523,12 +556,34 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
             for (int hc = 0; hc < 2; ++hc) {
                 const int pb = hc * 64;           // first pixel of this 64-pixel sub-block inside the patch
                 uint32_t v0[32], v1[32];
-                tmem_ld_32x32(taddr + grp * 128 + pb, v0);
-                tmem_ld_32x32(taddr + grp * 128 + pb + 32, v1);
-                tmem_ld_wait();
-                if (hc == 1) {
-                    tc_fence_before();
-                    mbar_arrive_a(tempty0 + as * 8);
+                if (ksplit > 1) {
+                    // sum of the partial tiles in split order 0 .. ksplit-1 (fixed order: bit-reproducible); 64 independent
+                    // L2 loads are in flight per thread and split (a per-element dependent chain would serialise latencies)
+                    const float* part = p.kpart + ((static_cast<long long>(tile) * ksplit * 2 + grp) * 128 + pb) * 128 + c;
+                    float a[64];
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) a[j] = __ldcg(part + j * 128);
+                    for (int sp = 1; sp < ksplit; ++sp) {
+                        const float* ps = part + static_cast<long long>(sp) * 2 * 128 * 128;
+                        float b[64];
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) b[j] = __ldcg(ps + j * 128);
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) a[j] += b[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {
+                        if (j < 32) v0[j] = __float_as_uint(a[j]);
+                        else v1[j - 32] = __float_as_uint(a[j]);
+                    }
+                } else {
+                    tmem_ld_32x32(taddr + grp * 128 + pb, v0);
+                    tmem_ld_32x32(taddr + grp * 128 + pb + 32, v1);
+                    tmem_ld_wait();
+                    if (hc == 1) {
+                        tc_fence_before();
+                        mbar_arrive_a(tempty0 + as * 8);
+                    }
                 }
                 if (lane == 0) tma_store_wait_read<0>();   // the warp's staging buffer has been read by its last store
                 __syncwarp();
@@ -860,7 +915,7 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         conv_igemm_halo_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));
         return static_cast<int>(cudaGetLastError());
     }
-    if (p.swap_ab) total = static_cast<long long>(p.phases) * ((p.patches_per_phase + 1) / 2) * p.n_tiles_n;
+    if (p.swap_ab) total = static_cast<long long>(p.phases) * ((p.patches_per_phase + 1) / 2) * p.n_tiles_n * (p.ksplit > 1 ? p.ksplit : 1);
     if (total <= 0 || total > 0x7fffffffLL) return static_cast<int>(cudaErrorInvalidValue);
     const int grid = static_cast<int>(total < num_sms ? total : num_sms);
     if (p.swap_ab) {

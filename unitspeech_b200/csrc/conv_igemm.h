@@ -73,6 +73,13 @@ struct ConvParams {
     // fp16 saturation report: incremented once per epilogue thread and tile in which a value reached the
     // fp16 limit (|v| >= 65504 before the satfinite pack); null = not reported
     unsigned long long* sat;
+    // split-K (swapped-operand kernel, small latency-bound calls only): a tile's K range is cut into `ksplit` work items
+    // run by different CTAs; each writes its fp32 partial tile to `kpart`, takes a ticket, and the CTA that arrives last
+    // sums the partials IN SPLIT ORDER (so the result does not depend on which CTA that is) and runs the epilogue.
+    // ksplit is a function of the layer geometry only, never of the batch (bitwise batch invariance).
+    int ksplit;                // 0 / 1 = off
+    float* kpart;              // [tiles * ksplit][2 patches][128 px][128 ch] fp32
+    int* ktick;                // [tiles], zero between launches (the reducing CTA resets its tile's ticket)
 };
 
 struct ConvOp {

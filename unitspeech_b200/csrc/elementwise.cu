@@ -220,37 +220,49 @@ int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
 // =====================================================================================================================
 // GroupNorm apply + Mish (+ embedding vector) (+ residual) * mask
 // =====================================================================================================================
-// out = (Mish(a*v + b) + add + res) * m for 8 channels, with Mish(x) = x - 2x/d, d = e^x(e^x + 2) + 2, and one
-// reciprocal shared by two channels.  12-13 issue slots per element (the kernel is close to issue-bound otherwise).
+// out = (Mish(a*v + b) + add + res) * m for 8 channels.  Mish(x) = x * tanh(softplus(x)) = x - 2x/d with d = e^x (e^x + 2) + 2
+// (exact for x > 20, the reference's softplus threshold, where 2/d rounds to 0).  The kernel is issue-bound, not
+// HBM-bound, unless the instruction count per element stays ~14 (ncu, profiles/): so
+//   * d is built negated and halved, dh = -d/2 = e (-e/2 - 1) - 1, and ONE reciprocal serves two channels:
+//     -2/d0 = dh1 * rcp(dh0 * dh1) (|dh| <= ~1.2e17 each: the product stays finite) -- no separate scale by -2;
+//   * the exponent argument is min(x, 20) * log2(e) from the normalised value itself (no second affine pair in registers);
+//   * the mask multiply is skipped for unmasked pixels (m == 1, warp-uniform almost everywhere).
 template <bool HAS_RES>
 __device__ __forceinline__ uint4 gn_mish8(const uint4& rv, const uint4& rr, const float (&a)[8], const float (&b)[8],
-                                          const float (&al)[8], const float (&bl)[8], const float (&ba)[8], float m) {
-    float v[8], r[8], x[8], d[8], y[8];
+                                          const float (&ba)[8], float m) {
+    float v[8], r[8], x[8], dh[8], y[8];
     unpack8(rv, v);
     if (HAS_RES) unpack8(rr, r);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         x[i] = fmaf(v[i], a[i], b[i]);
-        const float e = ex2_ftz(fminf(fmaf(v[i], al[i], bl[i]), 20.f * kLog2e));
-        d[i] = fmaf(e, e + 2.f, 2.f);
+        const float e = ex2_ftz(fminf(x[i], 20.f) * kLog2e);
+        dh[i] = fmaf(e, fmaf(e, -0.5f, -1.f), -1.f);
     }
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
-        const float rn = rcp_ftz(d[i] * d[i + 1]) * -2.f;   // d <= ~2.4e17 each: the product stays finite
-        float y0 = fmaf(x[i], d[i + 1] * rn, fmaf(v[i], a[i], ba[i]));           // x - 2x/d + (b + add - b) ...
-        float y1 = fmaf(x[i + 1], d[i] * rn, fmaf(v[i + 1], a[i + 1], ba[i + 1]));
+        const float rn = rcp_ftz(dh[i] * dh[i + 1]);
+        float y0 = fmaf(x[i], dh[i + 1] * rn, fmaf(v[i], a[i], ba[i]));           // x - 2x/d + add  (ba = b + add)
+        float y1 = fmaf(x[i + 1], dh[i] * rn, fmaf(v[i + 1], a[i + 1], ba[i + 1]));
         if (HAS_RES) {
             y0 += r[i];
             y1 += r[i + 1];
         }
-        y[i] = y0 * m;
-        y[i + 1] = y1 * m;
+        y[i] = y0;
+        y[i + 1] = y1;
+    }
+    if (m != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] *= m;
     }
     return pack8(y);
 }
 
+// lanes_mod = (pixels a thread advances per load) mod W, so the column of the next pixel is one add and one conditional
+// subtract
 template <bool HAS_RES>
-__global__ void __launch_bounds__(256, HAS_RES ? 2 : 3) gn_apply_kernel(const GnApplyParams p, int pix_per_block, int TP) {
+__global__ void __launch_bounds__(256, HAS_RES ? 2 : 3) gn_apply_kernel(const GnApplyParams p, int pix_per_block, int TP,
+                                                                       int lanes_mod) {
     constexpr int U = 4;  // pixels in flight per thread
     const int n = blockIdx.y;
     const int tq = threadIdx.x % TP;
@@ -263,15 +275,13 @@ __global__ void __launch_bounds__(256, HAS_RES ? 2 : 3) gn_apply_kernel(const Gn
         group_moments(p.stats, n, p.groups, threadIdx.x, count, p.eps, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
     }
     __syncthreads();
-    float a[8], b[8], al[8], bl[8], ba[8];
+    float a[8], b[8], ba[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = tq * 8 + i;
         const int g = c / cpg;
         a[i] = s_rstd[g] * __ldg(p.gamma + c);
         b[i] = __ldg(p.beta + c) - s_mean[g] * a[i];
-        al[i] = a[i] * kLog2e;
-        bl[i] = b[i] * kLog2e;
         ba[i] = b[i] + (p.addvec ? __ldg(p.addvec + static_cast<long long>(n) * p.addvec_stride + c) : 0.f);
     }
     const float* mk = p.mask + static_cast<long long>(n) * p.W;
@@ -292,14 +302,14 @@ __global__ void __launch_bounds__(256, HAS_RES ? 2 : 3) gn_apply_kernel(const Gn
                 if (HAS_RES) rr[u] = ldg_stream(reinterpret_cast<const uint4*>(p.res + o));
                 m[u] = __ldg(mk + xcol);
             }
-            xcol += lanes;
-            while (xcol >= p.W) xcol -= p.W;
+            xcol += lanes_mod;
+            if (xcol >= p.W) xcol -= p.W;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int pix = pix0 + u * lanes;
             if (pix < p_end) {
-                const uint4 o4 = gn_mish8<HAS_RES>(rv[u], rr[u], a, b, al, bl, ba, m[u]);
+                const uint4 o4 = gn_mish8<HAS_RES>(rv[u], rr[u], a, b, ba, m[u]);
                 const __half2* oh = reinterpret_cast<const __half2*>(&o4);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) amax2 = __hmax2(amax2, __habs2(oh[i]));
@@ -327,15 +337,15 @@ int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s) {
     GnApplyParams q = p;
     static const char* dbg_env = getenv("USB_DBG_GN");
     q.dbg = dbg_env ? atoi(dbg_env) : 0;
-    if (p.res) gn_apply_kernel<true><<<grid, threads, 0, s>>>(q, ppb, TP);
-    else gn_apply_kernel<false><<<grid, threads, 0, s>>>(q, ppb, TP);
+    if (p.res) gn_apply_kernel<true><<<grid, threads, 0, s>>>(q, ppb, TP, lanes % p.W);
+    else gn_apply_kernel<false><<<grid, threads, 0, s>>>(q, ppb, TP, lanes % p.W);
     return (int)cudaGetLastError();
 }
 
 // =====================================================================================================================
 // final block apply -> 1x1 conv -> classifier-free-guidance combine -> posterior update
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) final_kernel(const FinalParams p, int pix_per_block, int TP) {
+__global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int pix_per_block, int TP) {
     const int b = blockIdx.y;
     const int tq = threadIdx.x % TP;
     const int pl = threadIdx.x / TP;
@@ -363,12 +373,23 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalParams p, int pix
 #pragma unroll
     for (int i = 0; i < 8; ++i) wf[i] = __ldg(p.wf + tq * 8 + i);
     const float bf = __ldg(p.bf);
+    float c_x = p.c_x, c_s = p.c_s, sigma = p.sigma;
+    const float* noise = p.noise;
+    float* outp = p.out;
+    if (p.step_ctr) {
+        const int i = *p.step_ctr;
+        c_x = __ldg(p.step_tab + 4 * i);
+        c_s = __ldg(p.step_tab + 4 * i + 1);
+        sigma = __ldg(p.step_tab + 4 * i + 2);
+        if (__ldg(p.step_tab + 4 * i + 3) == 0.f) outp = nullptr;      // only the last step writes the caller-visible output
+        if (noise) noise += static_cast<long long>(i) * p.noise_step_stride;
+    }
     const float* mk = p.mask + static_cast<long long>(b) * p.W;
     const int p_begin = blockIdx.x * pix_per_block;
     const int p_end = min(p.P, p_begin + pix_per_block);
     // every lane of a pixel group must run the same number of iterations (shuffles below); U pixels x nb branches of
     // 16-byte loads are issued before any of them is consumed (the kernel is a pure HBM stream of `raw`)
-    constexpr int U = 4;
+    constexpr int U = 2;   // with two 256-thread blocks per SM: 2 x 256 x U x nb 16-byte loads in flight per SM
     const int iters = (p_end - p_begin + lanes * U - 1) / (lanes * U);
     for (int it = 0; it < iters; ++it) {
         uint4 rv[U][3];
@@ -398,8 +419,16 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalParams p, int pix
                     float dot = 0.f;
                     float v[8];
                     unpack8(rv[u][k], v);
+                    // Mish(x) = x - 2x/d, d = e^x (e^x + 2) + 2; one reciprocal serves two channels (MUFU is the scarce pipe)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dot += wf[i] * (mish_fast(v[i] * a[k][i] + sh[k][i]) * m[u]);
+                    for (int i = 0; i < 8; i += 2) {
+                        const float x0 = fmaf(v[i], a[k][i], sh[k][i]), x1 = fmaf(v[i + 1], a[k][i + 1], sh[k][i + 1]);
+                        const float e0 = ex2_ftz(fminf(x0, 20.f) * kLog2e), e1 = ex2_ftz(fminf(x1, 20.f) * kLog2e);
+                        const float d0 = fmaf(e0, e0 + 2.f, 2.f), d1 = fmaf(e1, e1 + 2.f, 2.f);
+                        const float rn = rcp_ftz(d0 * d1) * -2.f;      // d <= ~2.4e17 each: the product stays finite
+                        dot = fmaf(wf[i], fmaf(x0, d1 * rn, x0) * m[u], dot);
+                        dot = fmaf(wf[i + 1], fmaf(x1, d0 * rn, x1) * m[u], dot);
+                    }
                     for (int o = TP >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
                     sc[k] = (dot + bf) * m[u];
                 }
@@ -413,11 +442,11 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalParams p, int pix
                     float score = sf;
                     if (p.nb >= 2) score = score + p.a0 * (sf - sc[0]);
                     if (p.nb >= 3) score = score + p.a1 * (sf - sc[1]);
-                    const float nz = p.noise ? p.noise[q] : 0.f;
-                    const float xn = (p.c_x * p.xt[q] + p.c_s * score + p.sigma * nz) * m[u];
+                    const float nz = noise ? noise[q] : 0.f;
+                    const float xn = (c_x * p.xt[q] + c_s * score + sigma * nz) * m[u];
                     p.xt[q] = xn;
                     if (p.score) p.score[q] = score;
-                    if (p.out) {
+                    if (outp) {
                         float o = xn;
                         if (p.mel_min) {
                             const int yb = pix / p.W;
@@ -425,7 +454,7 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalParams p, int pix
                             // the reference's four separate fp32 ops (no contraction into an fma): bit-identical to the torch expression
                             o = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.f), 2.f), __fsub_rn(hi, lo)), lo);
                         }
-                        p.out[q] = o;
+                        outp[q] = o;
                     }
                 }
             }
@@ -552,14 +581,20 @@ int launch_downsample_mask(const float* src, float* dst, int N, int Wsrc, int Wd
 }
 
 // E[n][j] = T[j] + S[n][j]: per-step time part + per-row speaker part of the stacked ResnetBlock.mlp Linears
-__global__ void emb_combine_kernel(const float* t_part, const float* s_part, float* e, int N, int J) {
+__global__ void emb_combine_kernel(const float* t_part, const float* s_part, float* e, int N, int J, const int* step_ctr) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(N) * J) return;
+    if (step_ctr) t_part += static_cast<long long>(*step_ctr) * J;
     e[i] = t_part[i % J] + s_part[i];
 }
-int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, cudaStream_t s) {
+int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, const int* step_ctr, cudaStream_t s) {
     const long long total = static_cast<long long>(N) * J;
-    emb_combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(t_part, s_part, e, N, J);
+    emb_combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(t_part, s_part, e, N, J, step_ctr);
+    return (int)cudaGetLastError();
+}
+__global__ void step_advance_kernel(int* ctr) { *ctr += 1; }
+int launch_step_advance(int* ctr, cudaStream_t s) {
+    step_advance_kernel<<<1, 1, 0, s>>>(ctr);
     return (int)cudaGetLastError();
 }
 

@@ -130,6 +130,13 @@ enum ConvKind { K3S1 = 0, K3S2 = 1, K1 = 2, KT4 = 3, K3S2D = 4, KT4D = 5 };
 static inline bool kind_up(int kind) { return kind == KT4 || kind == K3S2D; }      // output 2H x 2W, four phases
 static inline bool kind_down(int kind) { return kind == K3S2 || kind == KT4D; }    // parity-split input, output H/2 x W/2
 constexpr int kAttnChunk = 2048;   // positions per attention partial block (upper bound)
+// auto graph mode: (CFG branches x utterances) x frames at or below this replays a captured sampler step (covers one
+// utterance of any practical length with CFG, or 16 utterances x 256 frames); larger workloads are GPU-bound already
+constexpr long long kGraphAutoRowsFrames = 12288;
+// auto split-K mode: one utterance with text + speaker guidance up to 1024 frames (or the same rows x frames otherwise).
+// Narrower than the graph threshold because split-K changes the fp32 summation order: calls on either side of the
+// threshold agree to ~1e-4, not bitwise (the Python layer decides per JOB, so micro-batches and shards of one job agree)
+constexpr long long kSplitKAutoRowsFrames = 3072;
 // positions per partial block: ~16 chunks per sample so small levels still fill the GPU, multiples of 64
 static inline int attn_chunk_for(int P) {
     int c = ((P / 16 + 63) / 64) * 64;
@@ -235,7 +242,28 @@ struct ConvEpilogue {
     const float* res_scale = nullptr;
     const float* mask = nullptr;  // [N][Wout]
     unsigned long long* sat = nullptr;
+    // split-K (latency mode, see ConvParams::ksplit): workspace of `kpart_items` partial tiles + ticket array
+    bool splitk = false;
+    float* kpart = nullptr;
+    int* ktick = nullptr;
+    long long kpart_items = 0;
+    int num_sms = 148;
+    int split_rows = 3;           // rows the split factor is derived for (3: sampler rule below; 0: the launch's own N)
 };
+
+// Split factor of a swapped-kernel conv in latency mode: a function of the per-sample geometry only -- the tile count is
+// taken AS IF the call had 3 rows (one utterance with text + speaker guidance) whatever the batch is, so an utterance is
+// reduced in the same order alone or inside a batch.  A split costs ~8 us (fp32 partial tile through L2, ticket, ordered
+// reduction), i.e. about 24 K steps of MMA time: every split keeps at least that much work, at most 8 splits.
+static int choose_ksplit(const ConvParams& p, int num_sms, int rows) {
+    const long long patches3 = (long long)(rows > 0 ? rows : p.N) * p.tiles_y * p.tiles_x;
+    const long long tiles3 = (long long)p.phases * ((patches3 + 1) / 2) * p.n_tiles_n;
+    const int ksteps = p.taps * (p.chunks0 + p.chunks1);
+    int ks = (int)(num_sms / (tiles3 > 0 ? tiles3 : 1));
+    if (ks > 8) ks = 8;
+    if (ks > ksteps / 24) ks = ksteps / 24;
+    return ks < 1 ? 1 : ks;
+}
 
 // Builds the parameter block + tensor maps of one convolution launch.
 // in0/in1: NHWC fp16 [N][H][W][Ctot*] of which the first C* channels are contracted; out: [N][Hout][Wout][Cout].
@@ -336,6 +364,17 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
         else op.a1 = op.a0;
         USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, 128));
         return make_act_map_yx(&op.o, out, N, H, W, Cout, Cout, 32, 8, 4);
+    }
+    if (p.swap_ab && ep.splitk) {
+        // the decision depends on the geometry only (choose_ksplit); a caller with a fixed-size workspace (the fine-tune
+        // entry) passes its capacity, the sampler plan sizes its workspace afterwards (conv_split_items)
+        const int ks = choose_ksplit(p, ep.num_sms, ep.split_rows);
+        const long long items = (long long)p.phases * ((p.patches_per_phase + 1) / 2) * p.n_tiles_n * ks;
+        if (ks > 1 && (ep.kpart == nullptr || items <= ep.kpart_items)) {
+            p.ksplit = ks;
+            p.kpart = ep.kpart;
+            p.ktick = ep.ktick;
+        }
     }
     USB_TRY(make_act_map(&op.a0, in0, N, H, W, C0tot, C0, kind_down(kind), p.BH, p.BW));
     if (in1) USB_TRY(make_act_map(&op.a1, in1, N, H, W, C1tot, C1, false, p.BH, p.BW));
@@ -440,6 +479,8 @@ struct Op {
 
 struct Plan {
     int Be = 0, T = 0;
+    bool splitk = false;          // latency mode: swapped-kernel convs with few tiles split their K range (ConvParams::ksplit)
+    void* kpart = nullptr;        // split-K partial tiles + tickets (own allocation: sized after the launches are planned)
     void* arena = nullptr;
     size_t arena_bytes = 0;
     std::vector<Op> ops;
@@ -461,6 +502,9 @@ struct Plan {
     __half* final_raw = nullptr;
     long long* final_stats = nullptr;
     float* xt = nullptr;          // [Be][P0] sampler state (only first B rows used)
+    // captured sampler step (one estimator evaluation + fused final update) per (CFG branch count, denorm) -- see
+    // reverse_diffusion; tied to this plan's buffers, destroyed with it
+    std::map<int, cudaGraphExec_t> step_graphs;
 };
 
 }  // namespace usb
@@ -494,9 +538,24 @@ struct usb_handle {
     float* stage_buf = nullptr;   // usb_reverse_diffusion_host: device copies of the host inputs / output
     size_t stage_cap = 0;
     PackBatch* pack = nullptr;    // fine-tune step: recorder of the per-conv data-gradient weight packs (train.h)
+    float* t_kpart = nullptr;     // fine-tune step: split-K workspace of usb_t_conv (2 items per SM) + tickets behind it
+    int* t_ktick = nullptr;
     float* loss_buf = nullptr;    // loss_t: xt, z*mask, cond*mask, score ([B][n_feats][T] each) + 512 doubles of partials
     size_t loss_cap = 0;
     long long launches = 0;
+    // graph-replayed sampler (small workloads are launch-bound: ~120 short kernels per step): staging copies of the
+    // caller's cond / noise / out at fixed addresses, the per-step scalar table and the device step counter
+    int graph_mode = -1;                 // -1 auto (rows x frames <= kGraphAutoRowsFrames), 0 off, 1 on
+    int splitk_mode = -1;                // same encoding: split-K of the few-tile convs (plan property)
+    cudaStream_t cap_stream = nullptr;
+    float* g_stage = nullptr;            // [B*P] cond, [B*P] out, [n*B*P] noise
+    size_t g_cap = 0;
+    float* step_tab = nullptr;           // [n][4]
+    int step_tab_cap = 0;
+    int* step_ctr = nullptr;
+    long long graph_steps = 0;           // sampler steps executed as graph replays (usb_graph_steps)
+    long long graph_launches_per_step = 0;
+    float graph_a0 = 0.f, graph_a1 = 0.f;
     unsigned long long* sat = nullptr;   // device counter of fp16 saturation events (usb_saturation_count)
     float* mel_range = nullptr;          // device [2][n_feats] (mel_min, mel_max) when output de-normalisation is on
     bool denorm = false;
@@ -719,16 +778,25 @@ struct Bump {
     }
 };
 
+static void drop_step_graphs(Plan& pl) {
+    for (auto& kv : pl.step_graphs) cudaGraphExecDestroy(kv.second);
+    pl.step_graphs.clear();
+}
+
 static void free_plan(Plan& pl) {
+    drop_step_graphs(pl);
+    if (pl.kpart) cudaFree(pl.kpart);
     if (pl.arena) cudaFree(pl.arena);
     pl = Plan();
 }
 
 static int build_plan(usb_handle* h, int Be, int T) {
     Plan& pl = h->plan;
-    if (pl.Be == Be && pl.T == T && pl.arena) return 0;
+    const bool splitk = h->splitk_mode == 1 || (h->splitk_mode < 0 && (long long)Be * T <= kSplitKAutoRowsFrames);
+    if (pl.Be == Be && pl.T == T && pl.arena && pl.splitk == splitk) return 0;
     cudaDeviceSynchronize();
     free_plan(pl);
+    pl.splitk = splitk;
     const usb_config& c = h->cfg;
     const int L = h->L, S = c.spk_emb_dim, dim = c.dim, G = c.groups, hid = h->hidden;
     if (T <= 0 || T % (1 << (L - 1))) return fail("T must be a positive multiple of 2^(len(dim_mults)-1)");
@@ -798,6 +866,7 @@ static int build_plan(usb_handle* h, int Be, int T) {
         pl.convs.emplace_back();
         ConvEpilogue eps = ep;
         eps.sat = h->sat;
+        eps.splitk = splitk; eps.num_sms = h->num_sms;
         USB_TRY(build_conv(pl.convs.back(), kind, in0, C0tot, C0, in1, C1tot, C1, Be, H[l], W[l], w ? w->w : wptr,
                            w ? w->Z : wZ, bmode, Cout, eps, out));
         pl.ops.push_back({Op::CONV, (int)pl.convs.size() - 1});
@@ -933,6 +1002,30 @@ static int build_plan(usb_handle* h, int Be, int T) {
                           pl.final_raw));
     }
     if (slot != n_slots) return fail("internal: stats slot count mismatch");
+    // split-K workspace: sized for the launch with the most work items, shared by all (launches are stream-ordered)
+    long long max_items = 0, max_tiles = 0;
+    for (const ConvOp& co : pl.convs)
+        if (co.p.ksplit > 1) {
+            const long long tiles = (long long)co.p.phases * ((co.p.patches_per_phase + 1) / 2) * co.p.n_tiles_n;
+            max_tiles = tiles > max_tiles ? tiles : max_tiles;
+            max_items = tiles * co.p.ksplit > max_items ? tiles * co.p.ksplit : max_items;
+        }
+    if (max_items > 0) {
+        const size_t part_bytes = (size_t)max_items * 2 * 128 * 128 * sizeof(float);
+        cudaError_t e = cudaMalloc(&pl.kpart, part_bytes + (size_t)max_tiles * sizeof(int));
+        if (e != cudaSuccess) {
+            pl.kpart = nullptr;
+            return fail("split-K workspace allocation of " + std::to_string(part_bytes >> 20) + " MiB failed: " + cudaGetErrorString(e));
+        }
+        int* ktick = reinterpret_cast<int*>(static_cast<char*>(pl.kpart) + part_bytes);
+        USB_CUDA(cudaMemset(ktick, 0, (size_t)max_tiles * sizeof(int)));
+        for (ConvOp& co : pl.convs)
+            if (co.p.ksplit > 1) {
+                co.p.kpart = static_cast<float*>(pl.kpart);
+                co.p.ktick = ktick;
+            }
+        pl.arena_bytes += part_bytes;
+    }
     return 0;
 }
 
@@ -1056,13 +1149,15 @@ static EmbedParams embed_params(usb_handle* h) {
     return ep;
 }
 
-static int run_estimator(usb_handle* h, const EstInputs& in, cudaStream_t s, const float* t_part = nullptr) {
+static int run_estimator(usb_handle* h, const EstInputs& in, cudaStream_t s, const float* t_part = nullptr,
+                         const int* step_ctr = nullptr) {
     Plan& pl = h->plan;
     const usb_config& c = h->cfg;
     if (t_part) {
-        // sampler path: E = (time part of this step, computed once per call) + (speaker part, once per call)
+        // sampler path: E = (time part of this step, computed once per call) + (speaker part, once per call);
+        // with step_ctr, t_part is the base of the per-step table and the device counter selects the row
         ProfScope ps(h, s, 3, 0.0);
-        USB_LAUNCH(h, launch_emb_combine(t_part, pl.Spart, pl.E, pl.Be, h->J, s));
+        USB_LAUNCH(h, launch_emb_combine(t_part, pl.Spart, pl.E, pl.Be, h->J, step_ctr, s));
     }
     EmbedParams ep;
     ep.t = in.t_rows; ep.spk = in.spk_rows; ep.freqs = h->freqs; ep.w0 = h->mlp_w0; ep.b0 = h->mlp_b0;
@@ -1197,6 +1292,7 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
         const size_t need = (size_t)n_steps * (1 + Kemb + h->J);
         if (need > h->tpart_cap) {
             USB_CUDA(cudaStreamSynchronize(s));
+            drop_step_graphs(pl);      // the captured step reads the per-step embedding table at its old address
             if (h->tpart_buf) cudaFree(h->tpart_buf);
             h->tpart_buf = nullptr; h->tpart_cap = 0;
             USB_CUDA(cudaMalloc(&h->tpart_buf, need * sizeof(float)));
@@ -1215,14 +1311,13 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
         h->launches += 2;
     }
     const float* d_tpart = h->tpart_buf + n_steps + (size_t)n_steps * Kemb;
-    EstInputs in{pl.xt, cond, h->text_uncon, pl.t_rows, pl.spk_rows};
-    for (int i = 0; i < n_steps; ++i) {
-        USB_TRY(run_estimator(h, in, s, d_tpart + (size_t)i * h->J));
+    const float a0 = nb == 3 ? tg : (use_t ? tg : sg);
+    auto sampler_final = [&](int i, const float* noise_i, cudaStream_t st) -> int {
         FinalParams f = final_params(h, B, nb);
-        f.a0 = nb == 3 ? tg : (use_t ? tg : sg);
+        f.a0 = a0;
         f.a1 = sg;
         f.xt = pl.xt;
-        f.noise = noise ? noise + (size_t)i * B * P : nullptr;
+        f.noise = noise_i;
         f.c_x = coef[i * 3 + 0]; f.c_s = coef[i * 3 + 1]; f.sigma = coef[i * 3 + 2];
         if (i == n_steps - 1) {
             // the reference returns xt * mask (:373; xt is already masked by the update): the last step writes the caller's
@@ -1230,14 +1325,115 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
             f.out = out;
             if (h->denorm) { f.mel_min = h->mel_range; f.mel_max = h->mel_range + c.n_feats; }
         }
-        {
-            // reads the final_block conv output of every CFG branch (fp16) + x_t and noise, writes x_t
-            ProfScope ps(h, s, 3, (double)Be * P * c.dim * 2.0 + (double)B * P * 12.0);
-            USB_LAUNCH(h, launch_final(f, h->num_sms, s));
+        // reads the final_block conv output of every CFG branch (fp16) + x_t and noise, writes x_t
+        ProfScope ps(h, st, 3, (double)Be * P * c.dim * 2.0 + (double)B * P * 12.0);
+        USB_LAUNCH(h, launch_final(f, h->num_sms, st));
+        return 0;
+    };
+    // ---- small workloads: replay ONE captured step (device step counter + per-step scalar table) instead of issuing
+    // ~120 launches per step from the host.  Same kernels, same arguments: results are bit-identical to the eager loop.
+    const bool want_graph = !h->profiling && !trace && n_steps > 2 &&
+                            (h->graph_mode == 1 || (h->graph_mode < 0 && (long long)Be * T <= kGraphAutoRowsFrames));
+    int first_graph_step = n_steps;
+    if (want_graph) {
+        const size_t BP = (size_t)B * P;
+        const size_t need = BP * (2 + (noise ? (size_t)n_steps : 0));
+        if (need > h->g_cap || n_steps > h->step_tab_cap) {
+            USB_CUDA(cudaStreamSynchronize(s));
+            drop_step_graphs(pl);
+            if (need > h->g_cap) {
+                if (h->g_stage) cudaFree(h->g_stage);
+                h->g_stage = nullptr; h->g_cap = 0;
+                USB_CUDA(cudaMalloc(&h->g_stage, need * sizeof(float)));
+                h->g_cap = need;
+            }
+            if (n_steps > h->step_tab_cap) {
+                if (h->step_tab) cudaFree(h->step_tab);
+                h->step_tab = nullptr; h->step_tab_cap = 0;
+                USB_CUDA(cudaMalloc(&h->step_tab, (size_t)n_steps * 4 * sizeof(float)));
+                h->step_tab_cap = n_steps;
+            }
         }
+        if (!h->step_ctr) {
+            USB_CUDA(cudaMalloc(&h->step_ctr, sizeof(int)));
+            USB_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        }
+        first_graph_step = 1;      // step 0 always runs eagerly: it also performs every lazy one-time kernel-attribute set-up
+    }
+    EstInputs in{pl.xt, cond, h->text_uncon, pl.t_rows, pl.spk_rows};
+    for (int i = 0; i < n_steps && i < first_graph_step; ++i) {
+        USB_TRY(run_estimator(h, in, s, d_tpart + (size_t)i * h->J));
+        USB_TRY(sampler_final(i, noise ? noise + (size_t)i * B * P : nullptr, s));
         if (trace)
             USB_CUDA(cudaMemcpyAsync(trace + (size_t)i * B * P, pl.xt, (size_t)B * P * sizeof(float),
                                      cudaMemcpyDeviceToDevice, s));
+    }
+    if (want_graph) {
+        const size_t BP = (size_t)B * P;
+        float *g_cond = h->g_stage, *g_out = g_cond + BP, *g_noise = g_out + BP;
+        std::vector<float> tab((size_t)n_steps * 4);
+        for (int i = 0; i < n_steps; ++i) {
+            tab[4 * i] = coef[i * 3]; tab[4 * i + 1] = coef[i * 3 + 1]; tab[4 * i + 2] = coef[i * 3 + 2];
+            tab[4 * i + 3] = i == n_steps - 1 ? 1.f : 0.f;
+        }
+        // (pageable source: the runtime stages the bytes before the call returns, so `tab` may go out of scope)
+        USB_CUDA(cudaMemcpyAsync(h->step_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        USB_CUDA(cudaMemcpyAsync(g_cond, cond, BP * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (noise)
+            USB_CUDA(cudaMemcpyAsync(g_noise, noise, (size_t)n_steps * BP * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        USB_CUDA(cudaMemsetAsync(h->step_ctr, 0, sizeof(int), s));      // step 0 is done; the graph's first node makes it 1
+        // key: everything baked into the captured arguments besides the plan's own buffers
+        const int key = nb | (h->denorm ? 8 : 0) | (noise ? 16 : 0) | (use_t ? 32 : 0);
+        auto it = pl.step_graphs.find(key);
+        if (it != pl.step_graphs.end() && (h->graph_a0 != a0 || h->graph_a1 != sg)) {   // guidance scales are kernel arguments
+            drop_step_graphs(pl);
+            it = pl.step_graphs.end();
+        }
+        if (it == pl.step_graphs.end()) {
+            cudaStream_t cs = h->cap_stream;
+            const long long launches_before = h->launches;
+            USB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+            int rc = 0;
+            {
+                int e = launch_step_advance(h->step_ctr, cs);
+                h->launches++;
+                if (e != 0) rc = fail("step_advance launch failed");
+            }
+            EstInputs gin{pl.xt, g_cond, h->text_uncon, pl.t_rows, pl.spk_rows};
+            if (!rc) rc = run_estimator(h, gin, cs, d_tpart, h->step_ctr);
+            if (!rc) {
+                FinalParams f = final_params(h, B, nb);
+                f.a0 = a0; f.a1 = sg; f.xt = pl.xt;
+                f.noise = noise ? g_noise : nullptr;
+                f.noise_step_stride = (long long)BP;
+                f.step_ctr = h->step_ctr; f.step_tab = h->step_tab;
+                f.out = g_out;
+                if (h->denorm) { f.mel_min = h->mel_range; f.mel_max = h->mel_range + c.n_feats; }
+                int e = launch_final(f, h->num_sms, cs);
+                h->launches++;
+                if (e != 0) rc = fail("final launch failed during capture");
+            }
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+            h->graph_launches_per_step = h->launches - launches_before;
+            h->launches = launches_before;
+            if (rc) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (ce != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            cudaGraphExec_t exec = nullptr;
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+            pl.step_graphs[key] = exec;
+            h->graph_a0 = a0; h->graph_a1 = sg;
+            it = pl.step_graphs.find(key);
+        }
+        for (int i = first_graph_step; i < n_steps; ++i) USB_CUDA(cudaGraphLaunch(it->second, s));
+        h->launches += h->graph_launches_per_step * (n_steps - first_graph_step);
+        h->graph_steps += n_steps - first_graph_step;
+        USB_CUDA(cudaMemcpyAsync(out, g_out, BP * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     USB_TRY(prof_collect(h, s));
     return 0;
@@ -1307,6 +1503,10 @@ void usb_destroy(usb_handle* h) {
     for (void* p : h->dev_allocs) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->tpart_buf) cudaFree(h->tpart_buf);
+    if (h->g_stage) cudaFree(h->g_stage);
+    if (h->step_tab) cudaFree(h->step_tab);
+    if (h->step_ctr) cudaFree(h->step_ctr);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->loss_buf) cudaFree(h->loss_buf);
     pack_batch_destroy(h->pack);
     if (h->stage_buf) cudaFree(h->stage_buf);
@@ -1447,6 +1647,20 @@ int usb_set_output_denorm(usb_handle* h, const float* mel_min_host, const float*
         USB_CUDA(cudaMemcpy(h->mel_range, mel_min_host, n, cudaMemcpyHostToDevice));
         USB_CUDA(cudaMemcpy(h->mel_range + h->cfg.n_feats, mel_max_host, n, cudaMemcpyHostToDevice));
     }
+    return 0;
+}
+
+int usb_set_graph_mode(usb_handle* h, int32_t mode) {
+    if (!h) return fail("null handle");
+    if (mode < -1 || mode > 1) return fail("graph mode must be -1 (auto), 0 (off) or 1 (on)");
+    h->graph_mode = mode;
+    return 0;
+}
+int64_t usb_graph_steps(usb_handle* h) { return h ? h->graph_steps : 0; }
+int usb_set_splitk_mode(usb_handle* h, int32_t mode) {
+    if (!h) return fail("null handle");
+    if (mode < -1 || mode > 1) return fail("split-K mode must be -1 (auto), 0 (off) or 1 (on)");
+    h->splitk_mode = mode;      // takes effect when the next call plans its workspace
     return 0;
 }
 
@@ -1620,6 +1834,23 @@ int usb_t_conv(usb_handle* h, int32_t kind, const void* in0, int32_t C0tot, int3
     ConvEpilogue ep;
     ep.bias = bias; ep.stats = reinterpret_cast<long long*>(stats); ep.groups = groups > 0 ? groups : 8;
     ep.res = static_cast<const __half*>(res); ep.res_scale = res_scale; ep.mask = mask;
+    // the fine-tune step runs on 8 short crops: the level-2/3 convolutions (forward and data gradient) have 20-100 output
+    // tiles for 148 SMs, so they split K (no batch-invariance contract here: the factor follows the launch's own tile count).
+    // All usb_t_conv launches are issued on one stream, so one workspace serves them.  USB_FT_NO_SPLITK=1 disables it.
+    static const bool no_split = getenv("USB_FT_NO_SPLITK") != nullptr;
+    if (!no_split) {
+        const long long items = 2LL * h->num_sms;
+        if (!h->t_kpart) {
+            void* p = nullptr;
+            USB_CUDA(cudaMalloc(&p, (size_t)items * 2 * 128 * 128 * sizeof(float) + (size_t)items * sizeof(int)));
+            h->dev_allocs.push_back(p);
+            h->t_kpart = static_cast<float*>(p);
+            h->t_ktick = reinterpret_cast<int*>(h->t_kpart + (size_t)items * 2 * 128 * 128);
+            USB_CUDA(cudaMemset(h->t_ktick, 0, (size_t)items * sizeof(int)));
+        }
+        ep.splitk = true; ep.kpart = h->t_kpart; ep.ktick = h->t_ktick; ep.kpart_items = items; ep.num_sms = h->num_sms;
+        ep.split_rows = 0;
+    }
     ConvOp op;
     USB_TRY(build_conv(op, kind, static_cast<const __half*>(in0), C0tot, C0, static_cast<const __half*>(in1), C1tot, C1, N, H, W,
                        static_cast<const __half*>(w), wZ, b_batch_mode, Cout, ep, static_cast<__half*>(out)));

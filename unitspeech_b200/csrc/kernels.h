@@ -68,6 +68,11 @@ struct FinalParams {
     float* out;            // [B][P] or null
     const float* mel_min;  // [H] device or null
     const float* mel_max;  // [H]
+    // graph-replayed sampler step: the per-step scalars come from a device table indexed by a device step counter, so ONE
+    // captured launch sequence serves every step (null step_ctr: the host-provided scalars above are used)
+    const int* step_ctr;          // current step i
+    const float* step_tab;        // [n][4] = c_x, c_s, sigma, (1 if last step else 0); a0 / a1 stay kernel arguments
+    long long noise_step_stride;  // elements between the noise slices of consecutive steps (noise then is the base)
 };
 int launch_final(const FinalParams& p, int num_sms, cudaStream_t s);
 
@@ -88,7 +93,10 @@ struct EmbedParams {
     float pe_scale;
 };
 int launch_embed(const EmbedParams& p, cudaStream_t s);   // t or spk may be null (that half of u is 0); bcat may be null
-int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, cudaStream_t s);
+// step_ctr != null: t_part is the base of the [n][J] per-step table and row *step_ctr is used
+int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, const int* step_ctr, cudaStream_t s);
+// *ctr += 1 (first node of the captured sampler step)
+int launch_step_advance(int* ctr, cudaStream_t s);
 
 // ---- LinearAttention context: softmax over positions of k, ctx = k_sm^T v, folded with to_out  (unitspeech.py:86-96)
 struct AttnParams {

@@ -226,6 +226,196 @@ __global__ void __launch_bounds__(256, 3) snake_act_kernel(const ActParams p) {
 
 #undef act_sidx
 
+// =====================================================================================================================
+// Activation1d, second version: register-resident 2x-rate signal.
+// The first kernel keeps the up-sampled, Snake'd signal in shared memory (25 128-bit shared-memory operations per 8
+// output values: it is shared-memory-bandwidth bound at 1/6 of the HBM roofline, ncu profiles/r1_snake_act_*).  Here a thread
+// owns 4 channels and a RUN of kAct2TO consecutive outputs and walks it sample by sample: step t computes the two
+// 2x-rate samples s[2t+5], s[2t+6] (the last two that output t needs; both are filters over the same six inputs
+// x[t .. t+5]) and scatters them into the six partial outputs t .. t+5 they contribute to (12 taps: out[t'] +=
+// f[10-2d] s[2t+5] + f[11-2d] s[2t+6], d = t' - t); output t is then complete.  The 2x-rate signal never leaves registers;
+// shared memory only holds the fp16 input tile (one 8-byte read per step).  A run re-computes the 10 samples before its
+// first output (5 warm-up steps): 24 steps for 19 outputs.
+// =====================================================================================================================
+constexpr int kAct2TO = 19;                 // outputs per run
+constexpr int kAct2Steps = kAct2TO + 5;     // + warm-up; a multiple of 6 (the step loop is unrolled by the 6 partial outputs)
+static_assert(kAct2Steps % 6 == 0, "the step loop is unrolled in groups of 6");
+
+static inline int act2_ncol(int creal) {    // 4-channel columns per block: the largest even divisor <= 16 of creal / 4
+    const int cols = (creal + 3) / 4;
+    for (int n = 16; n >= 2; n -= 2)
+        if (cols % n == 0) return n;
+    return 2;
+}
+static inline size_t act2_smem_bytes(int ncol) { return static_cast<size_t>((256 / ncol) * kAct2TO + 10) * ncol * 8; }
+
+// one 2x-rate sample for 4 channels from six consecutive input rows; ODD: i = 2m+1 uses f[10-2j], even uses f[11-2j]
+template <bool ODD>
+__device__ __forceinline__ void act2_srow(const float (&x)[6][4], const float (&f2)[12], const float (&al)[4],
+                                          const float (&ib)[4], float (&s)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float u = 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) u = fmaf(f2[ODD ? 10 - 2 * j : 11 - 2 * j], x[j][c], u);
+        // MUFU.SIN reduces its argument itself; absolute error ~|x| * 2^-24, far below the fp16 storage of the result
+        const float sn = __sinf(al[c] * u);
+        s[c] = fmaf(ib[c] * sn, sn, u);
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) snake_act2_kernel(const ActParams p, int ncol) {
+    extern __shared__ __align__(16) unsigned char act2_smem[];     // fp16 input tile [rows][ncol * 4 channels]
+    const int tid = threadIdx.x;
+    const int R = blockDim.x / ncol;                 // runs per block
+    const int TLB = R * kAct2TO;                     // outputs per block
+    const int t0 = blockIdx.x * TLB;
+    const int c_blk = blockIdx.y * ncol * 4;         // first channel of this block
+    const long long nbase = static_cast<long long>(blockIdx.z) * p.L;
+    const int pitch = ncol * 8;                      // bytes per tile row
+    const int rows = TLB + 10;                       // inputs t0-5 .. t0+TLB+4
+    if (blockIdx.y == 0) {                           // layout padding channels [Creal, C) are written as zeros
+        const int npad = (p.C - p.Creal) >> 3;
+        const int pad0 = p.Creal >> 3;
+        for (int idx = tid; idx < TLB * npad; idx += blockDim.x) {
+            const int t = t0 + idx / npad;
+            if (t < p.L)
+                *reinterpret_cast<uint4*>(p.out + (nbase + t) * p.C + (pad0 + idx % npad) * 8) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    {   // tile load, replicate padding at the signal ends (UpSample1d pads by replication, resample.py:26-29)
+        const int cpr = ncol >> 1;                   // 16-byte chunks per row
+        for (int idx = tid; idx < rows * cpr; idx += blockDim.x) {
+            const int row = idx / cpr, ch = idx - row * cpr;
+            int t = t0 - 5 + row;
+            t = t < 0 ? 0 : (t > p.L - 1 ? p.L - 1 : t);
+            *reinterpret_cast<uint4*>(act2_smem + row * pitch + ch * 16) =
+                __ldg(reinterpret_cast<const uint4*>(p.x + (nbase + t) * p.C + c_blk + ch * 8));
+        }
+    }
+    const int col = tid % ncol, run = tid / ncol;
+    const int c0 = c_blk + col * 4;
+    float al[4], ib[4], f2[12], f1[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        al[j] = __ldg(p.alpha + c0 + j);
+        ib[j] = __ldg(p.invbeta + c0 + j);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        f1[k] = p.filt[k];
+        f2[k] = 2.f * p.filt[k];      // UpSample1d multiplies by the ratio (resample.py:31)
+    }
+    __syncthreads();
+    const int tr = t0 + run * kAct2TO;               // first output of this run
+    if (tr >= p.L) return;
+    const unsigned char* xcol = act2_smem + col * 8;
+    const int imax = 2 * p.L - 1;
+    auto load_rows = [&](int t_first, float (&x)[6][4], int nrows_off) {
+        (void)nrows_off;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(xcol + (t_first + j - (t0 - 5)) * pitch);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            x[j][0] = a.x; x[j][1] = a.y; x[j][2] = b.x; x[j][3] = b.y;
+        }
+    };
+    // a sample whose index falls outside [0, 2L-1] is the replicate padding of the low-pass filter (filter.py:90):
+    // it equals s[0] / s[2L-1], recomputed from the inputs around that end
+    auto edge_sample = [&](int i, float (&sv)[4]) {
+        const int ic = i < 0 ? 0 : imax;
+        const int m = ic >> 1;
+        float x[6][4];
+        if (ic & 1) { load_rows(m - 2, x, 0); act2_srow<true>(x, f2, al, ib, sv); }
+        else { load_rows(m - 3, x, 0); act2_srow<false>(x, f2, al, ib, sv); }
+    };
+    float acc[6][4];
+#pragma unroll
+    for (int d = 0; d < 6; ++d)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[d][c] = 0.f;
+    for (int g = 0; g < kAct2Steps / 6; ++g) {
+        const int tg = tr - 5 + g * 6;               // first step of this group
+        if (tg >= p.L) break;                        // every remaining output lies beyond the signal
+        // inputs tg .. tg+10 serve the six steps of the group
+        float xw[11][4];
+#pragma unroll
+        for (int j = 0; j < 11; ++j) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(xcol + (tg + j - (t0 - 5)) * pitch);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            xw[j][0] = a.x; xw[j][1] = a.y; xw[j][2] = b.x; xw[j][3] = b.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int t = tg + k;                    // this step completes output t (slot k of acc)
+            float so[4], se[4];                      // s[2t+5] (odd index), s[2t+6] (even index)
+            const int io = 2 * t + 5, ie = 2 * t + 6;
+            if (io >= 0 && ie <= imax) {
+                float x6[6][4];
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) x6[j][c] = xw[k + j][c];
+                act2_srow<true>(x6, f2, al, ib, so);
+                act2_srow<false>(x6, f2, al, ib, se);
+            } else {
+                if (io >= 0 && io <= imax) {
+                    float x6[6][4];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) x6[j][c] = xw[k + j][c];
+                    act2_srow<true>(x6, f2, al, ib, so);
+                } else {
+                    edge_sample(io, so);
+                }
+                if (ie >= 0 && ie <= imax) {
+                    float x6[6][4];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) x6[j][c] = xw[k + j][c];
+                    act2_srow<false>(x6, f2, al, ib, se);
+                } else {
+                    edge_sample(ie, se);
+                }
+            }
+            // scatter into the partial outputs t .. t+5: slot (k + d) % 6 holds output t + d
+#pragma unroll
+            for (int d = 0; d < 6; ++d)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    acc[(k + d) % 6][c] = fmaf(f1[10 - 2 * d], so[c], fmaf(f1[11 - 2 * d], se[c], acc[(k + d) % 6][c]));
+            // output t is complete (all 12 taps added over steps t-5 .. t); emit it unless it is a warm-up step
+            if (t >= tr && t < p.L) {
+                uint2 pk;
+                *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(acc[k][0], acc[k][1]);
+                *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(acc[k][2], acc[k][3]);
+                *reinterpret_cast<uint2*>(p.out + (nbase + t) * p.C + c0) = pk;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[k][c] = 0.f;     // the slot now collects output t + 6
+        }
+    }
+}
+
+// USB_SNAKE_V1=1 selects the first (shared-memory) kernel for A/B measurements
+static void launch_snake_act(const ActParams& a, int N, cudaStream_t s) {
+    static const bool v1 = getenv("USB_SNAKE_V1") != nullptr;
+    if (v1 || (a.Creal & 7)) {
+        const int nvec = (a.Creal + 7) / 8;
+        const dim3 grid((a.L + kActTL - 1) / kActTL, (nvec + a.vb - 1) / a.vb, N);
+        snake_act_kernel<<<grid, 32 * a.vb, act_smem_bytes(a.vb), s>>>(a);
+        return;
+    }
+    const int ncol = act2_ncol(a.Creal);
+    const int R = 256 / ncol;
+    const dim3 grid((a.L + R * kAct2TO - 1) / (R * kAct2TO), (a.Creal / 4) / ncol, N);
+    snake_act2_kernel<<<grid, R * ncol, act2_smem_bytes(ncol), s>>>(a, ncol);
+}
+
 // mel (B, M, T) fp32 -> [B][T][Cp] fp16, zero padded channels.  mel_min != null: `mel` is the decoder's normalised
 // output and is de-normalised on the way in, (y + 1) / 2 * (mel_max - mel_min) + mel_min (inference.py:140)
 __global__ void mel_pack_kernel(const float* __restrict__ mel, __half* __restrict__ out, int B, int M, int T, int Cp,
@@ -718,9 +908,7 @@ static int voc_forward(usb_vocoder* h, const float* mel, int B, int T, float* ou
                 break;
             }
             case VocOp::ACT: {
-                const int nvec = (op.act.Creal + 7) / 8;
-                const dim3 grid((op.act.L + kActTL - 1) / kActTL, (nvec + op.act.vb - 1) / op.act.vb, op.N);
-                snake_act_kernel<<<grid, 32 * op.act.vb, act_smem_bytes(op.act.vb), s>>>(op.act);
+                launch_snake_act(op.act, op.N, s);
                 break;
             }
             case VocOp::ACCUM:
@@ -903,9 +1091,7 @@ int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, in
     p.vb = act_vb(c_real);
     kaiser_sinc_12(p.filt);
     VOC_CUDA(cudaFuncSetAttribute(snake_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kActSmemBytes));
-    const int nvec = (c_real + 7) / 8;
-    const dim3 grid((L + kActTL - 1) / kActTL, (nvec + p.vb - 1) / p.vb, N);
-    snake_act_kernel<<<grid, 32 * p.vb, act_smem_bytes(p.vb), reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    launch_snake_act(p, N, reinterpret_cast<cudaStream_t>(stream));
     VOC_CUDA(cudaGetLastError());
     return 0;
 }

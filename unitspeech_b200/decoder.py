@@ -150,6 +150,8 @@ class UnitSpeech(torch.nn.Module):
         self.estimator = GradLogPEstimator2d(dim, dim_mults=dim_mults, pe_scale=pe_scale, spk_emb_dim=spk_emb_dim)
         object.__setattr__(self.estimator, "_owner", self)
         self.max_rows_frames = 96 * 1000   # (CFG branches x utterances) x frames per library call; see reverse_diffusion
+        self._graph_mode = -1              # CUDA-graph replay of the sampler step: -1 auto (small calls), 0 off, 1 on
+        self._splitk_mode = -1             # split-K of the few-tile convolutions: same encoding
         self._handle = None
         self._handle_device = None
         self._weights_version = 0
@@ -224,6 +226,8 @@ class UnitSpeech(torch.nn.Module):
                 shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
                 abi.check(lib.usb_load_param(hp, key.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()))
             abi.check(lib.usb_finalize_params(hp))
+            abi.check(lib.usb_set_graph_mode(hp, int(self._graph_mode)))
+            abi.check(lib.usb_set_splitk_mode(hp, int(self._splitk_mode)))
         except Exception:
             lib.usb_destroy(hp)
             raise
@@ -241,6 +245,49 @@ class UnitSpeech(torch.nn.Module):
     @property
     def workspace_bytes(self) -> int:
         return int(abi.load_library().usb_workspace_bytes(self._handle)) if self._handle is not None else 0
+
+    @property
+    def graph_mode(self) -> int:
+        """-1: replay one captured CUDA graph per diffusion step when the call is small enough to be launch-bound
+        ((CFG branches x utterances) x frames <= 12288, e.g. the reference callers' one-utterance calls); 0: never; 1: always.
+        Results are bit-identical either way (same kernels, same arguments)."""
+        return self._graph_mode
+
+    @graph_mode.setter
+    def graph_mode(self, mode: int) -> None:
+        if int(mode) not in (-1, 0, 1):
+            raise ValueError("graph_mode must be -1 (auto), 0 (off) or 1 (on)")
+        self._graph_mode = int(mode)
+        if self._handle is not None:
+            abi.check(abi.load_library().usb_set_graph_mode(self._handle, self._graph_mode))
+
+    @property
+    def splitk_mode(self) -> int:
+        """-1: small (latency-bound) calls split the K range of the level-2/3 convolutions over otherwise idle SMs, with a
+        fixed-order reduction (deterministic; the split depends on the layer geometry only); 0: never; 1: always.  A call is
+        bit-identical to the same utterances sampled alone as long as both run in the same mode (auto: both
+        (CFG branches x utterances) x frames <= 12288, or both above); the two modes differ in the last fp32 bits."""
+        return self._splitk_mode
+
+    @splitk_mode.setter
+    def splitk_mode(self, mode: int) -> None:
+        if int(mode) not in (-1, 0, 1):
+            raise ValueError("splitk_mode must be -1 (auto), 0 (off) or 1 (on)")
+        self._splitk_mode = int(mode)
+        if self._handle is not None:
+            abi.check(abi.load_library().usb_set_splitk_mode(self._handle, self._splitk_mode))
+
+    SPLITK_AUTO_ROWS_FRAMES = 3072      # kSplitKAutoRowsFrames of csrc/engine.cu
+
+    def job_splitk_mode(self, rows_frames: int) -> int:
+        """The explicit mode (0 / 1) the auto rule picks for a job of `rows_frames` = (CFG branches x utterances) x frames.
+        Used to pin one decision for all parts of a job that is cut into micro-batches or shards."""
+        return self._splitk_mode if self._splitk_mode != -1 else (1 if rows_frames <= self.SPLITK_AUTO_ROWS_FRAMES else 0)
+
+    @property
+    def graph_steps(self) -> int:
+        """Diffusion steps executed as graph replays since the handle was created."""
+        return int(abi.load_library().usb_graph_steps(self._handle)) if self._handle is not None else 0
 
     def saturation_count(self, reset: bool = False) -> int:
         """Number of kernel epilogue threads that clamped a value to the fp16 limit (+-65504) since the handle was
@@ -312,13 +359,20 @@ class UnitSpeech(torch.nn.Module):
         max_b = max(1, int(self.max_rows_frames) // (nb * T))
         if B > max_b:
             outs, traces = [], []
-            for b0 in range(0, B, max_b):
-                sl = slice(b0, min(B, b0 + max_b))
-                r = self.reverse_diffusion(z[sl], mask[sl], cond[sl], spk_emb[sl], n_timesteps, text_gradient_scale,
-                                           spk_gradient_scale, noise=noise[:, sl], trace=trace, denorm=denorm)
-                outs.append(r[0] if trace else r)
-                if trace:
-                    traces.append(r[1])
+            # the split-K decision (which fixes the fp32 summation order) is taken for the JOB, so that every micro-batch
+            # -- including a short last one -- rounds like the others
+            saved = self._splitk_mode
+            self.splitk_mode = self.job_splitk_mode(nb * B * T)
+            try:
+                for b0 in range(0, B, max_b):
+                    sl = slice(b0, min(B, b0 + max_b))
+                    r = self.reverse_diffusion(z[sl], mask[sl], cond[sl], spk_emb[sl], n_timesteps, text_gradient_scale,
+                                               spk_gradient_scale, noise=noise[:, sl], trace=trace, denorm=denorm)
+                    outs.append(r[0] if trace else r)
+                    if trace:
+                        traces.append(r[1])
+            finally:
+                self.splitk_mode = saved
             out = torch.cat(outs, 0)
             return (out, torch.cat(traces, 1)) if trace else out
         coef = schedule.step_coefficients(n_timesteps, self.beta_min, self.beta_max).contiguous()

@@ -63,8 +63,19 @@ def sample_sharded(decoder, z, mask, cond, spk_emb, n_timesteps, text_gradient_s
         raise ValueError(f"noise holds {noise.shape[1]} utterances, expected {(e - b) if noise_is_local else n}")
     if e > b:
         local_noise = None if noise is None else (noise if noise_is_local else noise[:, b:e])
-        out = decoder(z[b:e], mask[b:e], cond[b:e], spk_emb[b:e], n_timesteps, text_gradient_scale, spk_gradient_scale,
-                      noise=local_noise)
+        # numerics decisions that depend on the call size (split-K mode of the CUDA decoder) are taken for the whole job,
+        # so a sharded job equals the same job on one GPU bit for bit
+        pin = getattr(decoder, "job_splitk_mode", None)
+        if pin is not None:
+            nb = 1 + (1 if float(text_gradient_scale) > 0 else 0) + (1 if float(spk_gradient_scale) > 0 else 0)
+            saved = decoder.splitk_mode
+            decoder.splitk_mode = pin(nb * n * z.shape[-1])
+        try:
+            out = decoder(z[b:e], mask[b:e], cond[b:e], spk_emb[b:e], n_timesteps, text_gradient_scale,
+                          spk_gradient_scale, noise=local_noise)
+        finally:
+            if pin is not None:
+                decoder.splitk_mode = saved
     else:
         out = z.new_zeros((0,) + tuple(z.shape[1:]))
     return gather_utterances(out, n, group)
