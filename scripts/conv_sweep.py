@@ -20,6 +20,13 @@ SHAPES = {  # name: kind, N, H, W, C0, C1, Cout, stats
     "qkv_l1": (2, 48, 40, 256, 256, 0, 384, 0),
     "res_l1": (2, 48, 40, 256, 128, 0, 256, 0),
     "res_u2": (2, 48, 40, 256, 256, 256, 128, 0),
+    # the per-GPU shard of BASELINE configs[2] (Be = 96, T = 1000): strided / transposed convs
+    "up_l1_T1000": (3, 96, 40, 500, 128, 0, 128, 0),
+    "up_l2_T1000": (3, 96, 20, 250, 256, 0, 256, 0),
+    "up_l3_T1000": (3, 96, 10, 125, 512, 0, 512, 0),
+    "down_l0_T1000": (1, 96, 80, 1000, 128, 0, 128, 0),
+    "down_l1_T1000": (1, 96, 40, 500, 256, 0, 256, 0),
+    "l0_128_T1000": (0, 96, 80, 1000, 128, 0, 128, 1),
 }
 
 def run_one(names):

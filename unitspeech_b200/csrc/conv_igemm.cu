@@ -535,7 +535,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                 __threadfence();
                 if (threadIdx.x == 4 * 32) p.ktick[tile] = 0;  // ready for the next launch
                 if (!pc.valid) continue;
-            } else if (!pc.valid) {   // odd patch count: the second half of the last pair holds no image
+            } else if (!pc.valid || (p.dbg_flags & 2)) {   // odd patch count: the second half of the last pair holds no image
                 tc_fence_before();
                 mbar_arrive_a(tempty0 + as * 8);
                 continue;

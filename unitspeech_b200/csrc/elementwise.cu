@@ -24,6 +24,34 @@ __device__ __forceinline__ float rcp_ftz(float x) {
 }
 constexpr float kLog2e = 1.4426950408889634f;
 
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2, two IEEE fp32 operations per issue slot; each lane rounds
+// exactly like the scalar instruction).  The streaming kernels below are issue-bound, not bandwidth-bound, so halving the
+// slots of their FMA work is what moves them towards the HBM roofline.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // x * tanh(softplus(x)) = x * w / (w + 2) with w = e^x (e^x + 2); exact for x > 20 (ratio rounds to 1), which is
 // the reference's softplus threshold (unitspeech.py:13-15).
 __device__ __forceinline__ float mish_fast(float x) {
@@ -88,10 +116,12 @@ __device__ __forceinline__ void group_moments(const long long* stats, int n, int
 // One block = one image row segment of up to 64 pixels: the masked 3 x 66 x 2 input halo is staged in shared memory
 // once; each warp then walks 8 pixels, every lane producing CL consecutive output channels (weights in registers),
 // so a warp writes one pixel's contiguous channel vector per store instruction.
-template <int CL>
-__global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p, int tiles_per_block) {
+template <int CL, int MINB>
+__global__ void __launch_bounds__(256, MINB) first_conv_kernel(const FirstConvParams p, int tiles_per_block) {
     constexpr int TW = 64;
-    __shared__ float tile[3][TW + 2][2];
+    constexpr int CP = CL / 2;                       // channel pairs per lane (packed fp32x2 arithmetic, see fma2)
+    // every input value is stored twice, (mu, mu, x, x): one 16-byte read yields the two packed multiplicands of a tap
+    __shared__ __align__(16) float tile[3][TW + 2][4];
     __shared__ unsigned long long gsum[16];
     const int n = blockIdx.y;
     const int W = p.W, H = p.H, P = H * W, C = p.C;
@@ -107,19 +137,19 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
     const int t_begin = blockIdx.x * tiles_per_block, t_end = min(n_tiles, t_begin + tiles_per_block);
     for (int ps = 0; ps < passes; ++ps) {
         const int c0 = ps * 32 * CL + lane * CL;
-        float w3[18][CL], w1[2][CL], b3[CL], b1[CL];
+        f32x2 w3[18][CP], w1[2][CP], b3[CP], b1[CP];
 #pragma unroll
         for (int k = 0; k < 18; ++k)
 #pragma unroll
-            for (int i = 0; i < CL; ++i) w3[k][i] = __ldg(p.w3 + k * C + c0 + i);
+            for (int i = 0; i < CP; ++i) w3[k][i] = pk2(__ldg(p.w3 + k * C + c0 + 2 * i), __ldg(p.w3 + k * C + c0 + 2 * i + 1));
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int i = 0; i < CL; ++i) w1[k][i] = __ldg(p.w1 + k * C + c0 + i);
+            for (int i = 0; i < CP; ++i) w1[k][i] = pk2(__ldg(p.w1 + k * C + c0 + 2 * i), __ldg(p.w1 + k * C + c0 + 2 * i + 1));
 #pragma unroll
-        for (int i = 0; i < CL; ++i) {
-            b3[i] = __ldg(p.b3 + c0 + i);
-            b1[i] = __ldg(p.b1 + c0 + i);
+        for (int i = 0; i < CP; ++i) {
+            b3[i] = pk2(__ldg(p.b3 + c0 + 2 * i), __ldg(p.b3 + c0 + 2 * i + 1));
+            b1[i] = pk2(__ldg(p.b1 + c0 + 2 * i), __ldg(p.b1 + c0 + 2 * i + 1));
         }
         // GroupNorm partials: one fp32 partial per (warp, row tile, group) -- a partition that does not depend on
         // the launch geometry -- converted to fixed point and accumulated as integers (bitwise batch invariance)
@@ -127,7 +157,7 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
         const int lpg = cpg / CL;  // lanes per group (power of two, <= 32); lanes of one group are adjacent
         long long is = 0, iss = 0;
         for (int t = t_begin; t < t_end; ++t) {
-            float s = 0.f, ss = 0.f;
+            f32x2 s2 = pk2(0.f, 0.f), ss2 = pk2(0.f, 0.f);
             const int y = t / tiles_x;
             const int x0 = (t - y * tiles_x) * TW;
             __syncthreads();   // previous tile fully consumed
@@ -140,17 +170,16 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
                     vm = (ms ? __ldg(ms + yy * W + xx) : __ldg(p.text_uncon + yy)) * m;   // channel 0 = mu
                     vx = __ldg(xs + yy * W + xx) * m;                                     // channel 1 = x_t
                 }
-                tile[r][c][0] = vm;
-                tile[r][c][1] = vx;
+                *reinterpret_cast<float4*>(&tile[r][c][0]) = make_float4(vm, vm, vx, vx);
             }
             __syncthreads();
             for (int j = 0; j < TW / 8; ++j) {
                 const int px = warp * (TW / 8) + j;
                 const int x = x0 + px;
                 if (x >= W) break;
-                float acc[CL], rr[CL];
+                f32x2 acc[CP], rr[CP];
 #pragma unroll
-                for (int i = 0; i < CL; ++i) {
+                for (int i = 0; i < CP; ++i) {
                     acc[i] = b3[i];
                     rr[i] = b1[i];
                 }
@@ -158,35 +187,45 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
                 for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
-                        const float2 v = *reinterpret_cast<const float2*>(&tile[dy][px + dx][0]);
+                        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tile[dy][px + dx][0]);   // (mu, mu), (x, x)
 #pragma unroll
-                        for (int i = 0; i < CL; ++i) {
-                            acc[i] = fmaf(v.x, w3[(dy * 3 + dx) * 2][i], acc[i]);
-                            acc[i] = fmaf(v.y, w3[(dy * 3 + dx) * 2 + 1][i], acc[i]);
+                        for (int i = 0; i < CP; ++i) {
+                            acc[i] = fma2(v.x, w3[(dy * 3 + dx) * 2][i], acc[i]);
+                            acc[i] = fma2(v.y, w3[(dy * 3 + dx) * 2 + 1][i], acc[i]);
                         }
                     }
                 {
-                    const float2 v = *reinterpret_cast<const float2*>(&tile[1][px + 1][0]);
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tile[1][px + 1][0]);
 #pragma unroll
-                    for (int i = 0; i < CL; ++i) rr[i] = fmaf(v.y, w1[1][i], fmaf(v.x, w1[0][i], rr[i]));
+                    for (int i = 0; i < CP; ++i) rr[i] = fma2(v.y, w1[1][i], fma2(v.x, w1[0][i], rr[i]));
                 }
 #pragma unroll
-                for (int i = 0; i < CL; ++i) {
-                    s += acc[i];
-                    ss = fmaf(acc[i], acc[i], ss);
+                for (int i = 0; i < CP; ++i) {
+                    s2 = add2(s2, acc[i]);
+                    ss2 = fma2(acc[i], acc[i], ss2);
                 }
                 const long long o = (static_cast<long long>(n) * P + static_cast<long long>(y) * W + x) * C + c0;
+                float a0, a1, r0, r1;
                 if (CL == 4) {
                     uint2 a, r;
-                    a.x = pack2(acc[0], acc[1]); a.y = pack2(acc[2], acc[3]);
-                    r.x = pack2(rr[0], rr[1]);   r.y = pack2(rr[2], rr[3]);
+                    upk2(acc[0], a0, a1); a.x = pack2(a0, a1);
+                    upk2(acc[CP - 1], a0, a1); a.y = pack2(a0, a1);
+                    upk2(rr[0], r0, r1); r.x = pack2(r0, r1);
+                    upk2(rr[CP - 1], r0, r1); r.y = pack2(r0, r1);
                     *reinterpret_cast<uint2*>(p.raw + o) = a;
                     *reinterpret_cast<uint2*>(p.res + o) = r;
                 } else {
-                    *reinterpret_cast<uint32_t*>(p.raw + o) = pack2(acc[0], acc[1]);
-                    *reinterpret_cast<uint32_t*>(p.res + o) = pack2(rr[0], rr[1]);
+                    upk2(acc[0], a0, a1);
+                    upk2(rr[0], r0, r1);
+                    *reinterpret_cast<uint32_t*>(p.raw + o) = pack2(a0, a1);
+                    *reinterpret_cast<uint32_t*>(p.res + o) = pack2(r0, r1);
                 }
             }
+            float s, sb, ss, ssb;
+            upk2(s2, s, sb);
+            upk2(ss2, ss, ssb);
+            s += sb;
+            ss += ssb;
             for (int o = lpg >> 1; o > 0; o >>= 1) {
                 s += __shfl_xor_sync(0xffffffffu, s, o);
                 ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -212,8 +251,12 @@ int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
     int tpb = 16;   // row tiles per block: amortises the per-lane weight loads; keep >= ~8 blocks per SM
     while (tpb > 1 && (long long)((n_tiles + tpb - 1) / tpb) * p.N < 148 * 8) tpb >>= 1;
     dim3 grid((n_tiles + tpb - 1) / tpb, p.N);
-    if (p.C == 64) first_conv_kernel<2><<<grid, 256, 0, s>>>(p, tpb);
-    else first_conv_kernel<4><<<grid, 256, 0, s>>>(p, tpb);
+    // CL = 4 needs 163 registers for its 44 packed weights: one block per SM without spills, or two with ~20 spilled words
+    // (USB_FIRST_MINB=1 selects the former for A/B measurements)
+    static const bool one_block = getenv("USB_FIRST_MINB") && atoi(getenv("USB_FIRST_MINB")) == 1;
+    if (p.C == 64) first_conv_kernel<2, 2><<<grid, 256, 0, s>>>(p, tpb);
+    else if (one_block) first_conv_kernel<4, 1><<<grid, 256, 0, s>>>(p, tpb);
+    else first_conv_kernel<4, 2><<<grid, 256, 0, s>>>(p, tpb);
     return (int)cudaGetLastError();
 }
 
@@ -228,34 +271,37 @@ int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
 //   * the exponent argument is min(x, 20) * log2(e) from the normalised value itself (no second affine pair in registers);
 //   * the mask multiply is skipped for unmasked pixels (m == 1, warp-uniform almost everywhere).
 template <bool HAS_RES>
-__device__ __forceinline__ uint4 gn_mish8(const uint4& rv, const uint4& rr, const float (&a)[8], const float (&b)[8],
-                                          const float (&ba)[8], float m) {
-    float v[8], r[8], x[8], dh[8], y[8];
-    unpack8(rv, v);
-    if (HAS_RES) unpack8(rr, r);
+__device__ __forceinline__ uint4 gn_mish8(const uint4& rv, const uint4& rr, const f32x2 (&a)[4], const f32x2 (&b)[4],
+                                          const f32x2 (&ba)[4], float m) {
+    const __half2* hv = reinterpret_cast<const __half2*>(&rv);
+    const __half2* hr = reinterpret_cast<const __half2*>(&rr);
+    const f32x2 klog = pk2(kLog2e, kLog2e), mhalf = pk2(-0.5f, -0.5f), mone = pk2(-1.f, -1.f);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        x[i] = fmaf(v[i], a[i], b[i]);
-        const float e = ex2_ftz(fminf(x[i], 20.f) * kLog2e);
-        dh[i] = fmaf(e, fmaf(e, -0.5f, -1.f), -1.f);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-        const float rn = rcp_ftz(dh[i] * dh[i + 1]);
-        float y0 = fmaf(x[i], dh[i + 1] * rn, fmaf(v[i], a[i], ba[i]));           // x - 2x/d + add  (ba = b + add)
-        float y1 = fmaf(x[i + 1], dh[i] * rn, fmaf(v[i + 1], a[i + 1], ba[i + 1]));
+    for (int i = 0; i < 4; ++i) {            // channel pair (2i, 2i+1)
+        const float2 vf = __half22float2(hv[i]);
+        const f32x2 v = pk2(vf.x, vf.y);
+        const f32x2 x = fma2(v, a[i], b[i]);
+        float t0, t1;
+        upk2(mul2(x, klog), t0, t1);
+        const float e0 = ex2_ftz(fminf(t0, 20.f * kLog2e)), e1 = ex2_ftz(fminf(t1, 20.f * kLog2e));
+        const f32x2 e = pk2(e0, e1);
+        float d0, d1;
+        upk2(fma2(e, fma2(e, mhalf, mone), mone), d0, d1);      // dh = -d/2
+        const float rn = rcp_ftz(d0 * d1);
+        const f32x2 q = pk2(d1 * rn, d0 * rn);                    // (-2/d0, -2/d1)
+        f32x2 y = fma2(x, q, fma2(v, a[i], ba[i]));               // x - 2x/d + add  (ba = b + add)
         if (HAS_RES) {
-            y0 += r[i];
-            y1 += r[i + 1];
+            const float2 rf = __half22float2(hr[i]);
+            y = add2(y, pk2(rf.x, rf.y));
         }
-        y[i] = y0;
-        y[i + 1] = y1;
+        if (m != 1.f) y = mul2(y, pk2(m, m));
+        float y0, y1;
+        upk2(y, y0, y1);
+        ow[i] = pack2(y0, y1);
     }
-    if (m != 1.f) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] *= m;
-    }
-    return pack8(y);
+    return o;
 }
 
 // lanes_mod = (pixels a thread advances per load) mod W, so the column of the next pixel is one add and one conditional
@@ -275,14 +321,21 @@ __global__ void __launch_bounds__(256, HAS_RES ? 2 : 3) gn_apply_kernel(const Gn
         group_moments(p.stats, n, p.groups, threadIdx.x, count, p.eps, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
     }
     __syncthreads();
-    float a[8], b[8], ba[8];
+    f32x2 a[4], b[4], ba[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = tq * 8 + i;
-        const int g = c / cpg;
-        a[i] = s_rstd[g] * __ldg(p.gamma + c);
-        b[i] = __ldg(p.beta + c) - s_mean[g] * a[i];
-        ba[i] = b[i] + (p.addvec ? __ldg(p.addvec + static_cast<long long>(n) * p.addvec_stride + c) : 0.f);
+    for (int i = 0; i < 4; ++i) {
+        float af[2], bf[2], baf[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = tq * 8 + 2 * i + j;
+            const int g = c / cpg;
+            af[j] = s_rstd[g] * __ldg(p.gamma + c);
+            bf[j] = __ldg(p.beta + c) - s_mean[g] * af[j];
+            baf[j] = bf[j] + (p.addvec ? __ldg(p.addvec + static_cast<long long>(n) * p.addvec_stride + c) : 0.f);
+        }
+        a[i] = pk2(af[0], af[1]);
+        b[i] = pk2(bf[0], bf[1]);
+        ba[i] = pk2(baf[0], baf[1]);
     }
     const float* mk = p.mask + static_cast<long long>(n) * p.W;
     const int p_begin = blockIdx.x * pix_per_block;
@@ -373,6 +426,7 @@ __global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int 
 #pragma unroll
     for (int i = 0; i < 8; ++i) wf[i] = __ldg(p.wf + tq * 8 + i);
     const float bf = __ldg(p.bf);
+    const f32x2 klog = pk2(kLog2e, kLog2e), mhalf = pk2(-0.5f, -0.5f), mone = pk2(-1.f, -1.f);
     float c_x = p.c_x, c_s = p.c_s, sigma = p.sigma;
     const float* noise = p.noise;
     float* outp = p.out;
@@ -420,14 +474,24 @@ __global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int 
                     float v[8];
                     unpack8(rv[u][k], v);
                     // Mish(x) = x - 2x/d, d = e^x (e^x + 2) + 2; one reciprocal serves two channels (MUFU is the scarce pipe)
+                    f32x2 dot2 = pk2(0.f, 0.f);
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {
-                        const float x0 = fmaf(v[i], a[k][i], sh[k][i]), x1 = fmaf(v[i + 1], a[k][i + 1], sh[k][i + 1]);
-                        const float e0 = ex2_ftz(fminf(x0, 20.f) * kLog2e), e1 = ex2_ftz(fminf(x1, 20.f) * kLog2e);
-                        const float d0 = fmaf(e0, e0 + 2.f, 2.f), d1 = fmaf(e1, e1 + 2.f, 2.f);
-                        const float rn = rcp_ftz(d0 * d1) * -2.f;      // d <= ~2.4e17 each: the product stays finite
-                        dot = fmaf(wf[i], fmaf(x0, d1 * rn, x0) * m[u], dot);
-                        dot = fmaf(wf[i + 1], fmaf(x1, d0 * rn, x1) * m[u], dot);
+                        // packed fp32x2 (see gn_mish8): x = a v + b; dh = -d/2; Mish(x) = x + x * (-2/d)
+                        const f32x2 x = fma2(pk2(v[i], v[i + 1]), pk2(a[k][i], a[k][i + 1]), pk2(sh[k][i], sh[k][i + 1]));
+                        float t0, t1;
+                        upk2(mul2(x, klog), t0, t1);
+                        const f32x2 e = pk2(ex2_ftz(fminf(t0, 20.f * kLog2e)), ex2_ftz(fminf(t1, 20.f * kLog2e)));
+                        float d0, d1;
+                        upk2(fma2(e, fma2(e, mhalf, mone), mone), d0, d1);
+                        const float rn = rcp_ftz(d0 * d1);             // |dh| <= ~1.2e17 each: the product stays finite
+                        const f32x2 y = fma2(x, pk2(d1 * rn, d0 * rn), x);
+                        dot2 = fma2(pk2(wf[i], wf[i + 1]), y, dot2);
+                    }
+                    {
+                        float s0, s1;
+                        upk2(dot2, s0, s1);
+                        dot = (s0 + s1) * m[u];     // the mask is per pixel: applied once to the 8-channel partial sum
                     }
                     for (int o = TP >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
                     sc[k] = (dot + bf) * m[u];
