@@ -9,6 +9,7 @@
 // Pass 3 (attn_fold_kernel): folds to_out into the per-sample fp16 weight consumed by the tcgen05 GEMM kernel.
 // All reductions run in a fixed order: results are bit-reproducible.
 #include "kernels.h"
+#include "pdl.h"
 
 namespace usb {
 
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(256) attn_partial_kernel(const AttnParams p, i
     // per warp: Kraw[2][32][40], V[2][32][40], P[32][40] halfs = 5 x 2560 B
     extern __shared__ __align__(16) unsigned char sbuf[];
     __shared__ float wscale_s[8][kDh];
+    pdl_wait_and_trigger();
     const int chunk_id = blockIdx.x, n = blockIdx.y;
     const int ld = p.ld;
     const int p0 = chunk_id * p.chunk;
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__(256) attn_partial_kernel(const AttnParams p, i
 // grid (heads, N), 256 threads: ctx[n][h][d][e] = sum_c part_c[d][e] exp(m_c[d] - M[d]) / sum_c s_c[d] exp(m_c[d] - M[d])
 __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnParams p, int nchunks, float* ctx_out) {
     __shared__ float M_s[kDh], S_s[kDh];
+    pdl_wait_and_trigger();
     const int h = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
     const float* ph = p.part + (static_cast<long long>(n) * p.heads + h) * nchunks * kPartStride;
     if (tid < kDh) {
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const AttnParams p, int
 template <int kFoldRows>
 __global__ void __launch_bounds__(256) attn_fold_kernel(const AttnParams p, const float* ctx_in) {
     extern __shared__ __align__(16) float sm[];   // ctx [heads*32][36], weff tile [32][hidden + 4], Wo tile [32][hidden]
+    pdl_wait_and_trigger();
     const int n = blockIdx.y, tid = threadIdx.x;
     const int heads = p.heads, hidden = heads * kDh;
     const int wld = hidden + 4;
@@ -353,14 +357,12 @@ int launch_attn_context(const AttnParams& p, cudaStream_t s) {
         part_attr = true;
     }
     dim3 g1(nchunks, p.N);
-    attn_partial_kernel<<<g1, 32 * p.heads, p.heads * 5 * kTileP * kRowHalfs * 2, s>>>(p, nchunks);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_k(attn_partial_kernel, g1, dim3(32 * p.heads), p.heads * 5 * kTileP * kRowHalfs * 2, s, p, nchunks);
     if (e != cudaSuccess) return (int)e;
     // merged context lives behind the partials in the same scratch buffer
     float* ctx = p.ctx_out ? p.ctx_out : p.part + static_cast<long long>(p.N) * p.heads * nchunks * kPartStride;
     dim3 g2(p.heads, p.N);
-    attn_merge_kernel<<<g2, 256, 0, s>>>(p, nchunks, ctx);
-    e = cudaGetLastError();
+    e = launch_k(attn_merge_kernel, g2, dim3(256), 0, s, p, nchunks, ctx);
     if (e != cudaSuccess) return (int)e;
     static bool fold_attr = false;
     if (!fold_attr) {   // ctx + Weff tile + Wo tile = 48.6 KB of dynamic shared memory
@@ -372,12 +374,13 @@ int launch_attn_context(const AttnParams& p, cudaStream_t s) {
     // every output element is computed by the same instruction sequence either way, so results do not change)
     if (static_cast<long long>((p.C + 31) / 32) * p.N < 2 * 148) {
         dim3 g3((p.C + 7) / 8, p.N);
-        attn_fold_kernel<8><<<g3, 256, (p.heads * kDh * kCtxLd + 8 * (2 * p.heads * kDh + 4)) * sizeof(float), s>>>(p, ctx);
+        return (int)launch_k(attn_fold_kernel<8>, g3, dim3(256), (p.heads * kDh * kCtxLd + 8 * (2 * p.heads * kDh + 4)) * sizeof(float),
+                             s, p, static_cast<const float*>(ctx));
     } else {
         dim3 g3((p.C + 31) / 32, p.N);
-        attn_fold_kernel<32><<<g3, 256, (p.heads * kDh * kCtxLd + 32 * (2 * p.heads * kDh + 4)) * sizeof(float), s>>>(p, ctx);
+        return (int)launch_k(attn_fold_kernel<32>, g3, dim3(256), (p.heads * kDh * kCtxLd + 32 * (2 * p.heads * kDh + 4)) * sizeof(float),
+                             s, p, static_cast<const float*>(ctx));
     }
-    return (int)cudaGetLastError();
 }
 
 size_t attn_scratch_bytes(int N, int heads, int P, int chunk) {

@@ -10,6 +10,7 @@
 //               slabs; warp w reads TMEM lanes 32*(w%4)..+31 (one output pixel per thread).
 // The epilogue of tile i overlaps the MMAs of tile i+1 (double-buffered accumulators).
 #include "conv_igemm.h"
+#include "pdl.h"
 #include "ptx.cuh"
 
 namespace usb {
@@ -174,6 +175,7 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait_and_trigger();   // everything above is local set-up; below this line the predecessor's output is read
 
     if (warp == 0) {
         // ---------------------------------------------------- TMA producer
@@ -405,6 +407,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait_and_trigger();   // everything above is local set-up; below this line the predecessor's output is read
 
     if (warp == 0) {
         // ---------------------------------------------------- TMA producer
@@ -488,6 +491,10 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
         // per-warp staging: 64 pixel rows x 32 channels (64 B rows, 64-byte swizzle) = 4 KB, stored by the warp's own
         // TMA (box {32 ch, 64 px}), so the epilogue needs no cross-warp barrier
         const uint32_t warp_buf = tiles_base + stages * kStageBytes + static_cast<uint32_t>(grp * 4 + ew) * 4096u;
+        // wide stores: one 64-pixel x 128-channel block per group, element (pixel j, channel c) at j*256 + c*2
+        const bool wide = p.wide_store != 0;
+        const uint32_t group_buf = tiles_base + stages * kStageBytes + static_cast<uint32_t>(grp) * 16384u;
+        const uint32_t wbase = group_buf + static_cast<uint32_t>(c) * 2u;
         // element (row j, channel lane): byte = j*64 + ((lane>>3) ^ ((j>>1)&3))*16 + (lane&7)*2; the XOR term only depends
         // on (j>>1)&3, so four per-thread bases + a compile-time row offset address every element
         uint32_t sbase[4];
@@ -585,8 +592,14 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                         mbar_arrive_a(tempty0 + as * 8);
                     }
                 }
-                if (lane == 0) tma_store_wait_read<0>();   // the warp's staging buffer has been read by its last store
-                __syncwarp();
+                // the staging buffer (the group's, or the warp's) has been read by the store issued from it last
+                if (wide) {
+                    if (ew == 0 && lane == 0) tma_store_wait_read<0>();
+                    named_bar_sync(1 + grp, 128);
+                } else {
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int j = 0; j < 64; ++j) {
                     float f = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]) + bias;
@@ -603,15 +616,17 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                     amax = fmaxf(amax, fabsf(f));
                     unsigned short hbits;
                     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hbits) : "f"(f));
-                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(sbase[(j >> 1) & 3] + j * 64), "h"(hbits) : "memory");
+                    const uint32_t addr = wide ? wbase + j * 256 : sbase[(j >> 1) & 3] + j * 64;
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(hbits) : "memory");
                 }
                 fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
+                if (wide) named_bar_sync(1 + grp, 128);
+                else __syncwarp();
+                if (lane == 0 && (!wide || ew == 0)) {
                     const int yb = pc.y0 + (pb >> bw_shift);
                     const int xb = pc.x0 + (pb & (p.BW - 1));
-                    const int cph = p.ox_off[ph] * p.out_c_phase_mul + nt * 128 + ew * 32;
-                    tma_store_5d_a(&map_out, warp_buf, cph, xb, p.oy_off[ph], yb, pc.n);
+                    const int cph = p.ox_off[ph] * p.out_c_phase_mul + nt * 128 + (wide ? 0 : ew * 32);
+                    tma_store_5d_a(&map_out, wide ? group_buf : warp_buf, cph, xb, p.oy_off[ph], yb, pc.n);
                     tma_store_commit();
                 }
             }
@@ -706,6 +721,7 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait_and_trigger();   // everything above is local set-up; below this line the predecessor's output is read
 
     if (warp == 0) {
         // ---------------------------------------------------- TMA producer
@@ -790,6 +806,11 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
         // per-warp staging: 32 pixel rows x 32 channels (64 B rows, 64-byte swizzle) = 2 KB, stored by the warp's own TMA
         // (box {32 ch, 8 rows, 4 columns})
         const uint32_t warp_buf = w_base + stages * kWBytes + static_cast<uint32_t>(grp * 4 + ew) * 2048u;
+        // wide stores (ConvParams::wide_store): one 32-pixel x 128-channel block per group, element (pixel j, channel c) at
+        // j*256 + c*2, stored by one thread with box {128 ch, 8 rows, 4 columns}
+        const bool wide = p.wide_store != 0;
+        const uint32_t group_buf = w_base + stages * kWBytes + static_cast<uint32_t>(grp) * 8192u;
+        const uint32_t wbase = group_buf + static_cast<uint32_t>(c) * 2u;
         uint32_t sbase[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -842,8 +863,13 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
                     tc_fence_before();
                     mbar_arrive_a(tempty0 + as * 8);
                 }
-                if (lane == 0) tma_store_wait_read<0>();
-                __syncwarp();
+                if (wide) {
+                    if (ew == 0 && lane == 0) tma_store_wait_read<0>();
+                    named_bar_sync(1 + grp, 128);
+                } else {
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float f = __uint_as_float(v0[j]) + bias;
@@ -858,12 +884,14 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
                     amax = fmaxf(amax, fabsf(f));
                     unsigned short hbits;
                     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hbits) : "f"(f));
-                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(sbase[(j >> 1) & 3] + j * 64), "h"(hbits) : "memory");
+                    const uint32_t addr = wide ? wbase + j * 256 : sbase[(j >> 1) & 3] + j * 64;
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(hbits) : "memory");
                 }
                 fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_4d_a(&map_out, warp_buf, nt * 128 + ew * 32, ty * 8, x0 + hc * 4, n);
+                if (wide) named_bar_sync(1 + grp, 128);
+                else __syncwarp();
+                if (lane == 0 && (!wide || ew == 0)) {
+                    tma_store_4d_a(&map_out, wide ? group_buf : warp_buf, nt * 128 + (wide ? 0 : ew * 32), ty * 8, x0 + hc * 4, n);
                     tma_store_commit();
                 }
             }
@@ -912,8 +940,8 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         const size_t smem = 1024 + 2 * halo_bytes + static_cast<size_t>(p.stages) * 16384 + 16384;
         if (smem > static_cast<size_t>(kConvSmemBytes) || p.stages > 8) return static_cast<int>(cudaErrorInvalidValue);
         const int grid = static_cast<int>(total < num_sms ? total : num_sms);
-        conv_igemm_halo_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));
-        return static_cast<int>(cudaGetLastError());
+        return static_cast<int>(launch_k(conv_igemm_halo_kernel, dim3(grid), dim3(kConvThreads), smem, stream, p, a0, a1, b, out,
+                                         static_cast<int>(total)));
     }
     if (p.swap_ab) total = static_cast<long long>(p.phases) * ((p.patches_per_phase + 1) / 2) * p.n_tiles_n * (p.ksplit > 1 ? p.ksplit : 1);
     if (total <= 0 || total > 0x7fffffffLL) return static_cast<int>(cudaErrorInvalidValue);
@@ -921,13 +949,13 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
     if (p.swap_ab) {
         const size_t smem = 1024 + static_cast<size_t>(p.stages) * 49152 + 2 * 16384;
         if (smem > static_cast<size_t>(kConvSmemBytes)) return static_cast<int>(cudaErrorInvalidValue);
-        conv_igemm_swapped_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));
-        return static_cast<int>(cudaGetLastError());
+        return static_cast<int>(launch_k(conv_igemm_swapped_kernel, dim3(grid), dim3(kConvThreads), smem, stream, p, a0, a1, b,
+                                         out, static_cast<int>(total)));
     }
     const size_t smem = 1024 + static_cast<size_t>(p.stages) * (16384 + static_cast<size_t>(p.BN) * 128) + 8 * 8192;
     if (smem > static_cast<size_t>(kConvSmemBytes)) return static_cast<int>(cudaErrorInvalidValue);
-    conv_igemm_kernel<<<grid, kConvThreads, smem, stream>>>(p, a0, a1, b, out, static_cast<int>(total));
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(launch_k(conv_igemm_kernel, dim3(grid), dim3(kConvThreads), smem, stream, p, a0, a1, b, out,
+                                     static_cast<int>(total)));
 }
 
 }  // namespace usb

@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "pdl.h"
 
 namespace usb {
 
@@ -116,13 +117,12 @@ __device__ __forceinline__ void group_moments(const long long* stats, int n, int
 // One block = one image row segment of up to 64 pixels: the masked 3 x 66 x 2 input halo is staged in shared memory
 // once; each warp then walks 8 pixels, every lane producing CL consecutive output channels (weights in registers),
 // so a warp writes one pixel's contiguous channel vector per store instruction.
-template <int CL, int MINB>
-__global__ void __launch_bounds__(256, MINB) first_conv_kernel(const FirstConvParams p, int tiles_per_block) {
+template <int CL>
+__global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p, int tiles_per_block) {
     constexpr int TW = 64;
-    constexpr int CP = CL / 2;                       // channel pairs per lane (packed fp32x2 arithmetic, see fma2)
-    // every input value is stored twice, (mu, mu, x, x): one 16-byte read yields the two packed multiplicands of a tap
-    __shared__ __align__(16) float tile[3][TW + 2][4];
+    __shared__ float tile[3][TW + 2][2];
     __shared__ unsigned long long gsum[16];
+    pdl_wait_and_trigger();
     const int n = blockIdx.y;
     const int W = p.W, H = p.H, P = H * W, C = p.C;
     const int tiles_x = (W + TW - 1) / TW;
@@ -137,19 +137,19 @@ __global__ void __launch_bounds__(256, MINB) first_conv_kernel(const FirstConvPa
     const int t_begin = blockIdx.x * tiles_per_block, t_end = min(n_tiles, t_begin + tiles_per_block);
     for (int ps = 0; ps < passes; ++ps) {
         const int c0 = ps * 32 * CL + lane * CL;
-        f32x2 w3[18][CP], w1[2][CP], b3[CP], b1[CP];
+        float w3[18][CL], w1[2][CL], b3[CL], b1[CL];
 #pragma unroll
         for (int k = 0; k < 18; ++k)
 #pragma unroll
-            for (int i = 0; i < CP; ++i) w3[k][i] = pk2(__ldg(p.w3 + k * C + c0 + 2 * i), __ldg(p.w3 + k * C + c0 + 2 * i + 1));
+            for (int i = 0; i < CL; ++i) w3[k][i] = __ldg(p.w3 + k * C + c0 + i);
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int i = 0; i < CP; ++i) w1[k][i] = pk2(__ldg(p.w1 + k * C + c0 + 2 * i), __ldg(p.w1 + k * C + c0 + 2 * i + 1));
+            for (int i = 0; i < CL; ++i) w1[k][i] = __ldg(p.w1 + k * C + c0 + i);
 #pragma unroll
-        for (int i = 0; i < CP; ++i) {
-            b3[i] = pk2(__ldg(p.b3 + c0 + 2 * i), __ldg(p.b3 + c0 + 2 * i + 1));
-            b1[i] = pk2(__ldg(p.b1 + c0 + 2 * i), __ldg(p.b1 + c0 + 2 * i + 1));
+        for (int i = 0; i < CL; ++i) {
+            b3[i] = __ldg(p.b3 + c0 + i);
+            b1[i] = __ldg(p.b1 + c0 + i);
         }
         // GroupNorm partials: one fp32 partial per (warp, row tile, group) -- a partition that does not depend on
         // the launch geometry -- converted to fixed point and accumulated as integers (bitwise batch invariance)
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256, MINB) first_conv_kernel(const FirstConvPa
         const int lpg = cpg / CL;  // lanes per group (power of two, <= 32); lanes of one group are adjacent
         long long is = 0, iss = 0;
         for (int t = t_begin; t < t_end; ++t) {
-            f32x2 s2 = pk2(0.f, 0.f), ss2 = pk2(0.f, 0.f);
+            float s = 0.f, ss = 0.f;
             const int y = t / tiles_x;
             const int x0 = (t - y * tiles_x) * TW;
             __syncthreads();   // previous tile fully consumed
@@ -170,16 +170,17 @@ __global__ void __launch_bounds__(256, MINB) first_conv_kernel(const FirstConvPa
                     vm = (ms ? __ldg(ms + yy * W + xx) : __ldg(p.text_uncon + yy)) * m;   // channel 0 = mu
                     vx = __ldg(xs + yy * W + xx) * m;                                     // channel 1 = x_t
                 }
-                *reinterpret_cast<float4*>(&tile[r][c][0]) = make_float4(vm, vm, vx, vx);
+                tile[r][c][0] = vm;
+                tile[r][c][1] = vx;
             }
             __syncthreads();
             for (int j = 0; j < TW / 8; ++j) {
                 const int px = warp * (TW / 8) + j;
                 const int x = x0 + px;
                 if (x >= W) break;
-                f32x2 acc[CP], rr[CP];
+                float acc[CL], rr[CL];
 #pragma unroll
-                for (int i = 0; i < CP; ++i) {
+                for (int i = 0; i < CL; ++i) {
                     acc[i] = b3[i];
                     rr[i] = b1[i];
                 }
@@ -187,45 +188,35 @@ __global__ void __launch_bounds__(256, MINB) first_conv_kernel(const FirstConvPa
                 for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
-                        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tile[dy][px + dx][0]);   // (mu, mu), (x, x)
+                        const float2 v = *reinterpret_cast<const float2*>(&tile[dy][px + dx][0]);
 #pragma unroll
-                        for (int i = 0; i < CP; ++i) {
-                            acc[i] = fma2(v.x, w3[(dy * 3 + dx) * 2][i], acc[i]);
-                            acc[i] = fma2(v.y, w3[(dy * 3 + dx) * 2 + 1][i], acc[i]);
+                        for (int i = 0; i < CL; ++i) {
+                            acc[i] = fmaf(v.x, w3[(dy * 3 + dx) * 2][i], acc[i]);
+                            acc[i] = fmaf(v.y, w3[(dy * 3 + dx) * 2 + 1][i], acc[i]);
                         }
                     }
                 {
-                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tile[1][px + 1][0]);
+                    const float2 v = *reinterpret_cast<const float2*>(&tile[1][px + 1][0]);
 #pragma unroll
-                    for (int i = 0; i < CP; ++i) rr[i] = fma2(v.y, w1[1][i], fma2(v.x, w1[0][i], rr[i]));
+                    for (int i = 0; i < CL; ++i) rr[i] = fmaf(v.y, w1[1][i], fmaf(v.x, w1[0][i], rr[i]));
                 }
 #pragma unroll
-                for (int i = 0; i < CP; ++i) {
-                    s2 = add2(s2, acc[i]);
-                    ss2 = fma2(acc[i], acc[i], ss2);
+                for (int i = 0; i < CL; ++i) {
+                    s += acc[i];
+                    ss = fmaf(acc[i], acc[i], ss);
                 }
                 const long long o = (static_cast<long long>(n) * P + static_cast<long long>(y) * W + x) * C + c0;
-                float a0, a1, r0, r1;
                 if (CL == 4) {
                     uint2 a, r;
-                    upk2(acc[0], a0, a1); a.x = pack2(a0, a1);
-                    upk2(acc[CP - 1], a0, a1); a.y = pack2(a0, a1);
-                    upk2(rr[0], r0, r1); r.x = pack2(r0, r1);
-                    upk2(rr[CP - 1], r0, r1); r.y = pack2(r0, r1);
+                    a.x = pack2(acc[0], acc[1]); a.y = pack2(acc[2], acc[3]);
+                    r.x = pack2(rr[0], rr[1]);   r.y = pack2(rr[2], rr[3]);
                     *reinterpret_cast<uint2*>(p.raw + o) = a;
                     *reinterpret_cast<uint2*>(p.res + o) = r;
                 } else {
-                    upk2(acc[0], a0, a1);
-                    upk2(rr[0], r0, r1);
-                    *reinterpret_cast<uint32_t*>(p.raw + o) = pack2(a0, a1);
-                    *reinterpret_cast<uint32_t*>(p.res + o) = pack2(r0, r1);
+                    *reinterpret_cast<uint32_t*>(p.raw + o) = pack2(acc[0], acc[1]);
+                    *reinterpret_cast<uint32_t*>(p.res + o) = pack2(rr[0], rr[1]);
                 }
             }
-            float s, sb, ss, ssb;
-            upk2(s2, s, sb);
-            upk2(ss2, ss, ssb);
-            s += sb;
-            ss += ssb;
             for (int o = lpg >> 1; o > 0; o >>= 1) {
                 s += __shfl_xor_sync(0xffffffffu, s, o);
                 ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -251,13 +242,10 @@ int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
     int tpb = 16;   // row tiles per block: amortises the per-lane weight loads; keep >= ~8 blocks per SM
     while (tpb > 1 && (long long)((n_tiles + tpb - 1) / tpb) * p.N < 148 * 8) tpb >>= 1;
     dim3 grid((n_tiles + tpb - 1) / tpb, p.N);
-    // CL = 4 needs 163 registers for its 44 packed weights: one block per SM without spills, or two with ~20 spilled words
-    // (USB_FIRST_MINB=1 selects the former for A/B measurements)
-    static const bool one_block = getenv("USB_FIRST_MINB") && atoi(getenv("USB_FIRST_MINB")) == 1;
-    if (p.C == 64) first_conv_kernel<2, 2><<<grid, 256, 0, s>>>(p, tpb);
-    else if (one_block) first_conv_kernel<4, 1><<<grid, 256, 0, s>>>(p, tpb);
-    else first_conv_kernel<4, 2><<<grid, 256, 0, s>>>(p, tpb);
-    return (int)cudaGetLastError();
+    // (a packed fp32x2 version of this kernel was measured and dropped: its 44 packed weights need 163 registers, and it is
+    // slower than this one both at one block per SM and at two with spills -- profiles/README.md)
+    if (p.C == 64) return (int)launch_k(first_conv_kernel<2>, grid, dim3(256), 0, s, p, tpb);
+    return (int)launch_k(first_conv_kernel<4>, grid, dim3(256), 0, s, p, tpb);
 }
 
 // =====================================================================================================================
@@ -306,10 +294,10 @@ __device__ __forceinline__ uint4 gn_mish8(const uint4& rv, const uint4& rr, cons
 
 // lanes_mod = (pixels a thread advances per load) mod W, so the column of the next pixel is one add and one conditional
 // subtract
-template <bool HAS_RES>
-__global__ void __launch_bounds__(256, HAS_RES ? 2 : 3) gn_apply_kernel(const GnApplyParams p, int pix_per_block, int TP,
-                                                                       int lanes_mod) {
-    constexpr int U = 4;  // pixels in flight per thread
+// U = pixels (16-byte loads per input tensor) in flight per thread, MINB = blocks per SM the register budget is cut for
+template <bool HAS_RES, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) gn_apply_kernel(const GnApplyParams p, int pix_per_block, int TP, int lanes_mod) {
+    pdl_wait_and_trigger();
     const int n = blockIdx.y;
     const int tq = threadIdx.x % TP;
     const int pl = threadIdx.x / TP;
@@ -390,15 +378,19 @@ int launch_gn_apply(const GnApplyParams& p, int num_sms, cudaStream_t s) {
     GnApplyParams q = p;
     static const char* dbg_env = getenv("USB_DBG_GN");
     q.dbg = dbg_env ? atoi(dbg_env) : 0;
-    if (p.res) gn_apply_kernel<true><<<grid, threads, 0, s>>>(q, ppb, TP, lanes % p.W);
-    else gn_apply_kernel<false><<<grid, threads, 0, s>>>(q, ppb, TP, lanes % p.W);
-    return (int)cudaGetLastError();
+    if (p.res) return (int)launch_k(gn_apply_kernel<true, 4, 2>, grid, dim3(threads), 0, s, q, ppb, TP, lanes % p.W);
+    // ncu (profiles/): with packed fp32x2 math the no-residual form is neither issue- nor DRAM-bound (61 % / 63 %) but
+    // waits on its loads; USB_GN_U8=1 trades occupancy (3 -> 2 blocks per SM) for twice the loads in flight per thread
+    static const bool u8 = getenv("USB_GN_U8") != nullptr;
+    if (u8) return (int)launch_k(gn_apply_kernel<false, 8, 2>, grid, dim3(threads), 0, s, q, ppb, TP, lanes % p.W);
+    return (int)launch_k(gn_apply_kernel<false, 4, 3>, grid, dim3(threads), 0, s, q, ppb, TP, lanes % p.W);
 }
 
 // =====================================================================================================================
 // final block apply -> 1x1 conv -> classifier-free-guidance combine -> posterior update
 // =====================================================================================================================
 __global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int pix_per_block, int TP) {
+    pdl_wait_and_trigger();
     const int b = blockIdx.y;
     const int tq = threadIdx.x % TP;
     const int pl = threadIdx.x / TP;
@@ -533,8 +525,7 @@ int launch_final(const FinalParams& p, int num_sms, cudaStream_t s) {
     int ppb = lanes * 32;
     while (ppb > lanes * 2 && (long long)((p.P + ppb - 1) / ppb) * p.B < (long long)num_sms * 8) ppb >>= 1;
     dim3 grid((p.P + ppb - 1) / ppb, p.B);
-    final_kernel<<<grid, 256, 0, s>>>(p, ppb, TP);
-    return (int)cudaGetLastError();
+    return (int)launch_k(final_kernel, grid, dim3(256), 0, s, p, ppb, TP);
 }
 
 // =====================================================================================================================
@@ -645,22 +636,27 @@ int launch_downsample_mask(const float* src, float* dst, int N, int Wsrc, int Wd
 }
 
 // E[n][j] = T[j] + S[n][j]: per-step time part + per-row speaker part of the stacked ResnetBlock.mlp Linears
-__global__ void emb_combine_kernel(const float* t_part, const float* s_part, float* e, int N, int J, const int* step_ctr) {
+__global__ void emb_combine_kernel(const float* t_part, const float* s_part, float* e, int N, int J, const int* step_ctr,
+                                   unsigned long long* zero, long long zero_count) {
+    pdl_wait_and_trigger();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < zero_count) zero[i] = 0ull;      // the GroupNorm statistics slots of the evaluation that follows
     if (i >= static_cast<long long>(N) * J) return;
     if (step_ctr) t_part += static_cast<long long>(*step_ctr) * J;
     e[i] = t_part[i % J] + s_part[i];
 }
-int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, const int* step_ctr, cudaStream_t s) {
-    const long long total = static_cast<long long>(N) * J;
-    emb_combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(t_part, s_part, e, N, J, step_ctr);
-    return (int)cudaGetLastError();
+int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, const int* step_ctr,
+                       unsigned long long* zero, long long zero_count, cudaStream_t s) {
+    const long long nj = static_cast<long long>(N) * J;
+    const long long total = nj > zero_count ? nj : zero_count;
+    return (int)launch_k(emb_combine_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, t_part, s_part, e,
+                         N, J, step_ctr, zero, zero_count);
 }
-__global__ void step_advance_kernel(int* ctr) { *ctr += 1; }
-int launch_step_advance(int* ctr, cudaStream_t s) {
-    step_advance_kernel<<<1, 1, 0, s>>>(ctr);
-    return (int)cudaGetLastError();
+__global__ void step_advance_kernel(int* ctr) {
+    pdl_wait_and_trigger();
+    *ctr += 1;
 }
+int launch_step_advance(int* ctr, cudaStream_t s) { return (int)launch_k(step_advance_kernel, dim3(1), dim3(1), 0, s, ctr); }
 
 __global__ void gather_rows_kernel(const float* src, const int* idx, float* dst, int N, int len) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

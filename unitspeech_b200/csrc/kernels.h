@@ -94,7 +94,10 @@ struct EmbedParams {
 };
 int launch_embed(const EmbedParams& p, cudaStream_t s);   // t or spk may be null (that half of u is 0); bcat may be null
 // step_ctr != null: t_part is the base of the [n][J] per-step table and row *step_ctr is used
-int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, const int* step_ctr, cudaStream_t s);
+// also zeroes `zero_count` 64-bit words at `zero` (the statistics slots of the evaluation that follows: no memset node
+// between the kernels of a step)
+int launch_emb_combine(const float* t_part, const float* s_part, float* e, int N, int J, const int* step_ctr,
+                       unsigned long long* zero, long long zero_count, cudaStream_t s);
 // *ctr += 1 (first node of the captured sampler step)
 int launch_step_advance(int* ctr, cudaStream_t s);
 

@@ -249,18 +249,43 @@ static inline int act2_ncol(int creal) {    // 4-channel columns per block: the 
 }
 static inline size_t act2_smem_bytes(int ncol) { return static_cast<size_t>((256 / ncol) * kAct2TO + 10) * ncol * 8; }
 
-// one 2x-rate sample for 4 channels from six consecutive input rows; ODD: i = 2m+1 uses f[10-2j], even uses f[11-2j]
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2: two IEEE fp32 operations per issue slot): a thread's 4 channels are two
+// packed pairs, which halves the issue slots of the kernel's ~100 FMAs per output step (ncu: issue- and FMA-pipe bound)
+typedef unsigned long long vf2;
+__device__ __forceinline__ vf2 vpk2(float lo, float hi) {
+    vf2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void vupk2(vf2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ vf2 vfma2(vf2 a, vf2 b, vf2 c) {
+    vf2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ vf2 vmul2(vf2 a, vf2 b) {
+    vf2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// one 2x-rate sample for 4 channels (two packed pairs) from six consecutive input rows; ODD: i = 2m+1 uses f[10-2j], even
+// uses f[11-2j] (f2 = the taps times the up-sampling ratio, replicated into both halves)
 template <bool ODD>
-__device__ __forceinline__ void act2_srow(const float (&x)[6][4], const float (&f2)[12], const float (&al)[4],
-                                          const float (&ib)[4], float (&s)[4]) {
+__device__ __forceinline__ void act2_srow(const vf2 (&x)[6][2], const vf2 (&f2)[12], const vf2 (&al)[2], const vf2 (&ib)[2],
+                                          vf2 (&s)[2]) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float u = 0.f;
+    for (int c = 0; c < 2; ++c) {
+        vf2 u = vmul2(f2[ODD ? 10 : 11], x[0][c]);
 #pragma unroll
-        for (int j = 0; j < 6; ++j) u = fmaf(f2[ODD ? 10 - 2 * j : 11 - 2 * j], x[j][c], u);
+        for (int j = 1; j < 6; ++j) u = vfma2(f2[ODD ? 10 - 2 * j : 11 - 2 * j], x[j][c], u);
         // MUFU.SIN reduces its argument itself; absolute error ~|x| * 2^-24, far below the fp16 storage of the result
-        const float sn = __sinf(al[c] * u);
-        s[c] = fmaf(ib[c] * sn, sn, u);
+        float a0, a1;
+        vupk2(vmul2(al[c], u), a0, a1);
+        const vf2 sn = vpk2(__sinf(a0), __sinf(a1));
+        s[c] = vfma2(vmul2(ib[c], sn), sn, u);
     }
 }
 
@@ -295,108 +320,87 @@ __global__ void __launch_bounds__(256, 2) snake_act2_kernel(const ActParams p, i
     }
     const int col = tid % ncol, run = tid / ncol;
     const int c0 = c_blk + col * 4;
-    float al[4], ib[4], f2[12], f1[12];
+    vf2 al[2], ib[2], f2[12], f1[12];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        al[j] = __ldg(p.alpha + c0 + j);
-        ib[j] = __ldg(p.invbeta + c0 + j);
+    for (int j = 0; j < 2; ++j) {
+        al[j] = vpk2(__ldg(p.alpha + c0 + 2 * j), __ldg(p.alpha + c0 + 2 * j + 1));
+        ib[j] = vpk2(__ldg(p.invbeta + c0 + 2 * j), __ldg(p.invbeta + c0 + 2 * j + 1));
     }
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
-        f1[k] = p.filt[k];
-        f2[k] = 2.f * p.filt[k];      // UpSample1d multiplies by the ratio (resample.py:31)
+        f1[k] = vpk2(p.filt[k], p.filt[k]);
+        f2[k] = vpk2(2.f * p.filt[k], 2.f * p.filt[k]);      // UpSample1d multiplies by the ratio (resample.py:31)
     }
     __syncthreads();
     const int tr = t0 + run * kAct2TO;               // first output of this run
     if (tr >= p.L) return;
     const unsigned char* xcol = act2_smem + col * 8;
     const int imax = 2 * p.L - 1;
-    auto load_rows = [&](int t_first, float (&x)[6][4], int nrows_off) {
-        (void)nrows_off;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const uint2 raw = *reinterpret_cast<const uint2*>(xcol + (t_first + j - (t0 - 5)) * pitch);
-            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-            x[j][0] = a.x; x[j][1] = a.y; x[j][2] = b.x; x[j][3] = b.y;
-        }
+    auto load_row = [&](int t, vf2 (&x)[2]) {        // input row t (tile-relative), 4 channels as two packed pairs
+        const uint2 raw = *reinterpret_cast<const uint2*>(xcol + (t - (t0 - 5)) * pitch);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        x[0] = vpk2(a.x, a.y);
+        x[1] = vpk2(b.x, b.y);
     };
     // a sample whose index falls outside [0, 2L-1] is the replicate padding of the low-pass filter (filter.py:90):
     // it equals s[0] / s[2L-1], recomputed from the inputs around that end
-    auto edge_sample = [&](int i, float (&sv)[4]) {
+    auto edge_sample = [&](int i, vf2 (&sv)[2]) {
         const int ic = i < 0 ? 0 : imax;
         const int m = ic >> 1;
-        float x[6][4];
-        if (ic & 1) { load_rows(m - 2, x, 0); act2_srow<true>(x, f2, al, ib, sv); }
-        else { load_rows(m - 3, x, 0); act2_srow<false>(x, f2, al, ib, sv); }
+        vf2 x[6][2];
+        if (ic & 1) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) load_row(m - 2 + j, x[j]);
+            act2_srow<true>(x, f2, al, ib, sv);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) load_row(m - 3 + j, x[j]);
+            act2_srow<false>(x, f2, al, ib, sv);
+        }
     };
-    float acc[6][4];
+    vf2 acc[6][2];
+    const vf2 zero2 = vpk2(0.f, 0.f);
 #pragma unroll
-    for (int d = 0; d < 6; ++d)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[d][c] = 0.f;
+    for (int d = 0; d < 6; ++d) acc[d][0] = acc[d][1] = zero2;
     for (int g = 0; g < kAct2Steps / 6; ++g) {
         const int tg = tr - 5 + g * 6;               // first step of this group
         if (tg >= p.L) break;                        // every remaining output lies beyond the signal
-        // inputs tg .. tg+10 serve the six steps of the group
-        float xw[11][4];
+        vf2 xw[11][2];                               // inputs tg .. tg+10 serve the six steps of the group
 #pragma unroll
-        for (int j = 0; j < 11; ++j) {
-            const uint2 raw = *reinterpret_cast<const uint2*>(xcol + (tg + j - (t0 - 5)) * pitch);
-            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-            xw[j][0] = a.x; xw[j][1] = a.y; xw[j][2] = b.x; xw[j][3] = b.y;
-        }
+        for (int j = 0; j < 11; ++j) load_row(tg + j, xw[j]);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             const int t = tg + k;                    // this step completes output t (slot k of acc)
-            float so[4], se[4];                      // s[2t+5] (odd index), s[2t+6] (even index)
+            vf2 so[2], se[2];                        // s[2t+5] (odd index), s[2t+6] (even index)
             const int io = 2 * t + 5, ie = 2 * t + 6;
-            if (io >= 0 && ie <= imax) {
-                float x6[6][4];
+            vf2 x6[6][2];
 #pragma unroll
-                for (int j = 0; j < 6; ++j)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) x6[j][c] = xw[k + j][c];
-                act2_srow<true>(x6, f2, al, ib, so);
-                act2_srow<false>(x6, f2, al, ib, se);
-            } else {
-                if (io >= 0 && io <= imax) {
-                    float x6[6][4];
-#pragma unroll
-                    for (int j = 0; j < 6; ++j)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) x6[j][c] = xw[k + j][c];
-                    act2_srow<true>(x6, f2, al, ib, so);
-                } else {
-                    edge_sample(io, so);
-                }
-                if (ie >= 0 && ie <= imax) {
-                    float x6[6][4];
-#pragma unroll
-                    for (int j = 0; j < 6; ++j)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) x6[j][c] = xw[k + j][c];
-                    act2_srow<false>(x6, f2, al, ib, se);
-                } else {
-                    edge_sample(ie, se);
-                }
+            for (int j = 0; j < 6; ++j) {
+                x6[j][0] = xw[k + j][0];
+                x6[j][1] = xw[k + j][1];
             }
+            if (io >= 0 && io <= imax) act2_srow<true>(x6, f2, al, ib, so);
+            else edge_sample(io, so);
+            if (ie >= 0 && ie <= imax) act2_srow<false>(x6, f2, al, ib, se);
+            else edge_sample(ie, se);
             // scatter into the partial outputs t .. t+5: slot (k + d) % 6 holds output t + d
 #pragma unroll
             for (int d = 0; d < 6; ++d)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    acc[(k + d) % 6][c] = fmaf(f1[10 - 2 * d], so[c], fmaf(f1[11 - 2 * d], se[c], acc[(k + d) % 6][c]));
+                for (int c = 0; c < 2; ++c)
+                    acc[(k + d) % 6][c] = vfma2(f1[10 - 2 * d], so[c], vfma2(f1[11 - 2 * d], se[c], acc[(k + d) % 6][c]));
             // output t is complete (all 12 taps added over steps t-5 .. t); emit it unless it is a warm-up step
             if (t >= tr && t < p.L) {
+                float o0, o1, o2, o3;
+                vupk2(acc[k][0], o0, o1);
+                vupk2(acc[k][1], o2, o3);
                 uint2 pk;
-                *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(acc[k][0], acc[k][1]);
-                *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(acc[k][2], acc[k][3]);
+                *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(o0, o1);
+                *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(o2, o3);
                 *reinterpret_cast<uint2*>(p.out + (nbase + t) * p.C + c0) = pk;
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[k][c] = 0.f;     // the slot now collects output t + 6
+            acc[k][0] = acc[k][1] = zero2;           // the slot now collects output t + 6
         }
     }
 }
