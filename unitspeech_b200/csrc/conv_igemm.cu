@@ -491,10 +491,6 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
         // per-warp staging: 64 pixel rows x 32 channels (64 B rows, 64-byte swizzle) = 4 KB, stored by the warp's own
         // TMA (box {32 ch, 64 px}), so the epilogue needs no cross-warp barrier
         const uint32_t warp_buf = tiles_base + stages * kStageBytes + static_cast<uint32_t>(grp * 4 + ew) * 4096u;
-        // wide stores: one 64-pixel x 128-channel block per group, element (pixel j, channel c) at j*256 + c*2
-        const bool wide = p.wide_store != 0;
-        const uint32_t group_buf = tiles_base + stages * kStageBytes + static_cast<uint32_t>(grp) * 16384u;
-        const uint32_t wbase = group_buf + static_cast<uint32_t>(c) * 2u;
         // element (row j, channel lane): byte = j*64 + ((lane>>3) ^ ((j>>1)&3))*16 + (lane&7)*2; the XOR term only depends
         // on (j>>1)&3, so four per-thread bases + a compile-time row offset address every element
         uint32_t sbase[4];
@@ -592,41 +588,37 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                         mbar_arrive_a(tempty0 + as * 8);
                     }
                 }
-                // the staging buffer (the group's, or the warp's) has been read by the store issued from it last
-                if (wide) {
-                    if (ew == 0 && lane == 0) tma_store_wait_read<0>();
-                    named_bar_sync(1 + grp, 128);
-                } else {
-                    if (lane == 0) tma_store_wait_read<0>();
-                    __syncwarp();
-                }
+                if (lane == 0) tma_store_wait_read<0>();   // the warp's staging buffer has been read by its last store
+                __syncwarp();
+                // two pixels per iteration: one packed convert, both halves stored (the statistics keep the pixel order)
 #pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    float f = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]) + bias;
+                for (int j = 0; j < 64; j += 2) {
+                    float f0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]) + bias;
+                    float f1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]) + bias;
                     if (stats_n) {
-                        if (full) {
-                            s += f;
-                            ss = fmaf(f, f, ss);
-                        } else if (((pb + j) & (p.BW - 1)) < wlim && ((pb + j) >> bw_shift) < hlim) {
-                            s += f;
-                            ss = fmaf(f, f, ss);
+                        if (full || (((pb + j) & (p.BW - 1)) < wlim && ((pb + j) >> bw_shift) < hlim)) {
+                            s += f0;
+                            ss = fmaf(f0, f0, ss);
+                        }
+                        if (full || (((pb + j + 1) & (p.BW - 1)) < wlim && ((pb + j + 1) >> bw_shift) < hlim)) {
+                            s += f1;
+                            ss = fmaf(f1, f1, ss);
                         }
                     }
-                    if (mrow) f *= mask_s[grp][(pb + j) & (p.BW - 1)];
-                    amax = fmaxf(amax, fabsf(f));
-                    unsigned short hbits;
-                    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hbits) : "f"(f));
-                    const uint32_t addr = wide ? wbase + j * 256 : sbase[(j >> 1) & 3] + j * 64;
-                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(hbits) : "memory");
+                    if (mrow) {
+                        f0 *= mask_s[grp][(pb + j) & (p.BW - 1)];
+                        f1 *= mask_s[grp][(pb + j + 1) & (p.BW - 1)];
+                    }
+                    amax = fmaxf(amax, fmaxf(fabsf(f0), fabsf(f1)));
+                    sts_f16_pair(sbase[(j >> 1) & 3] + j * 64, sbase[(j >> 1) & 3] + (j + 1) * 64, pack_f16x2_sat(f0, f1));
                 }
                 fence_proxy_async_smem();
-                if (wide) named_bar_sync(1 + grp, 128);
-                else __syncwarp();
-                if (lane == 0 && (!wide || ew == 0)) {
+                __syncwarp();
+                if (lane == 0) {
                     const int yb = pc.y0 + (pb >> bw_shift);
                     const int xb = pc.x0 + (pb & (p.BW - 1));
-                    const int cph = p.ox_off[ph] * p.out_c_phase_mul + nt * 128 + (wide ? 0 : ew * 32);
-                    tma_store_5d_a(&map_out, wide ? group_buf : warp_buf, cph, xb, p.oy_off[ph], yb, pc.n);
+                    const int cph = p.ox_off[ph] * p.out_c_phase_mul + nt * 128 + ew * 32;
+                    tma_store_5d_a(&map_out, warp_buf, cph, xb, p.oy_off[ph], yb, pc.n);
                     tma_store_commit();
                 }
             }
@@ -806,11 +798,6 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
         // per-warp staging: 32 pixel rows x 32 channels (64 B rows, 64-byte swizzle) = 2 KB, stored by the warp's own TMA
         // (box {32 ch, 8 rows, 4 columns})
         const uint32_t warp_buf = w_base + stages * kWBytes + static_cast<uint32_t>(grp * 4 + ew) * 2048u;
-        // wide stores (ConvParams::wide_store): one 32-pixel x 128-channel block per group, element (pixel j, channel c) at
-        // j*256 + c*2, stored by one thread with box {128 ch, 8 rows, 4 columns}
-        const bool wide = p.wide_store != 0;
-        const uint32_t group_buf = w_base + stages * kWBytes + static_cast<uint32_t>(grp) * 8192u;
-        const uint32_t wbase = group_buf + static_cast<uint32_t>(c) * 2u;
         uint32_t sbase[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -863,35 +850,33 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
                     tc_fence_before();
                     mbar_arrive_a(tempty0 + as * 8);
                 }
-                if (wide) {
-                    if (ew == 0 && lane == 0) tma_store_wait_read<0>();
-                    named_bar_sync(1 + grp, 128);
-                } else {
-                    if (lane == 0) tma_store_wait_read<0>();
-                    __syncwarp();
-                }
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+                float mk[4];                      // output mask of the four image columns of this block
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float f = __uint_as_float(v0[j]) + bias;
+                for (int i = 0; i < 4; ++i) mk[i] = mrow ? mask_s[grp][hc * 4 + i] : 1.f;
+                // two pixels (rows y, y+1 of one column) per iteration: one packed convert, both halves stored
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float f0 = __uint_as_float(v0[j]) + bias, f1 = __uint_as_float(v0[j + 1]) + bias;
                     const int xl = hc * 4 + (j >> 3);
-                    if (stats_n) {
-                        if (full || xl < wlim) {
-                            s += f;
-                            ss = fmaf(f, f, ss);
-                        }
+                    if (stats_n && (full || xl < wlim)) {
+                        s += f0;
+                        ss = fmaf(f0, f0, ss);
+                        s += f1;
+                        ss = fmaf(f1, f1, ss);
                     }
-                    if (mrow) f *= mask_s[grp][xl];
-                    amax = fmaxf(amax, fabsf(f));
-                    unsigned short hbits;
-                    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hbits) : "f"(f));
-                    const uint32_t addr = wide ? wbase + j * 256 : sbase[(j >> 1) & 3] + j * 64;
-                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(hbits) : "memory");
+                    if (mrow) {
+                        f0 *= mk[j >> 3];
+                        f1 *= mk[j >> 3];
+                    }
+                    amax = fmaxf(amax, fmaxf(fabsf(f0), fabsf(f1)));
+                    sts_f16_pair(sbase[(j >> 1) & 3] + j * 64, sbase[(j >> 1) & 3] + (j + 1) * 64, pack_f16x2_sat(f0, f1));
                 }
                 fence_proxy_async_smem();
-                if (wide) named_bar_sync(1 + grp, 128);
-                else __syncwarp();
-                if (lane == 0 && (!wide || ew == 0)) {
-                    tma_store_4d_a(&map_out, wide ? group_buf : warp_buf, nt * 128 + (wide ? 0 : ew * 32), ty * 8, x0 + hc * 4, n);
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d_a(&map_out, warp_buf, nt * 128 + ew * 32, ty * 8, x0 + hc * 4, n);
                     tma_store_commit();
                 }
             }

@@ -77,10 +77,6 @@ struct ConvParams {
     // run by different CTAs; each writes its fp32 partial tile to `kpart`, takes a ticket, and the CTA that arrives last
     // sums the partials IN SPLIT ORDER (so the result does not depend on which CTA that is) and runs the epilogue.
     // ksplit is a function of the layer geometry only, never of the batch (bitwise batch invariance).
-    // swapped-operand kernel: 1 = the four warps of an epilogue group stage a 64-pixel x 128-channel block ([px][256 B], no
-    // swizzle) and ONE thread stores it (256-byte rows); 0 = every warp stores its own 64 x 32-channel block (64-byte rows,
-    // four times the TMA row segments: measured store-bound on the short-K strided / transposed convs)
-    int wide_store;
     int ksplit;                // 0 / 1 = off
     float* kpart;              // [tiles * ksplit][2 patches][128 px][128 ch] fp32
     int* ktick;                // [tiles], zero between launches (the reducing CTA resets its tile's ticket)

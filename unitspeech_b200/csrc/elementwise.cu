@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int 
     const int pl = threadIdx.x / TP;
     const int lanes = blockDim.x / TP;
     const int C = p.C, cpg = C / p.groups;
-    float a[3][8], sh[3][8], wf[8];
+    f32x2 a[3][4], sh[3][4], wf[4];      // per channel pair (packed fp32x2, see fma2)
     __shared__ float s_mean[3][8], s_rstd[3][8];
     if (threadIdx.x < p.nb * p.groups) {
         const int k = threadIdx.x / p.groups, g = threadIdx.x % p.groups;
@@ -408,15 +408,21 @@ __global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int 
     for (int k = 0; k < 3; ++k) {
         if (k < p.nb) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = tq * 8 + i;
-                a[k][i] = s_rstd[k][c / cpg] * __ldg(p.gamma + c);
-                sh[k][i] = __ldg(p.beta + c) - s_mean[k][c / cpg] * a[k][i];
+            for (int i = 0; i < 4; ++i) {
+                float af[2], sf[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = tq * 8 + 2 * i + j;
+                    af[j] = s_rstd[k][c / cpg] * __ldg(p.gamma + c);
+                    sf[j] = __ldg(p.beta + c) - s_mean[k][c / cpg] * af[j];
+                }
+                a[k][i] = pk2(af[0], af[1]);
+                sh[k][i] = pk2(sf[0], sf[1]);
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) wf[i] = __ldg(p.wf + tq * 8 + i);
+    for (int i = 0; i < 4; ++i) wf[i] = pk2(__ldg(p.wf + tq * 8 + 2 * i), __ldg(p.wf + tq * 8 + 2 * i + 1));
     const float bf = __ldg(p.bf);
     const f32x2 klog = pk2(kLog2e, kLog2e), mhalf = pk2(-0.5f, -0.5f), mone = pk2(-1.f, -1.f);
     float c_x = p.c_x, c_s = p.c_s, sigma = p.sigma;
@@ -463,14 +469,14 @@ __global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int 
             for (int k = 0; k < 3; ++k) {
                 if (k < p.nb) {
                     float dot = 0.f;
-                    float v[8];
-                    unpack8(rv[u][k], v);
+                    const __half2* hv = reinterpret_cast<const __half2*>(&rv[u][k]);
                     // Mish(x) = x - 2x/d, d = e^x (e^x + 2) + 2; one reciprocal serves two channels (MUFU is the scarce pipe)
                     f32x2 dot2 = pk2(0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < 8; i += 2) {
+                    for (int i = 0; i < 4; ++i) {
                         // packed fp32x2 (see gn_mish8): x = a v + b; dh = -d/2; Mish(x) = x + x * (-2/d)
-                        const f32x2 x = fma2(pk2(v[i], v[i + 1]), pk2(a[k][i], a[k][i + 1]), pk2(sh[k][i], sh[k][i + 1]));
+                        const float2 vf = __half22float2(hv[i]);
+                        const f32x2 x = fma2(pk2(vf.x, vf.y), a[k][i], sh[k][i]);
                         float t0, t1;
                         upk2(mul2(x, klog), t0, t1);
                         const f32x2 e = pk2(ex2_ftz(fminf(t0, 20.f * kLog2e)), ex2_ftz(fminf(t1, 20.f * kLog2e)));
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int 
                         upk2(fma2(e, fma2(e, mhalf, mone), mone), d0, d1);
                         const float rn = rcp_ftz(d0 * d1);             // |dh| <= ~1.2e17 each: the product stays finite
                         const f32x2 y = fma2(x, pk2(d1 * rn, d0 * rn), x);
-                        dot2 = fma2(pk2(wf[i], wf[i + 1]), y, dot2);
+                        dot2 = fma2(wf[i], y, dot2);
                     }
                     {
                         float s0, s1;

@@ -109,7 +109,7 @@ static int make_act_map(CUtensorMap* m, const __half* base, int N, int H, int W,
     }
     cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)BW, 1, (cuuint32_t)BH, 1};
     return encode_map(m, base, 5, dims, strides, box,
-                      box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : (box_c == 128 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B));
+                      box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // 4-D activation view (c, y, x, n) of the same tensor: rows before columns, so a box lands in shared memory column
@@ -121,7 +121,7 @@ static int make_act_map_yx(CUtensorMap* m, const __half* base, int N, int H, int
     cuuint64_t strides[3] = {(cuuint64_t)W * Ctot * e, (cuuint64_t)Ctot * e, (cuuint64_t)H * W * Ctot * e};
     cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_y, (cuuint32_t)box_x, 1};
     return encode_map(m, base, 4, dims, strides, box,
-                      box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : (box_c == 128 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B));
+                      box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // weights [Z][Cout][K] fp16, K contiguous
@@ -374,9 +374,7 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
         if (in1) USB_TRY(make_act_map_yx(&op.a1, in1, N, H, W, C1tot, C1, 64, p.halo_hy, 34));
         else op.a1 = op.a0;
         USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, 128));
-        static const bool narrow = getenv("USB_NARROW_STORE") != nullptr;   // see the swapped kernel below
-        p.wide_store = narrow ? 0 : 1;
-        return make_act_map_yx(&op.o, out, N, H, W, Cout, Cout, narrow ? 32 : 128, 8, 4);
+        return make_act_map_yx(&op.o, out, N, H, W, Cout, Cout, 32, 8, 4);
     }
     if (p.swap_ab && ep.splitk) {
         // the decision depends on the geometry only (choose_ksplit); a caller with a fixed-size workspace (the fine-tune
@@ -395,14 +393,9 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
     USB_TRY(make_w_map(&op.b, wptr, wZ, Cout, K, p.BN));
     // output tile store: plain view, or the parity view of the upsampled tensor for the transposed conv;
     // the swapped kernel stores 64-pixel sub-blocks (64 / BW image rows) per TMA
-    if (p.swap_ab) {
-        // stores of 64-pixel sub-blocks: per group, 128 channels wide (256-byte rows, no swizzle), or -- USB_NARROW_STORE=1,
-        // the first version, kept for A/B runs -- per warp, 32 channels wide (64-byte rows, SWIZZLE_64B)
-        static const bool narrow = getenv("USB_NARROW_STORE") != nullptr;
-        p.wide_store = narrow ? 0 : 1;
+    if (p.swap_ab)   // per-warp stores: 64 pixels x 32 channels (64-byte rows, SWIZZLE_64B)
         USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind_up(kind), p.BW >= 64 ? 1 : 64 / p.BW,
-                             p.BW >= 64 ? 64 : p.BW, narrow ? 32 : 128));
-    }
+                             p.BW >= 64 ? 64 : p.BW, 32));
     else   // per-warp stores: 32 pixels (one TMEM lane quarter) x 64 channels
         USB_TRY(make_act_map(&op.o, out, N, Hout, Wout, Cout, Cout, kind_up(kind), p.BW >= 32 ? 1 : 32 / p.BW,
                              p.BW >= 32 ? 32 : p.BW));
@@ -453,11 +446,7 @@ int build_conv1d(ConvOp& op, const int8_t* dx, int taps, int phases, const __hal
     USB_TRY(make_act_map(&op.a0, in, N, 1, L, Cin, Cin, false, 1, 128));
     op.a1 = op.a0;
     USB_TRY(make_w_map(&op.b, w, phases, Cout, taps * Cin, p.BN));
-    if (p.swap_ab) {
-        static const bool narrow = getenv("USB_NARROW_STORE") != nullptr;
-        p.wide_store = narrow ? 0 : 1;
-        USB_TRY(make_act_map(&op.o, out, N, 1, L, phases * Cout, phases * Cout, false, 1, 64, narrow ? 32 : 128));
-    }
+    if (p.swap_ab) USB_TRY(make_act_map(&op.o, out, N, 1, L, phases * Cout, phases * Cout, false, 1, 64, 32));
     else USB_TRY(make_act_map(&op.o, out, N, 1, L, phases * Cout, phases * Cout, false, 1, 32));
     return 0;
 }
@@ -1384,10 +1373,12 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
         }
         first_graph_step = 1;      // step 0 always runs eagerly: it also performs every lazy one-time kernel-attribute set-up
     }
-    // latency mode also launches the step's kernels as programmatic dependents (pdl.h): the next kernel's blocks are
-    // scheduled and run their prologue while the current one finishes.  USB_NO_PDL=1 switches it off for A/B runs.
-    static const bool no_pdl = getenv("USB_NO_PDL") != nullptr;
-    PdlScope pdl_scope(want_graph && !no_pdl);
+    // USB_PDL=1: latency mode also launches the step's kernels as programmatic dependents (pdl.h): the next kernel's blocks
+    // are scheduled and run their prologue while the current one finishes.  Measured on B200 inside the replayed graph it
+    // gains nothing (105.1 vs 103.3 ms per 1 x 256 pass): graph replay has already removed the launch gaps and every kernel
+    // needs the predecessor's output from its first load.  Off by default, kept for A/B runs.
+    static const bool use_pdl = getenv("USB_PDL") != nullptr;
+    PdlScope pdl_scope(want_graph && use_pdl);
     EstInputs in{pl.xt, cond, h->text_uncon, pl.t_rows, pl.spk_rows};
     for (int i = 0; i < n_steps && i < first_graph_step; ++i) {
         USB_TRY(run_estimator(h, in, s, d_tpart + (size_t)i * h->J));

@@ -226,6 +226,19 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The two fp16 halves of `pk` to two shared-memory addresses (epilogue transposition: lo = pixel j, hi = pixel j+1 of one
+// channel).  Deliberately NO "memory" clobber: volatile asm statements keep their order among themselves (the
+// fence.proxy.async / TMA store that follow are volatile asm with the clobber), while ordinary shared-memory loads (the
+// output mask) may be scheduled across the stores -- with the clobber every store forced a reload of its mask value and
+// the dependent multiply stalled on it 128 times per tile (ncu source page, profiles/README.md).
+__device__ __forceinline__ void sts_f16_pair(uint32_t addr_lo, uint32_t addr_hi, uint32_t pk) {
+    asm volatile(
+        "{\n\t.reg .b16 lo, hi;\n\t"
+        "mov.b32 {lo, hi}, %2;\n\t"
+        "st.shared.b16 [%0], lo;\n\t"
+        "st.shared.b16 [%1], hi;\n\t}"
+        ::"r"(addr_lo), "r"(addr_hi), "r"(pk));
+}
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (the layout TMA SWIZZLE_128B writes for a
 // box whose inner dimension is 64 fp16 = 128 B): rows are 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused.

@@ -228,6 +228,11 @@ class FineTuner:
     def close(self):
         if getattr(self, "h", None) and self._trace is None:
             torch.cuda.synchronize(self.dev)
+            n_skipped = int(self.skipped.item())
+            if n_skipped:
+                import warnings
+                warnings.warn(f"FineTuner: {n_skipped} optimizer step(s) were skipped for a non-finite gradient norm "
+                              f"(loss_scale={self.loss_scale}); lower the loss scale", RuntimeWarning)
             self.lib.usb_destroy(self.h)
             self.h = None
 
@@ -739,8 +744,16 @@ class FineTuner:
         self.optimizer_step()
         self._pack_weights()          # fp16 operands of the updated weights, ready for the next step / the sampler
 
+    @property
+    def skipped_steps(self) -> int:
+        """Adam steps skipped because the (loss-scaled) gradient norm was not finite (host sync).  The loss scale is fixed
+        (default 8192, no GradScaler-style back-off): a count that keeps growing means the fp16 activation gradients
+        overflow at this scale -- lower ``loss_scale``."""
+        return int(self.skipped.item())
+
     def train_step(self, x0, mask, cond, t, spk_emb, z) -> torch.Tensor:
-        """zero_grad -> loss_t -> backward -> clip -> Adam.  Returns the device loss scalar (before the update).
+        """zero_grad -> loss_t -> backward -> clip -> Adam.  Returns the device loss scalar (before the update) -- the
+        tuner's own loss buffer, overwritten by the next step: ``float()`` or ``.clone()`` it to keep a value.
         After two eager steps per (B, T) the whole step is captured in a CUDA graph and replayed (the step is ~900 short
         launches; replaying removes the host from the loop).  All state the graph touches lives in buffers owned by this
         object; the Adam step number is a device counter."""
