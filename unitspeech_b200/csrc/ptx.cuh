@@ -222,8 +222,10 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
+// (no "memory" clobber, for the reason given at sts_f16_pair below: the bias / residual loads of the next 8-channel chunk
+// may then be scheduled above this store)
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // The two fp16 halves of `pk` to two shared-memory addresses (epilogue transposition: lo = pixel j, hi = pixel j+1 of one
