@@ -289,35 +289,38 @@ __device__ __forceinline__ void act2_srow(const vf2 (&x)[6][2], const vf2 (&f2)[
     }
 }
 
-__global__ void __launch_bounds__(256, 2) snake_act2_kernel(const ActParams p, int ncol) {
-    extern __shared__ __align__(16) unsigned char act2_smem[];     // fp16 input tile [rows][ncol * 4 channels]
+__device__ __forceinline__ void act2_cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// A block walks `tiles_per_block` consecutive time tiles with two input buffers: the next tile's inputs arrive by cp.async
+// while the current tile is computed (ncu of the one-tile-per-block version: warps stalled on the tile load, 58 % issue-active)
+__global__ void __launch_bounds__(256, 2) snake_act2_kernel(const ActParams p, int ncol, int tiles_per_block) {
+    extern __shared__ __align__(16) unsigned char act2_smem[];     // 2 x fp16 input tile [rows][ncol * 4 channels]
     const int tid = threadIdx.x;
     const int R = blockDim.x / ncol;                 // runs per block
-    const int TLB = R * kAct2TO;                     // outputs per block
-    const int t0 = blockIdx.x * TLB;
+    const int TLB = R * kAct2TO;                     // outputs per tile
     const int c_blk = blockIdx.y * ncol * 4;         // first channel of this block
     const long long nbase = static_cast<long long>(blockIdx.z) * p.L;
     const int pitch = ncol * 8;                      // bytes per tile row
     const int rows = TLB + 10;                       // inputs t0-5 .. t0+TLB+4
-    if (blockIdx.y == 0) {                           // layout padding channels [Creal, C) are written as zeros
-        const int npad = (p.C - p.Creal) >> 3;
-        const int pad0 = p.Creal >> 3;
-        for (int idx = tid; idx < TLB * npad; idx += blockDim.x) {
-            const int t = t0 + idx / npad;
-            if (t < p.L)
-                *reinterpret_cast<uint4*>(p.out + (nbase + t) * p.C + (pad0 + idx % npad) * 8) = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
-    {   // tile load, replicate padding at the signal ends (UpSample1d pads by replication, resample.py:26-29)
+    const int buf_bytes = (rows * pitch + 15) & ~15;
+    const int n_tiles_x = (p.L + TLB - 1) / TLB;
+    const int tile0 = blockIdx.x * tiles_per_block;
+    const int n_my = min(tiles_per_block, n_tiles_x - tile0);
+    const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(act2_smem));
+    // tile load, replicate padding at the signal ends (UpSample1d pads by replication, resample.py:26-29)
+    auto issue_load = [&](int tile, int buf) {
+        const int t0 = tile * TLB;
         const int cpr = ncol >> 1;                   // 16-byte chunks per row
         for (int idx = tid; idx < rows * cpr; idx += blockDim.x) {
             const int row = idx / cpr, ch = idx - row * cpr;
             int t = t0 - 5 + row;
             t = t < 0 ? 0 : (t > p.L - 1 ? p.L - 1 : t);
-            *reinterpret_cast<uint4*>(act2_smem + row * pitch + ch * 16) =
-                __ldg(reinterpret_cast<const uint4*>(p.x + (nbase + t) * p.C + c_blk + ch * 8));
+            act2_cp_async16(smem0 + buf * buf_bytes + row * pitch + ch * 16, p.x + (nbase + t) * p.C + c_blk + ch * 8);
         }
-    }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     const int col = tid % ncol, run = tid / ncol;
     const int c0 = c_blk + col * 4;
     vf2 al[2], ib[2], f2[12], f1[12];
@@ -331,77 +334,99 @@ __global__ void __launch_bounds__(256, 2) snake_act2_kernel(const ActParams p, i
         f1[k] = vpk2(p.filt[k], p.filt[k]);
         f2[k] = vpk2(2.f * p.filt[k], 2.f * p.filt[k]);      // UpSample1d multiplies by the ratio (resample.py:31)
     }
-    __syncthreads();
-    const int tr = t0 + run * kAct2TO;               // first output of this run
-    if (tr >= p.L) return;
-    const unsigned char* xcol = act2_smem + col * 8;
     const int imax = 2 * p.L - 1;
-    auto load_row = [&](int t, vf2 (&x)[2]) {        // input row t (tile-relative), 4 channels as two packed pairs
-        const uint2 raw = *reinterpret_cast<const uint2*>(xcol + (t - (t0 - 5)) * pitch);
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-        x[0] = vpk2(a.x, a.y);
-        x[1] = vpk2(b.x, b.y);
-    };
-    // a sample whose index falls outside [0, 2L-1] is the replicate padding of the low-pass filter (filter.py:90):
-    // it equals s[0] / s[2L-1], recomputed from the inputs around that end
-    auto edge_sample = [&](int i, vf2 (&sv)[2]) {
-        const int ic = i < 0 ? 0 : imax;
-        const int m = ic >> 1;
-        vf2 x[6][2];
-        if (ic & 1) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) load_row(m - 2 + j, x[j]);
-            act2_srow<true>(x, f2, al, ib, sv);
+    if (n_my > 0) issue_load(tile0, 0);
+    for (int kt = 0; kt < n_my; ++kt) {
+        const int buf = kt & 1;
+        const int t0 = (tile0 + kt) * TLB;
+        if (kt + 1 < n_my) {
+            issue_load(tile0 + kt + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) load_row(m - 3 + j, x[j]);
-            act2_srow<false>(x, f2, al, ib, sv);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-    };
-    vf2 acc[6][2];
-    const vf2 zero2 = vpk2(0.f, 0.f);
-#pragma unroll
-    for (int d = 0; d < 6; ++d) acc[d][0] = acc[d][1] = zero2;
-    for (int g = 0; g < kAct2Steps / 6; ++g) {
-        const int tg = tr - 5 + g * 6;               // first step of this group
-        if (tg >= p.L) break;                        // every remaining output lies beyond the signal
-        vf2 xw[11][2];                               // inputs tg .. tg+10 serve the six steps of the group
-#pragma unroll
-        for (int j = 0; j < 11; ++j) load_row(tg + j, xw[j]);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const int t = tg + k;                    // this step completes output t (slot k of acc)
-            vf2 so[2], se[2];                        // s[2t+5] (odd index), s[2t+6] (even index)
-            const int io = 2 * t + 5, ie = 2 * t + 6;
-            vf2 x6[6][2];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                x6[j][0] = xw[k + j][0];
-                x6[j][1] = xw[k + j][1];
+        __syncthreads();
+        if (blockIdx.y == 0) {                           // layout padding channels [Creal, C) are written as zeros
+            const int npad = (p.C - p.Creal) >> 3;
+            const int pad0 = p.Creal >> 3;
+            for (int idx = tid; idx < TLB * npad; idx += blockDim.x) {
+                const int t = t0 + idx / npad;
+                if (t < p.L)
+                    *reinterpret_cast<uint4*>(p.out + (nbase + t) * p.C + (pad0 + idx % npad) * 8) = make_uint4(0u, 0u, 0u, 0u);
             }
-            if (io >= 0 && io <= imax) act2_srow<true>(x6, f2, al, ib, so);
-            else edge_sample(io, so);
-            if (ie >= 0 && ie <= imax) act2_srow<false>(x6, f2, al, ib, se);
-            else edge_sample(ie, se);
-            // scatter into the partial outputs t .. t+5: slot (k + d) % 6 holds output t + d
-#pragma unroll
-            for (int d = 0; d < 6; ++d)
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-                    acc[(k + d) % 6][c] = vfma2(f1[10 - 2 * d], so[c], vfma2(f1[11 - 2 * d], se[c], acc[(k + d) % 6][c]));
-            // output t is complete (all 12 taps added over steps t-5 .. t); emit it unless it is a warm-up step
-            if (t >= tr && t < p.L) {
-                float o0, o1, o2, o3;
-                vupk2(acc[k][0], o0, o1);
-                vupk2(acc[k][1], o2, o3);
-                uint2 pk;
-                *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(o0, o1);
-                *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(o2, o3);
-                *reinterpret_cast<uint2*>(p.out + (nbase + t) * p.C + c0) = pk;
-            }
-            acc[k][0] = acc[k][1] = zero2;           // the slot now collects output t + 6
         }
+        const int tr = t0 + run * kAct2TO;               // first output of this run
+        if (tr < p.L) {
+            const unsigned char* xcol = act2_smem + buf * buf_bytes + col * 8;
+            auto load_row = [&](int t, vf2 (&x)[2]) {        // input row t (tile-relative), 4 channels as two packed pairs
+                const uint2 raw = *reinterpret_cast<const uint2*>(xcol + (t - (t0 - 5)) * pitch);
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                x[0] = vpk2(a.x, a.y);
+                x[1] = vpk2(b.x, b.y);
+            };
+            // a sample whose index falls outside [0, 2L-1] is the replicate padding of the low-pass filter (filter.py:90):
+            // it equals s[0] / s[2L-1], recomputed from the inputs around that end
+            auto edge_sample = [&](int i, vf2 (&sv)[2]) {
+                const int ic = i < 0 ? 0 : imax;
+                const int m = ic >> 1;
+                vf2 x[6][2];
+                if (ic & 1) {
+        #pragma unroll
+                    for (int j = 0; j < 6; ++j) load_row(m - 2 + j, x[j]);
+                    act2_srow<true>(x, f2, al, ib, sv);
+                } else {
+        #pragma unroll
+                    for (int j = 0; j < 6; ++j) load_row(m - 3 + j, x[j]);
+                    act2_srow<false>(x, f2, al, ib, sv);
+                }
+            };
+            vf2 acc[6][2];
+            const vf2 zero2 = vpk2(0.f, 0.f);
+        #pragma unroll
+            for (int d = 0; d < 6; ++d) acc[d][0] = acc[d][1] = zero2;
+            for (int g = 0; g < kAct2Steps / 6; ++g) {
+                const int tg = tr - 5 + g * 6;               // first step of this group
+                if (tg >= p.L) break;                        // every remaining output lies beyond the signal
+                vf2 xw[11][2];                               // inputs tg .. tg+10 serve the six steps of the group
+        #pragma unroll
+                for (int j = 0; j < 11; ++j) load_row(tg + j, xw[j]);
+        #pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int t = tg + k;                    // this step completes output t (slot k of acc)
+                    vf2 so[2], se[2];                        // s[2t+5] (odd index), s[2t+6] (even index)
+                    const int io = 2 * t + 5, ie = 2 * t + 6;
+                    vf2 x6[6][2];
+        #pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        x6[j][0] = xw[k + j][0];
+                        x6[j][1] = xw[k + j][1];
+                    }
+                    if (io >= 0 && io <= imax) act2_srow<true>(x6, f2, al, ib, so);
+                    else edge_sample(io, so);
+                    if (ie >= 0 && ie <= imax) act2_srow<false>(x6, f2, al, ib, se);
+                    else edge_sample(ie, se);
+                    // scatter into the partial outputs t .. t+5: slot (k + d) % 6 holds output t + d
+        #pragma unroll
+                    for (int d = 0; d < 6; ++d)
+        #pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            acc[(k + d) % 6][c] = vfma2(f1[10 - 2 * d], so[c], vfma2(f1[11 - 2 * d], se[c], acc[(k + d) % 6][c]));
+                    // output t is complete (all 12 taps added over steps t-5 .. t); emit it unless it is a warm-up step
+                    if (t >= tr && t < p.L) {
+                        float o0, o1, o2, o3;
+                        vupk2(acc[k][0], o0, o1);
+                        vupk2(acc[k][1], o2, o3);
+                        uint2 pk;
+                        *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(o0, o1);
+                        *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(o2, o3);
+                        *reinterpret_cast<uint2*>(p.out + (nbase + t) * p.C + c0) = pk;
+                    }
+                    acc[k][0] = acc[k][1] = zero2;           // the slot now collects output t + 6
+                }
+            }
+        }
+        __syncthreads();     // every thread is done with this buffer before the load issued next iteration overwrites it
     }
 }
 
@@ -416,8 +441,17 @@ static void launch_snake_act(const ActParams& a, int N, cudaStream_t s) {
     }
     const int ncol = act2_ncol(a.Creal);
     const int R = 256 / ncol;
-    const dim3 grid((a.L + R * kAct2TO - 1) / (R * kAct2TO), (a.Creal / 4) / ncol, N);
-    snake_act2_kernel<<<grid, R * ncol, act2_smem_bytes(ncol), s>>>(a, ncol);
+    const int tiles_x = (a.L + R * kAct2TO - 1) / (R * kAct2TO);
+    // several tiles per block (double-buffered inputs) as long as the grid keeps >= ~4 blocks per SM
+    int tpb = 4;
+    while (tpb > 1 && static_cast<long long>((tiles_x + tpb - 1) / tpb) * ((a.Creal / 4) / ncol) * N < 4 * 148) tpb >>= 1;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(snake_act2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr = true;
+    }
+    const dim3 grid((tiles_x + tpb - 1) / tpb, (a.Creal / 4) / ncol, N);
+    snake_act2_kernel<<<grid, R * ncol, 2 * ((act2_smem_bytes(ncol) + 15) & ~size_t(15)), s>>>(a, ncol, tpb);
 }
 
 // mel (B, M, T) fp32 -> [B][T][Cp] fp16, zero padded channels.  mel_min != null: `mel` is the decoder's normalised
