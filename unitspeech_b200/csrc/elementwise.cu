@@ -445,13 +445,21 @@ __global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int 
     const int iters = (p_end - p_begin + lanes * U - 1) / (lanes * U);
     for (int it = 0; it < iters; ++it) {
         uint4 rv[U][3];
-        float m[U];
+        float m[U], xt_in[U], nz_in[U];
         int pixs[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             pixs[u] = p_begin + (it * U + u) * lanes + pl;
             const bool ok = pixs[u] < p_end;
             m[u] = ok ? __ldg(mk + pixs[u] % p.W) : 0.f;
+            // the state and noise of the pixel are fetched with the activations, not after the reduction (the lane that
+            // applies the update would otherwise stall the whole warp on two dependent global loads per pixel)
+            xt_in[u] = nz_in[u] = 0.f;
+            if (ok && tq == 0 && p.xt != nullptr) {
+                const long long q = static_cast<long long>(b) * p.P + pixs[u];
+                xt_in[u] = p.xt[q];
+                if (noise) nz_in[u] = noise[q];
+            }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 rv[u][k] = make_uint4(0u, 0u, 0u, 0u);
@@ -504,8 +512,7 @@ __global__ void __launch_bounds__(256, 2) final_kernel(const FinalParams p, int 
                     float score = sf;
                     if (p.nb >= 2) score = score + p.a0 * (sf - sc[0]);
                     if (p.nb >= 3) score = score + p.a1 * (sf - sc[1]);
-                    const float nz = noise ? noise[q] : 0.f;
-                    const float xn = (c_x * p.xt[q] + c_s * score + sigma * nz) * m[u];
+                    const float xn = (c_x * xt_in[u] + c_s * score + sigma * nz_in[u]) * m[u];
                     p.xt[q] = xn;
                     if (p.score) p.score[q] = score;
                     if (outp) {
