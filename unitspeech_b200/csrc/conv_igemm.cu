@@ -358,6 +358,13 @@ __device__ __forceinline__ PatchCoord decode_patch(const ConvParams& p, int ph, 
 }
 }  // namespace
 
+// MC = true: launched as clusters of two CTAs that work on the SAME pair of pixel patches and two adjacent 128-channel
+// tiles.  Each CTA loads its own weight tile; CTA r loads patch r of the pair ONCE and TMA multicasts it into both CTAs'
+// shared memory, so the activation traffic from L2 per K step drops from 2 x 32 KB to 32 KB per cluster (48 -> 32 KB per
+// CTA).  A stage is refilled only after BOTH CTAs' MMAs have consumed it: the empty barrier counts two arrivals and every
+// MMA warp commits to the barrier of both CTAs (tcgen05.commit ... multicast::cluster).  Both CTAs walk identical item
+// sequences (same pair, same taps, same split), so their pipelines stay in lockstep by construction.
+template <bool MC>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0,
                           const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b,
@@ -381,7 +388,14 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
     const int ksteps_all = p.taps * ctot;
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;      // work item = (tile, K range); total_tiles counts items
     const int pairs_per_phase = (p.patches_per_phase + 1) >> 1;
-    const int tiles_per_phase = pairs_per_phase * p.n_tiles_n;
+    // work walked by this CTA: items blockIdx.x, +gridDim.x, ... of `total_tiles`; in cluster mode the walker is the
+    // CLUSTER (index blockIdx.x / 2 of gridDim.x / 2) over `total_tiles` cluster items = (patch pair, channel-tile pair,
+    // split), and CTA rank r takes channel tile 2q + r of the pair
+    const int crank = MC ? static_cast<int>(cluster_ctarank()) : 0;
+    const int walker = MC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int walkers = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int ntn = MC ? p.n_tiles_n >> 1 : p.n_tiles_n;      // channel tiles (MC: tile pairs) per patch pair
+    const int tiles_per_phase = pairs_per_phase * ntn;
     const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
     const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
 
@@ -394,7 +408,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < stages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], MC ? 2 : 1);      // MC: the MMA warps of both CTAs release a stage
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
@@ -411,18 +425,19 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (MC) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
     pdl_wait_and_trigger();   // everything above is local set-up; below this line the predecessor's output is read
 
     if (warp == 0) {
         // ---------------------------------------------------- TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
-            const int tile = item / ksplit, sp = item - tile * ksplit;
-            const int ph = tile / tiles_per_phase;
-            const int rem = tile - ph * tiles_per_phase;
-            const int nt = rem % p.n_tiles_n;
-            const int pair = rem / p.n_tiles_n;
+        for (int witem = walker; witem < total_tiles; witem += walkers) {
+            const int wtile = witem / ksplit, sp = witem - wtile * ksplit;
+            const int ph = wtile / tiles_per_phase;
+            const int rem = wtile - ph * tiles_per_phase;
+            const int nt = MC ? 2 * (rem % ntn) + crank : rem % ntn;
+            const int pair = rem / ntn;
             const PatchCoord c0 = decode_patch(p, ph, 2 * pair), c1 = decode_patch(p, ph, 2 * pair + 1);
             const int bz = p.b_batch_mode == 1 ? ph : 0;
             const uint32_t tx_bytes = kWBytes + kPBytes + (c1.valid ? kPBytes : 0u);
@@ -439,11 +454,17 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                     const uint32_t sw = tiles_base + stage * kStageBytes;
                     const uint32_t fb = full0 + stage * 8;
                     const int cch = tap.c + cc * kConvBK;
-                    mbar_arrive_expect_tx_a(fb, tx_bytes);
+                    mbar_arrive_expect_tx_a(fb, tx_bytes);      // (MC: includes the patch the peer multicasts to this CTA)
                     tma_load_3d_a(sw, &map_b, fb, ks * kConvBK, nt * 128, bz);
-                    tma_load_5d_a(sw + kWBytes, ma, fb, cch, c0.x0 + tap.dx, tap.p, c0.y0 + tap.dy, c0.n);
-                    if (c1.valid)
-                        tma_load_5d_a(sw + kWBytes + kPBytes, ma, fb, cch, c1.x0 + tap.dx, tap.p, c1.y0 + tap.dy, c1.n);
+                    if (!MC) {
+                        tma_load_5d_a(sw + kWBytes, ma, fb, cch, c0.x0 + tap.dx, tap.p, c0.y0 + tap.dy, c0.n);
+                        if (c1.valid)
+                            tma_load_5d_a(sw + kWBytes + kPBytes, ma, fb, cch, c1.x0 + tap.dx, tap.p, c1.y0 + tap.dy, c1.n);
+                    } else if (crank == 0) {
+                        tma_load_5d_mc_a(sw + kWBytes, ma, fb, cch, c0.x0 + tap.dx, tap.p, c0.y0 + tap.dy, c0.n, 3);
+                    } else if (c1.valid) {
+                        tma_load_5d_mc_a(sw + kWBytes + kPBytes, ma, fb, cch, c1.x0 + tap.dx, tap.p, c1.y0 + tap.dy, c1.n, 3);
+                    }
                 }
                 __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -458,10 +479,10 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++it) {
+        for (int witem = walker; witem < total_tiles; witem += walkers, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int sp = item % ksplit;
+            const int sp = witem % ksplit;
             const int ksteps = (sp + 1) * ksteps_all / ksplit - sp * ksteps_all / ksplit;
             mbar_wait_a(tempty0 + as * 8, aphase ^ 1u, 200 + as);
             tc_fence_after();
@@ -478,7 +499,8 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                         const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (x_lo + 2u * k);
                         tc_mma_f16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
                     }
-                    tc_commit_a(empty0 + stage * 8);
+                    if (MC) tc_commit_mc_a(empty0 + stage * 8, 3);      // frees the slot in both CTAs of the cluster
+                    else tc_commit_a(empty0 + stage * 8);
                     if (ks == ksteps - 1) tc_commit_a(tfull0 + as * 8);
                 }
                 __syncwarp();
@@ -504,12 +526,15 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
                        static_cast<uint32_t>(lane & 7) * 2u;
         float amax = 0.f;                         // largest |value| packed by this thread (saturation report)
         int it = 0;
-        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++it) {
-            const int tile = item / ksplit;
-            const int ph = tile / tiles_per_phase;
-            const int rem = tile - ph * tiles_per_phase;
-            const int nt = rem % p.n_tiles_n;
-            const PatchCoord pc = decode_patch(p, ph, 2 * (rem / p.n_tiles_n) + grp);
+        for (int witem = walker; witem < total_tiles; witem += walkers, ++it) {
+            const int wtile = witem / ksplit;
+            const int ph = wtile / tiles_per_phase;
+            const int rem = wtile - ph * tiles_per_phase;
+            const int nt = MC ? 2 * (rem % ntn) + crank : rem % ntn;
+            const PatchCoord pc = decode_patch(p, ph, 2 * (rem / ntn) + grp);
+            // per-CTA output tile / work item ids (split-K workspace and tickets): unique across the cluster's two CTAs
+            const int tile = MC ? wtile * 2 + crank : wtile;
+            const int item = tile * ksplit + (witem - wtile * ksplit);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait_a(tfull0 + as * 8, aphase, 400 + as);
@@ -665,6 +690,7 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (MC) cluster_sync_all();   // the peer's last commits arrive on this CTA's barriers: do not exit before it is done
 }
 
 // =====================================================================================================================
@@ -930,7 +956,9 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kConvSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
-        e = cudaFuncSetAttribute(conv_igemm_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
+        e = cudaFuncSetAttribute(conv_igemm_swapped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        e = cudaFuncSetAttribute(conv_igemm_swapped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
         e = cudaFuncSetAttribute(conv_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
@@ -952,7 +980,39 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
     if (p.swap_ab) {
         const size_t smem = 1024 + static_cast<size_t>(p.stages) * 49152 + 2 * 16384;
         if (smem > static_cast<size_t>(kConvSmemBytes)) return static_cast<int>(cudaErrorInvalidValue);
-        return static_cast<int>(launch_k(conv_igemm_swapped_kernel, dim3(grid), dim3(kConvThreads), smem, stream, p, a0, a1, b,
+        // cluster mode (see the kernel): an even number of 128-channel tiles, at least two clusters' worth of work
+        static const bool no_mc = getenv("USB_NO_MC") != nullptr;
+        if (!no_mc && p.n_tiles_n % 2 == 0 && total >= 4) {
+            const long long citems = total / 2;
+            // clusters that can be resident at once (GPC boundaries may leave a few SMs unpaired): queried once per
+            // shared-memory size, so that the persistent walk never waits for a cluster slot
+            static int max_clusters[2] = {0, 0};
+            int& mc = max_clusters[p.ksplit > 1 ? 1 : 0];
+            if (mc == 0) {
+                cudaLaunchConfig_t qc = {};
+                qc.gridDim = dim3(num_sms & ~1);
+                qc.blockDim = dim3(kConvThreads);
+                qc.dynamicSmemBytes = smem;
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = 2;
+                qa[0].val.clusterDim.y = 1;
+                qa[0].val.clusterDim.z = 1;
+                qc.attrs = qa;
+                qc.numAttrs = 1;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, conv_igemm_swapped_kernel<true>, &qc) != cudaSuccess || n < 1) {
+                    cudaGetLastError();
+                    n = num_sms / 2;
+                }
+                mc = n < num_sms / 2 ? n : num_sms / 2;
+            }
+            int clusters = mc;
+            if (citems < clusters) clusters = static_cast<int>(citems);
+            return static_cast<int>(launch_k_cluster(conv_igemm_swapped_kernel<true>, dim3(2 * clusters), dim3(kConvThreads), smem,
+                                                     stream, 2, p, a0, a1, b, out, static_cast<int>(citems)));
+        }
+        return static_cast<int>(launch_k(conv_igemm_swapped_kernel<false>, dim3(grid), dim3(kConvThreads), smem, stream, p, a0, a1, b,
                                          out, static_cast<int>(total)));
     }
     const size_t smem = 1024 + static_cast<size_t>(p.stages) * (16384 + static_cast<size_t>(p.BN) * 128) + 8 * 8192;
