@@ -169,3 +169,16 @@ def test_attention_context_matches_torch(ops, H, W):
     ref = torch.einsum("chE,bhdE->bchd", wo.reshape(C, heads, dh), ctx).reshape(N, C, heads * dh)
     out = ops.attn_context(qkv, wo)
     _check(out, ref, tol=2e-3)
+
+
+def test_cluster_multicast_conv_variant_in_a_subprocess():
+    """USB_MC=1 (read once per process) launches the swapped-operand conv as clusters of two CTAs that TMA-multicast the
+    activation patches to each other; the same conv cases must pass with it."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, USB_MC="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "test_conv_matches_torch or test_conv_stats_group_widths"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -980,9 +980,13 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
     if (p.swap_ab) {
         const size_t smem = 1024 + static_cast<size_t>(p.stages) * 49152 + 2 * 16384;
         if (smem > static_cast<size_t>(kConvSmemBytes)) return static_cast<int>(cudaErrorInvalidValue);
-        // cluster mode (see the kernel): an even number of 128-channel tiles, at least two clusters' worth of work
-        static const bool no_mc = getenv("USB_NO_MC") != nullptr;
-        if (!no_mc && p.n_tiles_n % 2 == 0 && total >= 4) {
+        // cluster mode (see the kernel; USB_MC=1): an even number of 128-channel tiles, at least two clusters' worth of work.
+        // OFF by default: measured on B200 it is neutral in throughput mode (8 979 vs 8 966 frames/s on the 32 x 1000 shard,
+        // conv class 2 719 vs 2 721 ms per pass) and 2 % slower for one-utterance calls (84.9 vs 83.2 ms): these launches are
+        // not bound by L2 -> shared-memory traffic (tensor pipe 86-89 % active at Be = 96; per-CTA TMA latency x 4 stages at
+        // Be = 3), so loading the activation patch once per cluster changes nothing.  tests/test_gpu_ops.py runs it.
+        static const bool use_mc = getenv("USB_MC") != nullptr;
+        if (use_mc && p.n_tiles_n % 2 == 0 && total >= 4) {
             const long long citems = total / 2;
             // clusters that can be resident at once (GPC boundaries may leave a few SMs unpaired): queried once per
             // shared-memory size, so that the persistent walk never waits for a cluster slot
