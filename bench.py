@@ -75,6 +75,15 @@ def _peaks():
     return {"tensor": 1400.0, "tensor_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
 
 
+def _build_info():
+    """What the loaded libunitspeech_b200.so was built from (written by unitspeech_b200/build.py next to the library)."""
+    try:
+        from unitspeech_b200 import build as b
+        return b.build_info() or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def _profile_json(name: str):
     """Committed evidence under profiles/ (ncu-derived traffic, per-step drift) that the line quotes; None if absent."""
     path = os.path.join(ROOT, "profiles", name)
@@ -434,6 +443,7 @@ def run_gpu_arm(args):
             "cpu_baseline": cpu,
             "per_step_drift": ({"file": f"profiles/r2_drift_T{T}.json", **{k: drift[k] for k in drift if k != "per_step"}}
                                if drift else None),
+            "build": _build_info(),
         }
         line.update(legs)
     if world > 1:

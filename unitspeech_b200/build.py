@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libunitspeech_b200.so")
 SOURCES = ["conv_igemm.cu", "elementwise.cu", "attention.cu", "engine.cu", "vocoder.cu", "train_kernels.cu", "wgrad_tc.cu", "frontend.cu"]
-HEADERS = ["ptx.cuh", "conv_igemm.h", "kernels.h", "train.h", os.path.join("..", "..", "include", "unitspeech_b200.h"),
+HEADERS = ["ptx.cuh", "pdl.h", "conv_igemm.h", "kernels.h", "train.h", os.path.join("..", "..", "include", "unitspeech_b200.h"),
            os.path.join("..", "..", "include", "unitspeech_b200_train.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
@@ -56,7 +56,39 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
+        _write_build_info(nvcc)
     return LIB_PATH
+
+
+BUILD_INFO = os.path.join(LIB_DIR, "build_info.json")
+
+
+def _write_build_info(nvcc: str) -> None:
+    """Record of what the shipped .so was built from (bench.py quotes it as `build`): compiler, flags, source digests."""
+    import hashlib
+    import json
+    import time
+    ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    files = SOURCES + [h for h in HEADERS]
+    digest = hashlib.sha256()
+    for f in sorted(set(files)):
+        path = os.path.normpath(os.path.join(CSRC, f))
+        if os.path.exists(path):
+            with open(path, "rb") as fh:
+                digest.update(fh.read())
+    info = {"nvcc": ver, "flags": NVCC_FLAGS, "sources": sorted(set(SOURCES)), "sources_sha256": digest.hexdigest(),
+            "built_at": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "host": os.uname().nodename}
+    with open(BUILD_INFO, "w") as f:
+        json.dump(info, f, indent=1)
+
+
+def build_info() -> dict:
+    import json
+    try:
+        with open(BUILD_INFO) as f:
+            return json.load(f)
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 if __name__ == "__main__":
