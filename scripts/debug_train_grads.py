@@ -1,6 +1,6 @@
 """Per-parameter gradient comparison of the CUDA fine-tune step against the oracle's autograd (GPU box only).
 
-usage: python tests/debug_train_grads.py [d64|full] [B] [T]
+usage: python scripts/debug_train_grads.py [d64|full] [B] [T]
 Prints loss, then one line per parameter (reverse graph order first) with relative L2 error and cosine.
 """
 
