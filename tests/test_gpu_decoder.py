@@ -139,6 +139,25 @@ def test_graph_replayed_sampler_is_bit_identical_to_the_eager_loop():
     assert torch.equal(dec(z, mask, cond, spk, n, 1.0, 1.0, noise=noise), eager.cpu())
 
 
+def test_graph_mode_survives_shape_and_step_count_changes():
+    """The captured step belongs to one (rows, frames) plan: changing the shape re-plans and re-captures; the step count,
+    the noise and the inputs are not part of the graph."""
+    s = 1.0 / 32
+    p = O.harness_params(dim=64, dim_mults=(1, 2), seed=1234, out_scale=s)
+    dec = _decoder(64, (1, 2), p)
+    want = {}
+    for mode in (0, 1):
+        dec.graph_mode = mode
+        for B, T, n, seed in ((1, 32, 5, 1), (2, 16, 4, 2), (1, 32, 7, 3), (2, 16, 3, 4), (1, 8, 4, 5)):
+            z, mask, cond, spk, noise = O.harness_inputs(B, T, n, seed=seed, scale=s)
+            out = dec(z.cuda(), mask.cuda(), cond.cuda(), spk.cuda(), n, 1.0, 1.0, noise=noise.cuda())
+            if mode == 0:
+                want[(B, T, n, seed)] = out
+            else:
+                assert torch.equal(out, want[(B, T, n, seed)]), (B, T, n)
+    assert dec.graph_steps > 0
+
+
 def test_split_k_mode_is_deterministic_batch_invariant_and_within_tolerance():
     """Latency mode: the level-2/3 convolutions split K over idle SMs; partial tiles are summed in split order."""
     B, T, n, s = 3, 64, 4, 1.0 / 512

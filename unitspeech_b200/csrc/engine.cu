@@ -1405,6 +1405,7 @@ static int reverse_diffusion(usb_handle* h, const float* z, const float* cond, c
         const int key = nb | (h->denorm ? 8 : 0) | (noise ? 16 : 0) | (use_t ? 32 : 0);
         auto it = pl.step_graphs.find(key);
         if (it != pl.step_graphs.end() && (h->graph_a0 != a0 || h->graph_a1 != sg)) {   // guidance scales are kernel arguments
+            USB_CUDA(cudaStreamSynchronize(s));     // replays of the old graph may still be in flight on this stream
             drop_step_graphs(pl);
             it = pl.step_graphs.end();
         }
