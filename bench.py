@@ -254,6 +254,7 @@ def run_reference_arm(args):
                          else "oracle/unitspeech_oracle.py (baseline/_ref absent)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "config1_cpu": cfg1,
+        "seconds_per_diffusion_step": {"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step)},
         "gpu_launches": 0,
     }
     _emit(line)
