@@ -126,6 +126,87 @@ __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const uint32_
     }
 }
 
+// Epilogue of the pixels-on-M kernels (warps 4-11): TMEM -> registers -> bias / statistics / residual / mask -> fp16 ->
+// per-warp swizzled staging -> TMA store.  `staging_base`: 8 warps x 8 KB of shared memory.
+__device__ __forceinline__ void plain_epilogue(const ConvParams& p, const CUtensorMap& map_out, uint32_t staging_base,
+                                               uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles,
+                                               int warp, int lane) {
+    const int ew = warp & 3;                 // TMEM lane quarter
+    const int grp = (warp - 4) >> 2;         // column half
+    const int row = ew * 32 + lane;
+    const int bw_shift = 31 - __clz(p.BW);
+    const int ty = row >> bw_shift;
+    const int tx = row & (p.BW - 1);
+    const int cpg = p.stats ? p.Cout / p.groups : 64;
+    const float rs = p.res_scale ? __ldg(p.res_scale) : 1.f;
+    // 64-column slabs of the tile: group 0 takes the first half (rounded up), group 1 the rest (BN == 64: none)
+    const int total_slabs = p.BN >> 6;
+    const int slab_begin = grp == 0 ? 0 : (total_slabs + 1) >> 1;
+    const int slabs = grp == 0 ? (total_slabs + 1) >> 1 : total_slabs - slab_begin;
+    // per-warp staging (32 pixel rows x 128 B) and per-warp TMA stores: no cross-warp barrier in the epilogue
+    // (two 4 KB buffers per warp, alternating, so a store only waits for the one issued two slabs earlier)
+    const uint32_t warp_buf0 = staging_base + static_cast<uint32_t>(grp * 4 + ew) * 8192u;
+    uint32_t buf_sel = 0;
+    float amax = 0.f;                             // largest |value| packed by this thread (saturation report)
+    const int q0 = ew * 32;                       // first tile pixel of this warp
+    const int wty0 = q0 >> bw_shift, wtx0 = q0 & (p.BW - 1);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int y = tc.y0 + ty, x = tc.x0 + tx;
+        const bool valid = x < p.Wm;
+        const int yo = y * p.oy_mul + p.oy_off[tc.ph];
+        const int xo = x * p.ox_mul + p.ox_off[tc.ph];
+        const float m = (p.mask && valid) ? __ldg(p.mask + static_cast<long long>(tc.n) * p.mask_stride + xo) : 1.f;
+        long long* stats_n = p.stats ? p.stats + static_cast<long long>(tc.n) * p.groups * 2 : nullptr;
+        const __half* res_px = p.res ? p.res + (tc.n * p.o_sn + yo * p.o_sy + xo * p.o_sx) : nullptr;
+
+        mbar_wait_a(tfull0 + as * 8, aphase, 400 + as);
+        tc_fence_after();
+        if (slabs == 0 || (p.dbg_flags & 2)) {
+            tc_fence_before();
+            mbar_arrive_a(tempty0 + as * 8);
+            continue;
+        }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
+        for (int sl = 0; sl < slabs; ++sl) {
+            const int col0 = (slab_begin + sl) * 64;
+            const int c_glob = tc.nt * p.BN + col0;
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(taddr + col0, v0);
+            tmem_ld_32x32(taddr + col0 + 32, v1);
+            tmem_ld_wait();
+            if (sl == slabs - 1) {
+                // this thread's accumulator reads are complete: hand the TMEM stage back to the MMA warp
+                tc_fence_before();
+                mbar_arrive_a(tempty0 + as * 8);
+            }
+            // this staging buffer is free once the store issued from it two slabs ago has been read
+            const uint32_t warp_buf = warp_buf0 + buf_sel * 4096u;
+            const uint32_t stage_row = warp_buf + static_cast<uint32_t>(lane) * 128u;
+            buf_sel ^= 1u;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            const __half* res_row = res_px ? res_px + c_glob : nullptr;
+            if (cpg >= 64) epilogue_slab<1>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
+            else if (cpg == 32) epilogue_slab<2>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
+            else if (cpg == 16) epilogue_slab<4>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
+            else epilogue_slab<8>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
+            fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_5d_a(&map_out, warp_buf, c_glob + p.ox_off[tc.ph] * p.out_c_phase_mul, tc.x0 + wtx0,
+                               p.oy_off[tc.ph], tc.y0 + wty0, tc.n);
+                tma_store_commit();
+            }
+        }
+    }
+    if (p.sat && amax >= 65504.f) atomicAdd(p.sat, 1ull);
+    if (lane == 0) tma_store_wait_all<0>();
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -250,79 +331,186 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
             }
         }
     } else if (warp >= 4) {
-        // ---------------------------------------------------- epilogue
-        const int ew = warp & 3;                 // TMEM lane quarter
-        const int grp = (warp - 4) >> 2;         // column half
-        const int row = ew * 32 + lane;
-        const int bw_shift = 31 - __clz(p.BW);
-        const int ty = row >> bw_shift;
-        const int tx = row & (p.BW - 1);
-        const int cpg = p.stats ? p.Cout / p.groups : 64;
-        const float rs = p.res_scale ? __ldg(p.res_scale) : 1.f;
-        const int half_cols = p.BN >= 128 ? p.BN >> 1 : p.BN;
-        const int slabs = (p.BN >= 128 || grp == 0) ? half_cols >> 6 : 0;  // BN == 64: group 1 has no columns
-        // per-warp staging (32 pixel rows x 128 B) and per-warp TMA stores: no cross-warp barrier in the epilogue
-        // (two 4 KB buffers per warp, alternating, so a store only waits for the one issued two slabs earlier)
-        const uint32_t warp_buf0 = tiles_base + stages * stage_bytes + static_cast<uint32_t>(grp * 4 + ew) * 8192u;
-        uint32_t buf_sel = 0;
-        float amax = 0.f;                             // largest |value| packed by this thread (saturation report)
-        const int q0 = ew * 32;                       // first tile pixel of this warp
-        const int wty0 = q0 >> bw_shift, wtx0 = q0 & (p.BW - 1);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const TileCoord tc = decode_tile(p, tile);
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            const int y = tc.y0 + ty, x = tc.x0 + tx;
-            const bool valid = x < p.Wm;
-            const int yo = y * p.oy_mul + p.oy_off[tc.ph];
-            const int xo = x * p.ox_mul + p.ox_off[tc.ph];
-            const float m = (p.mask && valid) ? __ldg(p.mask + static_cast<long long>(tc.n) * p.mask_stride + xo) : 1.f;
-            long long* stats_n = p.stats ? p.stats + static_cast<long long>(tc.n) * p.groups * 2 : nullptr;
-            const __half* res_px = p.res ? p.res + (tc.n * p.o_sn + yo * p.o_sy + xo * p.o_sx) : nullptr;
+        plain_epilogue(p, map_out, tiles_base + stages * stage_bytes, tmem_base, tfull0, tempty0, total_tiles, warp, lane);
+    }
 
-            mbar_wait_a(tfull0 + as * 8, aphase, 400 + as);
-            tc_fence_after();
-            if (slabs == 0 || (p.dbg_flags & 2)) {
-                tc_fence_before();
-                mbar_arrive_a(tempty0 + as * 8);
-                continue;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================================
+// 1-D halo variant of the kernel above (the vocoder's Conv1d layers, alias "same"-padded dilated convs of
+// unitspeech/vocoder/models.py:46-74): with one TMA load per (tap, chunk) every activation byte crosses L2 -> shared
+// memory `taps` times (3 / 7 / 11), and at 24-192 channels that traffic, not the tensor pipe, bounds the layer.  Here the
+// tile's 128 positions are loaded ONCE per 64-channel chunk together with the (k-1)*dilation positions the taps reach
+// (box of p.h1d_rows rows starting at x0 + h1d_dx0; out-of-range positions are zero-filled = the conv's zero padding) and
+// tap t is the UMMA descriptor whose start address is shifted by (dx_t - h1d_dx0) rows of 128 bytes.  The 128-byte
+// swizzle is a function of the absolute shared-memory address, so a start address that is not a multiple of 1024 reads
+// the rows the TMA wrote (same property conv_igemm_halo_kernel relies on).  Weight tiles are either streamed through
+// a ring (one per (chunk, tap)) or, when taps x chunks tiles fit (the 24- / 48-channel stages), loaded once per CTA and
+// kept resident.  K = 16 slices that hold only channel padding (h1d_klast) are not issued.
+// K order: chunk-major, taps inside (the packed weight's K coordinate is (tap * chunks + chunk) * 64).
+// =====================================================================================================================
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv1d_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_out, int total_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];      // weight ring
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t afull_bar[4];     // activation ring
+    __shared__ __align__(8) uint64_t aempty_bar[4];
+    __shared__ __align__(8) uint64_t wres_bar;         // resident weights loaded
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_bytes = static_cast<uint32_t>(p.h1d_rows) * 128u;            // one haloed activation chunk
+    const uint32_t a_stride = (a_bytes + 1023u) & ~1023u;
+    const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;                  // one weight tile
+    const int na = p.h1d_na;
+    const int chunks = p.chunks0;
+    const int wtiles = p.h1d_wres ? p.taps * chunks : p.stages;                  // weight tiles held in shared memory
+    const uint32_t w_base = tiles_base + static_cast<uint32_t>(na) * a_stride;
+    const uint32_t staging_base = w_base + static_cast<uint32_t>(wtiles) * b_bytes;
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t afull0 = smem_u32(&afull_bar[0]), aempty0 = smem_u32(&aempty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 3 && lane == 0) tma_prefetch_desc(&map_a);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 8; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&afull_bar[i], 1);
+            mbar_init(&aempty_bar[i], 1);
+        }
+        mbar_init(&wres_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], kConvEpilogueThreads);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&tmem_base_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait_and_trigger();
+
+    if (warp == 0) {
+        // ---------------------------------------------------- TMA producer
+        if (p.h1d_wres) {      // weights: every (tap, chunk) tile once, in packed-K order
+            if (elect_one()) {
+                const uint32_t wb = smem_u32(&wres_bar);
+                mbar_arrive_expect_tx_a(wb, static_cast<uint32_t>(wtiles) * b_bytes);
+                for (int i = 0; i < wtiles; ++i) tma_load_3d_a(w_base + i * b_bytes, &map_b, wb, i * kConvBK, 0, 0);
             }
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
-            for (int sl = 0; sl < slabs; ++sl) {
-                const int col0 = (p.BN >= 128 ? grp * half_cols : 0) + sl * 64;
-                const int c_glob = tc.nt * p.BN + col0;
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(taddr + col0, v0);
-                tmem_ld_32x32(taddr + col0 + 32, v1);
-                tmem_ld_wait();
-                if (sl == slabs - 1) {
-                    // this thread's accumulator reads are complete: hand the TMEM stage back to the MMA warp
-                    tc_fence_before();
-                    mbar_arrive_a(tempty0 + as * 8);
-                }
-                // this staging buffer is free once the store issued from it two slabs ago has been read
-                const uint32_t warp_buf = warp_buf0 + buf_sel * 4096u;
-                const uint32_t stage_row = warp_buf + static_cast<uint32_t>(lane) * 128u;
-                buf_sel ^= 1u;
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
-                const __half* res_row = res_px ? res_px + c_glob : nullptr;
-                if (cpg >= 64) epilogue_slab<1>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
-                else if (cpg == 32) epilogue_slab<2>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
-                else if (cpg == 16) epilogue_slab<4>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
-                else epilogue_slab<8>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
-                fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_5d_a(&map_out, warp_buf, c_glob + p.ox_off[tc.ph] * p.out_c_phase_mul, tc.x0 + wtx0,
-                                   p.oy_off[tc.ph], tc.y0 + wty0, tc.n);
-                    tma_store_commit();
+            __syncwarp();
+        }
+        if (!p.h1d_wres) {     // weights streamed: one tile per (chunk, tap), in the order the MMA warp consumes them
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int bn0 = (tile % p.n_tiles_n) * p.BN;
+                for (int cc = 0; cc < chunks; ++cc) {
+                    for (int t = 0; t < p.taps; ++t) {
+                        mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 100 + stage);
+                        if (elect_one()) {
+                            const uint32_t fb = full0 + stage * 8;
+                            mbar_arrive_expect_tx_a(fb, b_bytes);
+                            tma_load_3d_a(w_base + stage * b_bytes, &map_b, fb, (t * chunks + cc) * kConvBK, bn0, 0);
+                        }
+                        __syncwarp();
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
                 }
             }
         }
-        if (p.sat && amax >= 65504.f) atomicAdd(p.sat, 1ull);
-        if (lane == 0) tma_store_wait_all<0>();
+    } else if (warp == 3) {
+        // ---------------------------------------------------- activation producer (own warp: never waits behind a weight slot)
+        int ab = 0;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(p, tile);
+            for (int cc = 0; cc < chunks; ++cc) {
+                mbar_wait_a(aempty0 + ab * 8, aph ^ 1u, 500 + ab);
+                if (elect_one()) {
+                    const uint32_t fb = afull0 + ab * 8;
+                    mbar_arrive_expect_tx_a(fb, a_bytes);
+                    tma_load_5d_a(tiles_base + ab * a_stride, &map_a, fb, cc * kConvBK, tc.x0 + p.h1d_dx0, 0, 0, tc.n);
+                }
+                __syncwarp();
+                if (++ab == na) { ab = 0; aph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------- MMA issuer
+        const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(p.BN));
+        const uint32_t desc_hi = static_cast<uint32_t>(umma_desc_sw128(0) >> 32);
+        int stage = 0, ab = 0;
+        uint32_t phase = 0, aph = 0;
+        int it = 0;
+        if (p.h1d_wres) {
+            mbar_wait_a(smem_u32(&wres_bar), 0u, 600);
+            tc_fence_after();
+        }
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait_a(tempty0 + as * 8, aphase ^ 1u, 200 + as);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as) * 256u;
+            for (int cc = 0; cc < chunks; ++cc) {
+                mbar_wait_a(afull0 + ab * 8, aph, 700 + ab);
+                tc_fence_after();
+                const uint32_t a_buf = tiles_base + ab * a_stride;
+                const int nk = cc == chunks - 1 ? p.h1d_klast : kConvBK / 16;
+                for (int t = 0; t < p.taps; ++t) {
+                    uint32_t w_addr;
+                    if (p.h1d_wres) {
+                        w_addr = w_base + static_cast<uint32_t>(t * chunks + cc) * b_bytes;
+                    } else {
+                        mbar_wait_a(full0 + stage * 8, phase, 300 + stage);
+                        tc_fence_after();
+                        w_addr = w_base + stage * b_bytes;
+                    }
+                    if (elect_one()) {
+                        const int roff = p.tap[t].dx - p.h1d_dx0;      // rows into the haloed tile
+                        const uint32_t a_lo = ((a_buf + static_cast<uint32_t>(roff) * 128u) & 0x3FFFFu) >> 4;
+                        const uint32_t b_lo = (w_addr & 0x3FFFFu) >> 4;
+                        for (int k = 0; k < nk; ++k) {
+                            const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k);
+                            const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
+                            tc_mma_f16(tmem_d, da, db, idesc, (cc | t | k) != 0 ? 1u : 0u);
+                        }
+                        if (!p.h1d_wres) tc_commit_a(empty0 + stage * 8);
+                        if (t == p.taps - 1) {
+                            tc_commit_a(aempty0 + ab * 8);          // the chunk's MMAs have read the activation buffer
+                            if (cc == chunks - 1) tc_commit_a(tfull0 + as * 8);
+                        }
+                    }
+                    __syncwarp();
+                    if (!p.h1d_wres && ++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                if (++ab == na) { ab = 0; aph ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        plain_epilogue(p, map_out, staging_base, tmem_base, tfull0, tempty0, total_tiles, warp, lane);
     }
 
     tc_fence_before();
@@ -962,6 +1150,8 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         if (e != cudaSuccess) return static_cast<int>(e);
         e = cudaFuncSetAttribute(conv_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
+        e = cudaFuncSetAttribute(conv1d_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
     long long total = static_cast<long long>(p.phases) * p.N * p.tiles_y * p.tiles_x * p.n_tiles_n;
@@ -1018,6 +1208,16 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         }
         return static_cast<int>(launch_k(conv_igemm_swapped_kernel<false>, dim3(grid), dim3(kConvThreads), smem, stream, p, a0, a1, b,
                                          out, static_cast<int>(total)));
+    }
+    if (p.h1d) {
+        const size_t a_stride = (static_cast<size_t>(p.h1d_rows) * 128 + 1023) / 1024 * 1024;
+        const size_t wtiles = p.h1d_wres ? static_cast<size_t>(p.taps) * p.chunks0 : static_cast<size_t>(p.stages);
+        const size_t smem = 1024 + p.h1d_na * a_stride + wtiles * p.BN * 128 + 8 * 8192;
+        if (smem > static_cast<size_t>(kConvSmemBytes) || p.h1d_na < 1 || p.h1d_na > 4 || p.stages > 8 || p.h1d_klast < 1 || p.h1d_klast > 4 ||
+            (p.h1d_wres && (p.n_tiles_n != 1 || wtiles * p.BN * 128 >= (1u << 20))))
+            return static_cast<int>(cudaErrorInvalidValue);
+        return static_cast<int>(launch_k(conv1d_halo_kernel, dim3(grid), dim3(kConvThreads), smem, stream, p, a1, b, out,
+                                         static_cast<int>(total)));
     }
     const size_t smem = 1024 + static_cast<size_t>(p.stages) * (16384 + static_cast<size_t>(p.BN) * 128) + 8 * 8192;
     if (smem > static_cast<size_t>(kConvSmemBytes)) return static_cast<int>(cudaErrorInvalidValue);

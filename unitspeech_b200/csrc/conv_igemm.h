@@ -54,6 +54,14 @@ struct ConvParams {
     int halo;                  // 1: use conv_igemm_halo_kernel (tiles_y = Hm/8, tiles_x = ceil(Wm/32))
     int halo_hy;               // rows per column of the shared-memory halo tile: 10 (dense) or 16 (power-of-two stride)
     int halo_boff;             // 1: put (start_address >> 7) & 7 into the descriptor's base-offset field
+    // 1-D halo kernel (conv1d_halo_kernel; Hm == 1, one phase, one source): per 64-channel chunk the activation tile is loaded
+    // ONCE as a box of h1d_rows = 128 + (dx_max - dx_min) (rounded up to 8) positions starting at x0 + h1d_dx0, and the
+    // taps are descriptor offsets of (dx - h1d_dx0) rows into it
+    int h1d;                   // 1: use conv1d_halo_kernel (map_a1 = the haloed activation box)
+    int h1d_rows, h1d_dx0;
+    int h1d_na;                // activation buffers in the ring (2..4)
+    int h1d_wres;              // 1: all taps x chunks weight tiles stay resident in shared memory (loaded once per CTA)
+    int h1d_klast;             // K = 16 slices (1..4) of the LAST 64-channel chunk that hold real channels; the rest is padding
     ConvTap tap[kConvMaxTaps];
     // epilogue: v = acc + bias[c]; stats (sum, sumsq per (n, group)) on v; v = v*res_scale + res; v *= mask
     const float* bias;         // [Cout] or null
@@ -95,8 +103,9 @@ namespace usb {
 // engine.cu: CUDA device ordinal the handle is bound to
 int handle_device(const usb_handle* h);
 // engine.cu: parameter block + tensor maps of a 1-D (transposed) convolution over NLC fp16 tensors
+// (cin_real: input channels that carry data, <= Cin; the K slices of pure padding are skipped)
 int build_conv1d(ConvOp& op, const int8_t* dx, int taps, int phases, const __half* in, int Cin, int N, int L,
-                 const __half* w, int Cout, const float* bias, const __half* res, __half* out);
+                 const __half* w, int Cout, const float* bias, const __half* res, __half* out, int cin_real = 0);
 
 // launches on `stream`; returns cudaError_t as int
 int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,

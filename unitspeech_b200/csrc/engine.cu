@@ -406,7 +406,7 @@ static int build_conv(ConvOp& op, int kind, const __half* in0, int C0tot, int C0
 // taps x-offsets are explicit (dilated kernels); phases > 1 = ConvTranspose1d with stride `phases`, whose output
 // [N][phases*L][Cout] is addressed as [N][L][phases*Cout] (phase ph lands in channels [ph*Cout, (ph+1)*Cout)).
 int build_conv1d(ConvOp& op, const int8_t* dx, int taps, int phases, const __half* in, int Cin, int N, int L,
-                 const __half* w, int Cout, const float* bias, const __half* res, __half* out) {
+                 const __half* w, int Cout, const float* bias, const __half* res, __half* out, int cin_real) {
     USB_TRY(load_encode_fn());
     if (Cin % 64 || Cout % 64) return fail("conv channels must be multiples of 64");
     if (phases < 1 || phases > 4 || taps < 1 || phases * taps > kConvMaxTaps) return fail("unsupported 1-D conv tap table");
@@ -420,14 +420,20 @@ int build_conv1d(ConvOp& op, const int8_t* dx, int taps, int phases, const __hal
     p.Hm = 1;
     p.Wm = L;
     static const bool allow_swap = getenv("USB_NO_SWAP_AB") == nullptr;
-    p.swap_ab = (allow_swap && Cout % 128 == 0 && res == nullptr) ? 1 : 0;
+    // USB_H1D: 0 = never use the 1-D halo kernel, 2 = also where the swapped-operand kernel applies (Cout <= 256)
+    static const int h1d_mode = getenv("USB_H1D") ? atoi(getenv("USB_H1D")) : 1;
+    const bool swap_ok = allow_swap && Cout % 128 == 0 && res == nullptr;
+    const bool h1d_ok = h1d_mode != 0 && phases == 1 && taps >= 2;
+    p.h1d = (h1d_ok && (!swap_ok || (h1d_mode == 2 && Cout <= 256))) ? 1 : 0;
+    p.swap_ab = (swap_ok && !p.h1d) ? 1 : 0;
     p.BH = 1;
     p.BW = 128;
     p.tiles_y = 1;
     p.tiles_x = (L + 127) / 128;
     p.patches_per_phase = N * p.tiles_x;
     p.Cout = Cout;
-    p.BN = p.swap_ab ? 128 : (Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64));
+    if (p.h1d) p.BN = Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64));
+    else p.BN = p.swap_ab ? 128 : (Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64));
     p.n_tiles_n = Cout / p.BN;
     p.chunks0 = Cin / 64;
     p.chunks1 = 0;
@@ -445,6 +451,34 @@ int build_conv1d(ConvOp& op, const int8_t* dx, int taps, int phases, const __hal
     for (int ph = 0; ph < phases; ++ph) p.ox_off[ph] = (int8_t)(phases > 1 ? ph : 0);
     USB_TRY(make_act_map(&op.a0, in, N, 1, L, Cin, Cin, false, 1, 128));
     op.a1 = op.a0;
+    if (p.h1d) {
+        int dmin = dx[0], dmax = dx[0];
+        for (int t = 1; t < taps; ++t) {
+            dmin = dx[t] < dmin ? dx[t] : dmin;
+            dmax = dx[t] > dmax ? dx[t] : dmax;
+        }
+        p.h1d_dx0 = dmin;
+        p.h1d_rows = (128 + (dmax - dmin) + 7) / 8 * 8;
+        if (p.h1d_rows > 256) return fail("1-D conv taps reach further than 128 positions");
+        const long long budget = kConvSmemBytes - 1024 - 8 * 8192;
+        const long long a_stride = ((long long)p.h1d_rows * 128 + 1023) / 1024 * 1024;
+        const long long b_bytes = (long long)p.BN * 128;
+        const long long w_all = (long long)taps * p.chunks0 * b_bytes;
+        if (p.n_tiles_n == 1 && w_all + 2 * a_stride <= budget && getenv("USB_H1D_NO_WRES") == nullptr) {
+            p.h1d_wres = 1;
+            long long na = (budget - w_all) / a_stride;
+            p.h1d_na = (int)(na > 4 ? 4 : na);
+            p.stages = 1;
+        } else {
+            p.h1d_na = p.BN >= 192 ? 2 : 3;
+            long long st = (budget - p.h1d_na * a_stride) / b_bytes;
+            if (st < 2) return fail("1-D halo conv does not fit in shared memory");
+            p.stages = (int)(st > 8 ? 8 : st);
+        }
+        const int last_real = (cin_real > 0 ? cin_real : Cin) - (p.chunks0 - 1) * 64;
+        p.h1d_klast = last_real <= 0 ? 1 : (last_real >= 64 ? 4 : (last_real + 15) / 16);
+        USB_TRY(make_act_map(&op.a1, in, N, 1, L, Cin, Cin, false, 1, p.h1d_rows));
+    }
     USB_TRY(make_w_map(&op.b, w, phases, Cout, taps * Cin, p.BN));
     if (p.swap_ab) USB_TRY(make_act_map(&op.o, out, N, 1, L, phases * Cout, phases * Cout, false, 1, 64, 32));
     else USB_TRY(make_act_map(&op.o, out, N, 1, L, phases * Cout, phases * Cout, false, 1, 32));

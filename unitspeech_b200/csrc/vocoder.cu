@@ -587,6 +587,7 @@ struct VocConvW {
     __half* w = nullptr;
     float* bias = nullptr;
     int Cin = 0, Cout = 0;     // padded
+    int cin_real = 0;          // input channels that carry data
     int taps = 0, phases = 1;
     int8_t dx[kConvMaxTaps] = {0};
 };
@@ -693,6 +694,7 @@ static int voc_load_conv(usb_vocoder* h, const std::string& prefix, int Cout, in
     const int pad = (k * dil - dil) / 2;
     if (pad > 127) return set_error("dilation too large in " + prefix);
     w.Cin = pad64(Cin);
+    w.cin_real = Cin;
     w.Cout = pad64(Cout);
     w.taps = k;
     w.phases = 1;
@@ -818,7 +820,7 @@ static double conv1d_flops(const VocConvW& w, int N, int L) {
 static int voc_push_conv(usb_vocoder* h, const VocConvW& w, const __half* in, int N, int L, const __half* res, __half* out) {
     VocOp op;
     op.type = VocOp::CONV;
-    VOC_TRY(build_conv1d(op.conv, w.dx, w.taps, w.phases, in, w.Cin, N, L, w.w, w.Cout, w.bias, res, out));
+    VOC_TRY(build_conv1d(op.conv, w.dx, w.taps, w.phases, in, w.Cin, N, L, w.w, w.Cout, w.bias, res, out, w.cin_real));
     op.flops = conv1d_flops(w, N, L);
     h->flops_per_call += op.flops;
     h->ops.push_back(op);
