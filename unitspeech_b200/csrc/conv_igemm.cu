@@ -63,9 +63,9 @@ __device__ __forceinline__ void warp_reduce_items(float (&v)[NV], int lane) {
 // G = GroupNorm groups intersecting the slab (64/cpg, or 1 when a group spans >= 64 channels).
 template <int G>
 __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
-                                              int c_glob, bool valid, float m, float rs, const __half* res_row,
-                                              uint32_t stage_row, int row, long long* stats_n, int cpg, int lane,
-                                              float& amax) {
+                                              int c_glob, bool valid, float m, float rs, bool has_res,
+                                              const uint4 (&rr)[8], uint32_t stage_row, int row, long long* stats_n,
+                                              int cpg, int lane, float& amax) {
     constexpr int CPG8 = 8 / G;  // 8-column chunks per group inside the slab (G=8 -> 1, 4 -> 2, 2 -> 4, 1 -> 8)
     float acc[2 * G];
 #pragma unroll
@@ -92,8 +92,8 @@ __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const uint32_
             acc[q / CPG8] += s * vm;
             acc[G + q / CPG8] += ss * vm;
         }
-        if (res_row && valid) {
-            const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(res_row + q * 8));
+        if (has_res) {      // rr: the residual row, loaded before the accumulator was waited for (zeros outside the image)
+            const uint4 r4 = rr[q];
             const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -142,7 +142,10 @@ __device__ __forceinline__ void plain_epilogue(const ConvParams& p, const CUtens
     // 64-column slabs of the tile: group 0 takes the first half (rounded up), group 1 the rest (BN == 64: none)
     const int total_slabs = p.BN >> 6;
     const int slab_begin = grp == 0 ? 0 : (total_slabs + 1) >> 1;
-    const int slabs = grp == 0 ? (total_slabs + 1) >> 1 : total_slabs - slab_begin;
+    const int slabs_split = grp == 0 ? (total_slabs + 1) >> 1 : total_slabs - slab_begin;
+    // BN == 64 (one slab per tile): the two groups take alternate tiles instead, so that eight warps, not four, share the
+    // epilogue of the narrow layers (their tiles are short: the epilogue, not the tensor pipe, paces them)
+    const bool alternate = total_slabs == 1;
     // per-warp staging (32 pixel rows x 128 B) and per-warp TMA stores: no cross-warp barrier in the epilogue
     // (two 4 KB buffers per warp, alternating, so a store only waits for the one issued two slabs earlier)
     const uint32_t warp_buf0 = staging_base + static_cast<uint32_t>(grp * 4 + ew) * 8192u;
@@ -161,7 +164,17 @@ __device__ __forceinline__ void plain_epilogue(const ConvParams& p, const CUtens
         const int xo = x * p.ox_mul + p.ox_off[tc.ph];
         const float m = (p.mask && valid) ? __ldg(p.mask + static_cast<long long>(tc.n) * p.mask_stride + xo) : 1.f;
         long long* stats_n = p.stats ? p.stats + static_cast<long long>(tc.n) * p.groups * 2 : nullptr;
-        const __half* res_px = p.res ? p.res + (tc.n * p.o_sn + yo * p.o_sy + xo * p.o_sx) : nullptr;
+        const __half* res_px = (p.res && valid) ? p.res + (tc.n * p.o_sn + yo * p.o_sy + xo * p.o_sx) : nullptr;
+        const int slabs = alternate ? ((it & 1) == grp ? 1 : 0) : slabs_split;
+        const int sl_begin = alternate ? 0 : slab_begin;
+        // the residual does not depend on the accumulator: its loads are in flight while this thread waits for the MMAs
+        uint4 rr[8];
+        auto load_res = [&](int sl) {
+            const __half* rrow = res_px ? res_px + tc.nt * p.BN + (sl_begin + sl) * 64 : nullptr;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rr[q] = rrow ? __ldg(reinterpret_cast<const uint4*>(rrow) + q) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        if (p.res && slabs > 0) load_res(0);
 
         mbar_wait_a(tfull0 + as * 8, aphase, 400 + as);
         tc_fence_after();
@@ -172,7 +185,7 @@ __device__ __forceinline__ void plain_epilogue(const ConvParams& p, const CUtens
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as) * 256u;
         for (int sl = 0; sl < slabs; ++sl) {
-            const int col0 = (slab_begin + sl) * 64;
+            const int col0 = (sl_begin + sl) * 64;
             const int c_glob = tc.nt * p.BN + col0;
             uint32_t v0[32], v1[32];
             tmem_ld_32x32(taddr + col0, v0);
@@ -189,11 +202,12 @@ __device__ __forceinline__ void plain_epilogue(const ConvParams& p, const CUtens
             buf_sel ^= 1u;
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
-            const __half* res_row = res_px ? res_px + c_glob : nullptr;
-            if (cpg >= 64) epilogue_slab<1>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
-            else if (cpg == 32) epilogue_slab<2>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
-            else if (cpg == 16) epilogue_slab<4>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
-            else epilogue_slab<8>(p, v0, v1, c_glob, valid, m, rs, res_row, stage_row, lane, stats_n, cpg, lane, amax);
+            const bool has_res = p.res != nullptr;
+            if (cpg >= 64) epilogue_slab<1>(p, v0, v1, c_glob, valid, m, rs, has_res, rr, stage_row, lane, stats_n, cpg, lane, amax);
+            else if (cpg == 32) epilogue_slab<2>(p, v0, v1, c_glob, valid, m, rs, has_res, rr, stage_row, lane, stats_n, cpg, lane, amax);
+            else if (cpg == 16) epilogue_slab<4>(p, v0, v1, c_glob, valid, m, rs, has_res, rr, stage_row, lane, stats_n, cpg, lane, amax);
+            else epilogue_slab<8>(p, v0, v1, c_glob, valid, m, rs, has_res, rr, stage_row, lane, stats_n, cpg, lane, amax);
+            if (has_res && sl + 1 < slabs) load_res(sl + 1);      // next slab's residual: in flight during the store below
             fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();
             if (lane == 0) {
@@ -352,6 +366,7 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
 // kept resident.  K = 16 slices that hold only channel padding (h1d_klast) are not issued.
 // K order: chunk-major, taps inside (the packed weight's K coordinate is (tap * chunks + chunk) * 64).
 // =====================================================================================================================
+template <bool WRES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv1d_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_out, int total_tiles) {
@@ -373,7 +388,7 @@ conv1d_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a
     const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;                  // one weight tile
     const int na = p.h1d_na;
     const int chunks = p.chunks0;
-    const int wtiles = p.h1d_wres ? p.taps * chunks : p.stages;                  // weight tiles held in shared memory
+    const int wtiles = WRES ? p.taps * chunks : p.stages;                  // weight tiles held in shared memory
     const uint32_t w_base = tiles_base + static_cast<uint32_t>(na) * a_stride;
     const uint32_t staging_base = w_base + static_cast<uint32_t>(wtiles) * b_bytes;
     const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
@@ -413,7 +428,7 @@ conv1d_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a
 
     if (warp == 0) {
         // ---------------------------------------------------- TMA producer
-        if (p.h1d_wres) {      // weights: every (tap, chunk) tile once, in packed-K order
+        if (WRES) {      // weights: every (tap, chunk) tile once, in packed-K order
             if (elect_one()) {
                 const uint32_t wb = smem_u32(&wres_bar);
                 mbar_arrive_expect_tx_a(wb, static_cast<uint32_t>(wtiles) * b_bytes);
@@ -421,7 +436,7 @@ conv1d_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a
             }
             __syncwarp();
         }
-        if (!p.h1d_wres) {     // weights streamed: one tile per (chunk, tap), in the order the MMA warp consumes them
+        if (!WRES) {     // weights streamed: one tile per (chunk, tap), in the order the MMA warp consumes them
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -459,12 +474,25 @@ conv1d_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a
         }
     } else if (warp == 1) {
         // ---------------------------------------------------- MMA issuer
+        // At 24-48 channels a tap is two or three N = 64 instructions (~32 tensor cycles each): the issue loop itself is
+        // the critical path (ncu: a generic loop spent ~650 cycles per tap on ~95 scalar instructions, tensor pipe 10 %
+        // active).  So the tap loop is fully unrolled with the per-tap row offsets in registers, the K = 16 slice count is
+        // a compile-time constant of the instantiated chunk body, and with resident weights one elected lane issues a whole
+        // chunk without reconverging.
         const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(p.BN));
-        const uint32_t desc_hi = static_cast<uint32_t>(umma_desc_sw128(0) >> 32);
+        const uint64_t dhi = static_cast<uint64_t>(static_cast<uint32_t>(umma_desc_sw128(0) >> 32)) << 32;
+        const int taps = p.taps, klast = p.h1d_klast, stages = p.stages;
+        uint32_t toff[kConvMaxTaps];      // (dx_t - dx0) rows of 128 B, in 16-byte descriptor units
+#pragma unroll
+        for (int t = 0; t < kConvMaxTaps; ++t)
+            toff[t] = t < taps ? static_cast<uint32_t>(p.tap[t].dx - p.h1d_dx0) * 8u : 0u;
+        const uint32_t a_lo0 = (tiles_base & 0x3FFFFu) >> 4, a_step = a_stride >> 4;
+        const uint32_t w_lo0 = (w_base & 0x3FFFFu) >> 4, b_step = b_bytes >> 4;
+        const uint32_t w_tap_step = static_cast<uint32_t>(chunks) * b_step;      // resident tiles are stored tap-major
         int stage = 0, ab = 0;
         uint32_t phase = 0, aph = 0;
         int it = 0;
-        if (p.h1d_wres) {
+        if (WRES) {
             mbar_wait_a(smem_u32(&wres_bar), 0u, 600);
             tc_fence_after();
         }
@@ -477,35 +505,57 @@ conv1d_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a
             for (int cc = 0; cc < chunks; ++cc) {
                 mbar_wait_a(afull0 + ab * 8, aph, 700 + ab);
                 tc_fence_after();
-                const uint32_t a_buf = tiles_base + ab * a_stride;
-                const int nk = cc == chunks - 1 ? p.h1d_klast : kConvBK / 16;
-                for (int t = 0; t < p.taps; ++t) {
-                    uint32_t w_addr;
-                    if (p.h1d_wres) {
-                        w_addr = w_base + static_cast<uint32_t>(t * chunks + cc) * b_bytes;
-                    } else {
-                        mbar_wait_a(full0 + stage * 8, phase, 300 + stage);
-                        tc_fence_after();
-                        w_addr = w_base + stage * b_bytes;
-                    }
-                    if (elect_one()) {
-                        const int roff = p.tap[t].dx - p.h1d_dx0;      // rows into the haloed tile
-                        const uint32_t a_lo = ((a_buf + static_cast<uint32_t>(roff) * 128u) & 0x3FFFFu) >> 4;
-                        const uint32_t b_lo = (w_addr & 0x3FFFFu) >> 4;
-                        for (int k = 0; k < nk; ++k) {
-                            const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k);
-                            const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
-                            tc_mma_f16(tmem_d, da, db, idesc, (cc | t | k) != 0 ? 1u : 0u);
-                        }
-                        if (!p.h1d_wres) tc_commit_a(empty0 + stage * 8);
-                        if (t == p.taps - 1) {
+                const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(ab) * a_step;
+                const bool last_cc = cc == chunks - 1;
+                const uint32_t acc0 = cc != 0 ? 1u : 0u;      // the tile's first MMA overwrites the accumulator
+                auto chunk = [&](auto nkc) {
+                    constexpr int NK = decltype(nkc)::value;
+                    if constexpr (WRES) {
+                        if (elect_one()) {
+                            uint32_t w_lo = w_lo0 + static_cast<uint32_t>(cc) * b_step;
+#pragma unroll
+                            for (int t = 0; t < kConvMaxTaps; ++t) {
+                                if (t < taps) {
+#pragma unroll
+                                    for (int k = 0; k < NK; ++k)
+                                        tc_mma_f16(tmem_d, dhi | (a_lo + toff[t] + 2u * k), dhi | (w_lo + 2u * k), idesc,
+                                                   (t | k) != 0 ? 1u : acc0);
+                                    w_lo += w_tap_step;
+                                }
+                            }
                             tc_commit_a(aempty0 + ab * 8);          // the chunk's MMAs have read the activation buffer
-                            if (cc == chunks - 1) tc_commit_a(tfull0 + as * 8);
+                            if (last_cc) tc_commit_a(tfull0 + as * 8);
+                        }
+                        __syncwarp();
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < kConvMaxTaps; ++t) {
+                            if (t < taps) {
+                                mbar_wait_a(full0 + stage * 8, phase, 300 + stage);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const uint32_t w_lo = w_lo0 + static_cast<uint32_t>(stage) * b_step;
+#pragma unroll
+                                    for (int k = 0; k < NK; ++k)
+                                        tc_mma_f16(tmem_d, dhi | (a_lo + toff[t] + 2u * k), dhi | (w_lo + 2u * k), idesc,
+                                                   (t | k) != 0 ? 1u : acc0);
+                                    tc_commit_a(empty0 + stage * 8);
+                                    if (t == taps - 1) {
+                                        tc_commit_a(aempty0 + ab * 8);
+                                        if (last_cc) tc_commit_a(tfull0 + as * 8);
+                                    }
+                                }
+                                __syncwarp();
+                                if (++stage == stages) { stage = 0; phase ^= 1u; }
+                            }
                         }
                     }
-                    __syncwarp();
-                    if (!p.h1d_wres && ++stage == p.stages) { stage = 0; phase ^= 1u; }
-                }
+                };
+                const int nk = last_cc ? klast : kConvBK / 16;
+                if (nk == 4) chunk(std::integral_constant<int, 4>{});
+                else if (nk == 3) chunk(std::integral_constant<int, 3>{});
+                else if (nk == 2) chunk(std::integral_constant<int, 2>{});
+                else chunk(std::integral_constant<int, 1>{});
                 if (++ab == na) { ab = 0; aph ^= 1u; }
             }
         }
@@ -1150,7 +1200,9 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         if (e != cudaSuccess) return static_cast<int>(e);
         e = cudaFuncSetAttribute(conv_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
-        e = cudaFuncSetAttribute(conv1d_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
+        e = cudaFuncSetAttribute(conv1d_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        e = cudaFuncSetAttribute(conv1d_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
@@ -1216,7 +1268,10 @@ int launch_conv_igemm(const ConvParams& p, const CUtensorMap& a0, const CUtensor
         if (smem > static_cast<size_t>(kConvSmemBytes) || p.h1d_na < 1 || p.h1d_na > 4 || p.stages > 8 || p.h1d_klast < 1 || p.h1d_klast > 4 ||
             (p.h1d_wres && (p.n_tiles_n != 1 || wtiles * p.BN * 128 >= (1u << 20))))
             return static_cast<int>(cudaErrorInvalidValue);
-        return static_cast<int>(launch_k(conv1d_halo_kernel, dim3(grid), dim3(kConvThreads), smem, stream, p, a1, b, out,
+        if (p.h1d_wres)
+            return static_cast<int>(launch_k(conv1d_halo_kernel<true>, dim3(grid), dim3(kConvThreads), smem, stream, p, a1, b, out,
+                                             static_cast<int>(total)));
+        return static_cast<int>(launch_k(conv1d_halo_kernel<false>, dim3(grid), dim3(kConvThreads), smem, stream, p, a1, b, out,
                                          static_cast<int>(total)));
     }
     const size_t smem = 1024 + static_cast<size_t>(p.stages) * (16384 + static_cast<size_t>(p.BN) * 128) + 8 * 8192;
