@@ -17,6 +17,7 @@
 
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "../../include/unitspeech_b200.h"
@@ -273,14 +274,17 @@ __device__ __forceinline__ vf2 vmul2(vf2 a, vf2 b) {
 
 // one 2x-rate sample for 4 channels (two packed pairs) from six consecutive input rows; ODD: i = 2m+1 uses f[10-2j], even
 // uses f[11-2j] (f2 = the taps times the up-sampling ratio, replicated into both halves)
+// The 12-tap filter is symmetric, f[k] == f[11-k]: g[m] = f[2m] (m = 0..5) holds every tap, f[2m+1] = g[5-m]
+// (24 instead of 48 registers for the two packed tap tables).
+__host__ __device__ constexpr int act2_tap(int k) { return (k & 1) ? (11 - k) >> 1 : k >> 1; }
 template <bool ODD>
-__device__ __forceinline__ void act2_srow(const vf2 (&x)[6][2], const vf2 (&f2)[12], const vf2 (&al)[2], const vf2 (&ib)[2],
+__device__ __forceinline__ void act2_srow(const vf2 (&x)[6][2], const vf2 (&g2)[6], const vf2 (&al)[2], const vf2 (&ib)[2],
                                           vf2 (&s)[2]) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        vf2 u = vmul2(f2[ODD ? 10 : 11], x[0][c]);
+        vf2 u = vmul2(g2[act2_tap(ODD ? 10 : 11)], x[0][c]);
 #pragma unroll
-        for (int j = 1; j < 6; ++j) u = vfma2(f2[ODD ? 10 - 2 * j : 11 - 2 * j], x[j][c], u);
+        for (int j = 1; j < 6; ++j) u = vfma2(g2[act2_tap(ODD ? 10 - 2 * j : 11 - 2 * j)], x[j][c], u);
         // MUFU.SIN reduces its argument itself; absolute error ~|x| * 2^-24, far below the fp16 storage of the result
         float a0, a1;
         vupk2(vmul2(al[c], u), a0, a1);
@@ -323,16 +327,16 @@ __global__ void __launch_bounds__(256, 2) snake_act2_kernel(const ActParams p, i
     };
     const int col = tid % ncol, run = tid / ncol;
     const int c0 = c_blk + col * 4;
-    vf2 al[2], ib[2], f2[12], f1[12];
+    vf2 al[2], ib[2], f2[6], f1[6];      // taps f[2m], m = 0..5 (act2_tap)
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         al[j] = vpk2(__ldg(p.alpha + c0 + 2 * j), __ldg(p.alpha + c0 + 2 * j + 1));
         ib[j] = vpk2(__ldg(p.invbeta + c0 + 2 * j), __ldg(p.invbeta + c0 + 2 * j + 1));
     }
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-        f1[k] = vpk2(p.filt[k], p.filt[k]);
-        f2[k] = vpk2(2.f * p.filt[k], 2.f * p.filt[k]);      // UpSample1d multiplies by the ratio (resample.py:31)
+    for (int k = 0; k < 6; ++k) {
+        f1[k] = vpk2(p.filt[2 * k], p.filt[2 * k]);
+        f2[k] = vpk2(2.f * p.filt[2 * k], 2.f * p.filt[2 * k]);      // UpSample1d multiplies by the ratio (resample.py:31)
     }
     const int imax = 2 * p.L - 1;
     if (n_my > 0) issue_load(tile0, 0);
@@ -391,39 +395,56 @@ __global__ void __launch_bounds__(256, 2) snake_act2_kernel(const ActParams p, i
                 vf2 xw[11][2];                               // inputs tg .. tg+10 serve the six steps of the group
         #pragma unroll
                 for (int j = 0; j < 11; ++j) load_row(tg + j, xw[j]);
+                // interior group (all but the first and last of a signal): every 2x-rate sample s[2tg+5 .. 2tg+16] exists and
+                // every output tg .. tg+5 lies inside the signal, so the per-step range tests and their branches disappear
+                // (ncu: integer compares, branches and reconvergence points were ~15 % of the executed instructions)
+                const bool interior = 2 * tg + 5 >= 0 && 2 * tg + 16 <= imax && tg + 5 < p.L;
+                __half* outg = p.out + (nbase + tg) * p.C + c0;      // output row tg of this thread's channels
+                auto six_steps = [&](auto fast_c) {
+                    constexpr bool FAST = decltype(fast_c)::value;
         #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int t = tg + k;                    // this step completes output t (slot k of acc)
-                    vf2 so[2], se[2];                        // s[2t+5] (odd index), s[2t+6] (even index)
-                    const int io = 2 * t + 5, ie = 2 * t + 6;
-                    vf2 x6[6][2];
+                    for (int k = 0; k < 6; ++k) {
+                        const int t = tg + k;                    // this step completes output t (slot k of acc)
+                        vf2 so[2], se[2];                        // s[2t+5] (odd index), s[2t+6] (even index)
+                        vf2 x6[6][2];
         #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        x6[j][0] = xw[k + j][0];
-                        x6[j][1] = xw[k + j][1];
+                        for (int j = 0; j < 6; ++j) {
+                            x6[j][0] = xw[k + j][0];
+                            x6[j][1] = xw[k + j][1];
+                        }
+                        if (FAST) {
+                            act2_srow<true>(x6, f2, al, ib, so);
+                            act2_srow<false>(x6, f2, al, ib, se);
+                        } else {
+                            const int io = 2 * t + 5, ie = 2 * t + 6;
+                            if (io >= 0 && io <= imax) act2_srow<true>(x6, f2, al, ib, so);
+                            else edge_sample(io, so);
+                            if (ie >= 0 && ie <= imax) act2_srow<false>(x6, f2, al, ib, se);
+                            else edge_sample(ie, se);
+                        }
+                        // scatter into the partial outputs t .. t+5: slot (k + d) % 6 holds output t + d
+        #pragma unroll
+                        for (int d = 0; d < 6; ++d)
+        #pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                                acc[(k + d) % 6][c] = vfma2(f1[act2_tap(10 - 2 * d)], so[c],
+                                                            vfma2(f1[act2_tap(11 - 2 * d)], se[c], acc[(k + d) % 6][c]));
+                        // output t is complete (all 12 taps added over steps t-5 .. t); emit it unless it is a warm-up step
+                        // (t >= tr  <=>  6g + k >= 5)
+                        if ((g > 0 || k == 5) && (FAST || t < p.L)) {
+                            float o0, o1, o2, o3;
+                            vupk2(acc[k][0], o0, o1);
+                            vupk2(acc[k][1], o2, o3);
+                            uint2 pk;
+                            *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(o0, o1);
+                            *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(o2, o3);
+                            *reinterpret_cast<uint2*>(outg + static_cast<long long>(k) * p.C) = pk;
+                        }
+                        acc[k][0] = acc[k][1] = zero2;           // the slot now collects output t + 6
                     }
-                    if (io >= 0 && io <= imax) act2_srow<true>(x6, f2, al, ib, so);
-                    else edge_sample(io, so);
-                    if (ie >= 0 && ie <= imax) act2_srow<false>(x6, f2, al, ib, se);
-                    else edge_sample(ie, se);
-                    // scatter into the partial outputs t .. t+5: slot (k + d) % 6 holds output t + d
-        #pragma unroll
-                    for (int d = 0; d < 6; ++d)
-        #pragma unroll
-                        for (int c = 0; c < 2; ++c)
-                            acc[(k + d) % 6][c] = vfma2(f1[10 - 2 * d], so[c], vfma2(f1[11 - 2 * d], se[c], acc[(k + d) % 6][c]));
-                    // output t is complete (all 12 taps added over steps t-5 .. t); emit it unless it is a warm-up step
-                    if (t >= tr && t < p.L) {
-                        float o0, o1, o2, o3;
-                        vupk2(acc[k][0], o0, o1);
-                        vupk2(acc[k][1], o2, o3);
-                        uint2 pk;
-                        *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(o0, o1);
-                        *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(o2, o3);
-                        *reinterpret_cast<uint2*>(p.out + (nbase + t) * p.C + c0) = pk;
-                    }
-                    acc[k][0] = acc[k][1] = zero2;           // the slot now collects output t + 6
-                }
+                };
+                if (interior) six_steps(std::true_type{});
+                else six_steps(std::false_type{});
             }
         }
         __syncthreads();     // every thread is done with this buffer before the load issued next iteration overwrites it
@@ -575,7 +596,9 @@ static void kaiser_sinc_12(float* out) {
         f[n] = 2 * cutoff * win * sinc;
         sum += f[n];
     }
-    for (int n = 0; n < K; ++n) out[n] = static_cast<float>(f[n] / sum);
+    // the filter is symmetric (window and sinc are even about the centre); the two halves are forced to be bit-identical
+    // so that the kernels can keep six taps instead of twelve in registers
+    for (int n = 0; n < K / 2; ++n) out[n] = out[K - 1 - n] = static_cast<float>(0.5 * (f[n] + f[K - 1 - n]) / sum);
 }
 
 struct VocParam {
