@@ -446,8 +446,12 @@ conv1d_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a
                         mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 100 + stage);
                         if (elect_one()) {
                             const uint32_t fb = full0 + stage * 8;
-                            mbar_arrive_expect_tx_a(fb, b_bytes);
-                            tma_load_3d_a(w_base + stage * b_bytes, &map_b, fb, (t * chunks + cc) * kConvBK, bn0, 0);
+                            if (p.dbg_flags & 1) {      // experiment: no weight traffic (results are wrong)
+                                mbar_arrive_expect_tx_a(fb, 0u);
+                            } else {
+                                mbar_arrive_expect_tx_a(fb, b_bytes);
+                                tma_load_3d_a(w_base + stage * b_bytes, &map_b, fb, (t * chunks + cc) * kConvBK, bn0, 0);
+                            }
                         }
                         __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }

@@ -479,6 +479,7 @@ int build_conv1d(ConvOp& op, const int8_t* dx, int taps, int phases, const __hal
         p.h1d_klast = last_real <= 0 ? 1 : (last_real >= 64 ? 4 : (last_real + 15) / 16);
         USB_TRY(make_act_map(&op.a1, in, N, 1, L, Cin, Cin, false, 1, p.h1d_rows));
     }
+    if (const char* e = getenv("USB_DBG_FLAGS")) p.dbg_flags = atoi(e);
     USB_TRY(make_w_map(&op.b, w, phases, Cout, taps * Cin, p.BN));
     if (p.swap_ab) USB_TRY(make_act_map(&op.o, out, N, 1, L, phases * Cout, phases * Cout, false, 1, 64, 32));
     else USB_TRY(make_act_map(&op.o, out, N, 1, L, phases * Cout, phases * Cout, false, 1, 32));

@@ -500,7 +500,45 @@ __global__ void mel_pack_kernel(const float* __restrict__ mel, __half* __restric
     *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * T + t) * Cp + cg * 8) = pk;
 }
 
-// sum of the resblock outputs of one stage (models.py:177-184): mode 0: acc = r; 1: acc += r; 2: out = (acc + r)*scale;
+// Mean of up to three resblock outputs of one stage in ONE pass (models.py:177-184): out = ((r0 + r1) + r2) * scale with the
+// same fp32 additions, in the same order, as the accumulate-as-you-go kernel below -- 8 instead of 24 bytes per element
+// and one launch instead of three.  r1 / r2 may be null.
+__global__ void stage_mean_kernel(const __half* __restrict__ r0, const __half* __restrict__ r1, const __half* __restrict__ r2,
+                                  __half* __restrict__ out, long long n8, float scale) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    float v[8];
+    {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(r0) + i);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h2[j]);
+            v[2 * j] = f.x;
+            v[2 * j + 1] = f.y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const __half* r = k == 0 ? r1 : r2;
+        if (r == nullptr) continue;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(r) + i);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h2[j]);
+            v[2 * j] += f.x;
+            v[2 * j + 1] += f.y;
+        }
+    }
+    uint4 pk;
+    __half2* o2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(v[2 * j] * scale, v[2 * j + 1] * scale);
+    reinterpret_cast<uint4*>(out)[i] = pk;
+}
+
+// (more than three resblocks per stage) sum of the resblock outputs: mode 0: acc = r; 1: acc += r; 2: out = (acc + r)*scale;
 // 3: out = r * scale (single resblock)
 __global__ void stage_accum_kernel(const __half* __restrict__ r, float* __restrict__ acc, __half* __restrict__ out,
                                    long long n8, int mode, float scale) {
@@ -628,6 +666,8 @@ struct VocOp {
     int N = 0;
     // ACCUM
     const __half* r = nullptr;
+    const __half* r1 = nullptr;      // mode 4 (stage_mean_kernel): second / third resblock output
+    const __half* r2 = nullptr;
     float* acc = nullptr;
     __half* out16 = nullptr;
     long long n8 = 0;
@@ -889,6 +929,9 @@ static int voc_build_plan(usb_vocoder* h, int B, int T) {
     const int melC = h->conv_pre.Cin;
     const size_t mel_bytes = (static_cast<size_t>(B) * T * melC * 2 + 255) / 256 * 256;
     const size_t buf_bytes = (max_elems * 2 + 255) / 256 * 256;
+    // nk <= 3: every resblock of a stage keeps its own fp16 output (R, R1, R2) and one pass averages them; otherwise an
+    // fp32 accumulator (2 buffers' worth) is updated after every resblock
+    const bool one_pass_mean = h->nk <= 3;
     h->arena_bytes = mel_bytes + 5 * buf_bytes + 2 * buf_bytes;
     VOC_CUDA(cudaMalloc(&h->arena, h->arena_bytes));
     char* base = static_cast<char*>(h->arena);
@@ -899,6 +942,8 @@ static int voc_build_plan(usb_vocoder* h, int B, int T) {
     __half* A = reinterpret_cast<__half*>(base + mel_bytes + 3 * buf_bytes);
     __half* Cc = reinterpret_cast<__half*>(base + mel_bytes + 4 * buf_bytes);
     float* acc = reinterpret_cast<float*>(base + mel_bytes + 5 * buf_bytes);
+    __half* Rj[3] = {R, reinterpret_cast<__half*>(base + mel_bytes + 5 * buf_bytes),
+                     reinterpret_cast<__half*>(base + mel_bytes + 6 * buf_bytes)};      // (share the accumulator's space)
 
     int L = T;
     VOC_TRY(voc_push_conv(h, h->conv_pre, h->melp, B, L, nullptr, P));           // models.py:171
@@ -909,28 +954,36 @@ static int voc_build_plan(usb_vocoder* h, int B, int T) {
         L *= c.upsample_rates[i];
         const int Cp = pad64(h->ch[i + 1]);
         for (int j = 0; j < h->nk; ++j) {
+            __half* Ro = one_pass_mean ? Rj[j] : R;      // this resblock's running / final output
             for (int l = 0; l < h->nd; ++l) {
-                const __half* src = l == 0 ? X : R;
+                const __half* src = l == 0 ? X : Ro;
                 if (cpl == 2) {   // AMPBlock1.forward, models.py:60-69
                     voc_push_act(h, h->rb_acts[act_i + 2 * l], src, A, B, L);
                     VOC_TRY(voc_push_conv(h, h->rb_convs[conv_i + 2 * l], A, B, L, nullptr, Cc));
                     voc_push_act(h, h->rb_acts[act_i + 2 * l + 1], Cc, A, B, L);
-                    VOC_TRY(voc_push_conv(h, h->rb_convs[conv_i + 2 * l + 1], A, B, L, src, R));
+                    VOC_TRY(voc_push_conv(h, h->rb_convs[conv_i + 2 * l + 1], A, B, L, src, Ro));
                 } else {          // AMPBlock2.forward, models.py:105-112
                     voc_push_act(h, h->rb_acts[act_i + l], src, A, B, L);
-                    VOC_TRY(voc_push_conv(h, h->rb_convs[conv_i + l], A, B, L, src, R));
+                    VOC_TRY(voc_push_conv(h, h->rb_convs[conv_i + l], A, B, L, src, Ro));
                 }
             }
             conv_i += static_cast<size_t>(h->nd) * cpl;
             act_i += static_cast<size_t>(h->nd) * cpl;
+            if (one_pass_mean && j + 1 < h->nk) continue;      // averaged together after the last resblock
             VocOp op;
             op.type = VocOp::ACCUM;
             op.r = R;
             op.acc = acc;
             op.out16 = P;
             op.n8 = static_cast<long long>(B) * L * Cp / 8;
-            op.mode = h->nk == 1 ? 3 : (j == 0 ? 0 : (j == h->nk - 1 ? 2 : 1));
             op.scale = 1.0f / h->nk;
+            if (one_pass_mean) {
+                op.mode = 4;
+                op.r1 = h->nk > 1 ? Rj[1] : nullptr;
+                op.r2 = h->nk > 2 ? Rj[2] : nullptr;
+            } else {
+                op.mode = j == 0 ? 0 : (j == h->nk - 1 ? 2 : 1);
+            }
             h->ops.push_back(op);
         }
     }
@@ -975,8 +1028,12 @@ static int voc_forward(usb_vocoder* h, const float* mel, int B, int T, float* ou
                 break;
             }
             case VocOp::ACCUM:
-                stage_accum_kernel<<<static_cast<unsigned>((op.n8 + 255) / 256), 256, 0, s>>>(op.r, op.acc, op.out16, op.n8,
-                                                                                            op.mode, op.scale);
+                if (op.mode == 4)
+                    stage_mean_kernel<<<static_cast<unsigned>((op.n8 + 255) / 256), 256, 0, s>>>(op.r, op.r1, op.r2, op.out16,
+                                                                                               op.n8, op.scale);
+                else
+                    stage_accum_kernel<<<static_cast<unsigned>((op.n8 + 255) / 256), 256, 0, s>>>(op.r, op.acc, op.out16, op.n8,
+                                                                                                op.mode, op.scale);
                 break;
             default: break;
         }
@@ -995,7 +1052,7 @@ static int voc_forward(usb_vocoder* h, const float* mel, int B, int T, float* ou
             h->prof_launches[cls]++;
             if (cls == 0) h->prof_work[0] += op.flops;
             else if (cls == 1) h->prof_work[1] += 4.0 * op.N * op.act.L * op.act.Creal;
-            else h->prof_work[2] += static_cast<double>(op.n8) * 8 * (op.mode == 0 ? 6 : (op.mode == 1 ? 10 : (op.mode == 2 ? 8 : 4)));
+            else h->prof_work[2] += static_cast<double>(op.n8) * 8 * (op.mode == 0 ? 6 : (op.mode == 1 ? 10 : (op.mode == 2 ? 8 : (op.mode == 4 ? 2 + 2 * (1 + (op.r1 != nullptr) + (op.r2 != nullptr)) : 4))));
         }
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
     }
