@@ -243,8 +243,8 @@ conv_igemm_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a0
     const uint32_t stage_bytes = 16384u + b_bytes;
     const int stages = p.stages;
     const int ksteps = p.taps * (p.chunks0 + p.chunks1);
-    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+    const uint32_t full0 = smem_u32_pinned(&full_bar[0]), empty0 = smem_u32_pinned(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32_pinned(&tmem_full_bar[0]), tempty0 = smem_u32_pinned(&tmem_empty_bar[0]);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a0);
@@ -391,9 +391,9 @@ conv1d_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap map_a
     const int wtiles = WRES ? p.taps * chunks : p.stages;                  // weight tiles held in shared memory
     const uint32_t w_base = tiles_base + static_cast<uint32_t>(na) * a_stride;
     const uint32_t staging_base = w_base + static_cast<uint32_t>(wtiles) * b_bytes;
-    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-    const uint32_t afull0 = smem_u32(&afull_bar[0]), aempty0 = smem_u32(&aempty_bar[0]);
-    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+    const uint32_t full0 = smem_u32_pinned(&full_bar[0]), empty0 = smem_u32_pinned(&empty_bar[0]);
+    const uint32_t afull0 = smem_u32_pinned(&afull_bar[0]), aempty0 = smem_u32_pinned(&aempty_bar[0]);
+    const uint32_t tfull0 = smem_u32_pinned(&tmem_full_bar[0]), tempty0 = smem_u32_pinned(&tmem_empty_bar[0]);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_b);
@@ -638,8 +638,8 @@ conv_igemm_swapped_kernel(const ConvParams p, const __grid_constant__ CUtensorMa
     const int walkers = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const int ntn = MC ? p.n_tiles_n >> 1 : p.n_tiles_n;      // channel tiles (MC: tile pairs) per patch pair
     const int tiles_per_phase = pairs_per_phase * ntn;
-    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+    const uint32_t full0 = smem_u32_pinned(&full_bar[0]), empty0 = smem_u32_pinned(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32_pinned(&tmem_full_bar[0]), tempty0 = smem_u32_pinned(&tmem_empty_bar[0]);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a0);
@@ -968,9 +968,9 @@ conv_igemm_halo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap m
     const uint32_t w_base = tiles_base + 2u * halo_bytes;
     const int stages = p.stages;
     const int chunks = p.chunks0 + p.chunks1;
-    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-    const uint32_t hfull0 = smem_u32(&hfull_bar[0]), hempty0 = smem_u32(&hempty_bar[0]);
-    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+    const uint32_t full0 = smem_u32_pinned(&full_bar[0]), empty0 = smem_u32_pinned(&empty_bar[0]);
+    const uint32_t hfull0 = smem_u32_pinned(&hfull_bar[0]), hempty0 = smem_u32_pinned(&hempty_bar[0]);
+    const uint32_t tfull0 = smem_u32_pinned(&tmem_full_bar[0]), tempty0 = smem_u32_pinned(&tmem_empty_bar[0]);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a0);

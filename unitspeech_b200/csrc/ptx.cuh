@@ -11,6 +11,14 @@ namespace usb {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// Same address, but opaque to the optimiser: it is computed once and kept in a register.  nvcc otherwise rematerialises
+// the address of a __shared__ variable at every use as (SR_CgaCtaId << 24) + offset, i.e. an S2UR (tens of cycles of
+// latency) inside the single-warp producer / MMA-issue loops, whose instruction latency is the critical path of short K steps.
+__device__ __forceinline__ uint32_t smem_u32_pinned(const void* p) {
+    uint32_t a = smem_u32(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
