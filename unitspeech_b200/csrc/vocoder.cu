@@ -236,9 +236,9 @@ __global__ void __launch_bounds__(256, 3) snake_act_kernel(const ActParams p) {
 // x[t .. t+5]) and scatters them into the six partial outputs t .. t+5 they contribute to (12 taps: out[t'] +=
 // f[10-2d] s[2t+5] + f[11-2d] s[2t+6], d = t' - t); output t is then complete.  The 2x-rate signal never leaves registers;
 // shared memory only holds the fp16 input tile (one 8-byte read per step).  A run re-computes the 10 samples before its
-// first output (5 warm-up steps): 24 steps for 19 outputs.
+// first output (5 warm-up steps): 30 steps for 25 outputs (24 for 19 in the first version).
 // =====================================================================================================================
-constexpr int kAct2TO = 19;                 // outputs per run
+constexpr int kAct2TO = 25;                 // outputs per run (19: 24 steps per 19 outputs; 25: 30 per 25, two 51 KB buffers, still two blocks per SM)
 constexpr int kAct2Steps = kAct2TO + 5;     // + warm-up; a multiple of 6 (the step loop is unrolled by the 6 partial outputs)
 static_assert(kAct2Steps % 6 == 0, "the step loop is unrolled in groups of 6");
 
@@ -468,7 +468,7 @@ static void launch_snake_act(const ActParams& a, int N, cudaStream_t s) {
     while (tpb > 1 && static_cast<long long>((tiles_x + tpb - 1) / tpb) * ((a.Creal / 4) / ncol) * N < 4 * 148) tpb >>= 1;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(snake_act2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(snake_act2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         attr = true;
     }
     const dim3 grid((tiles_x + tpb - 1) / tpb, (a.Creal / 4) / ncol, N);

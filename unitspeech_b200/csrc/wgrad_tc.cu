@@ -72,8 +72,8 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap map_a
     const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = p.stages;
     const int kp = p.BH * p.BW;
-    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+    const uint32_t full0 = smem_u32_pinned(&full_bar[0]), empty0 = smem_u32_pinned(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32_pinned(&tmem_full_bar[0]), tempty0 = smem_u32_pinned(&tmem_empty_bar[0]);
     const uint32_t tmem_cols = 2u * static_cast<uint32_t>(p.n_tile);   // 256 or 512 (powers of two)
 
     if (warp == 0 && lane == 0) {
