@@ -221,6 +221,14 @@ int usb_vocoder_get_profile(usb_vocoder* h, double* ms3, double* work3, long lon
  * channels [c_real, C) are layout padding and are written as zeros. */
 int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, int32_t N, int32_t L, int32_t C,
                      int32_t c_real, void* out, uint64_t stream);
+/* One Conv1d layer of the generator (vocoder/models.py:46-58: kernel k odd, dilation d, "same" padding
+ * (k*d - d) / 2, xutils.py:get_padding) on NLC fp16 device tensors: x (N, L, c_in), w (c_out, k * c_in) with
+ * w[co][t * c_in + ci] = weight[co][ci][t], bias (c_out) fp32 or null, res (N, L, c_out) or null (out = conv + res; res
+ * may be `out`), out (N, L, c_out).  Channel counts are the padded ones (multiples of 64); input channels
+ * [c_in_real, c_in) must be zero.  The layer picks its kernel exactly as the vocoder does (swapped-operand kernel, or the
+ * 1-D halo kernel). */
+int usb_op_conv1d(const void* x, const void* w, const float* bias, const void* res, void* out, int32_t N, int32_t L,
+                  int32_t c_in, int32_t c_in_real, int32_t c_out, int32_t k, int32_t dilation, uint64_t stream);
 /* kaiser_sinc_filter1d(0.25, 0.3, 12) as the library computes it (alias_free_torch/filter.py:28-57) */
 int usb_vocoder_filter(float* out12);
 

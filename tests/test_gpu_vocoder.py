@@ -67,6 +67,62 @@ def test_snake_activation_kernel(N, L, C, Cr):
     assert float(err.max()) <= 4e-3 * max(1.0, float(ref.abs().max())), float(err.max())
 
 
+# (padded c_in, real c_in, padded c_out, real c_out, k, dilation, N, L, residual)
+CONV1D_CASES = [
+    (64, 24, 64, 24, 3, 1, 2, 300, False),       # resident weights, 2 of 4 K slices, ragged last tile
+    (64, 24, 64, 24, 11, 5, 1, 1000, True),      # widest halo (50 positions), in-place residual
+    (64, 48, 64, 48, 7, 3, 2, 129, True),        # 3 of 4 K slices, one position past a tile
+    (64, 64, 64, 64, 11, 1, 1, 17, False),       # signal shorter than the halo
+    (128, 96, 128, 96, 3, 5, 1, 515, True),      # two chunks, the second one half padding, resident weights
+    (128, 96, 128, 96, 11, 3, 2, 260, True),     # streamed weights, BN = 128
+    (192, 192, 192, 192, 7, 5, 1, 400, False),   # BN = 192 (three epilogue slabs over two groups)
+    (192, 192, 192, 192, 11, 1, 2, 131, True),
+    (384, 384, 384, 384, 3, 3, 1, 257, True),    # two N tiles of 192
+    (256, 256, 256, 256, 7, 1, 1, 384, True),    # BN = 256, two activation buffers
+    (128, 128, 128, 128, 7, 3, 1, 200, False),   # no residual, Cout % 128 == 0: the swapped-operand kernel
+    (64, 64, 64, 64, 1, 1, 1, 100, True),        # k = 1: the per-tap kernel
+]
+
+
+@pytest.mark.parametrize("ci,cir,co,cor,k,d,N,L,with_res", CONV1D_CASES)
+def test_conv1d_layer_matches_torch(ci, cir, co, cor, k, d, N, L, with_res):
+    """One generator Conv1d (vocoder/models.py:46-58, "same" padding of xutils.get_padding) through usb_op_conv1d against
+    torch.nn.functional.conv1d in fp32 on the same fp16-rounded operands: every kernel the layer can pick (1-D halo kernel
+    with resident / streamed weights and N = 64 / 128 / 192 / 256, swapped-operand kernel, per-tap kernel), ragged lengths,
+    channel padding, in-place residual."""
+    from unitspeech_b200 import abi
+    lib = abi.load_library()
+    g = torch.Generator().manual_seed(ci * 131 + k * 17 + d + L)
+    x = torch.zeros(N, ci, L)
+    x[:, :cir] = torch.randn(N, cir, L, generator=g)
+    x = x.half().float()
+    w = torch.zeros(co, ci, k)
+    w[:cor, :cir] = torch.randn(cor, cir, k, generator=g) / (cir * k) ** 0.5
+    w = w.half().float()
+    bias = torch.zeros(co)
+    bias[:cor] = torch.randn(cor, generator=g) * 0.1
+    res = torch.zeros(N, co, L)
+    res[:, :cor] = torch.randn(N, cor, L, generator=g)
+    res = res.half().float()
+    ref = torch.nn.functional.conv1d(x, w, bias, padding=(k * d - d) // 2, dilation=d)
+    if with_res:
+        ref = ref + res
+    xd = x.permute(0, 2, 1).contiguous().cuda().half()
+    wd = w.permute(0, 2, 1).contiguous().reshape(co, k * ci).cuda().half()      # [co][t * ci + c]
+    bd = bias.cuda()
+    out = res.permute(0, 2, 1).contiguous().cuda().half() if with_res else torch.full((N, L, co), float("nan"), device="cuda",
+                                                                                    dtype=torch.half)
+    abi.check(lib.usb_op_conv1d(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr() if with_res else None, out.data_ptr(),
+                                N, L, ci, cir, co, k, d, int(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    got = out.float().cpu().permute(0, 2, 1)
+    assert torch.isfinite(got).all()
+    assert float(got[:, cor:].abs().max()) == 0.0 if cor < co else True      # padding channels stay exactly zero
+    err = (got - ref).abs()
+    tol = 2e-3 * max(1.0, float(ref.abs().max()))      # fp16 output rounding (2^-11 relative) + fp32 accumulation order
+    assert float(err.max()) <= tol, (float(err.max()), tol)
+
+
 def test_library_filter_equals_reference_filter(golden_dir):
     from unitspeech_b200 import abi
     buf = (ctypes.c_float * 12)()

@@ -96,6 +96,8 @@ SIGNATURES = {
     "usb_vocoder_set_profiling": (c_int32, [c_void_p, c_int32]),
     "usb_vocoder_get_profile": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)]),
     "usb_op_snake_act": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_uint64]),
+    "usb_op_conv1d": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                c_int32, c_int32, c_uint64]),
     "usb_vocoder_filter": (c_int32, [POINTER(c_float)]),
     # ---- fine-tune step, operator level (include/unitspeech_b200_train.h)
     "usb_t_pack_conv": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_uint64]),

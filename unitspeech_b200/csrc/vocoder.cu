@@ -1216,6 +1216,28 @@ int usb_op_snake_act(const void* x, const float* alpha, const float* invbeta, in
     return 0;
 }
 
+int usb_op_conv1d(const void* x, const void* w, const float* bias, const void* res, void* out, int32_t N, int32_t L,
+                  int32_t c_in, int32_t c_in_real, int32_t c_out, int32_t k, int32_t dilation, uint64_t stream) {
+    if (!x || !w || !out) return set_error("null argument");
+    if (c_in % 64 || c_out % 64 || N < 1 || L < 1 || c_in_real < 1 || c_in_real > c_in)
+        return set_error("conv1d needs channel counts that are multiples of 64 and 1 <= c_in_real <= c_in");
+    if (k < 1 || k > kConvMaxTaps || (k & 1) == 0 || dilation < 1) return set_error("conv1d needs an odd kernel size <= 16");
+    const int pad = (k * dilation - dilation) / 2;
+    if (pad > 127) return set_error("dilation too large");
+    int8_t dx[kConvMaxTaps] = {0};
+    for (int t = 0; t < k; ++t) dx[t] = static_cast<int8_t>(t * dilation - pad);
+    int dev = 0, sms = 0;
+    VOC_CUDA(cudaGetDevice(&dev));
+    VOC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ConvOp op;
+    VOC_TRY(build_conv1d(op, dx, k, 1, static_cast<const __half*>(x), c_in, N, L, static_cast<const __half*>(w), c_out, bias,
+                         static_cast<const __half*>(res), static_cast<__half*>(out), c_in_real));
+    const int rc = launch_conv_igemm(op.p, op.a0, op.a1, op.b, op.o, sms, reinterpret_cast<cudaStream_t>(stream));
+    if (rc != 0) return set_error(std::string("conv1d launch failed: ") + cudaGetErrorString(static_cast<cudaError_t>(rc)));
+    VOC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int usb_vocoder_filter(float* out12) {
     if (!out12) return set_error("null argument");
     kaiser_sinc_12(out12);
