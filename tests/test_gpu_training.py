@@ -101,6 +101,13 @@ def test_clip_and_adam_trajectory_matches_reference(golden_dir, name):
         if want == 0.0:
             assert float(d.abs().max()) == 0.0, k
             continue
+        if d.numel() == 1:
+            # a Rezero gain starts at 0 and its gradient is of the order of Adam's eps (1e-8): the step lr * g / (|g| + eps) is
+            # then LINEAR in g, and the net displacement (a few % of lr * K) is as ill-conditioned as the gradient itself, which
+            # test_gradients_match_oracle_autograd_and_reference_golden bounds absolutely, not relatively.  Same rule here: 5 % of lr * K.
+            assert abs(float(d.double().norm()) - want) <= 5e-2 * lr * K, (k, float(d.double().norm()), want)
+            assert float(d) * float(p_or[k] - params[k]) > 0, k      # same direction as the oracle's trajectory
+            continue
         assert float(d.double().norm()) == pytest.approx(want, rel=5e-2), k
         do = p_or[k] - params[k]
         cos = float(torch.dot(d.reshape(-1), do.reshape(-1)) / (d.norm() * do.norm()))

@@ -258,33 +258,38 @@ int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
 //     -2/d0 = dh1 * rcp(dh0 * dh1) (|dh| <= ~1.2e17 each: the product stays finite) -- no separate scale by -2;
 //   * the exponent argument is min(x, 20) * log2(e) from the normalised value itself (no second affine pair in registers);
 //   * the mask multiply is skipped for unmasked pixels (m == 1, warp-uniform almost everywhere).
+// a2 = a log2(e), b2 = b log2(e): the exponent argument t = log2(e) x comes straight out of one FMA on the raw value,
+// and the normalised value x = t ln(2) is never formed: with dq = -((1 + e)^2 + 1) / (2 ln 2) built from e by two FMAs,
+// 1/dq = -2 ln(2) / d, so Mish(x) + add = x - 2x/d + add = t / dq + (a v + b + add).  One reciprocal serves a channel
+// pair (1/dq0 = dq1 / (dq0 dq1)); the clamp of t keeps dq0 dq1 finite.
 template <bool HAS_RES>
-__device__ __forceinline__ uint4 gn_mish8(const uint4& rv, const uint4& rr, const f32x2 (&a)[4], const f32x2 (&b)[4],
-                                          const f32x2 (&ba)[4], float m) {
+__device__ __forceinline__ uint4 gn_mish8(const uint4& rv, const uint4& rr, const f32x2 (&a)[4], const f32x2 (&a2)[4],
+                                          const f32x2 (&b2)[4], const f32x2 (&ba)[4], f32x2 m2) {
     const __half2* hv = reinterpret_cast<const __half2*>(&rv);
     const __half2* hr = reinterpret_cast<const __half2*>(&rr);
-    const f32x2 klog = pk2(kLog2e, kLog2e), mhalf = pk2(-0.5f, -0.5f), mone = pk2(-1.f, -1.f);
+    constexpr float kC = 0.72134752044448170368f;      // 1 / (2 ln 2)
+    const f32x2 mc = pk2(-kC, -kC), m2c = pk2(-2.f * kC, -2.f * kC);
     uint4 o;
     uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {            // channel pair (2i, 2i+1)
         const float2 vf = __half22float2(hv[i]);
         const f32x2 v = pk2(vf.x, vf.y);
-        const f32x2 x = fma2(v, a[i], b[i]);
         float t0, t1;
-        upk2(mul2(x, klog), t0, t1);
+        const f32x2 t = fma2(v, a2[i], b2[i]);
+        upk2(t, t0, t1);
         const float e0 = ex2_ftz(fminf(t0, 20.f * kLog2e)), e1 = ex2_ftz(fminf(t1, 20.f * kLog2e));
         const f32x2 e = pk2(e0, e1);
         float d0, d1;
-        upk2(fma2(e, fma2(e, mhalf, mone), mone), d0, d1);      // dh = -d/2
+        upk2(fma2(e, fma2(e, mc, m2c), m2c), d0, d1);            // dq = -(e^2 + 2e + 2) / (2 ln 2)
         const float rn = rcp_ftz(d0 * d1);
-        const f32x2 q = pk2(d1 * rn, d0 * rn);                    // (-2/d0, -2/d1)
-        f32x2 y = fma2(x, q, fma2(v, a[i], ba[i]));               // x - 2x/d + add  (ba = b + add)
+        const f32x2 q = pk2(d1 * rn, d0 * rn);                    // (1/dq0, 1/dq1)
+        f32x2 y = fma2(t, q, fma2(v, a[i], ba[i]));               // x - 2x/d + (x + add)  (ba = b + add)
         if (HAS_RES) {
             const float2 rf = __half22float2(hr[i]);
             y = add2(y, pk2(rf.x, rf.y));
         }
-        if (m != 1.f) y = mul2(y, pk2(m, m));
+        y = mul2(y, m2);      // unconditional: a test for m == 1 costs a predicate and register copies per pair
         float y0, y1;
         upk2(y, y0, y1);
         ow[i] = pack2(y0, y1);
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(256, MINB) gn_apply_kernel(const GnApplyParams
         group_moments(p.stats, n, p.groups, threadIdx.x, count, p.eps, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
     }
     __syncthreads();
-    f32x2 a[4], b[4], ba[4];
+    f32x2 a[4], a2[4], b2[4], ba[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float af[2], bf[2], baf[2];
@@ -322,7 +327,8 @@ __global__ void __launch_bounds__(256, MINB) gn_apply_kernel(const GnApplyParams
             baf[j] = bf[j] + (p.addvec ? __ldg(p.addvec + static_cast<long long>(n) * p.addvec_stride + c) : 0.f);
         }
         a[i] = pk2(af[0], af[1]);
-        b[i] = pk2(bf[0], bf[1]);
+        a2[i] = pk2(af[0] * kLog2e, af[1] * kLog2e);
+        b2[i] = pk2(bf[0] * kLog2e, bf[1] * kLog2e);
         ba[i] = pk2(baf[0], baf[1]);
     }
     const float* mk = p.mask + static_cast<long long>(n) * p.W;
@@ -331,14 +337,17 @@ __global__ void __launch_bounds__(256, MINB) gn_apply_kernel(const GnApplyParams
     const long long base = static_cast<long long>(n) * p.P * C + tq * 8;
     int xcol = (p_begin + pl) % p.W;   // column of the thread's next pixel, advanced incrementally
     __half2 amax2 = __float2half2_rn(0.f);   // largest |value| stored by this thread (saturation report)
-    for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += lanes * U) {
+    // element offset of the thread's current pixel, advanced by adds (no 64-bit multiply per 16-byte vector)
+    const long long ustride = static_cast<long long>(lanes) * C;
+    long long off0 = base + static_cast<long long>(p_begin + pl) * C;
+    for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += lanes * U, off0 += ustride * U) {
         uint4 rv[U], rr[U];
         float m[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int pix = pix0 + u * lanes;
             if (pix < p_end) {
-                const long long o = base + static_cast<long long>(pix) * C;
+                const long long o = off0 + u * ustride;
                 rv[u] = ldg_stream(reinterpret_cast<const uint4*>(p.raw + o));
                 if (HAS_RES) rr[u] = ldg_stream(reinterpret_cast<const uint4*>(p.res + o));
                 m[u] = __ldg(mk + xcol);
@@ -350,11 +359,11 @@ __global__ void __launch_bounds__(256, MINB) gn_apply_kernel(const GnApplyParams
         for (int u = 0; u < U; ++u) {
             const int pix = pix0 + u * lanes;
             if (pix < p_end) {
-                const uint4 o4 = gn_mish8<HAS_RES>(rv[u], rr[u], a, b, ba, m[u]);
+                const uint4 o4 = gn_mish8<HAS_RES>(rv[u], rr[u], a, a2, b2, ba, pk2(m[u], m[u]));
                 const __half2* oh = reinterpret_cast<const __half2*>(&o4);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) amax2 = __hmax2(amax2, __habs2(oh[i]));
-                if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(p.out + base + static_cast<long long>(pix) * C) = o4;
+                if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(p.out + off0 + u * ustride) = o4;
             }
         }
     }
