@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256, MINB) gn_apply_kernel(const GnApplyParams
         b2[i] = pk2(bf[0] * kLog2e, bf[1] * kLog2e);
         ba[i] = pk2(baf[0], baf[1]);
     }
-    const float* mk = p.mask + static_cast<long long>(n) * p.W;
+    const int mrow = n * p.W;      // 32-bit index of the sample's mask row (N * W < 2^31 always)
     const int p_begin = blockIdx.x * pix_per_block;
     const int p_end = min(p.P, p_begin + pix_per_block);
     const long long base = static_cast<long long>(n) * p.P * C + tq * 8;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256, MINB) gn_apply_kernel(const GnApplyParams
                 const long long o = off0 + u * ustride;
                 rv[u] = ldg_stream(reinterpret_cast<const uint4*>(p.raw + o));
                 if (HAS_RES) rr[u] = ldg_stream(reinterpret_cast<const uint4*>(p.res + o));
-                m[u] = __ldg(mk + xcol);
+                m[u] = __ldg(p.mask + (mrow + xcol));
             }
             xcol += lanes_mod;
             if (xcol >= p.W) xcol -= p.W;
