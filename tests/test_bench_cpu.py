@@ -48,3 +48,33 @@ def test_gpu_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
                        text=True, cwd=ROOT, timeout=300)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+@pytest.mark.parametrize("name", ["r2_bench_driver_style.json", "r2_bench_head_final.json", "r2_bench_8gpu.json", "r2_bench_2gpu.json"])
+def test_kept_bench_lines_carry_the_contract_keys(name):
+    """The bench lines kept under profiles/ (the ones README / DESIGN quote) are complete contract lines: metric and config
+    of BASELINE.json, e2e with its byte counts, roofline against MEASURED_PEAKS-style denominators, clocks without a
+    thermal / hardware slowdown, a non-zero launch count."""
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        pytest.skip(name + " not kept")
+    with open(path) as f:
+        line = json.load(f)
+    assert line["metric"] == "mel frames/s of 50-step CFG reverse diffusion" and line["unit"] == "frames/s"
+    assert line["higher_is_better"] is True and line["scaling"] == "weak" and line["data"] == "synthetic" and line["dtype"] == "f16"
+    assert line["n_gpus"] >= 1 and line["steps"] >= 1 and line["warmup"] >= 3 and line["value"] > 0 and line["ms_per_step"] > 0
+    cfg = line["config"]
+    assert "workload" in cfg and cfg["frames"] == 1000 and cfg["batch_per_gpu"] == 32 and cfg["diffusion_steps"] == 50
+    assert cfg["job_utterances"] == 32 * line["n_gpus"]
+    # value = frames of the whole job / time of one pass
+    assert line["value"] == pytest.approx(cfg["job_utterances"] * cfg["frames"] / (line["ms_per_step"] / 1e3), rel=1e-6)
+    e2e = line["e2e"]
+    assert e2e["unit"] == "frames/s" and 0 < e2e["value"] <= line["value"] * 1.02
+    assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
+    assert line["gpu_launches"] > 0
+    roof = line["roofline"]
+    assert roof["bound"] == "tensor" and roof["unit"] == "TFLOP/s" and roof["frac"] == pytest.approx(roof["achieved"] / roof["peak"], rel=1e-6)
+    assert 0.5 < roof["frac"] < 1.0
+    clocks = line["clocks"]
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks["reasons"])
+    assert line["vs_baseline"] is None      # BASELINE.md holds no published number for this metric
